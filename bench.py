@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py — decode tokens/s of the quantized-decode hot path (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--model llama3-70b] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A step = one decoded token (b=1) through every layer + lm_head of the named model with synthetic random-init weights in
+the Q4_K_M / Q5_K_M type mixture, positions continuing after a 128-token prompt (llama-bench tg protocol,
+examples/llama-bench/llama-bench.cpp:1433-1470).  N>1 = prima's layer-window pipeline re-targeted to NVLink: contiguous
+layer ranges per rank, hidden state handed off with one NCCL send/recv per stage boundary, strictly sequential tokens
+(the sampled token returns to rank 0 before the next step starts) — so per-token latency, not pipelined throughput.
+
+Prints ONE JSON line (rank 0).  `value`: device-resident steps (token id via kernel argument, logits stay in HBM);
+`e2e`: the llama_decode-equivalent host call (token id + position H2D from pinned memory, logits D2H every step).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+MODELS = {
+    "llama3-70b": dict(hp=dict(n_layer=80, n_embd=8192, n_head=64, n_head_kv=8, head_dim=128, n_ff=28672, n_vocab=128256, rope_mode=0,
+                               n_ctx_orig=8192, rope_freq_base=500000.0, rope_freq_scale=1.0, rms_eps=1e-5), ftype=0, name="Llama-3-70B Q4_K_M"),
+    "llama3-8b": dict(hp=dict(n_layer=32, n_embd=4096, n_head=32, n_head_kv=8, head_dim=128, n_ff=14336, n_vocab=128256, rope_mode=0,
+                              n_ctx_orig=8192, rope_freq_base=500000.0, rope_freq_scale=1.0, rms_eps=1e-5), ftype=0, name="Llama-3-8B Q4_K_M"),
+    "qwen2.5-72b": dict(hp=dict(n_layer=80, n_embd=8192, n_head=64, n_head_kv=8, head_dim=128, n_ff=29568, n_vocab=152064, rope_mode=2,
+                                n_ctx_orig=32768, rope_freq_base=1000000.0, rope_freq_scale=1.0, rms_eps=1e-6), ftype=1, name="Qwen2.5-72B Q5_K_M"),
+}
+PROMPT = 128
+METRIC = "decode tokens/sec Llama-3-70B Q4_K_M b=1 @1/2/4/8 B200; % HBM roofline"
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, STREAM-style copy)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "power_w_max": max(pw) if pw else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def token_at(i, n_vocab):
+    return (i * 7919 + 13) % n_vocab
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def cpu_reference(model_key, steps, warmup, sample_layers=2):
+    """Times the reference's own CPU ggml path (oracle/_ref, compiled unmodified from the reference) on a bounded sample
+    of the workload: `sample_layers` full-size layers + the lm_head, extrapolated to the full layer count."""
+    import numpy as np
+    import oracle_lib as O
+    from tiny_model import TinyModel
+    cfg = MODELS[model_key]
+    hp = dict(cfg["hp"])
+    L = hp["n_layer"]
+    kind = "reference" if O.have_ref() else "port"
+    threads = os.cpu_count() or 1
+    tm = TinyModel(n_layer=sample_layers, n_embd=hp["n_embd"], n_head=hp["n_head"], n_head_kv=hp["n_head_kv"], n_ff=hp["n_ff"], n_vocab=hp["n_vocab"],
+                   n_ctx=PROMPT + 64, arch="llama" if hp["rope_mode"] == 0 else "qwen2", ftype="q4_K_M" if cfg["ftype"] == 0 else "q5_K_M", seed=1)
+    # the sample's layers must carry the FULL model's average bytes: take one "normal" and one "more-bits" layer
+    tm.hp.update({k: hp[k] for k in ("rope_freq_base", "rms_eps", "n_ctx_orig")})
+    m = tm.oracle_struct()
+    nv, E = hp["n_vocab"], hp["n_embd"]
+    logits = np.zeros(nv, dtype=np.float32)
+    if kind == "reference":
+        ref = O.Ref(threads)
+        h = ref.graph.gref_create(C.byref(m), threads)
+
+        def one(i):
+            tok = np.array([token_at(i, nv)], dtype=np.int32)
+            rc = ref.graph.gref_decode(h, tok.ctypes.data_as(C.c_void_p), 1, PROMPT + (i % 32), logits.ctypes.data_as(C.c_void_p), None, 1 << 30)
+            assert rc == 0
+
+        def head_only():
+            t, a = tm.tensors["output.weight"]
+            x = np.ones(E, dtype=np.float32)
+            t0 = time.perf_counter()
+            ref.mul_mat(t, a, nv, E, x, n_threads=threads)
+            return time.perf_counter() - t0
+    else:
+        port = O.Port()
+        threads = 1
+
+        def one(i):
+            port.lib.port_llama_decode(C.byref(m), token_at(i, nv), PROMPT + (i % 32), logits.ctypes.data_as(C.c_void_p), None)
+
+        def head_only():
+            t, a = tm.tensors["output.weight"]
+            x = np.ones(E, dtype=np.float32)
+            t0 = time.perf_counter()
+            port.mul_mat(t, a, nv, E, x)
+            return time.perf_counter() - t0
+    for i in range(warmup):
+        one(i)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        one(warmup + i)
+    t_sample = (time.perf_counter() - t0) / steps
+    t_head = min(head_only() for _ in range(3))
+    t_layer = max(t_sample - t_head, 1e-9) / sample_layers
+    t_full = t_head + L * t_layer
+    return {"value": 1.0 / t_full, "unit": "tokens/s", "cores": threads, "kind": kind,
+            "sample": f"{steps} decode steps of {sample_layers} full-size layers + lm_head of {cfg['name']} (synthetic blocks) on the reference CPU "
+                      f"ggml backend ({O.ref_variant() if kind == 'reference' else 'C port'}, OpenMP, GGML_USE_LLAMAFILE off), "
+                      f"extrapolated to {L} layers: t_layer={t_layer * 1e3:.2f} ms, t_head={t_head * 1e3:.2f} ms",
+            "ms_per_step_sample": t_sample * 1e3, "ms_per_token_extrapolated": t_full * 1e3}
+
+
+# ------------------------------------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=128)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--model", default="llama3-70b", choices=sorted(MODELS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n-ctx", type=int, default=512)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg = MODELS[args.model]
+    hp = dict(cfg["hp"], n_ctx=args.n_ctx)
+    config = {"workload": f"{cfg['name']} decode b=1, synthetic random-init weights, {PROMPT}-token prompt then tg steps, n_ctx {args.n_ctx}, KV f16, FA off",
+              "parallelism": "single GPU" if world == 1 else f"layer pipeline pp{world} (NCCL send/recv hand-off)",
+              "l2": "no explicit flush: every step streams the shard's weights (>> 126 MB L2) once"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps, warm = min(args.steps, 6), min(args.warmup, 1)
+        cb = cpu_reference(args.model, steps, warm)
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "tokens/s", "n_gpus": args.gpus, "steps": steps,
+                          "warmup": warm, "ms_per_step": cb["ms_per_token_extrapolated"], "higher_is_better": True, "scaling": "strong",
+                          "vs_baseline": None, "dtype": "int8 x k-quant dot, f32 accumulate", "data": "synthetic", "config": config,
+                          "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import numpy as np
+    import torch
+    import pkgload
+    pkg = pkgload.load()
+    lib = pkg.Lib.get()
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    assert args.steps + args.warmup + PROMPT <= args.n_ctx, "n_ctx too small for prompt + warmup + steps"
+
+    L = hp["n_layer"]
+    # uniform contiguous layer windows (prima: n_layer_window; 8 identical B200s need no ILP scheduler)
+    bounds = [round(r * L / world) for r in range(world + 1)]
+    l0, l1 = bounds[rank], bounds[rank + 1]
+    H = pkg.HParams(**hp)
+    t0 = time.perf_counter()
+    eng = pkg.Model(H, local, (l0, l1), with_embd=(rank == 0), with_head=(rank == world - 1))
+    eng.synth(cfg["ftype"], 1234 + rank)
+    eng.finalize()
+    t_load = time.perf_counter() - t0
+    nv, E = hp["n_vocab"], hp["n_embd"]
+    ext = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", local))
+
+    class DevBuf:   # __cuda_array_interface__ view of an engine buffer so torch.distributed can send/recv it in place
+        def __init__(self, ptr, n):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+    hid_in = hid_out = None
+    if world > 1:
+        hid_in = torch.as_tensor(DevBuf(eng.hidden_in_ptr, E), device=torch.device("cuda", local))
+        hid_out = torch.as_tensor(DevBuf(eng.hidden_out_ptr, E), device=torch.device("cuda", local))
+    tok_t = torch.zeros(1, dtype=torch.int64, device=torch.device("cuda", local))
+    logits_t = torch.as_tensor(DevBuf(eng.logits_ptr, nv), device=torch.device("cuda", local)) if rank == world - 1 else None
+    logits_host = np.zeros(nv, dtype=np.float32)
+
+    def step(i, pos, host_io):
+        """One token through the pipeline.  Synthetic token ids (llama-bench tg uses random ids); in pipeline mode the last
+        stage still returns a token (argmax) to rank 0 so that steps are strictly sequential like real decoding."""
+        tok = token_at(i, nv)
+        with torch.cuda.stream(ext):
+            if world == 1:
+                if host_io:
+                    eng.decode(tok, pos, logits_host)
+                else:
+                    eng.decode_async(tok, pos)
+                return
+            if rank > 0:
+                dist.recv(hid_in, src=rank - 1)
+            if host_io and rank == world - 1:
+                eng.decode(tok, pos, logits_host)
+            else:
+                eng.decode_async(tok, pos)
+            if rank < world - 1:
+                dist.send(hid_out, dst=rank + 1)
+            # the sampled token closes the ring: last stage -> rank 0 (prima returns the result to the master, src/llama.cpp:18559)
+            if rank == world - 1:
+                tok_t.copy_(torch.argmax(logits_t).reshape(1))
+                dist.send(tok_t, dst=0)
+            if rank == 0:
+                dist.recv(tok_t, src=world - 1)
+                tok_t.cpu()   # the master must see the token before it can start the next step
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # prompt (untimed): fills the KV cache so the timed steps attend over a realistic window
+    for i in range(PROMPT):
+        step(i, i, False)
+    for i in range(args.warmup):
+        step(PROMPT + i, PROMPT + i, False)
+    barrier()
+
+    def timed(host_io, first):
+        sampler = ClockSampler(local)
+        sampler.start()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = lib.c.pb200_kernel_launches()
+        with torch.cuda.stream(ext):
+            e0.record()
+        for i in range(args.steps):
+            step(first + i, first + i, host_io)
+        with torch.cuda.stream(ext):
+            e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = lib.c.pb200_kernel_launches() - n0
+        clocks = sampler.stop()
+        if dist is not None:
+            t = torch.tensor([ms], device=torch.device("cuda", local))
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            lt = torch.tensor([launches], device=torch.device("cuda", local))
+            dist.all_reduce(lt)
+            launches = int(lt.item())
+        return ms, launches, clocks
+
+    first = PROMPT + args.warmup
+    ms_dev, launches, clocks = timed(False, first)
+    eng.kv_clear() if False else None
+    ms_e2e, _, clocks_e2e = timed(True, first)     # same positions again: the KV rows are simply rewritten
+    # live roofline of the dominant kernel (k_gemv_kquant): CUDA events around every GEMV launch of profiled steps
+    prof = [eng.profile_step(token_at(first + i, nv), first + i) for i in range(4)]
+    gemv_ms = sum(p["gemv_ms"] for p in prof) / len(prof)
+    gemv_bytes = prof[0]["gemv_bytes"]
+    gemv_launches = prof[0]["gemv_launches"]
+    wb = eng.weight_bytes
+    if dist is not None:
+        t = torch.tensor([float(wb), gemv_ms, float(gemv_bytes), float(gemv_launches)], device=torch.device("cuda", local), dtype=torch.float64)
+        dist.all_reduce(t)
+        wb, gemv_ms, gemv_bytes, gemv_launches = int(t[0].item()), float(t[1].item()), int(t[2].item()), int(t[3].item())
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = peaks()
+    ms_step = ms_dev / args.steps
+    ms_step_e2e = ms_e2e / args.steps
+    kv_bytes = 2 * L * (first + args.steps // 2) * hp["n_head_kv"] * 128 * 2
+    achieved = gemv_bytes / (gemv_ms * 1e-3) / 1e9
+    out = {
+        "metric": METRIC, "value": 1e3 / ms_step, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "int8 activations (q8_K) x k-quant weights, int32 dot, f32 accumulate", "data": "synthetic", "config": config,
+        "e2e": {"value": 1e3 / ms_step_e2e, "unit": "tokens/s", "h2d_bytes_per_step": 8, "d2h_bytes_per_step": nv * 4,
+                "ms_per_step": ms_step_e2e, "api": "pb200_decode (token id + position from pinned host memory in, n_vocab f32 logits out)"},
+        "gpu_launches": launches,
+        "clocks": clocks, "clocks_e2e": clocks_e2e,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "kernel": "k_gemv_kquant (TMA-staged k-quant GEMV)", "peak_source": peak_src,
+                     "how": f"algorithmic bytes of the {gemv_launches} GEMV launches of one token ({gemv_bytes} B = sum of ggml_nbytes of the weight "
+                            f"matrices read) / their summed CUDA-event durations ({gemv_ms:.3f} ms, events on the launching stream, mean of 4 profiled steps)",
+                     "whole_step": {"algorithmic_bytes_per_token": wb + kv_bytes, "achieved": (wb + kv_bytes) / (ms_step * 1e-3) / 1e9,
+                                    "frac": (wb + kv_bytes) / (ms_step * 1e-3) / 1e9 / peak,
+                                    "frac_of_8TBs_north_star": (wb + kv_bytes) / (ms_step * 1e-3) / 8e12}},
+        "model_load_s": t_load,
+    }
+    if not args.no_cpu_baseline:
+        try:
+            out["cpu_baseline"] = cpu_reference(args.model, 4, 1)
+        except Exception as ex:   # the checker must never take the measurement down
+            out["cpu_baseline"] = {"value": None, "unit": "tokens/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {ex!r}"}
+    print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

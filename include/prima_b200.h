@@ -1,0 +1,123 @@
+/*
+ * include/prima_b200.h — C ABI of libprima_b200.so, the B200-native (sm_100a) quantized-decode hot path of prima.cpp.
+ *
+ * Plain pointers and sizes only; no torch / ggml types.  All functions return 0 on success, a cudaError_t (>0) for
+ * CUDA failures or a negative PB200_E* code for argument errors; nothing throws or aborts across the ABI.
+ * Device pointers are raw CUDA device addresses, `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *
+ * What each entry point replaces in the reference (paths under /root/reference):
+ *   pb200_mul_mat_vec*      ggml_cuda_mul_mat -> ggml_cuda_op_mul_mat_vec_q -> mul_mat_vec_q<type,1>
+ *                           ggml/src/ggml-cuda.cu:1883-1948, ggml-cuda/mmvq.cu:55-202, vecdotq.cuh:357-787
+ *                           (+ the per-call quantize_row_q8_1_cuda, quantize.cu:129-141); CPU semantics:
+ *                           ggml_compute_forward_mul_mat ggml/src/ggml.c:12377-12600
+ *   pb200_quantize_act      quantize_q8_1 quantize.cu:4-38; CPU: quantize_row_q8_K_ref ggml-quants.c:3785-3822
+ *   pb200_rms_norm          ggml_cuda_op_rms_norm norm.cu:206-224; CPU ggml.c:11950-11996
+ *   pb200_rope              ggml_cuda_op_rope rope.cu:188-271; CPU ggml.c:14143-14266
+ *   pb200_soft_max          ggml_cuda_op_soft_max softmax.cu:170-206; CPU ggml.c:13783-13880
+ *   pb200_attn_decode       FA-off attention chain: ggml_cuda_mul_mat_batched_cublas x2 + soft_max + cont,
+ *                           ggml-cuda.cu:1737-1881; graph src/llama.cpp:10032-10165
+ *   pb200_get_rows          ggml_cuda_op_get_rows getrows.cu (k-quant rows are unsupported there, ggml-cuda.cu:3033-3047)
+ *   pb200_model_* / pb200_decode*   the per-token loop ggml_backend_cuda_graph_compute ggml-cuda.cu:2508-2778 over the
+ *                           graph of build_llama / build_qwen2 (src/llama.cpp:11000-11216, 12736-12916) — one fused,
+ *                           CUDA-graph-replayed launch sequence instead of ~30 launches per layer
+ *   (the ggml-backend plugin that exposes the same kernels through ggml_backend_reg/device/buffer vtables is
+ *    include/ggml_b200.h)
+ */
+#ifndef PRIMA_B200_H
+#define PRIMA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PB200_API __attribute__((visibility("default")))
+
+/* enum ggml_type values used on this path (ggml/include/ggml.h:356-395) */
+enum { PB200_TYPE_F32 = 0, PB200_TYPE_F16 = 1, PB200_TYPE_Q5_1 = 7, PB200_TYPE_Q8_0 = 8, PB200_TYPE_Q4_K = 12, PB200_TYPE_Q5_K = 13, PB200_TYPE_Q6_K = 14 };
+
+enum { PB200_EINVAL = -1, PB200_ENOMEM = -2, PB200_ENOTSUP = -3, PB200_ESTATE = -4 };
+
+/* ---- library ---- */
+PB200_API const char * pb200_version(void);
+PB200_API const char * pb200_error_string(int code);
+PB200_API int          pb200_device_count(void);
+PB200_API int          pb200_sm_count(void);              /* of the current device */
+PB200_API int64_t      pb200_row_bytes(int type, int64_t k);   /* ggml_row_size */
+PB200_API uint64_t     pb200_kernel_launches(void);       /* kernels launched by this library since load (bench `gpu_launches`) */
+
+/* ---- single ops, device buffers ---- */
+/* workspace for the quantized activation of length k (any mode): bytes to allocate */
+PB200_API size_t pb200_act_workspace_bytes(int64_t k);
+/* x[k] f32 -> activation workspace in the format the CPU backend uses for weight type wtype (q8_K / q8_0 / q8_1) */
+PB200_API int pb200_quantize_act(int wtype, const float * x, int64_t k, void * act_ws, void * stream);
+/* y[n] = W[n][k] . x   with W raw GGUF blocks of `type`; act_ws from pb200_quantize_act(type, x, k) */
+PB200_API int pb200_mul_mat_vec_q(int type, const void * W, int64_t n, int64_t k, const void * act_ws, float * y,
+                                  const float * bias, const float * resid, void * stream);
+/* convenience: quantize + mul_mat_vec in one call (what ggml_cuda_mul_mat does for ne11 == 1) */
+PB200_API int pb200_mul_mat_vec(int type, const void * W, int64_t n, int64_t k, const float * x, float * y, void * act_ws, void * stream);
+/* up to 3 matrices sharing one activation, one fused launch (q|k|v, gate|up) */
+PB200_API int pb200_mul_mat_vec_fused(int nmat, const int * types, const void * const * W, const int64_t * n, int64_t k,
+                                      const void * act_ws, float * const * y, void * stream);
+/* HOST buffers end to end (H2D of x, quantize, GEMV, D2H of y, synchronised): W must already be on the device */
+PB200_API int pb200_mul_mat_vec_host(int type, const void * W_dev, int64_t n, int64_t k, const float * x_host, float * y_host);
+
+PB200_API int pb200_rms_norm(const float * x, float * y, int64_t n, int64_t nrows, float eps, void * stream);
+PB200_API int pb200_rope(const float * x, float * y, int64_t n_tokens, int n_head, int head_dim, int n_dims, int mode, const int32_t * pos,
+                         float freq_base, float freq_scale, float ext_factor, float attn_factor, float beta_fast, float beta_slow,
+                         int n_ctx_orig, const float * freq_factors, void * stream);
+PB200_API int pb200_soft_max(const float * x, const float * mask, float * y, int64_t ncols, int64_t nrows, int64_t mask_rows, float scale, void * stream);
+PB200_API int pb200_silu_mul(const float * gate, const float * up, float * y, int64_t n, void * stream);
+PB200_API int pb200_get_rows(int type, const void * table, int64_t k, const int32_t * ids, int64_t n_ids, float * y, void * stream);
+/* decode attention over an f16 KV cache laid out [n_ctx][n_head_kv*head_dim]; n_kv = *pos_dev + 1 */
+PB200_API int pb200_attn_decode(const float * q, const void * k_cache_f16, const void * v_cache_f16, float * out, int n_head, int n_head_kv,
+                                int head_dim, const int32_t * pos_dev, int n_ctx, float scale, void * stream);
+
+/* ---- decode engine (one model shard per process / GPU) ---- */
+typedef struct pb200_hparams {
+    int32_t n_layer, n_embd, n_head, n_head_kv, head_dim, n_ff, n_vocab, n_ctx;
+    int32_t rope_mode;        /* 0 = NORM (llama), 2 = NEOX (qwen2) */
+    int32_t n_ctx_orig;
+    float   rope_freq_base, rope_freq_scale, rms_eps;
+} pb200_hparams;
+
+typedef struct pb200_model pb200_model;
+
+/* layers [layer_begin, layer_end) live on this device (prima's layer window, src/llama.cpp:3838-3883);
+ * with_embd / with_head: whether token_embd and output_norm+output live here (first / last pipeline stage) */
+PB200_API pb200_model * pb200_model_create(const pb200_hparams * hp, int device, int layer_begin, int layer_end, int with_embd, int with_head);
+PB200_API void          pb200_model_free(pb200_model * m);
+/* tensor names follow GGUF: "token_embd.weight", "output_norm.weight", "output.weight", "rope_freqs.weight",
+ * "blk.%d.{attn_norm,attn_q,attn_k,attn_v,attn_output,ffn_norm,ffn_gate,ffn_up,ffn_down}.weight", "blk.%d.attn_{q,k,v}.bias".
+ * data: HOST pointer to raw GGUF bytes (exactly ggml_nbytes) — the same bytes llm_load_tensors hands to set_tensor. */
+PB200_API int pb200_model_set_tensor(pb200_model * m, const char * name, int type, const void * host_data, size_t nbytes);
+/* random-init weights generated on the device with the Q4_K_M (ftype 0) or Q5_K_M (ftype 1) type mixture of
+ * llama_tensor_get_type (src/llama.cpp:19271-19556); for benchmarking without a checkpoint */
+PB200_API int pb200_model_synth(pb200_model * m, int ftype, uint64_t seed);
+PB200_API int pb200_model_finalize(pb200_model * m);     /* allocate KV cache + activations, capture the CUDA graph */
+PB200_API int64_t pb200_model_weight_bytes(const pb200_model * m);    /* algorithmic bytes read per decoded token on this shard */
+PB200_API int pb200_kv_clear(pb200_model * m);
+
+/* one decode step, HOST in/out (the llama_decode-equivalent call): token id + position in, n_vocab logits out.
+ * On a pipeline stage without the embedding / head the hidden state is exchanged through pb200_hidden_* instead. */
+PB200_API int pb200_decode(pb200_model * m, int32_t token, int32_t pos, float * logits_host);
+/* device-resident variant: enqueue one step on the model stream, no host copies, no synchronisation */
+PB200_API int pb200_decode_async(pb200_model * m, int32_t token, int32_t pos);
+PB200_API int pb200_synchronize(pb200_model * m);
+PB200_API float * pb200_logits_device(pb200_model * m);      /* [n_vocab] f32 */
+PB200_API float * pb200_hidden_in_device(pb200_model * m);   /* [n_embd] f32: input of layer_begin (written by the previous stage) */
+PB200_API float * pb200_hidden_out_device(pb200_model * m);  /* [n_embd] f32: output of layer_end-1 */
+PB200_API void *  pb200_stream(pb200_model * m);
+PB200_API int pb200_get_hidden(pb200_model * m, float * hidden_host);   /* copies hidden_out to the host (tests) */
+/* one step with CUDA events around every GEMV launch (direct launches): summed GEMV device time, the algorithmic
+ * weight bytes those launches read, their count and the whole-step time — the live roofline measurement of bench.py */
+PB200_API int pb200_profile_step(pb200_model * m, int32_t token, int32_t pos, double * gemv_ms, int64_t * gemv_bytes, int32_t * gemv_launches, double * step_ms);
+PB200_API int pb200_set_hidden(pb200_model * m, const float * hidden_host);   /* host -> hidden_in (tests, host-staged hand-off) */
+PB200_API int pb200_set_use_graph(pb200_model * m, int on);             /* CUDA-graph replay on/off (default on) */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PRIMA_B200_H */

@@ -1,0 +1,147 @@
+// prima.cpp_b200/csrc/common.cuh — shared device helpers for the sm_100a quantized-decode kernels.
+//
+// Wire formats are the reference's GGUF block layouts, read byte-for-byte from HBM
+// (ggml/src/ggml-common.h:173-204, 286-335).  Nothing here is copied from ggml-cuda: the kernels use a
+// different decomposition (one lane per super-block with the int8 activation resident in registers,
+// weights staged through shared memory by cp.async.bulk / TMA), and a different activation format
+// (q8_K, the CPU backend's, so results match the CPU oracle to fp32 summation order).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pb {
+
+// enum ggml_type values (ggml/include/ggml.h:356-395)
+enum : int { T_F32 = 0, T_F16 = 1, T_Q5_1 = 7, T_Q8_0 = 8, T_Q4_K = 12, T_Q5_K = 13, T_Q6_K = 14 };
+
+constexpr int QK_K = 256;
+constexpr int BYTES_Q4_K = 144, BYTES_Q5_K = 176, BYTES_Q6_K = 210, BYTES_Q8_0 = 34, BYTES_Q5_1 = 24;
+
+__host__ __device__ inline int64_t row_bytes(int type, int64_t k) {
+    switch (type) {
+        case T_F32: return k * 4;
+        case T_F16: return k * 2;
+        case T_Q4_K: return k / 256 * BYTES_Q4_K;
+        case T_Q5_K: return k / 256 * BYTES_Q5_K;
+        case T_Q6_K: return k / 256 * BYTES_Q6_K;
+        case T_Q8_0: return k / 32 * BYTES_Q8_0;
+        case T_Q5_1: return k / 32 * BYTES_Q5_1;
+    }
+    return -1;
+}
+__host__ __device__ inline bool is_kquant(int t) { return t == T_Q4_K || t == T_Q5_K || t == T_Q6_K; }
+__host__ __device__ inline int block_elems(int t) { return is_kquant(t) ? 256 : ((t == T_Q8_0 || t == T_Q5_1) ? 32 : 1); }
+
+// ---------------------------------------------------------------------------------------------
+// Quantized activation vector in HBM (SoA so that a lane can pull its super-block with 128-bit loads).
+//   mode Q8_K (for Q4_K/Q5_K/Q6_K weights; mirrors block_q8_K, ggml-common.h:330-335):
+//       qs[K] int8, d[K/256] f32, bsums[K/16] int16
+//   mode Q8_0 (for Q8_0 weights; block_q8_0): qs[K], d[K/32] = fp16-rounded scale widened to f32
+//   mode Q8_1 (for Q5_1 weights; block_q8_1): qs[K], d[K/32], s[K/32] (both fp16-rounded, widened)
+struct ActQ {
+    int8_t * qs;      // [K]           16-B aligned
+    float * d;        // [K/256] or [K/32]
+    int16_t * bsums;  // [K/16]        (Q8_K only)
+    float * s;        // [K/32]        (Q8_1 only)
+};
+enum : int { ACT_Q8_K = 0, ACT_Q8_0 = 1, ACT_Q8_1 = 2 };
+__host__ __device__ inline int act_mode_for(int wtype) { return is_kquant(wtype) ? ACT_Q8_K : (wtype == T_Q8_0 ? ACT_Q8_0 : ACT_Q8_1); }
+
+// ---------------------------------------------------------------------------------------------
+// small PTX wrappers
+__device__ __forceinline__ int dp4a_us(uint32_t a_u8x4, int b_s8x4, int c) {   // unsigned bytes x signed bytes
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_u8x4), "r"(b_s8x4), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int dp4a_ss(int a, int b, int c) { return __dp4a(a, b, c); }
+// dp2a: two signed 16-bit values of a times the low / high two unsigned bytes of b
+__device__ __forceinline__ int dp2a_lo_su(int a_s16x2, uint32_t b_u8x4, int c) {
+    int d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_s16x2), "r"(b_u8x4), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int dp2a_hi_su(int a_s16x2, uint32_t b_u8x4, int c) {
+    int d;
+    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_s16x2), "r"(b_u8x4), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int dp2a_lo_ss(int a_s16x2, int b_s8x4, int c) {
+    int d;
+    asm("dp2a.lo.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_s16x2), "r"(b_s8x4), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int dp2a_hi_ss(int a_s16x2, int b_s8x4, int c) {
+    int d;
+    asm("dp2a.hi.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_s16x2), "r"(b_s8x4), "r"(c));
+    return d;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void * p) { return (uint32_t) __cvta_generic_to_shared(p); }
+
+// ---- mbarrier + bulk async copy (TMA 1-D, SASS UBLKCP) ----
+__device__ __forceinline__ void mbar_init(uint64_t * bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t * bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t * bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t * bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// L2 eviction policy for streamed-once weights
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void bulk_g2s(void * smem_dst, const void * gsrc, uint32_t bytes, uint64_t * bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+
+// Programmatic dependent launch: wait for the producer grid's results / let the dependent grid start.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// nearest_int of ggml-quants.c:1639-1644 (round-half-even via the 1.5*2^23 magic add), bit-exact
+__device__ __forceinline__ int nearest_int_magic(float f) {
+    float v = __fadd_rn(f, 12582912.f);
+    return (__float_as_int(v) & 0x007fffff) - 0x00400000;
+}
+
+}  // namespace pb

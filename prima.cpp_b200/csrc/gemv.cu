@@ -1,0 +1,374 @@
+// prima.cpp_b200/csrc/gemv.cu — kernels + launchers for the decode GEMV (see gemv.cuh for the design).
+#include "gemv.cuh"
+#include "launch.h"
+
+namespace pb {
+
+struct __align__(16) GemvSmemCtl {
+    uint64_t full[GEMV_NSTAGE];
+    uint64_t empty[GEMV_NSTAGE];
+    float part[2][GEMV_NW];   // cross-warp partial sums (double-buffered by row slot parity)
+};
+
+__device__ __forceinline__ void tile_info(const GemvParams & P, int t, int & m, int & r0, int & nrows) {
+    m = 0;
+#pragma unroll
+    for (int i = 1; i < GEMV_MAX_MAT; i++)
+        if (i < P.nmat && t >= P.mat[i].tile0) m = i;
+    const GemvMat & M = P.mat[m];
+    r0 = (t - M.tile0) * M.rows_per_tile;
+    nrows = min(M.rows_per_tile, M.N - r0);
+}
+
+__global__ void __launch_bounds__(GEMV_THREADS, 1) k_gemv_kquant(const __grid_constant__ GemvParams P) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    GemvSmemCtl * ctl = reinterpret_cast<GemvSmemCtl *>(smem);
+    uint8_t * stages = smem + 128;   // ctl block is 128 B (static_assert below)
+    static_assert(sizeof(GemvSmemCtl) <= 128, "ctl block");
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < GEMV_NSTAGE; s++) {
+            mbar_init(&ctl->full[s], 1);
+            mbar_init(&ctl->empty[s], GEMV_NW);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp == GEMV_NW) {
+        // ===== producer: weights do not depend on the previous kernel, so the stream starts immediately =====
+        if (lane == 0) {
+            const uint64_t pol = policy_evict_first();
+            int it = 0;
+            for (int t = blockIdx.x; t < P.ntiles; t += gridDim.x, it++) {
+                const int s = it % GEMV_NSTAGE;
+                const uint32_t ph = (it / GEMV_NSTAGE) & 1;
+                if (it >= GEMV_NSTAGE) mbar_wait(&ctl->empty[s], ph ^ 1);
+                int m, r0, nrows;
+                tile_info(P, t, m, r0, nrows);
+                const GemvMat & M = P.mat[m];
+                const int64_t g0 = (int64_t) r0 * M.row_bytes;
+                const int64_t g1 = g0 + (int64_t) nrows * M.row_bytes;
+                const int64_t a0 = g0 & ~(int64_t) 15;
+                int64_t a1 = (g1 + 15) & ~(int64_t) 15;
+                const int64_t lim = (M.total_bytes + 15) & ~(int64_t) 15;   // allocations are 16-B granular
+                if (a1 > lim) a1 = lim;
+                const uint32_t bytes = (uint32_t) (a1 - a0);
+                mbar_arrive_expect_tx(&ctl->full[s], bytes);
+                bulk_g2s(stages + (size_t) s * GEMV_STAGE_BYTES, M.W + a0, bytes, &ctl->full[s], pol);
+            }
+        }
+        return;
+    }
+
+    // ===== consumers =====
+    const int wpr = P.wpr;
+    const int ngroups = GEMV_NW / wpr;
+    const int group = warp / wpr, wsub = warp % wpr;
+    const int blk = wsub * 32 + lane;
+    const bool valid = blk < P.nblk;
+
+    pdl_wait();   // the activation is produced by the previous kernel in the stream
+    ActRegs r;
+    load_act_regs(r, P.act, blk, valid);
+    pdl_trigger();
+
+    int it = 0;
+    int slot_parity = 0;
+    for (int t = blockIdx.x; t < P.ntiles; t += gridDim.x, it++) {
+        const int s = it % GEMV_NSTAGE;
+        const uint32_t ph = (it / GEMV_NSTAGE) & 1;
+        int m, r0, nrows;
+        tile_info(P, t, m, r0, nrows);
+        const GemvMat & M = P.mat[m];
+        const int type = M.type;
+        const int bpb = type == T_Q4_K ? BYTES_Q4_K : (type == T_Q5_K ? BYTES_Q5_K : BYTES_Q6_K);
+        const uint32_t mis = (uint32_t) (((int64_t) r0 * M.row_bytes) & 15);
+        const uint8_t * tile = stages + (size_t) s * GEMV_STAGE_BYTES + mis;
+        mbar_wait(&ctl->full[s], ph);
+        for (int slot = group; slot < nrows; slot += ngroups) {
+            const uint8_t * bp = tile + (size_t) slot * M.row_bytes + (size_t) blk * bpb;
+            float v = 0.f;
+            if (valid) {
+                if (type == T_Q4_K) v = dot_q4K(bp, r);
+                else if (type == T_Q6_K) v = dot_q6K(bp, r);
+                else v = dot_q5K(bp, r);
+            }
+            v = warp_sum(v);
+            const int row = r0 + slot;
+            if (wpr == 1) {
+                if (lane == 0) {
+                    if (M.bias) v += M.bias[row];
+                    if (M.resid) v += M.resid[row];
+                    M.y[row] = v;
+                }
+            } else {
+                if (lane == 0) ctl->part[slot_parity][warp] = v;
+                // named barrier among the wpr warps of this group (ids 1..8; 0 is __syncthreads)
+                asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(wpr * 32) : "memory");
+                if (wsub == 0 && lane == 0) {
+                    float acc = 0.f;
+                    for (int i = 0; i < wpr; i++) acc += ctl->part[slot_parity][group * wpr + i];
+                    if (M.bias) acc += M.bias[row];
+                    if (M.resid) acc += M.resid[row];
+                    M.y[row] = acc;
+                }
+                slot_parity ^= 1;
+            }
+        }
+        if (wpr > 1) {
+            // rows of a tile are not a multiple of ngroups in general: keep slot_parity warp-group-uniform
+            // (every warp of a group executes the same slots, so it already is).
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ctl->empty[s]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Generic fallback: one warp per row, direct global loads, every supported type (incl. the 32-element block types
+// Q8_0 / Q5_1 that Qwen2.5-72B's ffn_down falls back to, src/llama.cpp:19516-19551), any K.
+// Follows ggml_vec_dot_q8_0_q8_0 (ggml-quants.c:5518) and ggml_vec_dot_q5_1_q8_1 (:5144).
+__device__ __forceinline__ uint32_t ld_u16x2(const uint8_t * p) {   // 2-B aligned 32-bit read
+    const uint16_t * q = reinterpret_cast<const uint16_t *>(p);
+    return (uint32_t) q[0] | ((uint32_t) q[1] << 16);
+}
+
+struct GemvGenericParams {
+    const uint8_t * W;
+    float * y;
+    const float * bias;
+    const float * resid;
+    int64_t row_bytes;
+    int type, N, K;
+    ActQ act;
+};
+
+__global__ void __launch_bounds__(256) k_gemv_generic(const __grid_constant__ GemvGenericParams P) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 8 + warp;
+    pdl_wait();
+    pdl_trigger();
+    if (row >= P.N) return;
+    const uint8_t * wrow = P.W + (int64_t) row * P.row_bytes;
+    float acc = 0.f;
+    if (P.type == T_Q8_0) {
+        const int nb = P.K / 32;
+        for (int b = lane; b < nb; b += 32) {
+            const uint8_t * bp = wrow + (int64_t) b * BYTES_Q8_0;
+            const float d = __half2float(__ushort_as_half(*reinterpret_cast<const uint16_t *>(bp)));
+            const int4 * a = reinterpret_cast<const int4 *>(P.act.qs + (int64_t) b * 32);
+            const int4 a0 = a[0], a1 = a[1];
+            const int av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            int sumi = 0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) sumi = dp4a_ss((int) ld_u16x2(bp + 2 + 4 * i), av[i], sumi);
+            acc += (float) sumi * (d * P.act.d[b]);
+        }
+    } else if (P.type == T_Q5_1) {
+        const int nb = P.K / 32;
+        for (int b = lane; b < nb; b += 32) {
+            const uint8_t * bp = wrow + (int64_t) b * BYTES_Q5_1;   // 24 B: 8-B aligned rows, 4-B aligned fields
+            const uint32_t dmw = *reinterpret_cast<const uint32_t *>(bp);
+            const float d = __half2float(__ushort_as_half((unsigned short) (dmw & 0xffff)));
+            const float mm = __half2float(__ushort_as_half((unsigned short) (dmw >> 16)));
+            const uint32_t qh = *reinterpret_cast<const uint32_t *>(bp + 4);
+            const int4 * a = reinterpret_cast<const int4 *>(P.act.qs + (int64_t) b * 32);
+            const int4 a0 = a[0], a1 = a[1];
+            const int av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            int sumi = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const uint32_t w = *reinterpret_cast<const uint32_t *>(bp + 8 + 4 * i);   // qs bytes 4i..4i+3
+                // element j = 4i+k (low nibble) gets bit j of qh; element j+16 (high nibble) gets bit j+16
+                uint32_t hb_lo = 0, hb_hi = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    hb_lo |= ((qh >> (4 * i + k)) & 1u) << (8 * k + 4);
+                    hb_hi |= ((qh >> (4 * i + k + 16)) & 1u) << (8 * k + 4);
+                }
+                sumi = dp4a_us((w & 0x0f0f0f0fu) | hb_lo, av[i], sumi);
+                sumi = dp4a_us(((w >> 4) & 0x0f0f0f0fu) | hb_hi, av[4 + i], sumi);
+            }
+            acc += (d * P.act.d[b]) * (float) sumi + mm * P.act.s[b];
+        }
+    } else {
+        // k-quants without shared-memory staging (used when K > 65 536 or for tiny problems)
+        const int nb = P.K / 256;
+        for (int b = lane; b < nb; b += 32) {
+            ActRegs r;
+            load_act_regs(r, P.act, b, true);
+            // stage the block through registers -> local array is avoided by reading global memory directly with the
+            // same dot routines: they only need byte-addressable memory with the block's natural alignment.
+            const int bpb = P.type == T_Q4_K ? BYTES_Q4_K : (P.type == T_Q5_K ? BYTES_Q5_K : BYTES_Q6_K);
+            const uint8_t * bp = wrow + (int64_t) b * bpb;
+            // dot_q6K uses shared-memory addressing for its alignment probe; use the global-memory variant below
+            if (P.type == T_Q4_K && ((uintptr_t) bp & 15) == 0) acc += dot_q4K(bp, r);
+            else if (P.type == T_Q5_K && ((uintptr_t) bp & 15) == 0) acc += dot_q5K(bp, r);
+            else {
+                // byte-wise scalar path (rare): dequantize on the fly against int8 activations
+                const int8_t * a8 = P.act.qs + (int64_t) b * 256;
+                if (P.type == T_Q6_K) {
+                    const float d = __half2float(__ushort_as_half(*reinterpret_cast<const uint16_t *>(bp + 208)));
+                    const int8_t * sc = reinterpret_cast<const int8_t *>(bp + 192);
+                    int sumi = 0;
+                    for (int n = 0; n < 2; n++)
+                        for (int l = 0; l < 32; l++) {
+                            const uint8_t qa = bp[64 * n + l], qb = bp[64 * n + 32 + l], h = bp[128 + 32 * n + l];
+                            const int is = l / 16;
+                            const int q1 = (int) ((qa & 0xF) | (((h >> 0) & 3) << 4)) - 32;
+                            const int q2 = (int) ((qb & 0xF) | (((h >> 2) & 3) << 4)) - 32;
+                            const int q3 = (int) ((qa >> 4) | (((h >> 4) & 3) << 4)) - 32;
+                            const int q4 = (int) ((qb >> 4) | (((h >> 6) & 3) << 4)) - 32;
+                            sumi += sc[8 * n + is + 0] * q1 * a8[128 * n + l] + sc[8 * n + is + 2] * q2 * a8[128 * n + 32 + l] +
+                                    sc[8 * n + is + 4] * q3 * a8[128 * n + 64 + l] + sc[8 * n + is + 6] * q4 * a8[128 * n + 96 + l];
+                        }
+                    acc += (d * r.d) * (float) sumi;
+                } else {
+                    const bool q5 = P.type == T_Q5_K;
+                    const __half2 dm = *reinterpret_cast<const __half2 *>(bp);
+                    const uint8_t * scb = bp + 4;
+                    const uint8_t * qhb = bp + 16;
+                    const uint8_t * qs = bp + (q5 ? 48 : 16);
+                    int sumi = 0, summ = 0;
+                    for (int j = 0; j < 8; j++) {
+                        int sc, mn;
+                        if (j < 4) { sc = scb[j] & 63; mn = scb[j + 4] & 63; }
+                        else { sc = (scb[j + 4] & 0xF) | ((scb[j - 4] >> 6) << 4); mn = (scb[j + 4] >> 4) | ((scb[j] >> 6) << 4); }
+                        int dsum = 0, asum = 0;
+                        for (int l = 0; l < 32; l++) {
+                            const uint8_t byte = qs[32 * (j / 2) + l];
+                            int q = (j & 1) ? (byte >> 4) : (byte & 0xF);
+                            if (q5 && ((qhb[l] >> j) & 1)) q += 16;
+                            const int a = a8[32 * j + l];
+                            dsum += q * a;
+                            asum += a;
+                        }
+                        sumi += sc * dsum;
+                        summ += mn * asum;
+                    }
+                    acc += (__low2float(dm) * r.d) * (float) sumi - (__high2float(dm) * r.d) * (float) summ;
+                }
+            }
+        }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+        if (P.bias) acc += P.bias[row];
+        if (P.resid) acc += P.resid[row];
+        P.y[row] = acc;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+static int g_sm_count = 0;
+static bool g_attr_set = false;
+
+int gemv_smem_bytes() { return 128 + GEMV_NSTAGE * GEMV_STAGE_BYTES; }
+
+int sm_count() {
+    if (!g_sm_count) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+    }
+    return g_sm_count;
+}
+
+static int pick_rows_per_tile(int64_t row_bytes, int ngroups, int N) {
+    int fit = (int) ((GEMV_STAGE_BYTES - 16) / row_bytes);
+    if (fit < 1) return 0;
+    int tr = fit >= ngroups ? (fit / ngroups) * ngroups : fit;
+    if (tr > 2 * ngroups && ngroups >= 8) tr = ngroups;      // 8 rows per stage is plenty; more stages in flight instead
+    if (tr > 4 * ngroups) tr = 4 * ngroups;
+    if (tr > N) tr = N;
+    return tr;
+}
+
+// Fused launch of up to 3 k-quant matrices sharing one q8_K activation.  Returns cudaError_t as int.
+int launch_gemv_kquant(const GemvDesc * d, int nmat, int K, const ActQ & act, cudaStream_t stream, bool pdl) {
+    if (nmat < 1 || nmat > GEMV_MAX_MAT || K % 256 != 0) return (int) cudaErrorInvalidValue;
+    const int nblk = K / 256;
+    bool fast = nblk <= GEMV_MAX_NBLK;
+    GemvParams P{};
+    if (fast) {
+        int wpr = 1;
+        while (wpr * 32 < nblk) wpr *= 2;
+        P.wpr = wpr;
+        P.nblk = nblk;
+        P.K = K;
+        P.nmat = nmat;
+        P.act = act;
+        int tiles = 0;
+        for (int i = 0; i < nmat; i++) {
+            GemvMat & M = P.mat[i];
+            if (!is_kquant(d[i].type)) return (int) cudaErrorInvalidValue;
+            M.W = (const uint8_t *) d[i].W;
+            M.y = d[i].y;
+            M.bias = d[i].bias;
+            M.resid = d[i].resid;
+            M.type = d[i].type;
+            M.N = d[i].N;
+            M.row_bytes = row_bytes(d[i].type, K);
+            M.total_bytes = M.row_bytes * d[i].N;
+            M.rows_per_tile = pick_rows_per_tile(M.row_bytes, GEMV_NW / wpr, d[i].N);
+            if (M.rows_per_tile == 0 || ((uintptr_t) M.W & 15)) { fast = false; break; }
+            M.tile0 = tiles;
+            tiles += (d[i].N + M.rows_per_tile - 1) / M.rows_per_tile;
+        }
+        P.ntiles = tiles;
+    }
+    if (fast) {
+        if (!g_attr_set) {
+            cudaError_t e = cudaFuncSetAttribute(k_gemv_kquant, cudaFuncAttributeMaxDynamicSharedMemorySize, gemv_smem_bytes());
+            if (e != cudaSuccess) return (int) e;
+            g_attr_set = true;
+        }
+        int grid = sm_count();
+        if (grid > P.ntiles) grid = P.ntiles;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(GEMV_THREADS);
+        cfg.dynamicSmemBytes = gemv_smem_bytes();
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        return (int) cudaLaunchKernelEx(&cfg, k_gemv_kquant, P);
+    }
+    for (int i = 0; i < nmat; i++) {
+        int e = launch_gemv_generic(d[i], K, act, stream, pdl);
+        if (e) return e;
+    }
+    return 0;
+}
+
+int launch_gemv_generic(const GemvDesc & d, int K, const ActQ & act, cudaStream_t stream, bool pdl) {
+    GemvGenericParams P{};
+    P.W = (const uint8_t *) d.W;
+    P.y = d.y;
+    P.bias = d.bias;
+    P.resid = d.resid;
+    P.type = d.type;
+    P.N = d.N;
+    P.K = K;
+    P.row_bytes = row_bytes(d.type, K);
+    P.act = act;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((d.N + 7) / 8);
+    cfg.blockDim = dim3(256);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return (int) cudaLaunchKernelEx(&cfg, k_gemv_generic, P);
+}
+
+}  // namespace pb

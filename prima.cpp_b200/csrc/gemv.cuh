@@ -1,0 +1,222 @@
+// prima.cpp_b200/csrc/gemv.cuh — decode GEMV  y[N] = W[N,K] (GGUF k-quant blocks) . x[K]
+//
+// Replaces: ggml_cuda_mul_mat -> ggml_cuda_op_mul_mat_vec_q -> mul_mat_vec_q<type,1>
+//           (ggml/src/ggml-cuda.cu:1883-1948, ggml-cuda/mmvq.cu:55-202, vecdotq.cuh:357-787).
+// Numerics follow the CPU oracle instead (ggml_vec_dot_q{4,5,6}_K_q8_K, ggml-quants.c:7713-9566): the activation
+// is q8_K, every integer sub-result is exact, only the order of the final fp32 adds differs.
+//
+// B200 design (memory-bound, no tensor cores):
+//   * persistent grid, one CTA per SM; a producer warp streams row tiles of raw blocks HBM -> shared memory with
+//     cp.async.bulk (1-D TMA, SASS UBLKCP) into a 4-deep mbarrier ring (up to ~216 KB in flight per SM);
+//   * 8 consumer warps; ONE LANE OWNS ONE SUPER-BLOCK COLUMN: lane l of sub-warp s keeps the 256 int8 activations of
+//     super-block (32 s + l) plus its bsums and scale in registers for the whole kernel, so shared memory is read
+//     exactly once per weight byte (128-bit LDS, conflict-free at 144/176-B strides) and the activation costs no
+//     bandwidth at all after the prologue;
+//   * per row: integer dp4a/dp2a dot, one fp32 scale, a 5-step shuffle reduction; rows longer than 32 super-blocks
+//     are split over 2/4/8 warps and combined through a few floats of shared memory in a fixed order
+//     (deterministic, no atomics);
+//   * several matrices that share one activation (q|k|v, gate|up) run as ONE launch (tile list over matrices);
+//   * griddepcontrol (PDL): the weight stream starts before the producing kernel has finished.
+#pragma once
+#include "common.cuh"
+
+namespace pb {
+
+constexpr int GEMV_NW = 8;                       // consumer warps
+constexpr int GEMV_THREADS = (GEMV_NW + 1) * 32;  // + 1 producer warp
+constexpr int GEMV_NSTAGE = 4;
+constexpr int GEMV_STAGE_BYTES = 54 * 1024;       // >= 8 rows of Q6_K @ K=8192 (53 760 B) + 16 B alignment slack
+constexpr int GEMV_MAX_MAT = 3;
+constexpr int GEMV_MAX_NBLK = 256;               // K <= 65 536 (8 warps x 32 lanes x one super-block each)
+
+struct GemvMat {
+    const uint8_t * W;     // raw GGUF blocks, row-major [N][K/256 blocks]
+    float * y;             // [N]
+    const float * bias;    // optional [N]  (y = Wx + bias)                      -- Qwen2 q/k/v biases
+    const float * resid;   // optional [N]  (y = Wx (+bias) + resid)             -- residual adds of the layer
+    int64_t row_bytes;
+    int64_t total_bytes;   // N * row_bytes
+    int type;              // T_Q4_K / T_Q5_K / T_Q6_K
+    int N;
+    int rows_per_tile;
+    int tile0;             // index of this matrix' first tile in the launch-wide tile list
+};
+
+struct GemvParams {
+    GemvMat mat[GEMV_MAX_MAT];
+    int nmat;
+    int ntiles;
+    int K;
+    int nblk;      // K / 256
+    int wpr;       // warps per row: 1, 2, 4 or 8
+    ActQ act;      // q8_K activation
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// per-lane register-resident activation super-block
+struct ActRegs {
+    int a[64];      // 256 int8
+    int bs[8];      // 16 x int16 bsums (pairs)
+    int bs32[4];    // 8 x int16: bsums per 32 (pairs)
+    float d;        // q8_K scale (0 for an out-of-range block => contributes nothing)
+};
+
+__device__ __forceinline__ void load_act_regs(ActRegs & r, const ActQ & act, int blk, bool valid) {
+    if (valid) {
+        const int4 * q = reinterpret_cast<const int4 *>(act.qs + (int64_t) blk * 256);
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            int4 v = q[i];
+            r.a[4 * i + 0] = v.x; r.a[4 * i + 1] = v.y; r.a[4 * i + 2] = v.z; r.a[4 * i + 3] = v.w;
+        }
+        const int4 * b = reinterpret_cast<const int4 *>(act.bsums + (int64_t) blk * 16);
+        int4 b0 = b[0], b1 = b[1];
+        r.bs[0] = b0.x; r.bs[1] = b0.y; r.bs[2] = b0.z; r.bs[3] = b0.w;
+        r.bs[4] = b1.x; r.bs[5] = b1.y; r.bs[6] = b1.z; r.bs[7] = b1.w;
+        r.d = act.d[blk];
+    } else {
+#pragma unroll
+        for (int i = 0; i < 64; i++) r.a[i] = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) r.bs[i] = 0;
+        r.d = 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        // per-32 sums: (bs16[4k]+bs16[4k+1], bs16[4k+2]+bs16[4k+3]) packed as int16x2
+        int lo = (int)(short)(r.bs[2 * k] & 0xffff) + (r.bs[2 * k] >> 16);
+        int hi = (int)(short)(r.bs[2 * k + 1] & 0xffff) + (r.bs[2 * k + 1] >> 16);
+        r.bs32[k] = (lo & 0xffff) | (hi << 16);
+    }
+}
+
+// scales/mins of a Q4_K/Q5_K super-block as packed bytes (get_scale_min_k4, ggml-quants.c:1898-1905)
+__device__ __forceinline__ void unpack_scales_k4(uint32_t u0, uint32_t u1, uint32_t u2, uint32_t & sc_lo, uint32_t & sc_hi,
+                                                 uint32_t & m_lo, uint32_t & m_hi) {
+    sc_lo = u0 & 0x3f3f3f3fu;
+    m_lo = u1 & 0x3f3f3f3fu;
+    sc_hi = (u2 & 0x0f0f0f0fu) | (((u0 >> 6) & 0x03030303u) << 4);
+    m_hi = ((u2 >> 4) & 0x0f0f0f0fu) | (((u1 >> 6) & 0x03030303u) << 4);
+}
+__device__ __forceinline__ int ubyte(uint32_t w, int i) { return (int) ((w >> (8 * i)) & 0xffu); }
+
+// One Q4_K super-block (144 B, 16-B aligned in shared memory) against the lane's activation registers.
+__device__ __forceinline__ float dot_q4K(const uint8_t * blk, const ActRegs & r) {
+    const uint4 * p = reinterpret_cast<const uint4 *>(blk);
+    const uint4 h = p[0];
+    const __half2 dm = *reinterpret_cast<const __half2 *>(&h.x);
+    uint32_t sc_lo, sc_hi, m_lo, m_hi;
+    unpack_scales_k4(h.y, h.z, h.w, sc_lo, sc_hi, m_lo, m_hi);
+    int sumi = 0;
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        const uint4 q0 = p[1 + 2 * c], q1 = p[2 + 2 * c];
+        const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+        int dlo = 0, dhi = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            dlo = dp4a_us(w[i] & 0x0f0f0f0fu, r.a[16 * c + i], dlo);
+            dhi = dp4a_us(w[i] & 0xf0f0f0f0u, r.a[16 * c + 8 + i], dhi);   // 16 x the high-nibble dot (exact)
+        }
+        const uint32_t scw = c < 2 ? sc_lo : sc_hi;
+        sumi += ubyte(scw, (2 * c) & 3) * dlo + ubyte(scw, (2 * c + 1) & 3) * (dhi >> 4);
+    }
+    int summ = dp2a_lo_su(r.bs32[0], m_lo, 0);
+    summ = dp2a_hi_su(r.bs32[1], m_lo, summ);
+    summ = dp2a_lo_su(r.bs32[2], m_hi, summ);
+    summ = dp2a_hi_su(r.bs32[3], m_hi, summ);
+    const float d = __low2float(dm) * r.d, dmin = __high2float(dm) * r.d;
+    return d * (float) sumi - dmin * (float) summ;
+}
+
+// One Q5_K super-block (176 B, 16-B aligned): nibble dot + 16 x fifth-bit dot.
+__device__ __forceinline__ float dot_q5K(const uint8_t * blk, const ActRegs & r) {
+    const uint4 * p = reinterpret_cast<const uint4 *>(blk);
+    const uint4 h = p[0];
+    const __half2 dm = *reinterpret_cast<const __half2 *>(&h.x);
+    uint32_t sc_lo, sc_hi, m_lo, m_hi;
+    unpack_scales_k4(h.y, h.z, h.w, sc_lo, sc_hi, m_lo, m_hi);
+    const uint4 h0 = p[1], h1 = p[2];
+    const uint32_t qh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+    int sumi = 0;
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        const uint4 q0 = p[3 + 2 * c], q1 = p[4 + 2 * c];
+        const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+        int dlo = 0, dhi = 0, blo = 0, bhi = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            dlo = dp4a_us(w[i] & 0x0f0f0f0fu, r.a[16 * c + i], dlo);
+            dhi = dp4a_us(w[i] & 0xf0f0f0f0u, r.a[16 * c + 8 + i], dhi);
+            blo = dp4a_us((qh[i] >> (2 * c)) & 0x01010101u, r.a[16 * c + i], blo);
+            bhi = dp4a_us((qh[i] >> (2 * c + 1)) & 0x01010101u, r.a[16 * c + 8 + i], bhi);
+        }
+        const uint32_t scw = c < 2 ? sc_lo : sc_hi;
+        sumi += ubyte(scw, (2 * c) & 3) * (dlo + 16 * blo) + ubyte(scw, (2 * c + 1) & 3) * ((dhi >> 4) + 16 * bhi);
+    }
+    int summ = dp2a_lo_su(r.bs32[0], m_lo, 0);
+    summ = dp2a_hi_su(r.bs32[1], m_lo, summ);
+    summ = dp2a_lo_su(r.bs32[2], m_hi, summ);
+    summ = dp2a_hi_su(r.bs32[3], m_hi, summ);
+    const float d = __low2float(dm) * r.d, dmin = __high2float(dm) * r.d;
+    return d * (float) sumi - dmin * (float) summ;
+}
+
+// One Q6_K super-block (210 B, only 2-B aligned): aligned 32-bit loads + funnel shift by the misalignment.
+__device__ __forceinline__ float dot_q6K(const uint8_t * blk, const ActRegs & r) {
+    const uint32_t addr = smem_u32(blk);
+    const uint32_t sh = (addr & 3u) * 8u;
+    const uint32_t * base = reinterpret_cast<const uint32_t *>(blk - (addr & 3u));
+    // scales (bytes 192..207) and d (bytes 208..209)
+    uint32_t tail[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) tail[i] = base[48 + i];
+    int scw[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) scw[i] = (int) __funnelshift_r(tail[i], tail[i + 1], sh);
+    const uint32_t dword = __funnelshift_r(tail[4], tail[5], sh);
+    const float dw = __half2float(__ushort_as_half((unsigned short) (dword & 0xffffu)));
+
+    int sumi = 0;
+#pragma unroll
+    for (int n = 0; n < 2; n++) {
+        uint32_t ql[17], qh[9];
+#pragma unroll
+        for (int i = 0; i < 17; i++) ql[i] = base[16 * n + i];
+#pragma unroll
+        for (int i = 0; i < 9; i++) qh[i] = base[32 + 8 * n + i];
+        int acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[j] = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint32_t A = __funnelshift_r(ql[i], ql[i + 1], sh);
+            const uint32_t B = __funnelshift_r(ql[8 + i], ql[9 + i], sh);
+            const uint32_t H = __funnelshift_r(qh[i], qh[i + 1], sh);
+            const uint32_t v1 = (A & 0x0f0f0f0fu) | ((H << 4) & 0x30303030u);
+            const uint32_t v2 = (B & 0x0f0f0f0fu) | ((H << 2) & 0x30303030u);
+            const uint32_t v3 = ((A >> 4) & 0x0f0f0f0fu) | (H & 0x30303030u);
+            const uint32_t v4 = ((B >> 4) & 0x0f0f0f0fu) | ((H >> 2) & 0x30303030u);
+            const int g = i >> 2;   // which 16-element half of the 32-element run
+            acc[0 + g] = dp4a_us(v1, r.a[32 * n + i], acc[0 + g]);
+            acc[2 + g] = dp4a_us(v2, r.a[32 * n + 8 + i], acc[2 + g]);
+            acc[4 + g] = dp4a_us(v3, r.a[32 * n + 16 + i], acc[4 + g]);
+            acc[6 + g] = dp4a_us(v4, r.a[32 * n + 24 + i], acc[6 + g]);
+        }
+        // scales 8n .. 8n+7 are the signed bytes of scw[2n], scw[2n+1]
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int s = (int) (signed char) ((scw[2 * n + (j >> 2)] >> (8 * (j & 3))) & 0xff);
+            sumi += s * acc[j];
+        }
+    }
+    // - 32 * sum_j scale_j * bsum16_j   (q6 = u6 - 32)
+    int sb = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        sb = (k & 1) ? dp2a_hi_ss(r.bs[k], scw[k >> 1], sb) : dp2a_lo_ss(r.bs[k], scw[k >> 1], sb);
+    }
+    return (dw * r.d) * (float) (sumi - 32 * sb);
+}
+
+}  // namespace pb

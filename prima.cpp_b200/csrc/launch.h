@@ -1,0 +1,75 @@
+// prima.cpp_b200/csrc/launch.h — host-side launchers of the sm_100a kernels (internal C++ API; the public C ABI is
+// include/prima_b200.h).  Every launcher enqueues on `stream` and returns a cudaError_t as int (0 = success).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace pb {
+
+struct GemvDesc {
+    const void * W;        // raw GGUF blocks [N][K]
+    float * y;             // [N]
+    const float * bias;    // optional
+    const float * resid;   // optional
+    int type;
+    int N;
+};
+
+int sm_count();
+int gemv_smem_bytes();
+
+// y_i = W_i . act  for up to 3 k-quant matrices sharing one q8_K activation (TMA-staged persistent kernel)
+int launch_gemv_kquant(const GemvDesc * d, int nmat, int K, const ActQ & act, cudaStream_t stream, bool pdl);
+// any supported type / any K, one warp per row, direct global loads
+int launch_gemv_generic(const GemvDesc & d, int K, const ActQ & act, cudaStream_t stream, bool pdl);
+// picks the right kernel per weight type (all matrices must need the same activation mode)
+int launch_gemv(const GemvDesc * d, int nmat, int K, const ActQ & act, cudaStream_t stream, bool pdl);
+
+// activation quantization (mode = ACT_Q8_K / ACT_Q8_0 / ACT_Q8_1); K padded to 256 in the ActQ buffers
+int launch_quantize_act(const float * x, int K, int mode, const ActQ & out, cudaStream_t stream, bool pdl);
+// out = quant( silu(gate) * up )           [llm_build_ffn LLM_FFN_SILU/PAR, src/llama.cpp:9858-9907]
+int launch_silu_mul_quant(const float * gate, const float * up, int K, int mode, const ActQ & out, float * f32_out, cudaStream_t stream, bool pdl);
+// out = quant( rms_norm(x) * w ), optional f32 copy  [llm_build_norm, src/llama.cpp:9772-9802; ggml.c:11950-11996]
+int launch_rmsnorm_quant(const float * x, const float * w, int n, float eps, int mode, const ActQ & out, float * f32_out, cudaStream_t stream, bool pdl);
+// plain ops for the ggml-backend plugin (rows x n)
+int launch_rms_norm(const float * x, float * y, int n, int64_t nrows, float eps, cudaStream_t stream);
+
+struct RopeParams {
+    int n_dims, mode, n_ctx_orig;
+    float freq_base, freq_scale, ext_factor, attn_factor, beta_fast, beta_slow;
+    float theta_scale;      // powf(freq_base, -2/n_dims), computed on the host like ggml.c:14193
+    float corr_dims[2];     // ggml_rope_yarn_corr_dims, ggml.c:14133-14141
+};
+void rope_params_init(RopeParams & rp, int n_dims, int mode, int n_ctx_orig, float freq_base, float freq_scale, float ext_factor,
+                      float attn_factor, float beta_fast, float beta_slow);
+
+// RoPE on q [n_head][D] in place and on k [n_head_kv][D]; stores rope(k) and v as f16 rows `pos` of the KV cache
+// (rope.cu:188-271 + cpy_f32_f16 cpy.cu:34 + llm_build_kv_store src/llama.cpp:9673-9718).  pos is read from device memory.
+int launch_rope_kvstore(float * q, const float * k, const float * v, __half * kcache, __half * vcache, int n_head, int n_head_kv, int D,
+                        const int32_t * pos_dev, const RopeParams & rp, const float * freq_factors, cudaStream_t stream, bool pdl);
+// generic rope for the plugin: x [ntok][n_head][D] -> y, positions pos[ntok]
+int launch_rope(const float * x, float * y, int64_t ntok, int n_head, int D, int64_t tok_stride, int64_t head_stride, const int32_t * pos,
+                const RopeParams & rp, const float * freq_factors, cudaStream_t stream);
+
+// decode attention, FA-off numerics of the CPU backend (f16-rounded q and probabilities, f32 accumulation):
+//   out[h][:] = softmax(scale * K[0..n_kv) . q_h) . V   — GQA-aware, K/V read once per kv head.  n_kv = *pos_dev + 1.
+// Optionally quantizes out (n_head*D values) for the following wo GEMV.
+int launch_attn_decode(const float * q, const __half * kcache, const __half * vcache, float * out, int n_head, int n_head_kv, int D,
+                       const int32_t * pos_dev, int n_ctx, float scale, float * scratch, cudaStream_t stream, bool pdl);
+int attn_scratch_floats(int n_head, int n_ctx);
+
+// soft_max_ext for the plugin: y[r][:] = softmax(x[r][:]*scale + mask[r % mask_rows][:])  (softmax.cu:14-116)
+int launch_soft_max(const float * x, const float * mask, float * y, int ncols, int64_t nrows, int64_t rows_per_mask_cycle, float scale,
+                    cudaStream_t stream);
+
+// get_rows on a quantized / f16 / f32 table: y[i][:] = dequant(table[ids[i]])   (getrows.cu; ggml.c get_rows_q)
+int launch_get_rows(const void * table, int type, int K, const int32_t * ids, int n_ids, float * y, cudaStream_t stream, bool pdl);
+
+// element-wise helpers for the plugin
+int launch_binary(int op /*0 add, 1 mul*/, const float * a, const float * b, float * y, int64_t n, int64_t nb /*b broadcast period*/, cudaStream_t stream);
+int launch_silu(const float * x, float * y, int64_t n, cudaStream_t stream);
+int launch_cpy_f32_f16(const float * x, __half * y, int64_t n, cudaStream_t stream);
+
+}  // namespace pb

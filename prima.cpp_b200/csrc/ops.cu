@@ -1,0 +1,531 @@
+// prima.cpp_b200/csrc/ops.cu — the non-GEMV ops of the decode graph, fused the way the B200 decode loop needs them.
+//
+// Reference ops replaced (file:line under /root/reference/ggml/src/ggml-cuda): quantize.cu:4-38 (activation quant),
+// norm.cu:100-132 (rms_norm_f32) + binbcast.cu (MUL by the norm weight), rope.cu:32-109, cpy.cu:34 (f32->f16 KV store),
+// softmax.cu:14-116, the FA-off attention chain ggml-cuda.cu:1737-1881 (batched cuBLAS KQ / KQV), unary.cu (silu),
+// getrows.cu.  Numerics follow the CPU backend (ggml.c:11950, 14143, 13783, 12377), see each kernel.
+#include "launch.h"
+#include "quantize.cuh"
+
+#include <math.h>
+
+namespace pb {
+
+static inline int launch_cfg(cudaLaunchConfig_t & cfg, cudaLaunchAttribute * attr, dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                             bool pdl) {
+    cfg = cudaLaunchConfig_t{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// activation quantization: one warp per 256 values
+__global__ void __launch_bounds__(256) k_quantize_act(const float * __restrict__ x, int K, int mode, ActQ out) {
+    pdl_wait();
+    pdl_trigger();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t blk = (int64_t) blockIdx.x * 8 + warp;
+    const int64_t base = blk * 256 + lane * 8;
+    if (blk * 256 >= K) return;
+    float v[8];
+    if (base + 8 <= K) {
+        const float4 a = *reinterpret_cast<const float4 *>(x + base), b = *reinterpret_cast<const float4 *>(x + base + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = base + i < K ? x[base + i] : 0.f;
+    }
+    quantize_warp(mode, v, lane, blk, out);
+}
+
+__device__ __forceinline__ float silu_f32(float x) { return __fdiv_rn(x, 1.0f + expf(-x)); }   // ggml.c:2560
+
+__global__ void __launch_bounds__(256) k_silu_mul_quant(const float * __restrict__ g, const float * __restrict__ u, int K, int mode, ActQ out,
+                                                        float * __restrict__ f32_out) {
+    pdl_wait();
+    pdl_trigger();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t blk = (int64_t) blockIdx.x * 8 + warp;
+    const int64_t base = blk * 256 + lane * 8;
+    if (blk * 256 >= K) return;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = base + i < K ? __fmul_rn(silu_f32(g[base + i]), u[base + i]) : 0.f;
+    if (f32_out) {
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            if (base + i < K) f32_out[base + i] = v[i];
+    }
+    quantize_warp(mode, v, lane, blk, out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// y = rms_norm(x) * w, then quantize; single CTA (n <= 32 K), double-precision sum of squares like ggml.c:11976-11984
+__global__ void __launch_bounds__(1024) k_rmsnorm_quant(const float * __restrict__ x, const float * __restrict__ w, int n, float eps, int mode,
+                                                        ActQ out, float * __restrict__ f32_out) {
+    __shared__ double red[32];
+    __shared__ float s_scale;
+    pdl_wait();
+    pdl_trigger();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double sum = 0.0;
+    for (int i = threadIdx.x; i < n; i += 1024) {
+        const float v = x[i];
+        sum += (double) __fmul_rn(v, v);
+    }
+    sum = warp_sum_d(sum);
+    if (lane == 0) red[warp] = sum;
+    __syncthreads();
+    if (warp == 0) {
+        double t = red[lane];
+        t = warp_sum_d(t);
+        if (lane == 0) {
+            const float mean = (float) (t / (double) n);
+            s_scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, eps)));
+        }
+    }
+    __syncthreads();
+    const float scale = s_scale;
+    const int ngroups = (n + 255) / 256;
+    for (int gidx = warp; gidx < ngroups; gidx += 32) {
+        const int base = gidx * 256 + lane * 8;
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            float t = 0.f;
+            if (base + i < n) {
+                t = __fmul_rn(x[base + i], scale);          // ggml_vec_scale_f32
+                if (w) t = __fmul_rn(t, w[base + i]);       // ggml_mul by the norm weight
+                if (f32_out) f32_out[base + i] = t;
+            }
+            v[i] = t;
+        }
+        if (out.qs) quantize_warp(mode, v, lane, gidx, out);
+    }
+}
+
+// plain row-wise rms_norm for the plugin (no weight): one CTA per row
+__global__ void __launch_bounds__(256) k_rms_norm_rows(const float * __restrict__ x, float * __restrict__ y, int n, float eps) {
+    __shared__ double red[8];
+    __shared__ float s_scale;
+    const float * xr = x + (int64_t) blockIdx.x * n;
+    float * yr = y + (int64_t) blockIdx.x * n;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double sum = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) sum += (double) __fmul_rn(xr[i], xr[i]);
+    sum = warp_sum_d(sum);
+    if (lane == 0) red[warp] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0;
+        for (int i = 0; i < 8; i++) t += red[i];
+        const float mean = (float) (t / (double) n);
+        s_scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, eps)));
+    }
+    __syncthreads();
+    const float scale = s_scale;
+    for (int i = threadIdx.x; i < n; i += 256) yr[i] = __fmul_rn(xr[i], scale);
+}
+
+// ------------------------------------------------------------------------------------------------
+// RoPE (ggml.c:14087-14266).  theta for pair i is pos * theta_scale^i computed by i sequential fp32 multiplies, exactly
+// like ggml_rope_cache_init's running product, so the angle is bit-identical to the CPU's.
+__device__ __forceinline__ float rope_yarn_ramp(float low, float high, int i0) {
+    const float y = (i0 / 2 - low) / fmaxf(0.001f, high - low);
+    return 1.0f - fminf(1.0f, fmaxf(0.0f, y));
+}
+__device__ __forceinline__ void rope_cos_sin(const RopeParams & rp, int32_t pos, int pair, const float * freq_factors, float & c, float & s) {
+    float theta = (float) pos;
+    for (int j = 0; j < pair; j++) theta = __fmul_rn(theta, rp.theta_scale);
+    const float ff = freq_factors ? freq_factors[pair] : 1.0f;
+    const float theta_extrap = __fdiv_rn(theta, ff);
+    const float theta_interp = __fmul_rn(rp.freq_scale, theta_extrap);
+    float th = theta_interp, mscale = rp.attn_factor;
+    if (rp.ext_factor != 0.0f) {
+        const float ramp_mix = rope_yarn_ramp(rp.corr_dims[0], rp.corr_dims[1], 2 * pair) * rp.ext_factor;
+        th = theta_interp * (1 - ramp_mix) + theta_extrap * ramp_mix;
+        mscale *= 1.0f + 0.1f * logf(1.0f / rp.freq_scale);
+    }
+    c = __fmul_rn(cosf(th), mscale);
+    s = __fmul_rn(sinf(th), mscale);
+}
+__device__ __forceinline__ void rope_rotate(float x0, float x1, float c, float s, float & y0, float & y1) {
+    y0 = __fsub_rn(__fmul_rn(x0, c), __fmul_rn(x1, s));
+    y1 = __fadd_rn(__fmul_rn(x0, s), __fmul_rn(x1, c));
+}
+
+// grid = n_head + n_head_kv CTAs of D/2 threads: q heads rotate in place; k heads rotate into the f16 K cache and carry
+// the matching v head into the f16 V cache.
+__global__ void k_rope_kvstore(float * __restrict__ q, const float * __restrict__ k, const float * __restrict__ v, __half * __restrict__ kc,
+                               __half * __restrict__ vc, int n_head, int n_head_kv, int D, const int32_t * __restrict__ pos_dev, RopeParams rp,
+                               const float * __restrict__ freq_factors) {
+    pdl_wait();
+    pdl_trigger();
+    const int32_t pos = *pos_dev;
+    const int h = blockIdx.x, pair = threadIdx.x;
+    const int half_dims = rp.n_dims / 2;
+    const bool neox = rp.mode & 2;
+    float c = 1.f, s = 0.f;
+    if (pair < half_dims) rope_cos_sin(rp, pos, pair, freq_factors, c, s);
+    const int i0 = neox ? pair : 2 * pair, i1 = neox ? pair + half_dims : 2 * pair + 1;
+    if (h < n_head) {
+        if (pair < half_dims) {
+            float * x = q + (int64_t) h * D;
+            float y0, y1;
+            rope_rotate(x[i0], x[i1], c, s, y0, y1);
+            x[i0] = y0; x[i1] = y1;
+        }
+    } else {
+        const int hk = h - n_head;
+        const int64_t EK = (int64_t) n_head_kv * D;
+        const float * x = k + (int64_t) hk * D;
+        __half * kd = kc + (int64_t) pos * EK + (int64_t) hk * D;
+        __half * vd = vc + (int64_t) pos * EK + (int64_t) hk * D;
+        const float * vs = v + (int64_t) hk * D;
+        if (pair < half_dims) {
+            float y0, y1;
+            rope_rotate(x[i0], x[i1], c, s, y0, y1);
+            kd[i0] = __float2half_rn(y0); kd[i1] = __float2half_rn(y1);
+        }
+        for (int i = rp.n_dims + pair; i < D; i += blockDim.x) kd[i] = __float2half_rn(x[i]);   // un-rotated tail (n_dims < D)
+        for (int i = pair; i < D; i += blockDim.x) vd[i] = __float2half_rn(vs[i]);
+    }
+}
+
+// generic rope for the plugin: one CTA per (token, head)
+__global__ void k_rope(const float * __restrict__ x, float * __restrict__ y, int n_head, int D, int64_t tok_stride, int64_t head_stride,
+                       const int32_t * __restrict__ pos, RopeParams rp, const float * __restrict__ freq_factors) {
+    const int tok = blockIdx.x / n_head, h = blockIdx.x % n_head;
+    const float * xs = x + tok * tok_stride + h * head_stride;
+    float * yd = y + ((int64_t) tok * n_head + h) * D;
+    const int half_dims = rp.n_dims / 2;
+    const bool neox = rp.mode & 2;
+    for (int pair = threadIdx.x; pair < half_dims; pair += blockDim.x) {
+        float c, s;
+        rope_cos_sin(rp, pos[tok], pair, freq_factors, c, s);
+        const int i0 = neox ? pair : 2 * pair, i1 = neox ? pair + half_dims : 2 * pair + 1;
+        float y0, y1;
+        rope_rotate(xs[i0], xs[i1], c, s, y0, y1);
+        yd[i0] = y0; yd[i1] = y1;
+    }
+    for (int i = rp.n_dims + threadIdx.x; i < D; i += blockDim.x) yd[i] = xs[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Decode attention, one CTA (8 warps) per q head.  D == 128 (4 values per lane).
+//   s[p] = sum_d f32(K16[p][d]) * f32(f16(q[d]))            (CPU: mul_mat with f16 src0 rounds src1 to f16, ggml.c:12445)
+//   w    = softmax(s * scale)                               (ggml.c:13783; double sum, p = e * float(1/sum))
+//   o[d] = sum_p f32(V16[p][d]) * f32(f16(w[p]))            (second mul_mat, probabilities rounded to f16)
+__global__ void __launch_bounds__(256) k_attn_decode(const float * __restrict__ q, const __half * __restrict__ kc, const __half * __restrict__ vc,
+                                                     float * __restrict__ out, int n_head, int n_head_kv, int D, const int32_t * __restrict__ pos_dev,
+                                                     float scale) {
+    extern __shared__ float sm[];   // S[n_kv_pad] | red[8][128]
+    pdl_wait();
+    pdl_trigger();
+    const int n_kv = *pos_dev + 1;
+    const int h = blockIdx.x, hk = h / (n_head / n_head_kv);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t EK = (int64_t) n_head_kv * D;
+    float * S = sm;
+    float * red = sm + ((n_kv + 31) & ~31);
+    __shared__ float s_red[8];
+    __shared__ double s_redd[8];
+    __shared__ float s_max, s_inv;
+
+    const float4 qv = *reinterpret_cast<const float4 *>(q + (int64_t) h * D + 4 * lane);
+    const float q0 = __half2float(__float2half_rn(qv.x)), q1 = __half2float(__float2half_rn(qv.y));
+    const float q2 = __half2float(__float2half_rn(qv.z)), q3 = __half2float(__float2half_rn(qv.w));
+    for (int p = warp; p < n_kv; p += 8) {
+        const uint2 kraw = *reinterpret_cast<const uint2 *>(kc + (int64_t) p * EK + (int64_t) hk * D + 4 * lane);
+        const float2 k01 = __half22float2(*reinterpret_cast<const __half2 *>(&kraw.x));
+        const float2 k23 = __half22float2(*reinterpret_cast<const __half2 *>(&kraw.y));
+        float s = k01.x * q0;
+        s = fmaf(k01.y, q1, s);
+        s = fmaf(k23.x, q2, s);
+        s = fmaf(k23.y, q3, s);
+        s = warp_sum(s);
+        if (lane == 0) S[p] = __fmul_rn(s, scale);
+    }
+    __syncthreads();
+    // max
+    float m = -INFINITY;
+    for (int p = threadIdx.x; p < n_kv; p += 256) m = fmaxf(m, S[p]);
+    m = warp_max(m);
+    if (lane == 0) s_red[warp] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = s_red[0];
+        for (int i = 1; i < 8; i++) t = fmaxf(t, s_red[i]);
+        s_max = t;
+    }
+    __syncthreads();
+    const float mx = s_max;
+    double dsum = 0.0;
+    for (int p = threadIdx.x; p < n_kv; p += 256) {
+        const float e = expf(__fsub_rn(S[p], mx));
+        S[p] = e;
+        dsum += (double) e;
+    }
+    dsum = warp_sum_d(dsum);
+    if (lane == 0) s_redd[warp] = dsum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0;
+        for (int i = 0; i < 8; i++) t += s_redd[i];
+        s_inv = (float) (1.0 / t);
+    }
+    __syncthreads();
+    const float inv = s_inv;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int p = warp; p < n_kv; p += 8) {
+        const float w = __half2float(__float2half_rn(__fmul_rn(S[p], inv)));
+        const uint2 vraw = *reinterpret_cast<const uint2 *>(vc + (int64_t) p * EK + (int64_t) hk * D + 4 * lane);
+        const float2 v01 = __half22float2(*reinterpret_cast<const __half2 *>(&vraw.x));
+        const float2 v23 = __half22float2(*reinterpret_cast<const __half2 *>(&vraw.y));
+        a0 = fmaf(v01.x, w, a0); a1 = fmaf(v01.y, w, a1); a2 = fmaf(v23.x, w, a2); a3 = fmaf(v23.y, w, a3);
+    }
+    *reinterpret_cast<float4 *>(red + warp * 128 + 4 * lane) = make_float4(a0, a1, a2, a3);
+    __syncthreads();
+    if (threadIdx.x < 128) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; i++) t += red[i * 128 + threadIdx.x];
+        out[(int64_t) h * D + threadIdx.x] = t;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// soft_max_ext rows (plugin): y = softmax(x*scale + mask)
+__global__ void __launch_bounds__(256) k_soft_max(const float * __restrict__ x, const float * __restrict__ mask, float * __restrict__ y, int ncols,
+                                                  int64_t rows_per_mask_cycle, float scale) {
+    extern __shared__ float sm[];
+    __shared__ float s_red[8];
+    __shared__ double s_redd[8];
+    __shared__ float s_b;
+    const int64_t row = blockIdx.x;
+    const float * xr = x + row * ncols;
+    const float * mr = mask ? mask + (row % rows_per_mask_cycle) * ncols : nullptr;
+    float * yr = y + row * ncols;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float m = -INFINITY;
+    for (int i = threadIdx.x; i < ncols; i += 256) {
+        float v = __fmul_rn(xr[i], scale);
+        if (mr) v = __fadd_rn(v, mr[i]);
+        sm[i] = v;
+        m = fmaxf(m, v);
+    }
+    m = warp_max(m);
+    if (lane == 0) s_red[warp] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) { float t = s_red[0]; for (int i = 1; i < 8; i++) t = fmaxf(t, s_red[i]); s_b = t; }
+    __syncthreads();
+    const float mx = s_b;
+    double dsum = 0.0;
+    for (int i = threadIdx.x; i < ncols; i += 256) {
+        const float v = sm[i];
+        const float e = v == -INFINITY ? 0.f : expf(__fsub_rn(v, mx));
+        sm[i] = e;
+        dsum += (double) e;
+    }
+    dsum = warp_sum_d(dsum);
+    if (lane == 0) s_redd[warp] = dsum;
+    __syncthreads();
+    if (threadIdx.x == 0) { double t = 0; for (int i = 0; i < 8; i++) t += s_redd[i]; s_b = (float) (1.0 / t); }
+    __syncthreads();
+    const float inv = s_b;
+    for (int i = threadIdx.x; i < ncols; i += 256) yr[i] = __fmul_rn(sm[i], inv);
+}
+
+// ------------------------------------------------------------------------------------------------
+// get_rows: y[i][e] = dequant(table[ids[i]])[e]   (dequantize_row_q*_K, ggml-quants.c:2555-3006, 1589-1634)
+__device__ float dequant_elem(int type, const uint8_t * row, int e) {
+    switch (type) {
+        case T_F32: return reinterpret_cast<const float *>(row)[e];
+        case T_F16: return __half2float(reinterpret_cast<const __half *>(row)[e]);
+        case T_Q8_0: {
+            const uint8_t * b = row + (int64_t) (e / 32) * BYTES_Q8_0;
+            const float d = __half2float(__ushort_as_half(*reinterpret_cast<const uint16_t *>(b)));
+            return __fmul_rn((float) (int) (signed char) b[2 + (e & 31)], d);
+        }
+        case T_Q5_1: {
+            const uint8_t * b = row + (int64_t) (e / 32) * BYTES_Q5_1;
+            const float d = __half2float(__ushort_as_half(*reinterpret_cast<const uint16_t *>(b)));
+            const float m = __half2float(__ushort_as_half(*reinterpret_cast<const uint16_t *>(b + 2)));
+            const uint32_t qh = *reinterpret_cast<const uint32_t *>(b + 4);
+            const int j = e & 31;
+            const int q = j < 16 ? ((b[8 + j] & 0xF) | (((qh >> j) & 1) << 4)) : ((b[8 + j - 16] >> 4) | (((qh >> j) & 1) << 4));
+            return __fadd_rn(__fmul_rn((float) q, d), m);
+        }
+        case T_Q4_K:
+        case T_Q5_K: {
+            const bool q5 = type == T_Q5_K;
+            const uint8_t * b = row + (int64_t) (e / 256) * (q5 ? BYTES_Q5_K : BYTES_Q4_K);
+            const int i = e & 255, j = i / 32, l = i & 31;
+            const float d = __half2float(__ushort_as_half(*reinterpret_cast<const uint16_t *>(b)));
+            const float dmin = __half2float(__ushort_as_half(*reinterpret_cast<const uint16_t *>(b + 2)));
+            const uint8_t * scb = b + 4;
+            int sc, mn;
+            if (j < 4) { sc = scb[j] & 63; mn = scb[j + 4] & 63; }
+            else { sc = (scb[j + 4] & 0xF) | ((scb[j - 4] >> 6) << 4); mn = (scb[j + 4] >> 4) | ((scb[j] >> 6) << 4); }
+            const uint8_t * qs = b + (q5 ? 48 : 16);
+            const uint8_t byte = qs[32 * (j / 2) + l];
+            int qv = (j & 1) ? (byte >> 4) : (byte & 0xF);
+            if (q5 && ((b[16 + l] >> j) & 1)) qv += 16;
+            return __fsub_rn(__fmul_rn(__fmul_rn(d, (float) sc), (float) qv), __fmul_rn(dmin, (float) mn));
+        }
+        case T_Q6_K: {
+            const uint8_t * b = row + (int64_t) (e / 256) * BYTES_Q6_K;
+            const int i = e & 255, n = i / 128, r = i & 127, quarter = r / 32, l = r & 31;
+            const uint8_t * ql = b + 64 * n, * qh = b + 128 + 32 * n;
+            const int8_t * sc = reinterpret_cast<const int8_t *>(b + 192) + 8 * n;
+            const float d = __half2float(__ushort_as_half(*reinterpret_cast<const uint16_t *>(b + 208)));
+            const uint8_t lo = (quarter & 1) ? ql[l + 32] : ql[l];
+            const int nib = (quarter & 2) ? (lo >> 4) : (lo & 0xF);
+            const int qv = (nib | (((qh[l] >> (2 * quarter)) & 3) << 4)) - 32;
+            return __fmul_rn(__fmul_rn(d, (float) sc[l / 16 + 2 * quarter]), (float) qv);
+        }
+    }
+    return 0.f;
+}
+
+__global__ void __launch_bounds__(256) k_get_rows(const uint8_t * __restrict__ table, int type, int K, int64_t row_bytes_,
+                                                  const int32_t * __restrict__ ids, float * __restrict__ y) {
+    pdl_wait();
+    pdl_trigger();
+    const int64_t id = ids[blockIdx.y];
+    const uint8_t * row = table + id * row_bytes_;
+    const int e = blockIdx.x * 256 + threadIdx.x;
+    if (e < K) y[(int64_t) blockIdx.y * K + e] = dequant_elem(type, row, e);
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void k_binary(int op, const float * __restrict__ a, const float * __restrict__ b, float * __restrict__ y, int64_t n, int64_t nb) {
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float bv = b[i % nb];
+    y[i] = op == 0 ? __fadd_rn(a[i], bv) : __fmul_rn(a[i], bv);
+}
+__global__ void k_silu(const float * __restrict__ x, float * __restrict__ y, int64_t n) {
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = silu_f32(x[i]);
+}
+__global__ void k_cpy_f32_f16(const float * __restrict__ x, __half * __restrict__ y, int64_t n) {
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = __float2half_rn(x[i]);
+}
+
+// ================================================================================================ launchers
+int launch_quantize_act(const float * x, int K, int mode, const ActQ & out, cudaStream_t stream, bool pdl) {
+    cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1];
+    const int ngroups = (K + 255) / 256;
+    launch_cfg(cfg, attr, dim3((ngroups + 7) / 8), dim3(256), 0, stream, pdl);
+    return (int) cudaLaunchKernelEx(&cfg, k_quantize_act, x, K, mode, out);
+}
+int launch_silu_mul_quant(const float * gate, const float * up, int K, int mode, const ActQ & out, float * f32_out, cudaStream_t stream, bool pdl) {
+    cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1];
+    const int ngroups = (K + 255) / 256;
+    launch_cfg(cfg, attr, dim3((ngroups + 7) / 8), dim3(256), 0, stream, pdl);
+    return (int) cudaLaunchKernelEx(&cfg, k_silu_mul_quant, gate, up, K, mode, out, f32_out);
+}
+int launch_rmsnorm_quant(const float * x, const float * w, int n, float eps, int mode, const ActQ & out, float * f32_out, cudaStream_t stream, bool pdl) {
+    cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1];
+    launch_cfg(cfg, attr, dim3(1), dim3(1024), 0, stream, pdl);
+    return (int) cudaLaunchKernelEx(&cfg, k_rmsnorm_quant, x, w, n, eps, mode, out, f32_out);
+}
+int launch_rms_norm(const float * x, float * y, int n, int64_t nrows, float eps, cudaStream_t stream) {
+    k_rms_norm_rows<<<(unsigned) nrows, 256, 0, stream>>>(x, y, n, eps);
+    return (int) cudaGetLastError();
+}
+
+static float rope_yarn_corr_dim(int n_dims, int n_ctx_orig, float n_rot, float base) {
+    return n_dims * logf(n_ctx_orig / (n_rot * 2 * (float) M_PI)) / (2 * logf(base));
+}
+void rope_params_init(RopeParams & rp, int n_dims, int mode, int n_ctx_orig, float freq_base, float freq_scale, float ext_factor, float attn_factor,
+                      float beta_fast, float beta_slow) {
+    rp.n_dims = n_dims; rp.mode = mode; rp.n_ctx_orig = n_ctx_orig;
+    rp.freq_base = freq_base; rp.freq_scale = freq_scale; rp.ext_factor = ext_factor; rp.attn_factor = attn_factor;
+    rp.beta_fast = beta_fast; rp.beta_slow = beta_slow;
+    rp.theta_scale = powf(freq_base, -2.0f / n_dims);
+    const float start = floorf(rope_yarn_corr_dim(n_dims, n_ctx_orig, beta_fast, freq_base));
+    const float end = ceilf(rope_yarn_corr_dim(n_dims, n_ctx_orig, beta_slow, freq_base));
+    rp.corr_dims[0] = fmaxf(0.f, start);
+    rp.corr_dims[1] = fminf((float) n_dims - 1, end);
+}
+
+int launch_rope_kvstore(float * q, const float * k, const float * v, __half * kcache, __half * vcache, int n_head, int n_head_kv, int D,
+                        const int32_t * pos_dev, const RopeParams & rp, const float * freq_factors, cudaStream_t stream, bool pdl) {
+    cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1];
+    launch_cfg(cfg, attr, dim3(n_head + n_head_kv), dim3(D / 2), 0, stream, pdl);
+    return (int) cudaLaunchKernelEx(&cfg, k_rope_kvstore, q, k, v, kcache, vcache, n_head, n_head_kv, D, pos_dev, rp, freq_factors);
+}
+int launch_rope(const float * x, float * y, int64_t ntok, int n_head, int D, int64_t tok_stride, int64_t head_stride, const int32_t * pos,
+                const RopeParams & rp, const float * freq_factors, cudaStream_t stream) {
+    k_rope<<<(unsigned) (ntok * n_head), 64, 0, stream>>>(x, y, n_head, D, tok_stride, head_stride, pos, rp, freq_factors);
+    return (int) cudaGetLastError();
+}
+
+int attn_scratch_floats(int, int) { return 0; }
+static int g_attn_smem_set = 0;
+int launch_attn_decode(const float * q, const __half * kcache, const __half * vcache, float * out, int n_head, int n_head_kv, int D,
+                       const int32_t * pos_dev, int n_ctx, float scale, float *, cudaStream_t stream, bool pdl) {
+    if (D != 128) return (int) cudaErrorInvalidValue;
+    const size_t smem = ((size_t) ((n_ctx + 31) & ~31) + 8 * 128) * sizeof(float);
+    if ((int) smem > g_attn_smem_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_attn_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        if (e != cudaSuccess) return (int) e;
+        g_attn_smem_set = (int) smem;
+    }
+    cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1];
+    launch_cfg(cfg, attr, dim3(n_head), dim3(256), smem, stream, pdl);
+    return (int) cudaLaunchKernelEx(&cfg, k_attn_decode, q, kcache, vcache, out, n_head, n_head_kv, D, pos_dev, scale);
+}
+
+int launch_soft_max(const float * x, const float * mask, float * y, int ncols, int64_t nrows, int64_t rows_per_mask_cycle, float scale,
+                    cudaStream_t stream) {
+    const size_t smem = (size_t) ncols * sizeof(float);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_soft_max, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        if (e != cudaSuccess) return (int) e;
+    }
+    k_soft_max<<<(unsigned) nrows, 256, smem, stream>>>(x, mask, y, ncols, rows_per_mask_cycle, scale);
+    return (int) cudaGetLastError();
+}
+
+int launch_get_rows(const void * table, int type, int K, const int32_t * ids, int n_ids, float * y, cudaStream_t stream, bool pdl) {
+    cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1];
+    launch_cfg(cfg, attr, dim3((K + 255) / 256, n_ids), dim3(256), 0, stream, pdl);
+    return (int) cudaLaunchKernelEx(&cfg, k_get_rows, (const uint8_t *) table, type, K, row_bytes(type, K), ids, y);
+}
+
+int launch_binary(int op, const float * a, const float * b, float * y, int64_t n, int64_t nb, cudaStream_t stream) {
+    k_binary<<<(unsigned) ((n + 255) / 256), 256, 0, stream>>>(op, a, b, y, n, nb);
+    return (int) cudaGetLastError();
+}
+int launch_silu(const float * x, float * y, int64_t n, cudaStream_t stream) {
+    k_silu<<<(unsigned) ((n + 255) / 256), 256, 0, stream>>>(x, y, n);
+    return (int) cudaGetLastError();
+}
+int launch_cpy_f32_f16(const float * x, __half * y, int64_t n, cudaStream_t stream) {
+    k_cpy_f32_f16<<<(unsigned) ((n + 255) / 256), 256, 0, stream>>>(x, y, n);
+    return (int) cudaGetLastError();
+}
+
+int launch_gemv(const GemvDesc * d, int nmat, int K, const ActQ & act, cudaStream_t stream, bool pdl) {
+    bool allk = true;
+    for (int i = 0; i < nmat; i++) allk = allk && is_kquant(d[i].type);
+    if (allk) return launch_gemv_kquant(d, nmat, K, act, stream, pdl);
+    for (int i = 0; i < nmat; i++) {
+        int e = launch_gemv_generic(d[i], K, act, stream, pdl);
+        if (e) return e;
+    }
+    return 0;
+}
+
+}  // namespace pb
