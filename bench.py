@@ -151,6 +151,7 @@ def cpu_reference(model_key, steps, warmup, sample_layers=2):
 
 # ------------------------------------------------------------------------------------------------ main
 def main():
+    global PROMPT
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=128)
@@ -159,13 +160,16 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n-ctx", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--prompt", type=int, default=PROMPT, help="untimed prompt tokens decoded before the timed region")
+    ap.add_argument("--ncu", action="store_true", help="bracket the timed region with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     args = ap.parse_args()
+    PROMPT = args.prompt
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     cfg = MODELS[args.model]
     hp = dict(cfg["hp"], n_ctx=args.n_ctx)
-    config = {"workload": f"{cfg['name']} decode b=1, synthetic random-init weights, {PROMPT}-token prompt then tg steps, n_ctx {args.n_ctx}, KV f16, FA off",
+    config = {"workload": f"{cfg['name']} decode b=1, synthetic random-init weights, {args.prompt}-token prompt then tg steps, n_ctx {args.n_ctx}, KV f16, FA off",
               "parallelism": "single GPU" if world == 1 else f"layer pipeline pp{world} (NCCL send/recv hand-off)",
               "l2": "no explicit flush: every step streams the shard's weights (>> 126 MB L2) once"}
 
@@ -283,7 +287,11 @@ def main():
         return ms, launches, clocks
 
     first = PROMPT + args.warmup
+    if args.ncu:
+        torch.cuda.profiler.start()
     ms_dev, launches, clocks = timed(False, first)
+    if args.ncu:
+        torch.cuda.profiler.stop()
     eng.kv_clear() if False else None
     ms_e2e, _, clocks_e2e = timed(True, first)     # same positions again: the KV rows are simply rewritten
     # live roofline of the dominant kernel (k_gemv_kquant): CUDA events around every GEMV launch of profiled steps

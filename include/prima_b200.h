@@ -115,6 +115,7 @@ PB200_API int pb200_get_hidden(pb200_model * m, float * hidden_host);   /* copie
  * weight bytes those launches read, their count and the whole-step time — the live roofline measurement of bench.py */
 PB200_API int pb200_profile_step(pb200_model * m, int32_t token, int32_t pos, double * gemv_ms, int64_t * gemv_bytes, int32_t * gemv_launches, double * step_ms);
 PB200_API int pb200_set_hidden(pb200_model * m, const float * hidden_host);   /* host -> hidden_in (tests, host-staged hand-off) */
+PB200_API int pb200_debug_read(pb200_model * m, const char * name, float * host, int64_t n);   /* white-box tests: q,k,v,att,g,u,x_a,x_b,xn,logits */
 PB200_API int pb200_set_use_graph(pb200_model * m, int on);             /* CUDA-graph replay on/off (default on) */
 
 #ifdef __cplusplus

@@ -596,6 +596,17 @@ int pb200_set_hidden(pb200_model * m, const float * hidden_host) {
     CK(cudaStreamSynchronize(m->stream));
     return (int) cudaMemcpy(m->x_in, hidden_host, (size_t) m->hp.n_embd * 4, cudaMemcpyHostToDevice);
 }
+// debugging / white-box tests: copy a named internal activation buffer of the LAST step to the host
+int pb200_debug_read(pb200_model * m, const char * name, float * host, int64_t n) {
+    if (!m || !m->finalized || !name || !host) return PB200_EINVAL;
+    cudaSetDevice(m->device);
+    CK(cudaStreamSynchronize(m->stream));
+    const std::string s(name);
+    const float * p = s == "q" ? m->q : s == "k" ? m->k : s == "v" ? m->v : s == "att" ? m->att : s == "g" ? m->g : s == "u" ? m->u :
+                      s == "x_a" ? m->x_a : s == "x_b" ? m->x_b : s == "xn" ? m->xn : s == "x_in" ? m->x_in : s == "logits" ? m->logits : nullptr;
+    if (!p) return PB200_EINVAL;
+    return (int) cudaMemcpy(host, p, (size_t) n * 4, cudaMemcpyDeviceToHost);
+}
 int pb200_set_use_graph(pb200_model * m, int on) {
     if (!m) return PB200_EINVAL;
     m->use_graph = on != 0;

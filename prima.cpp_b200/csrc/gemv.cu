@@ -71,10 +71,10 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) k_gemv_kquant(const __grid_co
     const int blk = wsub * 32 + lane;
     const bool valid = blk < P.nblk;
 
-    pdl_wait();   // the activation is produced by the previous kernel in the stream
+    pdl_trigger();   // let the next kernel become resident as SMs drain; its own pdl_wait() orders the data
+    pdl_wait();      // the activation is produced by the previous kernel in the stream
     ActRegs r;
     load_act_regs(r, P.act, blk, valid);
-    pdl_trigger();
 
     int it = 0;
     int slot_parity = 0;
@@ -150,8 +150,8 @@ struct GemvGenericParams {
 __global__ void __launch_bounds__(256) k_gemv_generic(const __grid_constant__ GemvGenericParams P) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * 8 + warp;
+    pdl_trigger();   // dependents may launch now; they still wait for this grid's completion in their own pdl_wait()
     pdl_wait();
-    pdl_trigger();
     if (row >= P.N) return;
     const uint8_t * wrow = P.W + (int64_t) row * P.row_bytes;
     float acc = 0.f;

@@ -28,8 +28,8 @@ static inline int launch_cfg(cudaLaunchConfig_t & cfg, cudaLaunchAttribute * att
 // ------------------------------------------------------------------------------------------------
 // activation quantization: one warp per 256 values
 __global__ void __launch_bounds__(256) k_quantize_act(const float * __restrict__ x, int K, int mode, ActQ out) {
+    pdl_trigger();   // dependents may launch now; they still wait for this grid's completion in their own pdl_wait()
     pdl_wait();
-    pdl_trigger();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t blk = (int64_t) blockIdx.x * 8 + warp;
     const int64_t base = blk * 256 + lane * 8;
@@ -49,8 +49,8 @@ __device__ __forceinline__ float silu_f32(float x) { return __fdiv_rn(x, 1.0f + 
 
 __global__ void __launch_bounds__(256) k_silu_mul_quant(const float * __restrict__ g, const float * __restrict__ u, int K, int mode, ActQ out,
                                                         float * __restrict__ f32_out) {
+    pdl_trigger();   // dependents may launch now; they still wait for this grid's completion in their own pdl_wait()
     pdl_wait();
-    pdl_trigger();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t blk = (int64_t) blockIdx.x * 8 + warp;
     const int64_t base = blk * 256 + lane * 8;
@@ -72,8 +72,8 @@ __global__ void __launch_bounds__(1024) k_rmsnorm_quant(const float * __restrict
                                                         ActQ out, float * __restrict__ f32_out) {
     __shared__ double red[32];
     __shared__ float s_scale;
+    pdl_trigger();   // dependents may launch now; they still wait for this grid's completion in their own pdl_wait()
     pdl_wait();
-    pdl_trigger();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double sum = 0.0;
     for (int i = threadIdx.x; i < n; i += 1024) {
@@ -166,8 +166,8 @@ __device__ __forceinline__ void rope_rotate(float x0, float x1, float c, float s
 __global__ void k_rope_kvstore(float * __restrict__ q, const float * __restrict__ k, const float * __restrict__ v, __half * __restrict__ kc,
                                __half * __restrict__ vc, int n_head, int n_head_kv, int D, const int32_t * __restrict__ pos_dev, RopeParams rp,
                                const float * __restrict__ freq_factors) {
+    pdl_trigger();   // dependents may launch now; they still wait for this grid's completion in their own pdl_wait()
     pdl_wait();
-    pdl_trigger();
     const int32_t pos = *pos_dev;
     const int h = blockIdx.x, pair = threadIdx.x;
     const int half_dims = rp.n_dims / 2;
@@ -227,8 +227,8 @@ __global__ void __launch_bounds__(256) k_attn_decode(const float * __restrict__ 
                                                      float * __restrict__ out, int n_head, int n_head_kv, int D, const int32_t * __restrict__ pos_dev,
                                                      float scale) {
     extern __shared__ float sm[];   // S[n_kv_pad] | red[8][128]
+    pdl_trigger();   // dependents may launch now; they still wait for this grid's completion in their own pdl_wait()
     pdl_wait();
-    pdl_trigger();
     const int n_kv = *pos_dev + 1;
     const int h = blockIdx.x, hk = h / (n_head / n_head_kv);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -397,8 +397,8 @@ __device__ float dequant_elem(int type, const uint8_t * row, int e) {
 
 __global__ void __launch_bounds__(256) k_get_rows(const uint8_t * __restrict__ table, int type, int K, int64_t row_bytes_,
                                                   const int32_t * __restrict__ ids, float * __restrict__ y) {
+    pdl_trigger();   // dependents may launch now; they still wait for this grid's completion in their own pdl_wait()
     pdl_wait();
-    pdl_trigger();
     const int64_t id = ids[blockIdx.y];
     const uint8_t * row = table + id * row_bytes_;
     const int e = blockIdx.x * 256 + threadIdx.x;

@@ -81,6 +81,7 @@ class Lib:
             getattr(c, n).argtypes = [vp]
         c.pb200_get_hidden.argtypes = [vp, vp]
         c.pb200_set_hidden.argtypes = [vp, vp]
+        c.pb200_debug_read.argtypes = [vp, C.c_char_p, vp, i64]
         c.pb200_profile_step.argtypes = [vp, i32, i32, C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(i32), C.POINTER(C.c_double)]
         c.pb200_set_use_graph.argtypes = [vp, C.c_int]
 
@@ -145,6 +146,12 @@ class Model:
         g, b, n, st = C.c_double(), C.c_int64(), C.c_int32(), C.c_double()
         self.lib.check(self.lib.c.pb200_profile_step(self.h, token, pos, C.byref(g), C.byref(b), C.byref(n), C.byref(st)), "profile_step")
         return {"gemv_ms": g.value, "gemv_bytes": b.value, "gemv_launches": n.value, "step_ms": st.value}
+
+    def debug_read(self, name: str, n: int):
+        import numpy as np
+        out = np.empty(n, dtype=np.float32)
+        self.lib.check(self.lib.c.pb200_debug_read(self.h, name.encode(), out.ctypes.data_as(C.c_void_p), n), "debug_read")
+        return out
 
     def set_hidden(self, h) -> None:
         import numpy as np

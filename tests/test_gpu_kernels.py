@@ -29,7 +29,8 @@ def test_quantize_act_bit_exact(cuda, lib, port, t):
     z = np.zeros(K, np.float32); z[300] = -2.5; cases.append(z)
     for x in cases:
         ws = act_ws(lib, K)
-        lib.check(lib.c.pb200_quantize_act(t, ptr(dev_f32(x)), K, ptr(ws), None), "quantize_act")
+        xd = dev_f32(x)
+        lib.check(lib.c.pb200_quantize_act(t, ptr(xd), K, ptr(ws), None), "quantize_act")
         sync()
         got = act_ws_fields(ws, K, MODE[t])
         want = port.quantize_act(t, x)
@@ -87,7 +88,8 @@ def test_gemv_fused_bias_resid_and_host_path(cuda, lib, port):
     Ws = [O.synth_blocks(t, n, K, seed=7 + i) for i, (t, n) in enumerate(zip(types, Ns))]
     x = np.random.default_rng(1).standard_normal(K).astype(np.float32)
     ws = act_ws(lib, K)
-    lib.check(lib.c.pb200_quantize_act(O.Q4_K, ptr(dev_f32(x)), K, ptr(ws), None), "q")
+    xd = dev_f32(x)
+    lib.check(lib.c.pb200_quantize_act(O.Q4_K, ptr(xd), K, ptr(ws), None), "q")
     Wd = [dev_u8(w) for w in Ws]
     ys = [torch.zeros(n, device="cuda") for n in Ns]
     lib.check(lib.c.pb200_mul_mat_vec_fused(3, (C.c_int * 3)(*types), (C.c_void_p * 3)(*[w.data_ptr() for w in Wd]), (C.c_int64 * 3)(*Ns), K,
@@ -99,7 +101,8 @@ def test_gemv_fused_bias_resid_and_host_path(cuda, lib, port):
     # bias + residual epilogue
     b = np.random.default_rng(2).standard_normal(Ns[0]).astype(np.float32); r = np.random.default_rng(3).standard_normal(Ns[0]).astype(np.float32)
     y = torch.zeros(Ns[0], device="cuda")
-    lib.check(lib.c.pb200_mul_mat_vec_q(types[0], ptr(Wd[0]), Ns[0], K, ptr(ws), ptr(y), ptr(dev_f32(b)), ptr(dev_f32(r)), None), "epi")
+    bd, rd = dev_f32(b), dev_f32(r)
+    lib.check(lib.c.pb200_mul_mat_vec_q(types[0], ptr(Wd[0]), Ns[0], K, ptr(ws), ptr(y), ptr(bd), ptr(rd), None), "epi")
     sync()
     want = port.mul_mat(types[0], Ws[0], Ns[0], K, x)[0] + b + r
     assert np.max(np.abs(y.cpu().numpy() - want)) <= rel_tol(want)
@@ -122,7 +125,8 @@ def test_get_rows_dequant_bit_exact(cuda, lib, port, t):
     ids = np.array([8, 0, 3, 3], dtype=np.int32)
     y = torch.zeros(len(ids) * K, device="cuda")
     idd = torch.from_numpy(ids).cuda()
-    lib.check(lib.c.pb200_get_rows(t, ptr(dev_u8(tab)), K, ptr(idd), len(ids), ptr(y), None), "get_rows")
+    tabd = dev_u8(tab)
+    lib.check(lib.c.pb200_get_rows(t, ptr(tabd), K, ptr(idd), len(ids), ptr(y), None), "get_rows")
     sync()
     assert np.array_equal(y.cpu().numpy().reshape(len(ids), K), want_all[ids])
 
@@ -132,7 +136,8 @@ def test_rms_norm(cuda, lib, port):
     for n, rows, eps in ((8192, 3, 1e-5), (4096, 1, 1e-6), (64, 5, 1e-5), (29568, 2, 1e-6)):
         x = rng.standard_normal((rows, n)).astype(np.float32) * 3
         y = torch.zeros(rows * n, device="cuda")
-        lib.check(lib.c.pb200_rms_norm(ptr(dev_f32(x)), ptr(y), n, rows, eps, None), "rms_norm")
+        xd = dev_f32(x)
+        lib.check(lib.c.pb200_rms_norm(ptr(xd), ptr(y), n, rows, eps, None), "rms_norm")
         sync()
         want = np.stack([port.rms_norm(x[i], eps) for i in range(rows)])
         got = y.cpu().numpy().reshape(rows, n)
@@ -149,8 +154,9 @@ def test_rope(cuda, lib, port, mode, ff):
     pos = np.array([0, 1, 77, 4095], dtype=np.int32)
     freq = (1.0 + rng.uniform(0, 7, 64)).astype(np.float32) if ff else None
     y = torch.zeros(T * H * D, device="cuda")
-    lib.check(lib.c.pb200_rope(ptr(dev_f32(x)), ptr(y), T, H, D, D, mode, ptr(torch.from_numpy(pos).cuda()), 500000.0, 1.0, 0.0, 1.0, 32.0, 1.0, 8192,
-                               ptr(dev_f32(freq)) if ff else None, None), "rope")
+    xd, pd, fd = dev_f32(x), torch.from_numpy(pos).cuda(), (dev_f32(freq) if ff else None)
+    lib.check(lib.c.pb200_rope(ptr(xd), ptr(y), T, H, D, D, mode, ptr(pd), 500000.0, 1.0, 0.0, 1.0, 32.0, 1.0, 8192,
+                               ptr(fd) if ff else None, None), "rope")
     sync()
     got = y.cpu().numpy().reshape(T, H, D)
     want = np.stack([port.rope(x[i], H, D, mode, int(pos[i]), freq_factors=freq) for i in range(T)])
@@ -164,7 +170,8 @@ def test_rope_yarn_and_partial_dims(cuda, lib, port):
     x = rng.standard_normal((T, H, D)).astype(np.float32)
     pos = np.array([3, 900], dtype=np.int32)
     y = torch.zeros(T * H * D, device="cuda")
-    lib.check(lib.c.pb200_rope(ptr(dev_f32(x)), ptr(y), T, H, D, 64, 0, ptr(torch.from_numpy(pos).cuda()), 10000.0, 0.25, 1.0, 1.0, 32.0, 1.0, 4096, None, None), "rope")
+    xd, pd = dev_f32(x), torch.from_numpy(pos).cuda()
+    lib.check(lib.c.pb200_rope(ptr(xd), ptr(y), T, H, D, 64, 0, ptr(pd), 10000.0, 0.25, 1.0, 1.0, 32.0, 1.0, 4096, None, None), "rope")
     sync()
     want = np.stack([port.rope(x[i], H, D, 0, int(pos[i]), freq_base=10000.0, freq_scale=0.25, n_ctx_orig=4096, ext_factor=1.0, n_dims=64) for i in range(T)])
     assert np.max(np.abs(y.cpu().numpy().reshape(T, H, D) - want)) < 1e-5
@@ -176,7 +183,8 @@ def test_soft_max(cuda, lib, port):
     x = rng.standard_normal((rows, ncols)).astype(np.float32) * 4
     mask = np.zeros((2, ncols), np.float32); mask[0, 50:] = -np.inf; mask[1, 70:] = -np.inf
     y = torch.zeros(rows * ncols, device="cuda")
-    lib.check(lib.c.pb200_soft_max(ptr(dev_f32(x)), ptr(dev_f32(mask)), ptr(y), ncols, rows, 2, 0.088, None), "soft_max")
+    xd, md = dev_f32(x), dev_f32(mask)
+    lib.check(lib.c.pb200_soft_max(ptr(xd), ptr(md), ptr(y), ncols, rows, 2, 0.088, None), "soft_max")
     sync()
     got = y.cpu().numpy().reshape(rows, ncols)
     want = np.stack([port.soft_max(x[i], mask[i % 2], 0.088) for i in range(rows)])
@@ -192,8 +200,8 @@ def test_attn_decode(cuda, lib, port, n_kv):
     Vc = rng.standard_normal((n_ctx, HK * D)).astype(np.float16)
     out = torch.zeros(H * D, device="cuda")
     pos = torch.tensor([n_kv - 1], dtype=torch.int32, device="cuda")
-    lib.check(lib.c.pb200_attn_decode(ptr(dev_f32(q)), ptr(torch.from_numpy(Kc).cuda()), ptr(torch.from_numpy(Vc).cuda()), ptr(out), H, HK, D,
-                                      ptr(pos), n_ctx, 1.0 / np.sqrt(D), None), "attn")
+    qd, kd, vd = dev_f32(q), torch.from_numpy(Kc).cuda(), torch.from_numpy(Vc).cuda()
+    lib.check(lib.c.pb200_attn_decode(ptr(qd), ptr(kd), ptr(vd), ptr(out), H, HK, D, ptr(pos), n_ctx, 1.0 / np.sqrt(D), None), "attn")
     sync()
     want = port.attention_decode(q, Kc.view(np.uint16), Vc.view(np.uint16), H, HK, D, n_kv, 1.0 / np.sqrt(D))
     # same f16 roundings of q and of the probabilities as the CPU graph; only fp32 summation order and expf ulp differ.
@@ -206,7 +214,8 @@ def test_full_size_gemv_properties(cuda, lib):
     """BASELINE sizes (Llama-3-70B shapes): the fused TMA kernel must agree with an independent evaluation —
     dequantized weights (get_rows kernel, bit-exact vs the oracle above) times the dequantized q8_K activation in fp64."""
     import gpu_util
-    for t, N, K in ((O.Q4_K, 2048, 8192), (O.Q6_K, 1024, 8192), (O.Q5_K, 1024, 8192), (O.Q4_K, 1024, 28672), (O.Q6_K, 512, 28672)):
+    # N large enough that every CTA streams > 4 tiles: exercises the mbarrier ring wrap-around and both parities
+    for t, N, K in ((O.Q4_K, 8192, 8192), (O.Q6_K, 6000, 8192), (O.Q5_K, 6100, 8192), (O.Q4_K, 2500, 28672), (O.Q6_K, 2200, 28672)):
         W = O.synth_blocks(t, N, K, seed=K + N + t)
         x = np.random.default_rng(t).standard_normal(K).astype(np.float32)
         Wd, xd, ws = dev_u8(W), dev_f32(x), act_ws(lib, K)
@@ -224,6 +233,7 @@ def test_full_size_gemv_properties(cuda, lib):
         # linearity in the rows: duplicated rows give identical results (tile/warp assignment independence)
         W2 = np.concatenate([W.reshape(N, -1)[:64], W.reshape(N, -1)[:64]]).reshape(-1)
         y2 = torch.zeros(128, device="cuda")
-        lib.check(lib.c.pb200_mul_mat_vec_q(t, ptr(dev_u8(W2)), 128, K, ptr(ws), ptr(y2), None, None, None), "dup")
+        W2d = dev_u8(W2)
+        lib.check(lib.c.pb200_mul_mat_vec_q(t, ptr(W2d), 128, K, ptr(ws), ptr(y2), None, None, None), "dup")
         sync()
         assert torch.equal(y2[:64], y2[64:]) and torch.equal(y2[:64], y[:64])

@@ -17,7 +17,7 @@ class TinyModel:
     """Weights as raw GGUF blocks (uint8 arrays) + f32 vectors, keyed by GGUF tensor names."""
 
     def __init__(self, n_layer=2, n_embd=512, n_head=4, n_head_kv=2, n_ff=1024, n_vocab=320, n_ctx=64, arch="llama", ftype="q4_K_M",
-                 seed=0, quantizer=None, freq_factors=False, types=None):
+                 seed=0, quantizer=None, freq_factors=False, types=None, branch_scale=1.0):
         self.hp = dict(n_layer=n_layer, n_embd=n_embd, n_head=n_head, n_head_kv=n_head_kv, head_dim=128, n_ff=n_ff, n_vocab=n_vocab,
                        n_ctx=n_ctx, rope_mode=0 if arch == "llama" else 2, n_ctx_orig=8192,
                        rope_freq_base=500000.0 if arch == "llama" else 1000000.0, rope_freq_scale=1.0,
@@ -61,10 +61,10 @@ class TinyModel:
             qmat(p + "attn_q.weight", default, QD, E)
             qmat(p + "attn_k.weight", default, EK, E)
             qmat(p + "attn_v.weight", O.Q6_K if more else (O.Q5_K if default == O.Q4_K else default), EK, E)
-            qmat(p + "attn_output.weight", default, E, QD)
+            qmat(p + "attn_output.weight", default, E, QD, scale=branch_scale)
             qmat(p + "ffn_gate.weight", default, F, E)
             qmat(p + "ffn_up.weight", default, F, E)
-            qmat(p + "ffn_down.weight", O.Q6_K if more else default, E, F)
+            qmat(p + "ffn_down.weight", O.Q6_K if more else default, E, F, scale=branch_scale)
             if arch == "qwen2":
                 fvec(p + "attn_q.bias", QD, 0.0, 0.05)
                 fvec(p + "attn_k.bias", EK, 0.0, 0.05)
