@@ -347,14 +347,15 @@ static int enqueue_step(pb200_model * m, uint64_t * nlaunch) {
         for (int i = 0; i < 3 && (!x1 || !x2); i++)
             if (bufs[i] != x) { if (!x1) x1 = bufs[i]; else x2 = bufs[i]; }
         // --- attention block ---
-        const bool qkv_k = is_kquant(L.wq.type) && is_kquant(L.wk.type) && is_kquant(L.wv.type);
+        const bool qkv_k = is_kquant(L.wq.type) && is_kquant(L.wk.type) && is_kquant(L.wv.type) && gemv_fused_prologue_ok(E);
         if (qkv_k) {
-            CK(launch_rmsnorm_quant(x, L.attn_norm, E, hp.rms_eps, ACT_Q8_K, m->actE.q, nullptr, st, pdl)); n++;
+            // rms_norm * attn_norm + q8_K quantization run as the GEMV's prologue (no separate kernel)
             GemvDesc d[3] = {{L.wq.data, m->q, L.bq, nullptr, L.wq.type, QD},
                              {L.wk.data, m->k, L.bk, nullptr, L.wk.type, EK},
                              {L.wv.data, m->v, L.bv, nullptr, L.wv.type, EK}};
+            GemvFused pro; pro.kind = 1; pro.in0 = x; pro.in1 = L.attn_norm; pro.eps = hp.rms_eps;
             CK(prof_begin(m, tbytes(L.wq) + tbytes(L.wk) + tbytes(L.wv)));
-            CK(launch_gemv_kquant(d, 3, E, m->actE.q, st, pdl)); n++;
+            CK(launch_gemv_kquant_fused(d, 3, E, m->actE.q, pro, st, pdl)); n++;
             CK(prof_end(m));
         } else {
             ActQ none{};
@@ -368,22 +369,26 @@ static int enqueue_step(pb200_model * m, uint64_t * nlaunch) {
                 CK(launch_gemv(&d1, 1, E, m->actE.q, st, pdl)); n++;
             }
         }
-        CK(launch_rope_kvstore(m->q, m->k, m->v, kc, vc, H, HK, D, pos_dev, m->rp, m->rope_ff, st, pdl)); n++;
-        CK(launch_attn_decode(m->q, kc, vc, m->att, H, HK, D, pos_dev, hp.n_ctx, kq_scale, nullptr, st, pdl)); n++;
-        CK(launch_quantize_act(m->att, QD, act_mode_for(L.wo.type), m->actQD.q, st, pdl)); n++;
+        CK(launch_attn_fused(m->q, m->k, m->v, kc, vc, m->att, H, HK, D, pos_dev, hp.n_ctx, m->rp, m->rope_ff, kq_scale, st, pdl)); n++;
         {
             GemvDesc d1 = {L.wo.data, x1, nullptr, x, L.wo.type, E};   // ffn_inp = wo.att + inpSA
             CK(prof_begin(m, tbytes(L.wo)));
-            CK(launch_gemv(&d1, 1, QD, m->actQD.q, st, pdl)); n++;
+            if (is_kquant(L.wo.type) && gemv_fused_prologue_ok(QD)) {
+                GemvFused pro; pro.kind = 2; pro.in0 = m->att;
+                CK(launch_gemv_kquant_fused(&d1, 1, QD, m->actQD.q, pro, st, pdl)); n++;
+            } else {
+                CK(launch_quantize_act(m->att, QD, act_mode_for(L.wo.type), m->actQD.q, st, pdl)); n++;
+                CK(launch_gemv(&d1, 1, QD, m->actQD.q, st, pdl)); n++;
+            }
             CK(prof_end(m));
         }
         // --- FFN block ---
-        const bool gu_k = is_kquant(L.gate.type) && is_kquant(L.up.type);
+        const bool gu_k = is_kquant(L.gate.type) && is_kquant(L.up.type) && gemv_fused_prologue_ok(E);
         if (gu_k) {
-            CK(launch_rmsnorm_quant(x1, L.ffn_norm, E, hp.rms_eps, ACT_Q8_K, m->actE.q, nullptr, st, pdl)); n++;
             GemvDesc d[2] = {{L.gate.data, m->g, nullptr, nullptr, L.gate.type, F}, {L.up.data, m->u, nullptr, nullptr, L.up.type, F}};
+            GemvFused pro; pro.kind = 1; pro.in0 = x1; pro.in1 = L.ffn_norm; pro.eps = hp.rms_eps;
             CK(prof_begin(m, tbytes(L.gate) + tbytes(L.up)));
-            CK(launch_gemv_kquant(d, 2, E, m->actE.q, st, pdl)); n++;
+            CK(launch_gemv_kquant_fused(d, 2, E, m->actE.q, pro, st, pdl)); n++;
             CK(prof_end(m));
         } else {
             ActQ none{};
@@ -396,11 +401,16 @@ static int enqueue_step(pb200_model * m, uint64_t * nlaunch) {
                 CK(launch_gemv(&d1, 1, E, m->actE.q, st, pdl)); n++;
             }
         }
-        CK(launch_silu_mul_quant(m->g, m->u, F, act_mode_for(L.down.type), m->actF.q, nullptr, st, pdl)); n++;
         {
             GemvDesc d1 = {L.down.data, x2, nullptr, x1, L.down.type, E};   // l_out = down.act + ffn_inp
             CK(prof_begin(m, tbytes(L.down)));
-            CK(launch_gemv(&d1, 1, F, m->actF.q, st, pdl)); n++;
+            if (is_kquant(L.down.type) && gemv_fused_prologue_ok(F)) {
+                GemvFused pro; pro.kind = 3; pro.in0 = m->g; pro.in1 = m->u;
+                CK(launch_gemv_kquant_fused(&d1, 1, F, m->actF.q, pro, st, pdl)); n++;
+            } else {
+                CK(launch_silu_mul_quant(m->g, m->u, F, act_mode_for(L.down.type), m->actF.q, nullptr, st, pdl)); n++;
+                CK(launch_gemv(&d1, 1, F, m->actF.q, st, pdl)); n++;
+            }
             CK(prof_end(m));
         }
         x = x2;
@@ -408,10 +418,15 @@ static int enqueue_step(pb200_model * m, uint64_t * nlaunch) {
     // hidden_out: keep a stable address for the next pipeline stage / tests
     if (x != m->x_b) { CK(cudaMemcpyAsync(m->x_b, x, (size_t) E * 4, cudaMemcpyDeviceToDevice, st)); }
     if (m->with_head) {
-        CK(launch_rmsnorm_quant(m->x_b, m->output_norm, E, hp.rms_eps, act_mode_for(m->output.type), m->actE.q, nullptr, st, false)); n++;
         GemvDesc d1 = {m->output.data, m->logits, nullptr, nullptr, m->output.type, hp.n_vocab};
         CK(prof_begin(m, tbytes(m->output)));
-        CK(launch_gemv(&d1, 1, E, m->actE.q, st, pdl)); n++;
+        if (is_kquant(m->output.type) && gemv_fused_prologue_ok(E)) {
+            GemvFused pro; pro.kind = 1; pro.in0 = m->x_b; pro.in1 = m->output_norm; pro.eps = hp.rms_eps;
+            CK(launch_gemv_kquant_fused(&d1, 1, E, m->actE.q, pro, st, false)); n++;
+        } else {
+            CK(launch_rmsnorm_quant(m->x_b, m->output_norm, E, hp.rms_eps, act_mode_for(m->output.type), m->actE.q, nullptr, st, false)); n++;
+            CK(launch_gemv(&d1, 1, E, m->actE.q, st, pdl)); n++;
+        }
         CK(prof_end(m));
     }
     if (nlaunch) *nlaunch = n;

@@ -1,6 +1,7 @@
 // prima.cpp_b200/csrc/gemv.cu — kernels + launchers for the decode GEMV (see gemv.cuh for the design).
 #include "gemv.cuh"
 #include "launch.h"
+#include "quantize.cuh"
 
 namespace pb {
 
@@ -8,7 +9,54 @@ struct __align__(16) GemvSmemCtl {
     uint64_t full[GEMV_NSTAGE];
     uint64_t empty[GEMV_NSTAGE];
     float part[2][GEMV_NW];   // cross-warp partial sums (double-buffered by row slot parity)
+    double red[GEMV_NW];      // rms_norm partial sums of squares
+    float scale;
 };
+constexpr int GEMV_CTL_BYTES = 256;
+
+__device__ __forceinline__ void consumer_bar() {   // the 8 consumer warps only (the producer warp never joins)
+    asm volatile("bar.sync 9, %0;" ::"n"(GEMV_NW * 32) : "memory");
+}
+__device__ __forceinline__ float silu_f(float x) { return __fdiv_rn(x, 1.0f + expf(-x)); }   // ggml.c:2560
+
+// Fused prologue executed by the 8 consumer warps: quantize the activation into shared memory (see PRO_* in gemv.cuh).
+__device__ __forceinline__ void gemv_prologue(const GemvParams & P, GemvSmemCtl * ctl, const ActQ & sa, int warp, int lane) {
+    const int tid = warp * 32 + lane;
+    float scale = 1.f;
+    if (P.prologue == PRO_RMSNORM) {
+        double sum = 0.0;
+        for (int i = tid; i < P.K; i += GEMV_NW * 32) {
+            const float v = P.in0[i];
+            sum += (double) __fmul_rn(v, v);
+        }
+        sum = warp_sum_d(sum);
+        if (lane == 0) ctl->red[warp] = sum;
+        consumer_bar();
+        if (tid == 0) {
+            double t = 0.0;
+#pragma unroll
+            for (int i = 0; i < GEMV_NW; i++) t += ctl->red[i];
+            const float mean = (float) (t / (double) P.K);
+            ctl->scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, P.eps)));
+        }
+        consumer_bar();
+        scale = ctl->scale;
+    }
+    for (int b = warp; b < P.nblk; b += GEMV_NW) {
+        const int base = b * 256 + lane * 8;
+        const float4 a0 = *reinterpret_cast<const float4 *>(P.in0 + base), a1 = *reinterpret_cast<const float4 *>(P.in0 + base + 4);
+        float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        if (P.prologue != PRO_QUANT) {
+            const float4 w0 = *reinterpret_cast<const float4 *>(P.in1 + base), w1 = *reinterpret_cast<const float4 *>(P.in1 + base + 4);
+            const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                v[i] = P.prologue == PRO_RMSNORM ? __fmul_rn(__fmul_rn(v[i], scale), w[i]) : __fmul_rn(silu_f(v[i]), w[i]);
+        }
+        quantize_warp_q8K(v, lane, b, sa);
+    }
+    consumer_bar();
+}
 
 __device__ __forceinline__ void tile_info(const GemvParams & P, int t, int & m, int & r0, int & nrows) {
     m = 0;
@@ -23,8 +71,9 @@ __device__ __forceinline__ void tile_info(const GemvParams & P, int t, int & m, 
 __global__ void __launch_bounds__(GEMV_THREADS, 1) k_gemv_kquant(const __grid_constant__ GemvParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
     GemvSmemCtl * ctl = reinterpret_cast<GemvSmemCtl *>(smem);
-    uint8_t * stages = smem + 128;   // ctl block is 128 B (static_assert below)
-    static_assert(sizeof(GemvSmemCtl) <= 128, "ctl block");
+    uint8_t * stages = smem + GEMV_CTL_BYTES;
+    uint8_t * act_smem = stages + (size_t) GEMV_NSTAGE * GEMV_STAGE_BYTES;
+    static_assert(sizeof(GemvSmemCtl) <= GEMV_CTL_BYTES, "ctl block");
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -74,7 +123,17 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) k_gemv_kquant(const __grid_co
     pdl_trigger();   // let the next kernel become resident as SMs drain; its own pdl_wait() orders the data
     pdl_wait();      // the activation is produced by the previous kernel in the stream
     ActRegs r;
-    load_act_regs(r, P.act, blk, valid);
+    if (P.prologue == PRO_NONE) {
+        load_act_regs(r, P.act, blk, valid);
+    } else {
+        ActQ sa;
+        sa.qs = reinterpret_cast<int8_t *>(act_smem);
+        sa.bsums = reinterpret_cast<int16_t *>(act_smem + P.K);
+        sa.d = reinterpret_cast<float *>(act_smem + P.K + P.K / 8);
+        sa.s = nullptr;
+        gemv_prologue(P, ctl, sa, warp, lane);
+        load_act_regs(r, sa, blk, valid);
+    }
 
     int it = 0;
     int slot_parity = 0;
@@ -89,7 +148,15 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) k_gemv_kquant(const __grid_co
         const uint32_t mis = (uint32_t) (((int64_t) r0 * M.row_bytes) & 15);
         const uint8_t * tile = stages + (size_t) s * GEMV_STAGE_BYTES + mis;
         mbar_wait(&ctl->full[s], ph);
+        const bool leader = wsub == 0 && lane == 0;
         for (int slot = group; slot < nrows; slot += ngroups) {
+            const int row = r0 + slot;
+            // epilogue operands are requested before the dot so that their L2 latency is off the critical path
+            float extra = 0.f;
+            if (leader) {
+                if (M.bias) extra = M.bias[row];
+                if (M.resid) extra += M.resid[row];
+            }
             const uint8_t * bp = tile + (size_t) slot * M.row_bytes + (size_t) blk * bpb;
             float v = 0.f;
             if (valid) {
@@ -97,34 +164,30 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) k_gemv_kquant(const __grid_co
                 else if (type == T_Q6_K) v = dot_q6K(bp, r);
                 else v = dot_q5K(bp, r);
             }
+            if (slot + ngroups >= nrows) {
+                // last row of this stage for this warp: hand the buffer back to the producer before reducing
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ctl->empty[s]);
+            }
             v = warp_sum(v);
-            const int row = r0 + slot;
             if (wpr == 1) {
-                if (lane == 0) {
-                    if (M.bias) v += M.bias[row];
-                    if (M.resid) v += M.resid[row];
-                    M.y[row] = v;
-                }
+                if (lane == 0) M.y[row] = v + extra;
             } else {
                 if (lane == 0) ctl->part[slot_parity][warp] = v;
                 // named barrier among the wpr warps of this group (ids 1..8; 0 is __syncthreads)
                 asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(wpr * 32) : "memory");
-                if (wsub == 0 && lane == 0) {
+                if (leader) {
                     float acc = 0.f;
                     for (int i = 0; i < wpr; i++) acc += ctl->part[slot_parity][group * wpr + i];
-                    if (M.bias) acc += M.bias[row];
-                    if (M.resid) acc += M.resid[row];
-                    M.y[row] = acc;
+                    M.y[row] = acc + extra;
                 }
                 slot_parity ^= 1;
             }
         }
-        if (wpr > 1) {
-            // rows of a tile are not a multiple of ngroups in general: keep slot_parity warp-group-uniform
-            // (every warp of a group executes the same slots, so it already is).
+        if (group >= nrows) {   // this warp had no row in the tile (ragged last tile): still release the stage
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ctl->empty[s]);
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&ctl->empty[s]);
     }
 }
 
@@ -267,7 +330,7 @@ __global__ void __launch_bounds__(256) k_gemv_generic(const __grid_constant__ Ge
 static int g_sm_count = 0;
 static bool g_attr_set = false;
 
-int gemv_smem_bytes() { return 128 + GEMV_NSTAGE * GEMV_STAGE_BYTES; }
+int gemv_smem_bytes() { return GEMV_CTL_BYTES + GEMV_NSTAGE * GEMV_STAGE_BYTES + GEMV_ACT_SMEM; }
 
 int sm_count() {
     if (!g_sm_count) {
@@ -290,7 +353,15 @@ static int pick_rows_per_tile(int64_t row_bytes, int ngroups, int N) {
 
 // Fused launch of up to 3 k-quant matrices sharing one q8_K activation.  Returns cudaError_t as int.
 int launch_gemv_kquant(const GemvDesc * d, int nmat, int K, const ActQ & act, cudaStream_t stream, bool pdl) {
+    GemvFused none{};
+    return launch_gemv_kquant_fused(d, nmat, K, act, none, stream, pdl);
+}
+
+bool gemv_fused_prologue_ok(int K) { return K % 256 == 0 && K / 256 <= GEMV_MAX_NBLK && K + K / 8 + K / 64 + 64 <= GEMV_ACT_SMEM; }
+
+int launch_gemv_kquant_fused(const GemvDesc * d, int nmat, int K, const ActQ & act, const GemvFused & pro, cudaStream_t stream, bool pdl) {
     if (nmat < 1 || nmat > GEMV_MAX_MAT || K % 256 != 0) return (int) cudaErrorInvalidValue;
+    if (pro.kind != PRO_NONE && !gemv_fused_prologue_ok(K)) return (int) cudaErrorInvalidValue;
     const int nblk = K / 256;
     bool fast = nblk <= GEMV_MAX_NBLK;
     GemvParams P{};
@@ -302,6 +373,10 @@ int launch_gemv_kquant(const GemvDesc * d, int nmat, int K, const ActQ & act, cu
         P.K = K;
         P.nmat = nmat;
         P.act = act;
+        P.prologue = pro.kind;
+        P.in0 = pro.in0;
+        P.in1 = pro.in1;
+        P.eps = pro.eps;
         int tiles = 0;
         for (int i = 0; i < nmat; i++) {
             GemvMat & M = P.mat[i];
@@ -341,6 +416,7 @@ int launch_gemv_kquant(const GemvDesc * d, int nmat, int K, const ActQ & act, cu
         cfg.numAttrs = 1;
         return (int) cudaLaunchKernelEx(&cfg, k_gemv_kquant, P);
     }
+    if (pro.kind != PRO_NONE) return (int) cudaErrorInvalidValue;   // callers must check gemv_fused_prologue_ok / alignment
     for (int i = 0; i < nmat; i++) {
         int e = launch_gemv_generic(d[i], K, act, stream, pdl);
         if (e) return e;

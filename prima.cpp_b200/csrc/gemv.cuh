@@ -25,7 +25,8 @@ namespace pb {
 constexpr int GEMV_NW = 8;                       // consumer warps
 constexpr int GEMV_THREADS = (GEMV_NW + 1) * 32;  // + 1 producer warp
 constexpr int GEMV_NSTAGE = 4;
-constexpr int GEMV_STAGE_BYTES = 54 * 1024;       // >= 8 rows of Q6_K @ K=8192 (53 760 B) + 16 B alignment slack
+constexpr int GEMV_STAGE_BYTES = 48 * 1024;       // 8 rows of Q4_K/Q5_K or 7 rows of Q6_K @ K=8192; 2 rows @ K=28672
+constexpr int GEMV_ACT_SMEM = 28672 + 28672 / 8 + 28672 / 64 + 64;   // fused-prologue activation (qs | bsums | d), K <= 28 672
 constexpr int GEMV_MAX_MAT = 3;
 constexpr int GEMV_MAX_NBLK = 256;               // K <= 65 536 (8 warps x 32 lanes x one super-block each)
 
@@ -42,6 +43,14 @@ struct GemvMat {
     int tile0;             // index of this matrix' first tile in the launch-wide tile list
 };
 
+// Fused prologue: every CTA produces the q8_K activation itself (redundantly, from L2) while its producer warp is already
+// streaming weights, instead of a separate tiny kernel + launch in front of each GEMV:
+//   PRO_NONE     activation already quantized in HBM (`act`)
+//   PRO_RMSNORM  act = q8_K( rms_norm(in0) * in1 )          llm_build_norm + quantize_row_q8_K   (in1 = norm weight)
+//   PRO_QUANT    act = q8_K( in0 )                          attention output -> wo
+//   PRO_SILU_MUL act = q8_K( silu(in0) * in1 )              llm_build_ffn LLM_FFN_SILU / LLM_FFN_PAR -> ffn_down
+enum : int { PRO_NONE = 0, PRO_RMSNORM = 1, PRO_QUANT = 2, PRO_SILU_MUL = 3 };
+
 struct GemvParams {
     GemvMat mat[GEMV_MAX_MAT];
     int nmat;
@@ -49,7 +58,11 @@ struct GemvParams {
     int K;
     int nblk;      // K / 256
     int wpr;       // warps per row: 1, 2, 4 or 8
-    ActQ act;      // q8_K activation
+    ActQ act;      // q8_K activation (PRO_NONE)
+    int prologue;
+    const float * in0;
+    const float * in1;
+    float eps;
 };
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -17,11 +17,20 @@ struct GemvDesc {
     int N;
 };
 
+struct GemvFused {       // fused activation prologue of the k-quant GEMV (PRO_* in gemv.cuh)
+    int kind = 0;        // 0 none, 1 rms_norm(in0)*in1, 2 quantize(in0), 3 silu(in0)*in1
+    const float * in0 = nullptr;
+    const float * in1 = nullptr;
+    float eps = 0.f;
+};
+
 int sm_count();
 int gemv_smem_bytes();
 
 // y_i = W_i . act  for up to 3 k-quant matrices sharing one q8_K activation (TMA-staged persistent kernel)
 int launch_gemv_kquant(const GemvDesc * d, int nmat, int K, const ActQ & act, cudaStream_t stream, bool pdl);
+int launch_gemv_kquant_fused(const GemvDesc * d, int nmat, int K, const ActQ & act, const GemvFused & pro, cudaStream_t stream, bool pdl);
+bool gemv_fused_prologue_ok(int K);
 // any supported type / any K, one warp per row, direct global loads
 int launch_gemv_generic(const GemvDesc & d, int K, const ActQ & act, cudaStream_t stream, bool pdl);
 // picks the right kernel per weight type (all matrices must need the same activation mode)
@@ -59,6 +68,10 @@ int launch_rope(const float * x, float * y, int64_t ntok, int n_head, int D, int
 int launch_attn_decode(const float * q, const __half * kcache, const __half * vcache, float * out, int n_head, int n_head_kv, int D,
                        const int32_t * pos_dev, int n_ctx, float scale, float * scratch, cudaStream_t stream, bool pdl);
 int attn_scratch_floats(int n_head, int n_ctx);
+// rope(q), rope(k) -> f16 K row, v -> f16 V row, cache store and attention in one launch (the engine's per-token path)
+int launch_attn_fused(const float * q, const float * k, const float * v, __half * kcache, __half * vcache, float * out, int n_head, int n_head_kv,
+                      int D, const int32_t * pos_dev, int n_ctx, const RopeParams & rp, const float * freq_factors, float scale, cudaStream_t stream,
+                      bool pdl);
 
 // soft_max_ext for the plugin: y[r][:] = softmax(x[r][:]*scale + mask[r % mask_rows][:])  (softmax.cu:14-116)
 int launch_soft_max(const float * x, const float * mask, float * y, int ncols, int64_t nrows, int64_t rows_per_mask_cycle, float scale,

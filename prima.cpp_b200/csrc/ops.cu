@@ -302,6 +302,125 @@ __global__ void __launch_bounds__(256) k_attn_decode(const float * __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Fused RoPE + KV store + decode attention: one CTA (8 warps) per q head.  Replaces k_rope_kvstore + k_attn_decode in the
+// engine's per-token loop (same arithmetic, one launch): the CTA rotates its q head and its kv head's k in shared memory,
+// rounds k / v to f16 exactly like the cache store does, attends over cache rows [0, pos) plus the fresh row from shared
+// memory, and the first q head of each GQA group writes the fresh K/V row to the cache for later tokens.
+__global__ void __launch_bounds__(256) k_attn_fused(const float * __restrict__ q, const float * __restrict__ k, const float * __restrict__ v,
+                                                    __half * __restrict__ kc, __half * __restrict__ vc, float * __restrict__ out, int n_head,
+                                                    int n_head_kv, const int32_t * __restrict__ pos_dev, RopeParams rp,
+                                                    const float * __restrict__ freq_factors, float scale) {
+    constexpr int D = 128;
+    extern __shared__ float sm[];   // S[n_kv_pad] | red[8][128]
+    __shared__ float q_s[D];
+    __shared__ __align__(16) __half k_s[D];
+    __shared__ __align__(16) __half v_s[D];
+    __shared__ float s_red[8];
+    __shared__ double s_redd[8];
+    __shared__ float s_max, s_inv;
+    pdl_trigger();
+    pdl_wait();
+    const int pos = *pos_dev;
+    const int n_kv = pos + 1;
+    const int gqa = n_head / n_head_kv;
+    const int h = blockIdx.x, hk = h / gqa;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t EK = (int64_t) n_head_kv * D;
+    float * S = sm;
+    float * red = sm + ((n_kv + 31) & ~31);
+
+    {   // RoPE: threads 0..63 rotate q (pair = tid), threads 64..127 rotate k, threads 128..255 convert v
+        const int half_dims = rp.n_dims / 2;
+        const bool neox = rp.mode & 2;
+        if (threadIdx.x < 128) {
+            const int pair = threadIdx.x & 63;
+            const bool is_q = threadIdx.x < 64;
+            const float * src = is_q ? q + (int64_t) h * D : k + (int64_t) hk * D;
+            if (pair < half_dims) {
+                float c, s;
+                rope_cos_sin(rp, pos, pair, freq_factors, c, s);
+                const int i0 = neox ? pair : 2 * pair, i1 = neox ? pair + half_dims : 2 * pair + 1;
+                float y0, y1;
+                rope_rotate(src[i0], src[i1], c, s, y0, y1);
+                if (is_q) { q_s[i0] = __half2float(__float2half_rn(y0)); q_s[i1] = __half2float(__float2half_rn(y1)); }
+                else { k_s[i0] = __float2half_rn(y0); k_s[i1] = __float2half_rn(y1); }
+            }
+            for (int i = rp.n_dims + pair; i < D; i += 64) {   // un-rotated tail when n_dims < D
+                if (is_q) q_s[i] = __half2float(__float2half_rn(src[i]));
+                else k_s[i] = __float2half_rn(src[i]);
+            }
+        } else {
+            const int i = threadIdx.x - 128;
+            v_s[i] = __float2half_rn(v[(int64_t) hk * D + i]);
+        }
+    }
+    __syncthreads();
+    if (h % gqa == 0 && threadIdx.x < 32) {   // one CTA per kv head publishes the fresh row (8 B per lane, coalesced)
+        *reinterpret_cast<uint2 *>(kc + (int64_t) pos * EK + (int64_t) hk * D + 4 * lane) = *reinterpret_cast<const uint2 *>(k_s + 4 * lane);
+        *reinterpret_cast<uint2 *>(vc + (int64_t) pos * EK + (int64_t) hk * D + 4 * lane) = *reinterpret_cast<const uint2 *>(v_s + 4 * lane);
+    }
+    const float q0 = q_s[4 * lane], q1 = q_s[4 * lane + 1], q2 = q_s[4 * lane + 2], q3 = q_s[4 * lane + 3];
+    for (int p = warp; p < n_kv; p += 8) {
+        const __half * krow = p == pos ? k_s : kc + (int64_t) p * EK + (int64_t) hk * D;
+        const uint2 kraw = *reinterpret_cast<const uint2 *>(krow + 4 * lane);
+        const float2 k01 = __half22float2(*reinterpret_cast<const __half2 *>(&kraw.x));
+        const float2 k23 = __half22float2(*reinterpret_cast<const __half2 *>(&kraw.y));
+        float s = k01.x * q0;
+        s = fmaf(k01.y, q1, s);
+        s = fmaf(k23.x, q2, s);
+        s = fmaf(k23.y, q3, s);
+        s = warp_sum(s);
+        if (lane == 0) S[p] = __fmul_rn(s, scale);
+    }
+    __syncthreads();
+    float m = -INFINITY;
+    for (int p = threadIdx.x; p < n_kv; p += 256) m = fmaxf(m, S[p]);
+    m = warp_max(m);
+    if (lane == 0) s_red[warp] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = s_red[0];
+        for (int i = 1; i < 8; i++) t = fmaxf(t, s_red[i]);
+        s_max = t;
+    }
+    __syncthreads();
+    const float mx = s_max;
+    double dsum = 0.0;
+    for (int p = threadIdx.x; p < n_kv; p += 256) {
+        const float e = expf(__fsub_rn(S[p], mx));
+        S[p] = e;
+        dsum += (double) e;
+    }
+    dsum = warp_sum_d(dsum);
+    if (lane == 0) s_redd[warp] = dsum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0;
+        for (int i = 0; i < 8; i++) t += s_redd[i];
+        s_inv = (float) (1.0 / t);
+    }
+    __syncthreads();
+    const float inv = s_inv;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int p = warp; p < n_kv; p += 8) {
+        const float w = __half2float(__float2half_rn(__fmul_rn(S[p], inv)));
+        const __half * vrow = p == pos ? v_s : vc + (int64_t) p * EK + (int64_t) hk * D;
+        const uint2 vraw = *reinterpret_cast<const uint2 *>(vrow + 4 * lane);
+        const float2 v01 = __half22float2(*reinterpret_cast<const __half2 *>(&vraw.x));
+        const float2 v23 = __half22float2(*reinterpret_cast<const __half2 *>(&vraw.y));
+        a0 = fmaf(v01.x, w, a0); a1 = fmaf(v01.y, w, a1); a2 = fmaf(v23.x, w, a2); a3 = fmaf(v23.y, w, a3);
+    }
+    *reinterpret_cast<float4 *>(red + warp * 128 + 4 * lane) = make_float4(a0, a1, a2, a3);
+    __syncthreads();
+    if (threadIdx.x < 128) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; i++) t += red[i * 128 + threadIdx.x];
+        out[(int64_t) h * D + threadIdx.x] = t;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // soft_max_ext rows (plugin): y = softmax(x*scale + mask)
 __global__ void __launch_bounds__(256) k_soft_max(const float * __restrict__ x, const float * __restrict__ mask, float * __restrict__ y, int ncols,
                                                   int64_t rows_per_mask_cycle, float scale) {
@@ -485,6 +604,22 @@ int launch_attn_decode(const float * q, const __half * kcache, const __half * vc
     cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1];
     launch_cfg(cfg, attr, dim3(n_head), dim3(256), smem, stream, pdl);
     return (int) cudaLaunchKernelEx(&cfg, k_attn_decode, q, kcache, vcache, out, n_head, n_head_kv, D, pos_dev, scale);
+}
+
+static int g_attnf_smem_set = 0;
+int launch_attn_fused(const float * q, const float * k, const float * v, __half * kcache, __half * vcache, float * out, int n_head, int n_head_kv,
+                      int D, const int32_t * pos_dev, int n_ctx, const RopeParams & rp, const float * freq_factors, float scale, cudaStream_t stream,
+                      bool pdl) {
+    if (D != 128) return (int) cudaErrorInvalidValue;
+    const size_t smem = ((size_t) ((n_ctx + 31) & ~31) + 8 * 128) * sizeof(float);
+    if ((int) smem > g_attnf_smem_set && smem > 40 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_attn_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        if (e != cudaSuccess) return (int) e;
+        g_attnf_smem_set = (int) smem;
+    }
+    cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1];
+    launch_cfg(cfg, attr, dim3(n_head), dim3(256), smem, stream, pdl);
+    return (int) cudaLaunchKernelEx(&cfg, k_attn_fused, q, k, v, kcache, vcache, out, n_head, n_head_kv, pos_dev, rp, freq_factors, scale);
 }
 
 int launch_soft_max(const float * x, const float * mask, float * y, int ncols, int64_t nrows, int64_t rows_per_mask_cycle, float scale,
