@@ -10,6 +10,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -328,7 +329,7 @@ static int enqueue_step(pb200_model * m, uint64_t * nlaunch) {
     const int E = hp.n_embd, H = hp.n_head, HK = hp.n_head_kv, D = hp.head_dim, F = hp.n_ff;
     const int QD = H * D, EK = HK * D;
     cudaStream_t st = m->stream;
-    const bool pdl = true;
+    static const bool pdl = getenv("PB200_NO_PDL") == nullptr;   // programmatic dependent launch on every kernel of the step
     uint64_t n = 0;
     const int32_t * tok_dev = m->tokpos_dev, * pos_dev = m->tokpos_dev + 1;
     float * x = m->x_in;
@@ -404,7 +405,9 @@ static int enqueue_step(pb200_model * m, uint64_t * nlaunch) {
         {
             GemvDesc d1 = {L.down.data, x2, nullptr, x1, L.down.type, E};   // l_out = down.act + ffn_inp
             CK(prof_begin(m, tbytes(L.down)));
-            if (is_kquant(L.down.type) && gemv_fused_prologue_ok(F)) {
+            if (false && is_kquant(L.down.type) && gemv_fused_prologue_ok(F)) {
+                // measured (profiles/r1_launches.md): recomputing silu(g)*u in all 148 CTAs costs +17 us per layer, the separate
+                // 14-CTA kernel 5 us -> keep the kernel; the fused path stays available for the persistent design
                 GemvFused pro; pro.kind = 3; pro.in0 = m->g; pro.in1 = m->u;
                 CK(launch_gemv_kquant_fused(&d1, 1, F, m->actF.q, pro, st, pdl)); n++;
             } else {

@@ -8,11 +8,11 @@ namespace pb {
 struct __align__(16) GemvSmemCtl {
     uint64_t full[GEMV_NSTAGE];
     uint64_t empty[GEMV_NSTAGE];
-    float part[2][GEMV_NW];   // cross-warp partial sums (double-buffered by row slot parity)
-    double red[GEMV_NW];      // rms_norm partial sums of squares
-    float scale;
+    uint64_t pbar[GEMV_NSTAGE][4];        // wpr > 1: "partials of this stage's row are in shared memory" per warp group
+    float part[GEMV_NSTAGE][GEMV_NW];     // cross-warp partial sums, one slot per stage in flight
+    double red[GEMV_NW];                  // rms_norm partial sums of squares
 };
-constexpr int GEMV_CTL_BYTES = 256;
+constexpr int GEMV_CTL_BYTES = 512;
 
 __device__ __forceinline__ void consumer_bar() {   // the 8 consumer warps only (the producer warp never joins)
     asm volatile("bar.sync 9, %0;" ::"n"(GEMV_NW * 32) : "memory");
@@ -20,40 +20,72 @@ __device__ __forceinline__ void consumer_bar() {   // the 8 consumer warps only 
 __device__ __forceinline__ float silu_f(float x) { return __fdiv_rn(x, 1.0f + expf(-x)); }   // ggml.c:2560
 
 // Fused prologue executed by the 8 consumer warps: quantize the activation into shared memory (see PRO_* in gemv.cuh).
+// Warp w owns super-blocks w, w+8, w+16, ... ; lane l owns elements 8l..8l+7 of each.  Blocks are processed four at a
+// time with every global load issued up front, and for PRO_RMSNORM the same registers feed the sum of squares, so the
+// vector is read exactly once (K <= 8192 in one batch; longer vectors loop over batches for the sum, then again to quantize).
+__device__ __forceinline__ void load8(const float * p, float (&v)[8]) {
+    const float4 a0 = *reinterpret_cast<const float4 *>(p), a1 = *reinterpret_cast<const float4 *>(p + 4);
+    v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
+}
 __device__ __forceinline__ void gemv_prologue(const GemvParams & P, GemvSmemCtl * ctl, const ActQ & sa, int warp, int lane) {
     const int tid = warp * 32 + lane;
+    constexpr int B = 4;   // blocks in flight per warp
+    const bool single_batch = P.nblk <= GEMV_NW * B;
+    float x[B][8], w[B][8];
     float scale = 1.f;
     if (P.prologue == PRO_RMSNORM) {
         double sum = 0.0;
-        for (int i = tid; i < P.K; i += GEMV_NW * 32) {
-            const float v = P.in0[i];
-            sum += (double) __fmul_rn(v, v);
+        if (single_batch) {
+#pragma unroll
+            for (int j = 0; j < B; j++) {
+                const int b = warp + j * GEMV_NW;
+                if (b < P.nblk) { load8(P.in0 + b * 256 + lane * 8, x[j]); load8(P.in1 + b * 256 + lane * 8, w[j]); }
+            }
+#pragma unroll
+            for (int j = 0; j < B; j++) {
+                const int b = warp + j * GEMV_NW;
+                if (b < P.nblk) {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) sum += (double) __fmul_rn(x[j][i], x[j][i]);
+                }
+            }
+        } else {
+            for (int i = tid; i < P.K; i += GEMV_NW * 32) { const float v = P.in0[i]; sum += (double) __fmul_rn(v, v); }
         }
         sum = warp_sum_d(sum);
         if (lane == 0) ctl->red[warp] = sum;
         consumer_bar();
-        if (tid == 0) {
-            double t = 0.0;
+        double t = 0.0;
 #pragma unroll
-            for (int i = 0; i < GEMV_NW; i++) t += ctl->red[i];
-            const float mean = (float) (t / (double) P.K);
-            ctl->scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, P.eps)));
-        }
-        consumer_bar();
-        scale = ctl->scale;
+        for (int i = 0; i < GEMV_NW; i++) t += ctl->red[i];     // every thread: same order, same result
+        const float mean = (float) (t / (double) P.K);
+        scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, P.eps)));
     }
-    for (int b = warp; b < P.nblk; b += GEMV_NW) {
-        const int base = b * 256 + lane * 8;
-        const float4 a0 = *reinterpret_cast<const float4 *>(P.in0 + base), a1 = *reinterpret_cast<const float4 *>(P.in0 + base + 4);
-        float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-        if (P.prologue != PRO_QUANT) {
-            const float4 w0 = *reinterpret_cast<const float4 *>(P.in1 + base), w1 = *reinterpret_cast<const float4 *>(P.in1 + base + 4);
-            const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+    for (int b0 = 0; b0 < P.nblk; b0 += GEMV_NW * B) {
+        if (!(P.prologue == PRO_RMSNORM && single_batch)) {
 #pragma unroll
-            for (int i = 0; i < 8; i++)
-                v[i] = P.prologue == PRO_RMSNORM ? __fmul_rn(__fmul_rn(v[i], scale), w[i]) : __fmul_rn(silu_f(v[i]), w[i]);
+            for (int j = 0; j < B; j++) {
+                const int b = b0 + warp + j * GEMV_NW;
+                if (b < P.nblk) {
+                    load8(P.in0 + b * 256 + lane * 8, x[j]);
+                    if (P.prologue != PRO_QUANT) load8(P.in1 + b * 256 + lane * 8, w[j]);
+                }
+            }
         }
-        quantize_warp_q8K(v, lane, b, sa);
+#pragma unroll
+        for (int j = 0; j < B; j++) {
+            const int b = b0 + warp + j * GEMV_NW;
+            if (b < P.nblk) {
+                if (P.prologue == PRO_RMSNORM) {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) x[j][i] = __fmul_rn(__fmul_rn(x[j][i], scale), w[j][i]);
+                } else if (P.prologue == PRO_SILU_MUL) {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) x[j][i] = __fmul_rn(silu_f(x[j][i]), w[j][i]);
+                }
+                quantize_warp_q8K(x[j], lane, b, sa);
+            }
+        }
     }
     consumer_bar();
 }
@@ -82,6 +114,8 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) k_gemv_kquant(const __grid_co
         for (int s = 0; s < GEMV_NSTAGE; s++) {
             mbar_init(&ctl->full[s], 1);
             mbar_init(&ctl->empty[s], GEMV_NW);
+#pragma unroll
+            for (int g = 0; g < 4; g++) mbar_init(&ctl->pbar[s][g], P.wpr > 1 ? P.wpr - 1 : 1);
         }
         mbar_fence_init();
     }
@@ -136,7 +170,6 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) k_gemv_kquant(const __grid_co
     }
 
     int it = 0;
-    int slot_parity = 0;
     for (int t = blockIdx.x; t < P.ntiles; t += gridDim.x, it++) {
         const int s = it % GEMV_NSTAGE;
         const uint32_t ph = (it / GEMV_NSTAGE) & 1;
@@ -148,45 +181,72 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) k_gemv_kquant(const __grid_co
         const uint32_t mis = (uint32_t) (((int64_t) r0 * M.row_bytes) & 15);
         const uint8_t * tile = stages + (size_t) s * GEMV_STAGE_BYTES + mis;
         mbar_wait(&ctl->full[s], ph);
-        const bool leader = wsub == 0 && lane == 0;
-        for (int slot = group; slot < nrows; slot += ngroups) {
+        if (wpr == 1) {
+            for (int slot = group; slot < nrows; slot += ngroups) {
+                const int row = r0 + slot;
+                // epilogue operands are requested before the dot so that their L2 latency is off the critical path
+                float extra = 0.f;
+                if (lane == 0) {
+                    if (M.bias) extra = M.bias[row];
+                    if (M.resid) extra += M.resid[row];
+                }
+                const uint8_t * bp = tile + (size_t) slot * M.row_bytes + (size_t) blk * bpb;
+                float v = 0.f;
+                if (valid) {
+                    if (type == T_Q4_K) v = dot_q4K(bp, r);
+                    else if (type == T_Q6_K) v = dot_q6K(bp, r);
+                    else v = dot_q5K(bp, r);
+                }
+                if (slot + ngroups >= nrows) {
+                    // last row of this stage for this warp: hand the buffer back to the producer before reducing
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&ctl->empty[s]);
+                }
+                v = warp_sum(v);
+                if (lane == 0) M.y[row] = v + extra;
+            }
+            if (group >= nrows) {   // this warp had no row in the tile (ragged last tile): still release the stage
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ctl->empty[s]);
+            }
+        } else {
+            // rows split over wpr warps; rows_per_tile == ngroups, i.e. at most one row per warp group and stage.
+            // Non-leader warps publish their partial and move on; only the group's leader warp waits for them
+            // (mbarrier instead of bar.sync), and it releases the stage last so part[s] cannot be overwritten early.
+            const int slot = group;
+            const bool has_row = slot < nrows;
             const int row = r0 + slot;
-            // epilogue operands are requested before the dot so that their L2 latency is off the critical path
+            const bool lead = wsub == 0;
             float extra = 0.f;
-            if (leader) {
+            if (has_row && lead && lane == 0) {
                 if (M.bias) extra = M.bias[row];
                 if (M.resid) extra += M.resid[row];
             }
-            const uint8_t * bp = tile + (size_t) slot * M.row_bytes + (size_t) blk * bpb;
             float v = 0.f;
-            if (valid) {
+            if (has_row && valid) {
+                const uint8_t * bp = tile + (size_t) slot * M.row_bytes + (size_t) blk * bpb;
                 if (type == T_Q4_K) v = dot_q4K(bp, r);
                 else if (type == T_Q6_K) v = dot_q6K(bp, r);
                 else v = dot_q5K(bp, r);
             }
-            if (slot + ngroups >= nrows) {
-                // last row of this stage for this warp: hand the buffer back to the producer before reducing
+            if (!lead) {
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&ctl->empty[s]);
-            }
-            v = warp_sum(v);
-            if (wpr == 1) {
-                if (lane == 0) M.y[row] = v + extra;
-            } else {
-                if (lane == 0) ctl->part[slot_parity][warp] = v;
-                // named barrier among the wpr warps of this group (ids 1..8; 0 is __syncthreads)
-                asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(wpr * 32) : "memory");
-                if (leader) {
-                    float acc = 0.f;
-                    for (int i = 0; i < wpr; i++) acc += ctl->part[slot_parity][group * wpr + i];
-                    M.y[row] = acc + extra;
+                v = warp_sum(v);
+                if (lane == 0) {
+                    ctl->part[s][warp] = v;
+                    mbar_arrive(&ctl->pbar[s][group]);   // release semantics: the partial is visible to the waiter
                 }
-                slot_parity ^= 1;
+            } else {
+                v = warp_sum(v);
+                mbar_wait(&ctl->pbar[s][group], ph);
+                if (lane == 0) {
+                    float acc = v;
+                    for (int i = 1; i < wpr; i++) acc += ctl->part[s][group * wpr + i];
+                    if (has_row) M.y[row] = acc + extra;
+                    mbar_arrive(&ctl->empty[s]);
+                }
             }
-        }
-        if (group >= nrows) {   // this warp had no row in the tile (ragged last tile): still release the stage
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&ctl->empty[s]);
         }
     }
 }
@@ -347,6 +407,7 @@ static int pick_rows_per_tile(int64_t row_bytes, int ngroups, int N) {
     int tr = fit >= ngroups ? (fit / ngroups) * ngroups : fit;
     if (tr > 2 * ngroups && ngroups >= 8) tr = ngroups;      // 8 rows per stage is plenty; more stages in flight instead
     if (tr > 4 * ngroups) tr = 4 * ngroups;
+    if (ngroups < GEMV_NW && tr > ngroups) tr = ngroups;     // split rows (wpr > 1): one row per warp group and stage
     if (tr > N) tr = N;
     return tr;
 }
