@@ -9,7 +9,7 @@ struct __align__(16) GemvSmemCtl {
     uint64_t full[GEMV_NSTAGE];
     uint64_t empty[GEMV_NSTAGE];
     uint64_t pbar[GEMV_NSTAGE][4];        // wpr > 1: "partials of this stage's row are in shared memory" per warp group
-    float part[GEMV_NSTAGE][GEMV_NW];     // cross-warp partial sums, one slot per stage in flight
+    float part[GEMV_NSTAGE][GEMV_TEAM_W]; // cross-warp partial sums, one slot per stage in flight
     double red[GEMV_NW];                  // rms_norm partial sums of squares
 };
 constexpr int GEMV_CTL_BYTES = 512;
@@ -29,7 +29,7 @@ __device__ __forceinline__ void load8(const float * p, float (&v)[8]) {
 }
 __device__ __forceinline__ void gemv_prologue(const GemvParams & P, GemvSmemCtl * ctl, const ActQ & sa, int warp, int lane) {
     const int tid = warp * 32 + lane;
-    constexpr int B = 4;   // blocks in flight per warp
+    constexpr int B = 2;   // blocks in flight per warp (16 warps x 2 = one batch for K = 8192)
     const bool single_batch = P.nblk <= GEMV_NW * B;
     float x[B][8], w[B][8];
     float scale = 1.f;
@@ -100,7 +100,7 @@ __device__ __forceinline__ void tile_info(const GemvParams & P, int t, int & m, 
     nrows = min(M.rows_per_tile, M.N - r0);
 }
 
-__global__ void __launch_bounds__(GEMV_THREADS, 1) k_gemv_kquant(const __grid_constant__ GemvParams P) {
+__global__ void __maxnreg__(120) k_gemv_kquant(const __grid_constant__ GemvParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
     GemvSmemCtl * ctl = reinterpret_cast<GemvSmemCtl *>(smem);
     uint8_t * stages = smem + GEMV_CTL_BYTES;
@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) k_gemv_kquant(const __grid_co
 #pragma unroll
         for (int s = 0; s < GEMV_NSTAGE; s++) {
             mbar_init(&ctl->full[s], 1);
-            mbar_init(&ctl->empty[s], GEMV_NW);
+            mbar_init(&ctl->empty[s], GEMV_TEAM_W);
 #pragma unroll
             for (int g = 0; g < 4; g++) mbar_init(&ctl->pbar[s][g], P.wpr > 1 ? P.wpr - 1 : 1);
         }
@@ -148,9 +148,10 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) k_gemv_kquant(const __grid_co
     }
 
     // ===== consumers =====
+    const int team = warp / GEMV_TEAM_W, tw = warp % GEMV_TEAM_W;
     const int wpr = P.wpr;
-    const int ngroups = GEMV_NW / wpr;
-    const int group = warp / wpr, wsub = warp % wpr;
+    const int ngroups = GEMV_TEAM_W / wpr;
+    const int group = tw / wpr, wsub = tw % wpr;
     const int blk = wsub * 32 + lane;
     const bool valid = blk < P.nblk;
 
@@ -169,8 +170,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) k_gemv_kquant(const __grid_co
         load_act_regs(r, sa, blk, valid);
     }
 
-    int it = 0;
-    for (int t = blockIdx.x; t < P.ntiles; t += gridDim.x, it++) {
+    for (int it = team, t = blockIdx.x + team * gridDim.x; t < P.ntiles; t += GEMV_NTEAM * gridDim.x, it += GEMV_NTEAM) {
         const int s = it % GEMV_NSTAGE;
         const uint32_t ph = (it / GEMV_NSTAGE) & 1;
         int m, r0, nrows;
@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) k_gemv_kquant(const __grid_co
                 if (lane == 0) mbar_arrive(&ctl->empty[s]);
                 v = warp_sum(v);
                 if (lane == 0) {
-                    ctl->part[s][warp] = v;
+                    ctl->part[s][tw] = v;
                     mbar_arrive(&ctl->pbar[s][group]);   // release semantics: the partial is visible to the waiter
                 }
             } else {
@@ -407,7 +407,7 @@ static int pick_rows_per_tile(int64_t row_bytes, int ngroups, int N) {
     int tr = fit >= ngroups ? (fit / ngroups) * ngroups : fit;
     if (tr > 2 * ngroups && ngroups >= 8) tr = ngroups;      // 8 rows per stage is plenty; more stages in flight instead
     if (tr > 4 * ngroups) tr = 4 * ngroups;
-    if (ngroups < GEMV_NW && tr > ngroups) tr = ngroups;     // split rows (wpr > 1): one row per warp group and stage
+    if (ngroups < GEMV_TEAM_W && tr > ngroups) tr = ngroups;  // split rows (wpr > 1): one row per warp group and stage
     if (tr > N) tr = N;
     return tr;
 }
@@ -450,7 +450,7 @@ int launch_gemv_kquant_fused(const GemvDesc * d, int nmat, int K, const ActQ & a
             M.N = d[i].N;
             M.row_bytes = row_bytes(d[i].type, K);
             M.total_bytes = M.row_bytes * d[i].N;
-            M.rows_per_tile = pick_rows_per_tile(M.row_bytes, GEMV_NW / wpr, d[i].N);
+            M.rows_per_tile = pick_rows_per_tile(M.row_bytes, GEMV_TEAM_W / wpr, d[i].N);
             if (M.rows_per_tile == 0 || ((uintptr_t) M.W & 15)) { fast = false; break; }
             M.tile0 = tiles;
             tiles += (d[i].N + M.rows_per_tile - 1) / M.rows_per_tile;

@@ -8,7 +8,7 @@
 // B200 design (memory-bound, no tensor cores):
 //   * persistent grid, one CTA per SM; a producer warp streams row tiles of raw blocks HBM -> shared memory with
 //     cp.async.bulk (1-D TMA, SASS UBLKCP) into a 4-deep mbarrier ring (up to ~216 KB in flight per SM);
-//   * 8 consumer warps; ONE LANE OWNS ONE SUPER-BLOCK COLUMN: lane l of sub-warp s keeps the 256 int8 activations of
+//   * 16 consumer warps in two teams that alternate ring stages; ONE LANE OWNS ONE SUPER-BLOCK COLUMN: lane l of sub-warp s keeps the 256 int8 activations of
 //     super-block (32 s + l) plus its bsums and scale in registers for the whole kernel, so shared memory is read
 //     exactly once per weight byte (128-bit LDS, conflict-free at 144/176-B strides) and the activation costs no
 //     bandwidth at all after the prologue;
@@ -22,7 +22,10 @@
 
 namespace pb {
 
-constexpr int GEMV_NW = 8;                       // consumer warps
+constexpr int GEMV_TEAM_W = 8;                    // consumer warps that share one stage (a "team")
+constexpr int GEMV_NTEAM = 2;                     // teams alternate stages: team t consumes iterations t, t+2, ... — twice the
+                                                  // per-stage latency budget, 4 warps per scheduler instead of 2
+constexpr int GEMV_NW = GEMV_TEAM_W * GEMV_NTEAM;  // consumer warps
 constexpr int GEMV_THREADS = (GEMV_NW + 1) * 32;  // + 1 producer warp
 constexpr int GEMV_NSTAGE = 4;
 constexpr int GEMV_STAGE_BYTES = 48 * 1024;       // 8 rows of Q4_K/Q5_K or 7 rows of Q6_K @ K=8192; 2 rows @ K=28672
