@@ -7,7 +7,8 @@ namespace pb {
 
 struct __align__(16) GemvSmemCtl {
     uint64_t full[GEMV_NSTAGE];
-    uint64_t empty[GEMV_NSTAGE];
+    int cnt[GEMV_NSTAGE];                 // consumer warps done with the stage; the last one refills it
+    int pad_[GEMV_NSTAGE];
     uint64_t pbar[GEMV_NSTAGE][4];        // wpr > 1: "partials of this stage's row are in shared memory" per warp group
     float part[GEMV_NSTAGE][GEMV_TEAM_W]; // cross-warp partial sums, one slot per stage in flight
     double red[GEMV_NW];                  // rms_norm partial sums of squares
@@ -100,7 +101,35 @@ __device__ __forceinline__ void tile_info(const GemvParams & P, int t, int & m, 
     nrows = min(M.rows_per_tile, M.N - r0);
 }
 
-__global__ void __maxnreg__(120) k_gemv_kquant(const __grid_constant__ GemvParams P) {
+// one bulk copy (TMA 1-D) of tile t into ring stage s; arms the stage's mbarrier with the byte count first
+__device__ __forceinline__ void issue_tile(const GemvParams & P, GemvSmemCtl * ctl, uint8_t * stages, int s, int t, uint64_t pol) {
+    int m, r0, nrows;
+    tile_info(P, t, m, r0, nrows);
+    const GemvMat & M = P.mat[m];
+    const int64_t g0 = (int64_t) r0 * M.row_bytes;
+    const int64_t g1 = g0 + (int64_t) nrows * M.row_bytes;
+    const int64_t a0 = g0 & ~(int64_t) 15;
+    int64_t a1 = (g1 + 15) & ~(int64_t) 15;
+    const int64_t lim = (M.total_bytes + 15) & ~(int64_t) 15;   // allocations are 16-B granular
+    if (a1 > lim) a1 = lim;
+    const uint32_t bytes = (uint32_t) (a1 - a0);
+    mbar_arrive_expect_tx(&ctl->full[s], bytes);
+    bulk_g2s(stages + (size_t) s * GEMV_STAGE_BYTES, M.W + a0, bytes, &ctl->full[s], pol);
+}
+// called by lane 0 of a consumer warp when the warp no longer needs stage s (iteration it)
+__device__ __forceinline__ void release_stage(const GemvParams & P, GemvSmemCtl * ctl, uint8_t * stages, int s, int it, uint64_t pol) {
+    __threadfence_block();
+    if (atomicAdd(&ctl->cnt[s], 1) == GEMV_TEAM_W - 1) {
+        ctl->cnt[s] = 0;
+        const int t = blockIdx.x + (it + GEMV_NSTAGE) * gridDim.x;
+        if (t < P.ntiles) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy reads of the stage before the async-proxy refill
+            issue_tile(P, ctl, stages, s, t, pol);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(GEMV_THREADS, 1) k_gemv_kquant(const __grid_constant__ GemvParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
     GemvSmemCtl * ctl = reinterpret_cast<GemvSmemCtl *>(smem);
     uint8_t * stages = smem + GEMV_CTL_BYTES;
@@ -109,43 +138,24 @@ __global__ void __maxnreg__(120) k_gemv_kquant(const __grid_constant__ GemvParam
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+    const uint64_t pol = policy_evict_first();
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int s = 0; s < GEMV_NSTAGE; s++) {
             mbar_init(&ctl->full[s], 1);
-            mbar_init(&ctl->empty[s], GEMV_TEAM_W);
+            ctl->cnt[s] = 0;
 #pragma unroll
             for (int g = 0; g < 4; g++) mbar_init(&ctl->pbar[s][g], P.wpr > 1 ? P.wpr - 1 : 1);
         }
         mbar_fence_init();
+        // weights do not depend on the previous kernel: fill the whole ring before waiting on anything
+#pragma unroll
+        for (int it = 0; it < GEMV_NSTAGE; it++) {
+            const int t = blockIdx.x + it * gridDim.x;
+            if (t < P.ntiles) issue_tile(P, ctl, stages, it, t, pol);
+        }
     }
     __syncthreads();
-
-    if (warp == GEMV_NW) {
-        // ===== producer: weights do not depend on the previous kernel, so the stream starts immediately =====
-        if (lane == 0) {
-            const uint64_t pol = policy_evict_first();
-            int it = 0;
-            for (int t = blockIdx.x; t < P.ntiles; t += gridDim.x, it++) {
-                const int s = it % GEMV_NSTAGE;
-                const uint32_t ph = (it / GEMV_NSTAGE) & 1;
-                if (it >= GEMV_NSTAGE) mbar_wait(&ctl->empty[s], ph ^ 1);
-                int m, r0, nrows;
-                tile_info(P, t, m, r0, nrows);
-                const GemvMat & M = P.mat[m];
-                const int64_t g0 = (int64_t) r0 * M.row_bytes;
-                const int64_t g1 = g0 + (int64_t) nrows * M.row_bytes;
-                const int64_t a0 = g0 & ~(int64_t) 15;
-                int64_t a1 = (g1 + 15) & ~(int64_t) 15;
-                const int64_t lim = (M.total_bytes + 15) & ~(int64_t) 15;   // allocations are 16-B granular
-                if (a1 > lim) a1 = lim;
-                const uint32_t bytes = (uint32_t) (a1 - a0);
-                mbar_arrive_expect_tx(&ctl->full[s], bytes);
-                bulk_g2s(stages + (size_t) s * GEMV_STAGE_BYTES, M.W + a0, bytes, &ctl->full[s], pol);
-            }
-        }
-        return;
-    }
 
     // ===== consumers =====
     const int team = warp / GEMV_TEAM_W, tw = warp % GEMV_TEAM_W;
@@ -200,14 +210,14 @@ __global__ void __maxnreg__(120) k_gemv_kquant(const __grid_constant__ GemvParam
                 if (slot + ngroups >= nrows) {
                     // last row of this stage for this warp: hand the buffer back to the producer before reducing
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&ctl->empty[s]);
+                    if (lane == 0) release_stage(P, ctl, stages, s, it, pol);
                 }
                 v = warp_sum(v);
                 if (lane == 0) M.y[row] = v + extra;
             }
             if (group >= nrows) {   // this warp had no row in the tile (ragged last tile): still release the stage
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&ctl->empty[s]);
+                if (lane == 0) release_stage(P, ctl, stages, s, it, pol);
             }
         } else {
             // rows split over wpr warps; rows_per_tile == ngroups, i.e. at most one row per warp group and stage.
@@ -231,7 +241,7 @@ __global__ void __maxnreg__(120) k_gemv_kquant(const __grid_constant__ GemvParam
             }
             if (!lead) {
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&ctl->empty[s]);
+                if (lane == 0) release_stage(P, ctl, stages, s, it, pol);
                 v = warp_sum(v);
                 if (lane == 0) {
                     ctl->part[s][tw] = v;
@@ -244,7 +254,7 @@ __global__ void __maxnreg__(120) k_gemv_kquant(const __grid_constant__ GemvParam
                     float acc = v;
                     for (int i = 1; i < wpr; i++) acc += ctl->part[s][group * wpr + i];
                     if (has_row) M.y[row] = acc + extra;
-                    mbar_arrive(&ctl->empty[s]);
+                    release_stage(P, ctl, stages, s, it, pol);
                 }
             }
         }

@@ -6,8 +6,10 @@
 // is q8_K, every integer sub-result is exact, only the order of the final fp32 adds differs.
 //
 // B200 design (memory-bound, no tensor cores):
-//   * persistent grid, one CTA per SM; a producer warp streams row tiles of raw blocks HBM -> shared memory with
-//     cp.async.bulk (1-D TMA, SASS UBLKCP) into a 4-deep mbarrier ring (up to ~216 KB in flight per SM);
+//   * persistent grid, one CTA per SM; row tiles of raw blocks stream HBM -> shared memory with cp.async.bulk (1-D TMA,
+//     SASS UBLKCP) into a 4-deep ring (up to ~192 KB in flight per SM).  There is no producer warp: the consumer warp
+//     that finishes a stage last re-arms its mbarrier and issues the refill itself (zero polling latency, 512 threads
+//     = 128 registers each);
 //   * 16 consumer warps in two teams that alternate ring stages; ONE LANE OWNS ONE SUPER-BLOCK COLUMN: lane l of sub-warp s keeps the 256 int8 activations of
 //     super-block (32 s + l) plus its bsums and scale in registers for the whole kernel, so shared memory is read
 //     exactly once per weight byte (128-bit LDS, conflict-free at 144/176-B strides) and the activation costs no
@@ -26,7 +28,7 @@ constexpr int GEMV_TEAM_W = 8;                    // consumer warps that share o
 constexpr int GEMV_NTEAM = 2;                     // teams alternate stages: team t consumes iterations t, t+2, ... — twice the
                                                   // per-stage latency budget, 4 warps per scheduler instead of 2
 constexpr int GEMV_NW = GEMV_TEAM_W * GEMV_NTEAM;  // consumer warps
-constexpr int GEMV_THREADS = (GEMV_NW + 1) * 32;  // + 1 producer warp
+constexpr int GEMV_THREADS = GEMV_NW * 32;        // no producer warp: the last consumer of a stage issues its refill
 constexpr int GEMV_NSTAGE = 4;
 constexpr int GEMV_STAGE_BYTES = 48 * 1024;       // 8 rows of Q4_K/Q5_K or 7 rows of Q6_K @ K=8192; 2 rows @ K=28672
 constexpr int GEMV_ACT_SMEM = 28672 + 28672 / 8 + 28672 / 64 + 64;   // fused-prologue activation (qs | bsums | d), K <= 28 672
