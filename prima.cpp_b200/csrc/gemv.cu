@@ -28,11 +28,24 @@ __device__ __forceinline__ void load8(const float * p, float (&v)[8]) {
     const float4 a0 = *reinterpret_cast<const float4 *>(p), a1 = *reinterpret_cast<const float4 *>(p + 4);
     v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
 }
-__device__ __forceinline__ void gemv_prologue(const GemvParams & P, GemvSmemCtl * ctl, const ActQ & sa, int warp, int lane) {
+// Phase A issues the global loads of the first batch (nothing else), phase B does the arithmetic.  The ring fill is
+// issued BETWEEN the two: requested first, the few KB of activation are not queued behind ~28 MB of weight prefetch
+// (measured: that queueing cost every GEMV launch 4-5 us, profiles/r1_launches.md).
+struct ProRegs { float x[2][8], w[2][8]; };
+__device__ __forceinline__ void prologue_load(const GemvParams & P, ProRegs & R, int warp, int lane, int b0) {
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+        const int b = b0 + warp + j * GEMV_NW;
+        if (b < P.nblk) {
+            load8(P.in0 + b * 256 + lane * 8, R.x[j]);
+            if (P.prologue != PRO_QUANT) load8(P.in1 + b * 256 + lane * 8, R.w[j]);
+        }
+    }
+}
+__device__ __forceinline__ void prologue_compute(const GemvParams & P, GemvSmemCtl * ctl, const ActQ & sa, ProRegs & R, int warp, int lane) {
     const int tid = warp * 32 + lane;
     constexpr int B = 2;   // blocks in flight per warp (16 warps x 2 = one batch for K = 8192)
     const bool single_batch = P.nblk <= GEMV_NW * B;
-    float x[B][8], w[B][8];
     float scale = 1.f;
     if (P.prologue == PRO_RMSNORM) {
         double sum = 0.0;
@@ -40,14 +53,9 @@ __device__ __forceinline__ void gemv_prologue(const GemvParams & P, GemvSmemCtl 
 #pragma unroll
             for (int j = 0; j < B; j++) {
                 const int b = warp + j * GEMV_NW;
-                if (b < P.nblk) { load8(P.in0 + b * 256 + lane * 8, x[j]); load8(P.in1 + b * 256 + lane * 8, w[j]); }
-            }
-#pragma unroll
-            for (int j = 0; j < B; j++) {
-                const int b = warp + j * GEMV_NW;
                 if (b < P.nblk) {
 #pragma unroll
-                    for (int i = 0; i < 8; i++) sum += (double) __fmul_rn(x[j][i], x[j][i]);
+                    for (int i = 0; i < 8; i++) sum += (double) __fmul_rn(R.x[j][i], R.x[j][i]);
                 }
             }
         } else {
@@ -63,28 +71,19 @@ __device__ __forceinline__ void gemv_prologue(const GemvParams & P, GemvSmemCtl 
         scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, P.eps)));
     }
     for (int b0 = 0; b0 < P.nblk; b0 += GEMV_NW * B) {
-        if (!(P.prologue == PRO_RMSNORM && single_batch)) {
-#pragma unroll
-            for (int j = 0; j < B; j++) {
-                const int b = b0 + warp + j * GEMV_NW;
-                if (b < P.nblk) {
-                    load8(P.in0 + b * 256 + lane * 8, x[j]);
-                    if (P.prologue != PRO_QUANT) load8(P.in1 + b * 256 + lane * 8, w[j]);
-                }
-            }
-        }
+        if (b0 > 0) prologue_load(P, R, warp, lane, b0);
 #pragma unroll
         for (int j = 0; j < B; j++) {
             const int b = b0 + warp + j * GEMV_NW;
             if (b < P.nblk) {
                 if (P.prologue == PRO_RMSNORM) {
 #pragma unroll
-                    for (int i = 0; i < 8; i++) x[j][i] = __fmul_rn(__fmul_rn(x[j][i], scale), w[j][i]);
+                    for (int i = 0; i < 8; i++) R.x[j][i] = __fmul_rn(__fmul_rn(R.x[j][i], scale), R.w[j][i]);
                 } else if (P.prologue == PRO_SILU_MUL) {
 #pragma unroll
-                    for (int i = 0; i < 8; i++) x[j][i] = __fmul_rn(silu_f(x[j][i]), w[j][i]);
+                    for (int i = 0; i < 8; i++) R.x[j][i] = __fmul_rn(silu_f(R.x[j][i]), R.w[j][i]);
                 }
-                quantize_warp_q8K(x[j], lane, b, sa);
+                quantize_warp_q8K(R.x[j], lane, b, sa);
             }
         }
     }
@@ -148,16 +147,10 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) k_gemv_kquant(const __grid_co
             for (int g = 0; g < 4; g++) mbar_init(&ctl->pbar[s][g], P.wpr > 1 ? P.wpr - 1 : 1);
         }
         mbar_fence_init();
-        // weights do not depend on the previous kernel: fill the whole ring before waiting on anything
-#pragma unroll
-        for (int it = 0; it < GEMV_NSTAGE; it++) {
-            const int t = blockIdx.x + it * gridDim.x;
-            if (t < P.ntiles) issue_tile(P, ctl, stages, it, t, pol);
-        }
     }
     __syncthreads();
 
-    // ===== consumers =====
+    // ===== consumers (all 16 warps) =====
     const int team = warp / GEMV_TEAM_W, tw = warp % GEMV_TEAM_W;
     const int wpr = P.wpr;
     const int ngroups = GEMV_TEAM_W / wpr;
@@ -168,17 +161,30 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) k_gemv_kquant(const __grid_co
     pdl_trigger();   // let the next kernel become resident as SMs drain; its own pdl_wait() orders the data
     pdl_wait();      // the activation is produced by the previous kernel in the stream
     ActRegs r;
-    if (P.prologue == PRO_NONE) {
-        load_act_regs(r, P.act, blk, valid);
-    } else {
+    ProRegs pr;
+    // 1) request the (small) activation first ...
+    if (P.prologue == PRO_NONE) load_act_regs(r, P.act, blk, valid);
+    else prologue_load(P, pr, warp, lane, 0);
+    __syncthreads();   // every warp has ISSUED its loads (not waited for them)
+    // 2) ... then start the weight stream: fill the whole ring
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int it = 0; it < GEMV_NSTAGE; it++) {
+            const int t = blockIdx.x + it * gridDim.x;
+            if (t < P.ntiles) issue_tile(P, ctl, stages, it, t, pol);
+        }
+    }
+    // 3) quantize while the first tiles are in flight
+    if (P.prologue != PRO_NONE) {
         ActQ sa;
         sa.qs = reinterpret_cast<int8_t *>(act_smem);
         sa.bsums = reinterpret_cast<int16_t *>(act_smem + P.K);
         sa.d = reinterpret_cast<float *>(act_smem + P.K + P.K / 8);
         sa.s = nullptr;
-        gemv_prologue(P, ctl, sa, warp, lane);
+        prologue_compute(P, ctl, sa, pr, warp, lane);
         load_act_regs(r, sa, blk, valid);
     }
+    finish_act_regs(r);
 
     for (int it = team, t = blockIdx.x + team * gridDim.x; t < P.ntiles; t += GEMV_NTEAM * gridDim.x, it += GEMV_NTEAM) {
         const int s = it % GEMV_NSTAGE;
@@ -334,6 +340,7 @@ __global__ void __launch_bounds__(256) k_gemv_generic(const __grid_constant__ Ge
         for (int b = lane; b < nb; b += 32) {
             ActRegs r;
             load_act_regs(r, P.act, b, true);
+            finish_act_regs(r);
             // stage the block through registers -> local array is avoided by reading global memory directly with the
             // same dot routines: they only need byte-addressable memory with the block's natural alignment.
             const int bpb = P.type == T_Q4_K ? BYTES_Q4_K : (P.type == T_Q5_K ? BYTES_Q5_K : BYTES_Q6_K);

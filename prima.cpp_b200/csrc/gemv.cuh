@@ -99,6 +99,9 @@ __device__ __forceinline__ void load_act_regs(ActRegs & r, const ActQ & act, int
         for (int i = 0; i < 8; i++) r.bs[i] = 0;
         r.d = 0.f;
     }
+}
+// second half of load_act_regs, kept separate so that callers can put work between issuing the loads and using them
+__device__ __forceinline__ void finish_act_regs(ActRegs & r) {
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         // per-32 sums: (bs16[4k]+bs16[4k+1], bs16[4k+2]+bs16[4k+3]) packed as int16x2
