@@ -64,6 +64,9 @@ PB200_API int pb200_mul_mat_vec_fused(int nmat, const int * types, const void * 
 /* HOST buffers end to end (H2D of x, quantize, GEMV, D2H of y, synchronised): W must already be on the device */
 PB200_API int pb200_mul_mat_vec_host(int type, const void * W_dev, int64_t n, int64_t k, const float * x_host, float * y_host);
 
+/* debugging: k_gemv_kquant writes 8 %globaltimer stamps per CTA into dev_buf (u64[grid*8]); NULL disables */
+PB200_API int pb200_debug_set_trace(void * dev_buf);
+
 PB200_API int pb200_rms_norm(const float * x, float * y, int64_t n, int64_t nrows, float eps, void * stream);
 PB200_API int pb200_rope(const float * x, float * y, int64_t n_tokens, int n_head, int head_dim, int n_dims, int mode, const int32_t * pos,
                          float freq_base, float freq_scale, float ext_factor, float attn_factor, float beta_fast, float beta_slow,

@@ -5,6 +5,17 @@
 
 namespace pb {
 
+// optional per-CTA timeline (debugging / profiles): 8 x %globaltimer stamps per CTA, enabled with pb200_debug_set_trace
+__device__ unsigned long long * g_gemv_trace = nullptr;
+__device__ __forceinline__ void trace(int k) {
+    if (g_gemv_trace && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_gemv_trace[blockIdx.x * 8 + k] = t;
+    }
+}
+int gemv_set_trace(unsigned long long * dev_buf) { return (int) cudaMemcpyToSymbol(g_gemv_trace, &dev_buf, sizeof(dev_buf)); }
+
 struct __align__(16) GemvSmemCtl {
     uint64_t full[GEMV_NSTAGE];
     int cnt[GEMV_NSTAGE];                 // consumer warps done with the stage; the last one refills it
@@ -136,7 +147,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) k_gemv_kquant(const __grid_co
     static_assert(sizeof(GemvSmemCtl) <= GEMV_CTL_BYTES, "ctl block");
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
+    trace(0);
     const uint64_t pol = policy_evict_first();
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -160,12 +171,32 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) k_gemv_kquant(const __grid_co
 
     pdl_trigger();   // let the next kernel become resident as SMs drain; its own pdl_wait() orders the data
     pdl_wait();      // the activation is produced by the previous kernel in the stream
+    trace(1);
     ActRegs r;
     ProRegs pr;
-    // 1) request the (small) activation first ...
-    if (P.prologue == PRO_NONE) load_act_regs(r, P.act, blk, valid);
-    else prologue_load(P, pr, warp, lane, 0);
+    ActQ sa;   // the CTA's activation in shared memory: qs[K] | bsums[K/16] i16 | d[K/256] f32
+    sa.qs = reinterpret_cast<int8_t *>(act_smem);
+    sa.bsums = reinterpret_cast<int16_t *>(act_smem + P.K);
+    sa.d = reinterpret_cast<float *>(act_smem + P.K + P.K / 8);
+    sa.s = nullptr;
+    // 1) request the (small) activation first: ONE coalesced copy per CTA (every warp fetching its own registers from
+    //    global memory moved 16x the bytes through L2 and cost ~4 us per launch, profiles/r1_gemv_timeline.md) ...
+    int4 cq[4], cb;
+    float cd = 0.f;
+    const int nq = P.K / 16, nb16 = P.K / 128;   // int4 counts of qs and bsums
+    if (P.prologue == PRO_NONE) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int i = threadIdx.x + j * GEMV_THREADS;
+            if (i < nq) cq[j] = reinterpret_cast<const int4 *>(P.act.qs)[i];
+        }
+        if ((int) threadIdx.x < nb16) cb = reinterpret_cast<const int4 *>(P.act.bsums)[threadIdx.x];
+        if ((int) threadIdx.x < P.nblk) cd = P.act.d[threadIdx.x];
+    } else {
+        prologue_load(P, pr, warp, lane, 0);
+    }
     __syncthreads();   // every warp has ISSUED its loads (not waited for them)
+    trace(2);
     // 2) ... then start the weight stream: fill the whole ring
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -174,17 +205,23 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) k_gemv_kquant(const __grid_co
             if (t < P.ntiles) issue_tile(P, ctl, stages, it, t, pol);
         }
     }
-    // 3) quantize while the first tiles are in flight
-    if (P.prologue != PRO_NONE) {
-        ActQ sa;
-        sa.qs = reinterpret_cast<int8_t *>(act_smem);
-        sa.bsums = reinterpret_cast<int16_t *>(act_smem + P.K);
-        sa.d = reinterpret_cast<float *>(act_smem + P.K + P.K / 8);
-        sa.s = nullptr;
+    trace(3);
+    // 3) stage / quantize the activation in shared memory while the first tiles are in flight
+    if (P.prologue == PRO_NONE) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int i = threadIdx.x + j * GEMV_THREADS;
+            if (i < nq) reinterpret_cast<int4 *>(sa.qs)[i] = cq[j];
+        }
+        if ((int) threadIdx.x < nb16) reinterpret_cast<int4 *>(sa.bsums)[threadIdx.x] = cb;
+        if ((int) threadIdx.x < P.nblk) sa.d[threadIdx.x] = cd;
+        consumer_bar();
+    } else {
         prologue_compute(P, ctl, sa, pr, warp, lane);
-        load_act_regs(r, sa, blk, valid);
     }
+    load_act_regs(r, sa, blk, valid);
     finish_act_regs(r);
+    trace(4);
 
     for (int it = team, t = blockIdx.x + team * gridDim.x; t < P.ntiles; t += GEMV_NTEAM * gridDim.x, it += GEMV_NTEAM) {
         const int s = it % GEMV_NSTAGE;
@@ -197,6 +234,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) k_gemv_kquant(const __grid_co
         const uint32_t mis = (uint32_t) (((int64_t) r0 * M.row_bytes) & 15);
         const uint8_t * tile = stages + (size_t) s * GEMV_STAGE_BYTES + mis;
         mbar_wait(&ctl->full[s], ph);
+        if (it == 0) trace(5);
         if (wpr == 1) {
             for (int slot = group; slot < nrows; slot += ngroups) {
                 const int row = r0 + slot;
@@ -265,6 +303,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) k_gemv_kquant(const __grid_co
             }
         }
     }
+    trace(6);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -441,7 +480,7 @@ int launch_gemv_kquant_fused(const GemvDesc * d, int nmat, int K, const ActQ & a
     if (nmat < 1 || nmat > GEMV_MAX_MAT || K % 256 != 0) return (int) cudaErrorInvalidValue;
     if (pro.kind != PRO_NONE && !gemv_fused_prologue_ok(K)) return (int) cudaErrorInvalidValue;
     const int nblk = K / 256;
-    bool fast = nblk <= GEMV_MAX_NBLK;
+    bool fast = nblk <= GEMV_MAX_NBLK && gemv_fused_prologue_ok(K);   // the activation is staged in shared memory
     GemvParams P{};
     if (fast) {
         int wpr = 1;

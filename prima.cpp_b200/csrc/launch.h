@@ -25,6 +25,7 @@ struct GemvFused {       // fused activation prologue of the k-quant GEMV (PRO_*
 };
 
 int sm_count();
+int gemv_set_trace(unsigned long long * dev_buf);   // debugging: per-CTA %globaltimer stamps of k_gemv_kquant
 int gemv_smem_bytes();
 
 // y_i = W_i . act  for up to 3 k-quant matrices sharing one q8_K activation (TMA-staged persistent kernel)
