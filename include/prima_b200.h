@@ -73,6 +73,15 @@ PB200_API int pb200_rope(const float * x, float * y, int64_t n_tokens, int n_hea
                          int n_ctx_orig, const float * freq_factors, void * stream);
 PB200_API int pb200_soft_max(const float * x, const float * mask, float * y, int64_t ncols, int64_t nrows, int64_t mask_rows, float scale, void * stream);
 PB200_API int pb200_silu_mul(const float * gate, const float * up, float * y, int64_t n, void * stream);
+/* element-wise glue of the graph (binbcast.cu / unary.cu / cpy.cu): y = a (+|*) b[i % nb]  (op 0 add, 1 mul); y = silu(x);
+ * 4-D strided copy f32 -> f32|f16 (byte strides; dst logical order) — CPY / CONT / DUP incl. the transposed V-cache store */
+PB200_API int pb200_binary(int op, const float * a, const float * b, float * y, int64_t n, int64_t nb, void * stream);
+PB200_API int pb200_silu(const float * x, float * y, int64_t n, void * stream);
+PB200_API int pb200_copy_strided(const void * src_f32, void * dst, int dst_is_f16, const int64_t * ne, const int64_t * src_strides,
+                                 const int64_t * dst_strides, void * stream);
+/* d[i0,i1,i2,i3] = sum_k a_f16[k,i0,i2/r2,i3/r3] * f16(b[k,i1,i2,i3]) — the FA-off KQ / KQV products (ggml-cuda.cu:1737-1881), byte strides */
+PB200_API int pb200_mul_mat_f16(const void * a_f16, const float * b_f32, float * d, int64_t k, const int64_t * ne, int64_t r2, int64_t r3,
+                                const int64_t * a_strides, const int64_t * b_strides, const int64_t * d_strides, void * stream);
 PB200_API int pb200_get_rows(int type, const void * table, int64_t k, const int32_t * ids, int64_t n_ids, float * y, void * stream);
 /* decode attention over an f16 KV cache laid out [n_ctx][n_head_kv*head_dim]; n_kv = *pos_dev + 1 */
 PB200_API int pb200_attn_decode(const float * q, const void * k_cache_f16, const void * v_cache_f16, float * out, int n_head, int n_head_kv,

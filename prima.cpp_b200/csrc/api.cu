@@ -157,6 +157,29 @@ int pb200_silu_mul(const float * gate, const float * up, float * y, int64_t n, v
     return launch_binary(1, y, up, y, n, n, (cudaStream_t) stream);
 }
 
+int pb200_binary(int op, const float * a, const float * b, float * y, int64_t n, int64_t nb, void * stream) {
+    if (!a || !b || !y || n <= 0 || nb <= 0 || (op != 0 && op != 1)) return PB200_EINVAL;
+    g_launches++;
+    return launch_binary(op, a, b, y, n, nb, (cudaStream_t) stream);
+}
+int pb200_silu(const float * x, float * y, int64_t n, void * stream) {
+    if (!x || !y || n <= 0) return PB200_EINVAL;
+    g_launches++;
+    return launch_silu(x, y, n, (cudaStream_t) stream);
+}
+int pb200_copy_strided(const void * src_f32, void * dst, int dst_is_f16, const int64_t * ne, const int64_t * src_strides, const int64_t * dst_strides,
+                       void * stream) {
+    if (!src_f32 || !dst || !ne || !src_strides || !dst_strides) return PB200_EINVAL;
+    g_launches++;
+    return launch_copy_strided(src_f32, dst, dst_is_f16, ne, src_strides, dst_strides, (cudaStream_t) stream);
+}
+int pb200_mul_mat_f16(const void * a_f16, const float * b_f32, float * d, int64_t k, const int64_t * ne, int64_t r2, int64_t r3,
+                      const int64_t * a_strides, const int64_t * b_strides, const int64_t * d_strides, void * stream) {
+    if (!a_f16 || !b_f32 || !d || !ne || !a_strides || !b_strides || !d_strides || k <= 0 || r2 <= 0 || r3 <= 0) return PB200_EINVAL;
+    g_launches++;
+    return launch_mul_mat_f16(a_f16, b_f32, d, k, ne, r2, r3, a_strides, b_strides, d_strides, (cudaStream_t) stream);
+}
+
 int pb200_get_rows(int type, const void * table, int64_t k, const int32_t * ids, int64_t n_ids, float * y, void * stream) {
     if (!table || !ids || !y || k <= 0 || n_ids <= 0) return PB200_EINVAL;
     if (!(type_ok(type) || type == T_F32 || type == T_F16)) return PB200_ENOTSUP;

@@ -85,5 +85,8 @@ int launch_get_rows(const void * table, int type, int K, const int32_t * ids, in
 int launch_binary(int op /*0 add, 1 mul*/, const float * a, const float * b, float * y, int64_t n, int64_t nb /*b broadcast period*/, cudaStream_t stream);
 int launch_silu(const float * x, float * y, int64_t n, cudaStream_t stream);
 int launch_cpy_f32_f16(const float * x, __half * y, int64_t n, cudaStream_t stream);
+int launch_copy_strided(const void * src, void * dst, int dst_is_f16, const int64_t ne[4], const int64_t sb[4], const int64_t db[4], cudaStream_t stream);
+int launch_mul_mat_f16(const void * A, const void * B, void * D, int64_t K, const int64_t ne[4], int64_t r2, int64_t r3, const int64_t ab[4],
+                       const int64_t bb[4], const int64_t db[4], cudaStream_t stream);
 
 }  // namespace pb

@@ -540,7 +540,70 @@ __global__ void k_cpy_f32_f16(const float * __restrict__ x, __half * __restrict_
     if (i < n) y[i] = __float2half_rn(x[i]);
 }
 
+// ------------------------------------------------------------------------------------------------
+// generic 4-D strided copy f32 -> f32 / f16 (CPY, CONT, DUP of views: K store, transposed V store, kqv merge)
+struct Copy4 { int64_t ne[4]; int64_t sb[4]; int64_t db[4]; };   // element counts, src / dst BYTE strides
+template <typename T>
+__global__ void k_copy_strided(const char * __restrict__ src, char * __restrict__ dst, Copy4 c, int64_t n) {
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    // dst index space is enumerated in dst logical order; src may have a different shape with the same element count
+    int64_t r = i;
+    const int64_t i0 = r % c.ne[0]; r /= c.ne[0];
+    const int64_t i1 = r % c.ne[1]; r /= c.ne[1];
+    const int64_t i2 = r % c.ne[2]; r /= c.ne[2];
+    const int64_t i3 = r;
+    const float v = *reinterpret_cast<const float *>(src + i0 * c.sb[0] + i1 * c.sb[1] + i2 * c.sb[2] + i3 * c.sb[3]);
+    T * d = reinterpret_cast<T *>(dst + i0 * c.db[0] + i1 * c.db[1] + i2 * c.db[2] + i3 * c.db[3]);
+    if constexpr (sizeof(T) == 2) *d = __float2half_rn(v); else *d = v;
+}
+
+// dst[i0,i1,i2,i3] = sum_k src0_f16[k,i0,i2/r2,i3/r3] * f16(src1_f32[k,i1,i2,i3])   (ggml mul_mat with F16 src0: the CPU backend
+// rounds src1 to f16 and accumulates in f32, ggml.c:12445-12473).  One warp per output element; byte strides.
+struct MM16 { int64_t K, ne0, ne1, ne2, ne3, r2, r3; int64_t a[4]; int64_t b[4]; int64_t d[4]; };
+__global__ void __launch_bounds__(256) k_mul_mat_f16(const char * __restrict__ A, const char * __restrict__ B, char * __restrict__ D, MM16 m) {
+    const int64_t w = (int64_t) blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const int64_t total = m.ne0 * m.ne1 * m.ne2 * m.ne3;
+    if (w >= total) return;
+    int64_t r = w;
+    const int64_t i0 = r % m.ne0; r /= m.ne0;
+    const int64_t i1 = r % m.ne1; r /= m.ne1;
+    const int64_t i2 = r % m.ne2; r /= m.ne2;
+    const int64_t i3 = r;
+    const char * a = A + i0 * m.a[1] + (i2 / m.r2) * m.a[2] + (i3 / m.r3) * m.a[3];
+    const char * b = B + i1 * m.b[1] + i2 * m.b[2] + i3 * m.b[3];
+    float acc = 0.f;
+    for (int64_t k = lane; k < m.K; k += 32) {
+        const float av = __half2float(*reinterpret_cast<const __half *>(a + k * m.a[0]));
+        const float bv = __half2float(__float2half_rn(*reinterpret_cast<const float *>(b + k * m.b[0])));
+        acc = fmaf(av, bv, acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) *reinterpret_cast<float *>(D + i0 * m.d[0] + i1 * m.d[1] + i2 * m.d[2] + i3 * m.d[3]) = acc;
+}
+
 // ================================================================================================ launchers
+int launch_copy_strided(const void * src, void * dst, int dst_is_f16, const int64_t ne[4], const int64_t sb[4], const int64_t db[4], cudaStream_t stream) {
+    Copy4 c;
+    int64_t n = 1;
+    for (int i = 0; i < 4; i++) { c.ne[i] = ne[i]; c.sb[i] = sb[i]; c.db[i] = db[i]; n *= ne[i]; }
+    if (n == 0) return 0;
+    if (dst_is_f16) k_copy_strided<__half><<<(unsigned) ((n + 255) / 256), 256, 0, stream>>>((const char *) src, (char *) dst, c, n);
+    else k_copy_strided<float><<<(unsigned) ((n + 255) / 256), 256, 0, stream>>>((const char *) src, (char *) dst, c, n);
+    return (int) cudaGetLastError();
+}
+int launch_mul_mat_f16(const void * A, const void * B, void * D, int64_t K, const int64_t ne[4], int64_t r2, int64_t r3, const int64_t ab[4],
+                       const int64_t bb[4], const int64_t db[4], cudaStream_t stream) {
+    MM16 m;
+    m.K = K; m.ne0 = ne[0]; m.ne1 = ne[1]; m.ne2 = ne[2]; m.ne3 = ne[3]; m.r2 = r2; m.r3 = r3;
+    for (int i = 0; i < 4; i++) { m.a[i] = ab[i]; m.b[i] = bb[i]; m.d[i] = db[i]; }
+    const int64_t total = ne[0] * ne[1] * ne[2] * ne[3];
+    if (total == 0) return 0;
+    k_mul_mat_f16<<<(unsigned) ((total + 7) / 8), 256, 0, stream>>>((const char *) A, (const char *) B, (char *) D, m);
+    return (int) cudaGetLastError();
+}
+
 int launch_quantize_act(const float * x, int K, int mode, const ActQ & out, cudaStream_t stream, bool pdl) {
     cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1];
     const int ngroups = (K + 255) / 256;
