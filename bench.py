@@ -221,32 +221,29 @@ def main():
     logits_t = torch.as_tensor(DevBuf(eng.logits_ptr, nv), device=torch.device("cuda", local)) if rank == world - 1 else None
     logits_host = np.zeros(nv, dtype=np.float32)
 
-    def step(i, pos, host_io):
-        """One token through the pipeline.  Synthetic token ids (llama-bench tg uses random ids); in pipeline mode the last
-        stage still returns a token (argmax) to rank 0 so that steps are strictly sequential like real decoding."""
-        tok = token_at(i, nv)
-        with torch.cuda.stream(ext):
-            if world == 1:
-                if host_io:
-                    eng.decode(tok, pos, logits_host)
-                else:
-                    eng.decode_async(tok, pos)
-                return
-            if rank > 0:
-                dist.recv(hid_in, src=rank - 1)
-            if host_io and rank == world - 1:
-                eng.decode(tok, pos, logits_host)
+    class EngineStage:
+        """adapter: the engine's device buffers as torch tensors for prima.cpp_b200.pipeline.PipelineRunner"""
+        hidden_in, hidden_out, logits = hid_in, hid_out, logits_t
+        host_io = False
+
+        def decode_async(self, token, pos):
+            if self.host_io and rank == world - 1:
+                eng.decode(token, pos, logits_host)       # token+pos H2D from pinned memory, logits D2H, synchronised
+            elif self.host_io and world == 1:
+                eng.decode(token, pos, logits_host)
             else:
-                eng.decode_async(tok, pos)
-            if rank < world - 1:
-                dist.send(hid_out, dst=rank + 1)
-            # the sampled token closes the ring: last stage -> rank 0 (prima returns the result to the master, src/llama.cpp:18559)
-            if rank == world - 1:
-                tok_t.copy_(torch.argmax(logits_t).reshape(1))
-                dist.send(tok_t, dst=0)
-            if rank == 0:
-                dist.recv(tok_t, src=world - 1)
-                tok_t.cpu()   # the master must see the token before it can start the next step
+                eng.decode_async(token, pos)
+
+    stage = EngineStage()
+    runner = pkg.PipelineRunner(stage, rank, world, dist, tok_t)
+
+    def step(i, pos, host_io):
+        """One token through the pipeline.  Synthetic token ids (llama-bench tg uses random ids, llama-bench.cpp:1452-1470);
+        in pipeline mode the last stage still returns a sampled token (argmax) to rank 0 so that steps stay strictly
+        sequential like real decoding."""
+        stage.host_io = host_io
+        with torch.cuda.stream(ext):
+            runner.step(token_at(i, nv), pos, sample=lambda lg: torch.argmax(lg))
 
     def barrier():
         torch.cuda.synchronize()

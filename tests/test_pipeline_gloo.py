@@ -1,0 +1,91 @@
+"""CPU: the N>1 host logic (layer windows + hidden-state hand-off + token ring) over gloo, world_size 2 and 3, against a
+single-process run of the same toy layers (bit-identical, like the N-rank == 1-rank requirement of SURVEY §8e)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+class ToyStage:
+    """Stands in for the engine: layer l multiplies by a fixed matrix and adds the position; exact in fp32 order."""
+    E, V, L = 16, 11, 6
+
+    def __init__(self, l0, l1, first, last):
+        g = torch.Generator().manual_seed(0)
+        self.W = [torch.randn(self.E, self.E, generator=g) / 4 for _ in range(self.L)]
+        self.emb = torch.randn(self.V, self.E, generator=g)
+        self.head = torch.randn(self.V, self.E, generator=g)
+        self.l0, self.l1, self.first, self.last = l0, l1, first, last
+        self.hidden_in, self.hidden_out, self.logits = torch.zeros(self.E), torch.zeros(self.E), torch.zeros(self.V)
+
+    def decode_async(self, token, pos):
+        x = self.emb[token].clone() if self.first else self.hidden_in.clone()
+        for l in range(self.l0, self.l1):
+            x = torch.tanh(self.W[l] @ x) + 0.01 * pos
+        self.hidden_out.copy_(x)
+        if self.last:
+            self.logits.copy_(self.head @ x)
+
+
+def _worker(rank, world, port, q):
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+    import pkgload
+    import torch.distributed as dist
+    pkg = pkgload.load()
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    b = pkg.layer_windows(ToyStage.L, world)
+    st = ToyStage(b[rank], b[rank + 1], rank == 0, rank == world - 1)
+    run = pkg.PipelineRunner(st, rank, world, dist, torch.zeros(1, dtype=torch.int64))
+    tok, toks, outs = 3, [], []
+    for pos in range(5):
+        nxt = run.step(tok, pos, sample=lambda lg: torch.argmax(lg))
+        if rank == world - 1:
+            outs.append(st.logits.clone())
+        # every rank needs the same next token to stay in lock-step: rank 0 broadcasts it (as llama_send_meta does, :17870)
+        t = torch.tensor([nxt if rank == 0 else 0], dtype=torch.int64)
+        dist.broadcast(t, src=0)
+        tok = int(t.item())
+        toks.append(tok)
+    if rank == world - 1:
+        q.put((toks, torch.stack(outs)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_pipeline_matches_single_process(world):
+    single = ToyStage(0, ToyStage.L, True, True)
+    tok, want_toks, want = 3, [], []
+    for pos in range(5):
+        single.decode_async(tok, pos)
+        want.append(single.logits.clone())
+        tok = int(torch.argmax(single.logits))
+        want_toks.append(tok)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    [p.start() for p in procs]
+    toks, outs = q.get(timeout=120)
+    [p.join(60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    assert toks == want_toks
+    assert torch.equal(outs, torch.stack(want))
+
+
+def test_layer_windows(pkg):
+    assert pkg.layer_windows(80, 1) == [0, 80]
+    assert pkg.layer_windows(80, 8) == [0, 10, 20, 30, 40, 50, 60, 70, 80]
+    b = pkg.layer_windows(32, 3)
+    assert b[0] == 0 and b[-1] == 32 and all(b[i] < b[i + 1] for i in range(3))
+    with pytest.raises(ValueError):
+        pkg.layer_windows(2, 3)
