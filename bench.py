@@ -291,6 +291,21 @@ def main():
         torch.cuda.profiler.stop()
     eng.kv_clear() if False else None
     ms_e2e, _, clocks_e2e = timed(True, first)     # same positions again: the KV rows are simply rewritten
+    # pipeline only: every rank times the same number of steps of its OWN stage with no communication; the difference between
+    # the pipelined step and the sum of the stage times is the exposed hand-off (NVLink + NCCL launch + token return) time
+    stage_ms = None
+    if world > 1:
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(ext):
+            e0.record()
+            for i in range(args.steps):
+                eng.decode_async(token_at(first + i, nv), first + i)
+            e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / args.steps], device=torch.device("cuda", local), dtype=torch.float64)
+        dist.all_reduce(t)
+        stage_ms = float(t.item())
     # live roofline of the dominant kernel (k_gemv_kquant): CUDA events around every GEMV launch of profiled steps
     prof = [eng.profile_step(token_at(first + i, nv), first + i) for i in range(4)]
     gemv_ms = sum(p["gemv_ms"] for p in prof) / len(prof)
@@ -328,6 +343,10 @@ def main():
                                     "frac_of_8TBs_north_star": (wb + kv_bytes) / (ms_step * 1e-3) / 8e12}},
         "model_load_s": t_load,
     }
+    if stage_ms is not None:
+        out["pipeline"] = {"stages": world, "hand_offs_per_token": world, "sum_of_stage_ms": stage_ms, "pipelined_ms_per_token": ms_step,
+                           "exposed_handoff_ms": max(0.0, ms_step - stage_ms), "exposed_frac": max(0.0, ms_step - stage_ms) / ms_step,
+                           "note": "b=1 decode is serial across stages (SURVEY H7): N GPUs hold N x the model, they do not cut the token latency"}
     if not args.no_cpu_baseline:
         try:
             out["cpu_baseline"] = cpu_reference(args.model, 4, 1)

@@ -134,6 +134,11 @@ __device__ __forceinline__ void bulk_g2s(void * smem_dst, const void * gsrc, uin
         : "memory");
 }
 
+// fire-and-forget prefetch of a 16-B-granular global range into L2 (no destination, no barrier)
+__device__ __forceinline__ void bulk_prefetch_l2(const void * gsrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
+}
+
 // Programmatic dependent launch: wait for the producer grid's results / let the dependent grid start.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

@@ -323,6 +323,12 @@ static int prof_end(pb200_model * m) {
 }
 static int64_t tbytes(const Tensor & t) { return (int64_t) t.bytes; }
 
+static void set_next(GemvFused & pro, const Tensor & t, int K) {
+    static const bool on = getenv("PB200_NO_PREFETCH") == nullptr;
+    const uint32_t tb = on ? gemv_tile_bytes(t.type, K, (int) t.N) : 0;
+    if (tb) { pro.next_W = t.data; pro.next_total_bytes = (int64_t) t.bytes; pro.next_tile_bytes = tb; }
+}
+
 // one decode step enqueued on m->stream (captured into the CUDA graph by finalize)
 static int enqueue_step(pb200_model * m, uint64_t * nlaunch) {
     const pb200_hparams & hp = m->hp;
@@ -355,6 +361,7 @@ static int enqueue_step(pb200_model * m, uint64_t * nlaunch) {
                              {L.wk.data, m->k, L.bk, nullptr, L.wk.type, EK},
                              {L.wv.data, m->v, L.bv, nullptr, L.wv.type, EK}};
             GemvFused pro; pro.kind = 1; pro.in0 = x; pro.in1 = L.attn_norm; pro.eps = hp.rms_eps;
+            set_next(pro, L.wo, QD);
             CK(prof_begin(m, tbytes(L.wq) + tbytes(L.wk) + tbytes(L.wv)));
             CK(launch_gemv_kquant_fused(d, 3, E, m->actE.q, pro, st, pdl)); n++;
             CK(prof_end(m));
@@ -376,6 +383,7 @@ static int enqueue_step(pb200_model * m, uint64_t * nlaunch) {
             CK(prof_begin(m, tbytes(L.wo)));
             if (is_kquant(L.wo.type) && gemv_fused_prologue_ok(QD)) {
                 GemvFused pro; pro.kind = 2; pro.in0 = m->att;
+                set_next(pro, L.gate, E);
                 CK(launch_gemv_kquant_fused(&d1, 1, QD, m->actQD.q, pro, st, pdl)); n++;
             } else {
                 CK(launch_quantize_act(m->att, QD, act_mode_for(L.wo.type), m->actQD.q, st, pdl)); n++;
@@ -388,6 +396,7 @@ static int enqueue_step(pb200_model * m, uint64_t * nlaunch) {
         if (gu_k) {
             GemvDesc d[2] = {{L.gate.data, m->g, nullptr, nullptr, L.gate.type, F}, {L.up.data, m->u, nullptr, nullptr, L.up.type, F}};
             GemvFused pro; pro.kind = 1; pro.in0 = x1; pro.in1 = L.ffn_norm; pro.eps = hp.rms_eps;
+            set_next(pro, L.down, F);
             CK(prof_begin(m, tbytes(L.gate) + tbytes(L.up)));
             CK(launch_gemv_kquant_fused(d, 2, E, m->actE.q, pro, st, pdl)); n++;
             CK(prof_end(m));
@@ -412,7 +421,14 @@ static int enqueue_step(pb200_model * m, uint64_t * nlaunch) {
                 CK(launch_gemv_kquant_fused(&d1, 1, F, m->actF.q, pro, st, pdl)); n++;
             } else {
                 CK(launch_silu_mul_quant(m->g, m->u, F, act_mode_for(L.down.type), m->actF.q, nullptr, st, pdl)); n++;
-                CK(launch_gemv(&d1, 1, F, m->actF.q, st, pdl)); n++;
+                if (is_kquant(L.down.type)) {
+                    GemvFused pro;   // PRO_NONE; only carries the prefetch target: next layer's wq, or the lm_head after the last layer
+                    if (il + 1 < m->l1) set_next(pro, m->layers[il + 1 - m->l0].wq, E);
+                    else if (m->with_head) set_next(pro, m->output, E);
+                    CK(launch_gemv_kquant_fused(&d1, 1, F, m->actF.q, pro, st, pdl)); n++;
+                } else {
+                    CK(launch_gemv(&d1, 1, F, m->actF.q, st, pdl)); n++;
+                }
             }
             CK(prof_end(m));
         }

@@ -135,6 +135,18 @@ __device__ __forceinline__ void release_stage(const GemvParams & P, GemvSmemCtl 
         if (t < P.ntiles) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy reads of the stage before the async-proxy refill
             issue_tile(P, ctl, stages, s, t, pol);
+        } else if (P.next_W) {
+            // nothing left to stream for this stage: keep the memory pipe busy with the next launch's first tiles
+            const int n_my = (P.ntiles - (int) blockIdx.x + (int) gridDim.x - 1) / (int) gridDim.x;
+            const int j = it + GEMV_NSTAGE - n_my;                     // 0 .. NSTAGE-1
+            const int64_t off = ((int64_t) blockIdx.x + (int64_t) j * gridDim.x) * P.next_tile_bytes;
+            if (j >= 0 && j < GEMV_NSTAGE && off < P.next_total_bytes) {
+                int64_t a0 = off & ~(int64_t) 15;
+                int64_t a1 = (off + P.next_tile_bytes + 15) & ~(int64_t) 15;
+                const int64_t lim = P.next_total_bytes & ~(int64_t) 15;
+                if (a1 > lim) a1 = lim;
+                if (a1 > a0) bulk_prefetch_l2(P.next_W + a0, (uint32_t) (a1 - a0));
+            }
         }
     }
 }
@@ -443,6 +455,8 @@ __global__ void __launch_bounds__(256) k_gemv_generic(const __grid_constant__ Ge
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+static int pick_rows_per_tile(int64_t row_bytes, int ngroups, int N);
+bool gemv_fused_prologue_ok(int K);
 static int g_sm_count = 0;
 static bool g_attr_set = false;
 
@@ -474,6 +488,16 @@ int launch_gemv_kquant(const GemvDesc * d, int nmat, int K, const ActQ & act, cu
     return launch_gemv_kquant_fused(d, nmat, K, act, none, stream, pdl);
 }
 
+// bytes of one ring tile of a [N,K] matrix of `type` in the fast kernel (0 if the fast kernel does not apply)
+uint32_t gemv_tile_bytes(int type, int K, int N) {
+    if (!is_kquant(type) || !gemv_fused_prologue_ok(K)) return 0;
+    int wpr = 1;
+    while (wpr * 32 < K / 256) wpr *= 2;
+    const int64_t rb = row_bytes(type, K);
+    const int tr = pick_rows_per_tile(rb, GEMV_TEAM_W / wpr, N);
+    return (uint32_t) (tr * rb);
+}
+
 bool gemv_fused_prologue_ok(int K) { return K % 256 == 0 && K / 256 <= GEMV_MAX_NBLK && K + K / 8 + K / 64 + 64 <= GEMV_ACT_SMEM; }
 
 int launch_gemv_kquant_fused(const GemvDesc * d, int nmat, int K, const ActQ & act, const GemvFused & pro, cudaStream_t stream, bool pdl) {
@@ -494,6 +518,10 @@ int launch_gemv_kquant_fused(const GemvDesc * d, int nmat, int K, const ActQ & a
         P.in0 = pro.in0;
         P.in1 = pro.in1;
         P.eps = pro.eps;
+        P.next_W = (const uint8_t *) pro.next_W;
+        P.next_total_bytes = pro.next_total_bytes;
+        P.next_tile_bytes = pro.next_tile_bytes;
+        if (pro.next_W && (((uintptr_t) pro.next_W & 15) || pro.next_tile_bytes == 0)) P.next_W = nullptr;
         int tiles = 0;
         for (int i = 0; i < nmat; i++) {
             GemvMat & M = P.mat[i];

@@ -68,6 +68,11 @@ struct GemvParams {
     const float * in0;
     const float * in1;
     float eps;
+    // cross-kernel prefetch: when this CTA's ring stops refilling (its last tiles are in flight) it pulls the tiles the NEXT
+    // GEMV launch will request first (tile c, c+G, c+2G, c+3G of its first matrix) into L2, so that launch's ramp-up reads L2
+    const uint8_t * next_W;
+    int64_t next_total_bytes;
+    uint32_t next_tile_bytes;
 };
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -22,7 +22,12 @@ struct GemvFused {       // fused activation prologue of the k-quant GEMV (PRO_*
     const float * in0 = nullptr;
     const float * in1 = nullptr;
     float eps = 0.f;
+    // optional: first matrix of the NEXT k-quant GEMV launch in the stream (cross-kernel L2 prefetch of its first tiles)
+    const void * next_W = nullptr;
+    int64_t next_total_bytes = 0;
+    uint32_t next_tile_bytes = 0;
 };
+uint32_t gemv_tile_bytes(int type, int K, int N);
 
 int sm_count();
 int gemv_set_trace(unsigned long long * dev_buf);   // debugging: per-CTA %globaltimer stamps of k_gemv_kquant
