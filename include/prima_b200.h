@@ -128,6 +128,10 @@ PB200_API int pb200_get_hidden(pb200_model * m, float * hidden_host);   /* copie
 PB200_API int pb200_profile_step(pb200_model * m, int32_t token, int32_t pos, double * gemv_ms, int64_t * gemv_bytes, int32_t * gemv_launches, double * step_ms);
 PB200_API int pb200_set_hidden(pb200_model * m, const float * hidden_host);   /* host -> hidden_in (tests, host-staged hand-off) */
 PB200_API int pb200_debug_read(pb200_model * m, const char * name, float * host, int64_t n);   /* white-box tests: q,k,v,att,g,u,x_a,x_b,xn,logits */
+/* persistent token kernel (one cooperative launch per token, PB200_PERSISTENT=1 at finalize makes it the captured default);
+ * toggling after finalize switches to direct launches.  _error: 1 if a grid barrier ever timed out. */
+PB200_API int pb200_set_persistent(pb200_model * m, int on);
+PB200_API int pb200_persistent_error(pb200_model * m);
 PB200_API int pb200_set_use_graph(pb200_model * m, int on);             /* CUDA-graph replay on/off (default on) */
 
 #ifdef __cplusplus

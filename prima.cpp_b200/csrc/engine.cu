@@ -88,6 +88,9 @@ struct pb200_model {
     int64_t weight_bytes = 0;
     std::vector<void *> allocs;
     bool profiling = false;
+    MkHandle * mk = nullptr;          // persistent token kernel (all GEMV phases in one cooperative launch)
+    bool use_mk = false;
+    float * mk_final_x = nullptr;
     std::vector<cudaEvent_t> prof_ev;
     std::vector<int64_t> prof_bytes;
     size_t prof_n = 0;
@@ -217,6 +220,7 @@ void pb200_model_free(pb200_model * m) {
     cudaSetDevice(m->device);
     cudaStreamSynchronize(m->stream);
     if (m->graph_exec) cudaGraphExecDestroy(m->graph_exec);
+    if (m->mk) mk_free(m->mk);
     for (void * p : m->allocs) cudaFree(p);
     if (m->tokpos_host) cudaFreeHost(m->tokpos_host);
     if (m->logits_host) cudaFreeHost(m->logits_host);
@@ -343,6 +347,13 @@ static int enqueue_step(pb200_model * m, uint64_t * nlaunch) {
         CK(launch_get_rows(m->tok_embd.data, m->tok_embd.type, E, tok_dev, 1, m->x_a, st, pdl)); n++;
         x = m->x_a;
     }
+    if (m->use_mk && m->mk && !m->profiling) {
+        // whole token = embedding gather + ONE cooperative launch (+ a 32-KB copy that keeps hidden_out at a stable address)
+        CK(mk_launch(m->mk, st)); n++;
+        if (m->mk_final_x != m->x_b) CK(cudaMemcpyAsync(m->x_b, m->mk_final_x, (size_t) E * 4, cudaMemcpyDeviceToDevice, st));
+        if (nlaunch) *nlaunch = n;
+        return 0;
+    }
     const float kq_scale = 1.0f / sqrtf((float) D);
     // three rotating hidden-state buffers so that a residual source is never overwritten by its consumer
     float * bufs[3] = {m->x_a, m->x_b, m->xn};
@@ -452,6 +463,59 @@ static int enqueue_step(pb200_model * m, uint64_t * nlaunch) {
     return 0;
 }
 
+// descriptors of the persistent token kernel: same dataflow as enqueue_step (buffer rotation included)
+static void build_mk(pb200_model * m) {
+    const pb200_hparams & hp = m->hp;
+    const int E = hp.n_embd, H = hp.n_head, HK = hp.n_head_kv, D = hp.head_dim, F = hp.n_ff;
+    const int QD = H * D, EK = HK * D;
+    const size_t nl = m->layers.size();
+    if (nl == 0) return;
+    std::vector<MkLayerDesc> L(nl);
+    float * x = m->with_embd ? m->x_a : m->x_in;
+    float * bufs[3] = {m->x_a, m->x_b, m->xn};
+    for (size_t i = 0; i < nl; i++) {
+        Layer & Ly = m->layers[i];
+        const Tensor * all[7] = {&Ly.wq, &Ly.wk, &Ly.wv, &Ly.wo, &Ly.gate, &Ly.up, &Ly.down};
+        for (const Tensor * t : all) if (!is_kquant(t->type)) return;
+        float * x1 = nullptr, * x2 = nullptr;
+        for (int j = 0; j < 3 && (!x1 || !x2); j++)
+            if (bufs[j] != x) { if (!x1) x1 = bufs[j]; else x2 = bufs[j]; }
+        MkLayerDesc & d = L[i];
+        d.ph[0].nmat = 3; d.ph[0].K = E;
+        d.ph[0].d[0] = {Ly.wq.data, m->q, Ly.bq, nullptr, Ly.wq.type, QD};
+        d.ph[0].d[1] = {Ly.wk.data, m->k, Ly.bk, nullptr, Ly.wk.type, EK};
+        d.ph[0].d[2] = {Ly.wv.data, m->v, Ly.bv, nullptr, Ly.wv.type, EK};
+        d.ph[0].pro.kind = 1; d.ph[0].pro.in0 = x; d.ph[0].pro.in1 = Ly.attn_norm; d.ph[0].pro.eps = hp.rms_eps;
+        d.ph[1].nmat = 1; d.ph[1].K = QD;
+        d.ph[1].d[0] = {Ly.wo.data, x1, nullptr, x, Ly.wo.type, E};
+        d.ph[1].pro.kind = 2; d.ph[1].pro.in0 = m->att;
+        d.ph[2].nmat = 2; d.ph[2].K = E;
+        d.ph[2].d[0] = {Ly.gate.data, m->g, nullptr, nullptr, Ly.gate.type, F};
+        d.ph[2].d[1] = {Ly.up.data, m->u, nullptr, nullptr, Ly.up.type, F};
+        d.ph[2].pro.kind = 1; d.ph[2].pro.in0 = x1; d.ph[2].pro.in1 = Ly.ffn_norm; d.ph[2].pro.eps = hp.rms_eps;
+        d.ph[3].nmat = 1; d.ph[3].K = F;
+        d.ph[3].d[0] = {Ly.down.data, x2, nullptr, x1, Ly.down.type, E};
+        d.ph[3].pro.kind = 0; d.ph[3].act = m->actF.q;
+        d.q = m->q; d.k = m->k; d.v = m->v;
+        d.kc = m->kcache + i * (size_t) hp.n_ctx * EK; d.vc = m->vcache + i * (size_t) hp.n_ctx * EK; d.att = m->att;
+        d.g = m->g; d.u = m->u; d.actF = m->actF.q; d.F = F;
+        x = x2;
+    }
+    MkTokenDesc T{};
+    T.layers = L.data(); T.n_layers = (int) nl;
+    T.with_head = m->with_head;
+    if (m->with_head) {
+        if (!is_kquant(m->output.type)) return;
+        T.head.nmat = 1; T.head.K = E;
+        T.head.d[0] = {m->output.data, m->logits, nullptr, nullptr, m->output.type, hp.n_vocab};
+        T.head.pro.kind = 1; T.head.pro.in0 = x; T.head.pro.in1 = m->output_norm; T.head.pro.eps = hp.rms_eps;
+    }
+    T.pos_dev = m->tokpos_dev + 1; T.freq_factors = m->rope_ff; T.kq_scale = 1.0f / sqrtf((float) D);
+    T.n_head = H; T.n_head_kv = HK; T.n_ctx = hp.n_ctx;
+    m->mk = mk_build(T, m->rp);
+    m->mk_final_x = x;
+}
+
 int pb200_model_finalize(pb200_model * m) {
     if (!m) return PB200_EINVAL;
     if (m->finalized) return 0;
@@ -508,6 +572,8 @@ int pb200_model_finalize(pb200_model * m) {
     CK(cudaMallocHost((void **) &m->tokpos_host, 16));
     if (m->with_head) CK(cudaMallocHost((void **) &m->logits_host, (size_t) hp.n_vocab * 4));
     rope_params_init(m->rp, hp.head_dim, hp.rope_mode, hp.n_ctx_orig, hp.rope_freq_base, hp.rope_freq_scale, 0.0f, 1.0f, 32.0f, 1.0f);
+    build_mk(m);
+    m->use_mk = m->mk != nullptr && getenv("PB200_PERSISTENT") != nullptr && atoi(getenv("PB200_PERSISTENT")) != 0;
     CK(cudaDeviceSynchronize());
 
     // warm-up (sets kernel attributes outside of capture), then capture the whole token as one graph
@@ -641,6 +707,14 @@ int pb200_debug_read(pb200_model * m, const char * name, float * host, int64_t n
     if (!p) return PB200_EINVAL;
     return (int) cudaMemcpy(host, p, (size_t) n * 4, cudaMemcpyDeviceToHost);
 }
+int pb200_set_persistent(pb200_model * m, int on) {
+    if (!m) return PB200_EINVAL;
+    if (on && !m->mk) return PB200_ENOTSUP;
+    // the captured graph contains whichever path was active at finalize: switch to direct launches when toggled
+    if ((on != 0) != m->use_mk) { m->use_mk = on != 0; m->use_graph = false; }
+    return 0;
+}
+int pb200_persistent_error(pb200_model * m) { return (m && m->mk) ? mk_error(m->mk) : 0; }
 int pb200_set_use_graph(pb200_model * m, int on) {
     if (!m) return PB200_EINVAL;
     m->use_graph = on != 0;

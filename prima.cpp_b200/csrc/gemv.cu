@@ -2,6 +2,9 @@
 #include "gemv.cuh"
 #include "launch.h"
 #include "quantize.cuh"
+#include "rope.cuh"
+
+#include <vector>
 
 namespace pb {
 
@@ -318,6 +321,396 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) k_gemv_kquant(const __grid_co
     trace(6);
 }
 
+
+// =================================================================================================================
+// Persistent token kernel: ALL GEMV phases of a decode step (4 per layer + lm_head) in ONE cooperative launch.
+// The weight ring is never drained: a stage freed in phase g is refilled with the CTA's next tile in global order, which may
+// belong to phase g+1 (or the next layer), so while the consumers sit in a grid barrier / fused prologue / the attention
+// phase, up to 4 stages (192 KB per SM, 28 MB chip-wide = 3.8 us of HBM time) of the next phase are already landing.
+// This removes the per-launch ramp measured in profiles/r1_gemv_timeline.txt (~9 us x 4 launches per layer).
+// Phases per layer: qkv[rmsnorm fused] | barrier | rope+kv-store+attention (CTA h < n_head) | barrier | wo[quant fused] |
+// barrier | gate,up[rmsnorm fused] | barrier | silu*up -> q8_K (CTA b < F/256) | barrier | down | barrier.
+// =================================================================================================================
+struct MkPhase {
+    GemvMat mat[GEMV_MAX_MAT];
+    int nmat, ntiles, K, nblk, wpr, prologue;
+    const float * in0;
+    const float * in1;
+    float eps;
+    ActQ act;   // PRO_NONE source (ffn_down: written by the silu phase)
+};
+struct MkLayer {
+    MkPhase ph[4];                                              // qkv, wo, gate|up, down
+    const float * q; const float * k; const float * v;          // attention inputs (pre-RoPE)
+    __half * kc; __half * vc; float * att;
+    const float * g; const float * u; ActQ actF; int F;          // silu*up -> q8_K
+};
+struct MkParams {
+    const MkLayer * layers;
+    int n_layers;
+    MkPhase head;
+    int with_head;
+    const int32_t * pos_dev;
+    RopeParams rp;
+    const float * freq_factors;
+    float kq_scale;
+    int n_head, n_head_kv, n_ctx;
+    unsigned int * barrier;   // zeroed before every launch
+    int * error_flag;
+};
+constexpr int MK_MAX_PHASES = 4 * 160 + 1;
+
+struct __align__(16) MkSmem {
+    GemvSmemCtl ctl;
+    uint16_t cnt[MK_MAX_PHASES + 7];   // tiles of this CTA per phase
+    MkPhase cur;                       // descriptor of the phase being consumed
+};
+constexpr int MK_HDR_BYTES = 2560;
+static_assert(sizeof(MkSmem) <= MK_HDR_BYTES, "MkSmem header");
+
+__device__ __forceinline__ const MkPhase * mk_phase(const MkParams & P, int g) {
+    return g < 4 * P.n_layers ? &P.layers[g >> 2].ph[g & 3] : &P.head;
+}
+template <class D>
+__device__ __forceinline__ void tile_info_t(const D & P, int t, int & m, int & r0, int & nrows) {
+    m = 0;
+#pragma unroll
+    for (int i = 1; i < GEMV_MAX_MAT; i++)
+        if (i < P.nmat && t >= P.mat[i].tile0) m = i;
+    const GemvMat & M = P.mat[m];
+    r0 = (t - M.tile0) * M.rows_per_tile;
+    nrows = min(M.rows_per_tile, M.N - r0);
+}
+__device__ __forceinline__ void mk_issue(const MkPhase * ph, GemvSmemCtl * ctl, uint8_t * stages, int s, int t, uint64_t pol) {
+    int m, r0, nrows;
+    tile_info_t(*ph, t, m, r0, nrows);
+    const GemvMat & M = ph->mat[m];
+    const int64_t g0 = (int64_t) r0 * M.row_bytes;
+    const int64_t g1 = g0 + (int64_t) nrows * M.row_bytes;
+    const int64_t a0 = g0 & ~(int64_t) 15;
+    int64_t a1 = (g1 + 15) & ~(int64_t) 15;
+    const int64_t lim = (M.total_bytes + 15) & ~(int64_t) 15;
+    if (a1 > lim) a1 = lim;
+    const uint32_t bytes = (uint32_t) (a1 - a0);
+    mbar_arrive_expect_tx(&ctl->full[s], bytes);
+    bulk_g2s(stages + (size_t) s * GEMV_STAGE_BYTES, M.W + a0, bytes, &ctl->full[s], pol);
+}
+// issue global iteration G of this CTA (searching forward from phase g whose first iteration is `base`)
+__device__ __forceinline__ void mk_issue_iter(const MkParams & P, MkSmem * sm, uint8_t * stages, int n_phases, int g, int base, int G, uint64_t pol) {
+    while (g < n_phases && G >= base + (int) sm->cnt[g]) { base += sm->cnt[g]; g++; }
+    if (g >= n_phases) return;
+    mk_issue(mk_phase(P, g), &sm->ctl, stages, G % GEMV_NSTAGE, (int) blockIdx.x + (G - base) * (int) gridDim.x, pol);
+}
+__device__ __forceinline__ void mk_release(const MkParams & P, MkSmem * sm, uint8_t * stages, int n_phases, int g, int base, int G, uint64_t pol) {
+    __threadfence_block();
+    const int s = G % GEMV_NSTAGE;
+    if (atomicAdd(&sm->ctl.cnt[s], 1) == GEMV_TEAM_W - 1) {
+        sm->ctl.cnt[s] = 0;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mk_issue_iter(P, sm, stages, n_phases, g, base, G + GEMV_NSTAGE, pol);
+    }
+}
+__device__ __forceinline__ void mk_grid_barrier(const MkParams & P, unsigned & bar_idx) {
+    __syncthreads();
+    ++bar_idx;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(P.barrier, 1u);
+        const unsigned target = bar_idx * gridDim.x;
+        const long long t0 = clock64();
+        unsigned v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(P.barrier) : "memory");
+            if (clock64() - t0 > (1ll << 33)) { *P.error_flag = 1; __trap(); }   // ~4 s: never hang the GPU on a logic error
+        } while (v < target);
+        __threadfence();   // gpu-scope fence: invalidates this SM's L1 so plain loads below see the other CTAs' results
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ void bar256() { asm volatile("bar.sync 10, 256;" ::: "memory"); }
+
+// RoPE + KV store + attention for q head h by warps 0..7 (256 threads); same arithmetic as k_attn_fused (ops.cu)
+__device__ void mk_attention(const MkParams & P, const MkLayer & L, int h, float * sm, int warp, int lane) {
+    constexpr int D = 128;
+    const int tid = warp * 32 + lane;
+    const int pos = *P.pos_dev, n_kv = pos + 1;
+    const int gqa = P.n_head / P.n_head_kv, hk = h / gqa;
+    const int64_t EK = (int64_t) P.n_head_kv * D;
+    float * S = sm;                                   // [n_kv padded to 32]
+    float * red = sm + ((P.n_ctx + 31) & ~31);       // [8][128]
+    float * q_s = red + 8 * 128;                      // [128]
+    __half * k_s = reinterpret_cast<__half *>(q_s + D);
+    __half * v_s = k_s + D;
+    float * s_red = reinterpret_cast<float *>(v_s + D);   // [8] floats, then [8] doubles, then 2 floats
+    double * s_redd = reinterpret_cast<double *>(s_red + 8);
+    float * s_bc = reinterpret_cast<float *>(s_redd + 8);
+    const RopeParams & rp = P.rp;
+    {
+        const int half_dims = rp.n_dims / 2;
+        const bool neox = rp.mode & 2;
+        if (tid < 128) {
+            const int pair = tid & 63;
+            const bool is_q = tid < 64;
+            const float * src = is_q ? L.q + (int64_t) h * D : L.k + (int64_t) hk * D;
+            if (pair < half_dims) {
+                float c, s;
+                rope_cos_sin(rp, pos, pair, P.freq_factors, c, s);
+                const int i0 = neox ? pair : 2 * pair, i1 = neox ? pair + half_dims : 2 * pair + 1;
+                float y0, y1;
+                rope_rotate(__ldcg(src + i0), __ldcg(src + i1), c, s, y0, y1);
+                if (is_q) { q_s[i0] = __half2float(__float2half_rn(y0)); q_s[i1] = __half2float(__float2half_rn(y1)); }
+                else { k_s[i0] = __float2half_rn(y0); k_s[i1] = __float2half_rn(y1); }
+            }
+            for (int i = rp.n_dims + pair; i < D; i += 64) {
+                if (is_q) q_s[i] = __half2float(__float2half_rn(__ldcg(src + i)));
+                else k_s[i] = __float2half_rn(__ldcg(src + i));
+            }
+        } else {
+            v_s[tid - 128] = __float2half_rn(__ldcg(L.v + (int64_t) hk * D + tid - 128));
+        }
+    }
+    bar256();
+    if (h % gqa == 0 && tid < 32) {
+        *reinterpret_cast<uint2 *>(L.kc + (int64_t) pos * EK + (int64_t) hk * D + 4 * lane) = *reinterpret_cast<const uint2 *>(k_s + 4 * lane);
+        *reinterpret_cast<uint2 *>(L.vc + (int64_t) pos * EK + (int64_t) hk * D + 4 * lane) = *reinterpret_cast<const uint2 *>(v_s + 4 * lane);
+    }
+    const float q0 = q_s[4 * lane], q1 = q_s[4 * lane + 1], q2 = q_s[4 * lane + 2], q3 = q_s[4 * lane + 3];
+    for (int p = warp; p < n_kv; p += 8) {
+        const __half * krow = p == pos ? k_s : L.kc + (int64_t) p * EK + (int64_t) hk * D;
+        const uint2 kraw = *reinterpret_cast<const uint2 *>(krow + 4 * lane);
+        const float2 k01 = __half22float2(*reinterpret_cast<const __half2 *>(&kraw.x));
+        const float2 k23 = __half22float2(*reinterpret_cast<const __half2 *>(&kraw.y));
+        float s = k01.x * q0;
+        s = fmaf(k01.y, q1, s);
+        s = fmaf(k23.x, q2, s);
+        s = fmaf(k23.y, q3, s);
+        s = warp_sum(s);
+        if (lane == 0) S[p] = __fmul_rn(s, P.kq_scale);
+    }
+    bar256();
+    float m = -INFINITY;
+    for (int p = tid; p < n_kv; p += 256) m = fmaxf(m, S[p]);
+    m = warp_max(m);
+    if (lane == 0) s_red[warp] = m;
+    bar256();
+    if (tid == 0) {
+        float t = s_red[0];
+        for (int i = 1; i < 8; i++) t = fmaxf(t, s_red[i]);
+        s_bc[0] = t;
+    }
+    bar256();
+    const float mx = s_bc[0];
+    double dsum = 0.0;
+    for (int p = tid; p < n_kv; p += 256) {
+        const float e = expf(__fsub_rn(S[p], mx));
+        S[p] = e;
+        dsum += (double) e;
+    }
+    dsum = warp_sum_d(dsum);
+    if (lane == 0) s_redd[warp] = dsum;
+    bar256();
+    if (tid == 0) {
+        double t = 0;
+        for (int i = 0; i < 8; i++) t += s_redd[i];
+        s_bc[1] = (float) (1.0 / t);
+    }
+    bar256();
+    const float inv = s_bc[1];
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int p = warp; p < n_kv; p += 8) {
+        const float w = __half2float(__float2half_rn(__fmul_rn(S[p], inv)));
+        const __half * vrow = p == pos ? v_s : L.vc + (int64_t) p * EK + (int64_t) hk * D;
+        const uint2 vraw = *reinterpret_cast<const uint2 *>(vrow + 4 * lane);
+        const float2 v01 = __half22float2(*reinterpret_cast<const __half2 *>(&vraw.x));
+        const float2 v23 = __half22float2(*reinterpret_cast<const __half2 *>(&vraw.y));
+        a0 = fmaf(v01.x, w, a0); a1 = fmaf(v01.y, w, a1); a2 = fmaf(v23.x, w, a2); a3 = fmaf(v23.y, w, a3);
+    }
+    *reinterpret_cast<float4 *>(red + warp * 128 + 4 * lane) = make_float4(a0, a1, a2, a3);
+    bar256();
+    if (tid < 128) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; i++) t += red[i * 128 + tid];
+        L.att[(int64_t) h * D + tid] = t;
+    }
+}
+
+__global__ void __launch_bounds__(GEMV_THREADS, 1) k_token_persistent(const __grid_constant__ MkParams P) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    MkSmem * sm = reinterpret_cast<MkSmem *>(smem);
+    GemvSmemCtl * ctl = &sm->ctl;
+    uint8_t * stages = smem + MK_HDR_BYTES;
+    uint8_t * act_smem = stages + (size_t) GEMV_NSTAGE * GEMV_STAGE_BYTES;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_phases = 4 * P.n_layers + (P.with_head ? 1 : 0);
+    const uint64_t pol = policy_evict_first();
+
+    // the wpr > 1 phases of a model all share one wpr (checked on the host): pbar counts are fixed at init
+    int wpr_split = 1;
+    for (int g = threadIdx.x; g < n_phases; g += GEMV_THREADS) {
+        const MkPhase * ph = mk_phase(P, g);
+        const int nt = ph->ntiles;
+        sm->cnt[g] = (uint16_t) (nt > (int) blockIdx.x ? (nt - (int) blockIdx.x + (int) gridDim.x - 1) / (int) gridDim.x : 0);
+    }
+    for (int g = 0; g < min(n_phases, 5); g++) wpr_split = max(wpr_split, mk_phase(P, g)->wpr);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < GEMV_NSTAGE; s++) {
+            mbar_init(&ctl->full[s], 1);
+            ctl->cnt[s] = 0;
+#pragma unroll
+            for (int gI = 0; gI < 4; gI++) mbar_init(&ctl->pbar[s][gI], wpr_split > 1 ? wpr_split - 1 : 1);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int G = 0; G < GEMV_NSTAGE; G++) mk_issue_iter(P, sm, stages, n_phases, 0, 0, G, pol);   // prime the ring
+    }
+
+    const int team = warp / GEMV_TEAM_W, tw = warp % GEMV_TEAM_W;
+    unsigned bar_idx = 0;
+    int base = 0;                 // global iteration index of this CTA's first tile of phase g
+    uint32_t puse = 0;            // bit s = parity of completed uses of pbar[s][*]
+    ActQ sa;
+    ActRegs r;
+    ProRegs pr;
+
+    for (int g = 0; g < n_phases; g++) {
+        const int li = g >> 2, pi = g < 4 * P.n_layers ? (g & 3) : 4;
+        // ---------------- dependencies of this phase ----------------
+        if (g > 0) mk_grid_barrier(P, bar_idx);                       // previous GEMV phase complete everywhere
+        if (pi == 1) {                                                // wo needs the attention output
+            const MkLayer & L = P.layers[li];
+            if ((int) blockIdx.x < P.n_head && warp < 8) mk_attention(P, L, blockIdx.x, reinterpret_cast<float *>(act_smem), warp, lane);
+            mk_grid_barrier(P, bar_idx);
+        } else if (pi == 3) {                                         // ffn_down needs silu(g)*u quantized
+            const MkLayer & L = P.layers[li];
+            const int b = blockIdx.x;
+            if (b < L.F / 256 && warp == 0) {
+                float v[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) v[i] = __fmul_rn(silu_f(__ldcg(L.g + b * 256 + lane * 8 + i)), __ldcg(L.u + b * 256 + lane * 8 + i));
+                quantize_warp_q8K(v, lane, b, L.actF);
+            }
+            mk_grid_barrier(P, bar_idx);
+        }
+        // ---------------- descriptor -> shared memory ----------------
+        {
+            const int * src = reinterpret_cast<const int *>(mk_phase(P, g));
+            int * dst = reinterpret_cast<int *>(&sm->cur);
+            for (int i = threadIdx.x; i < (int) (sizeof(MkPhase) / 4); i += GEMV_THREADS) dst[i] = src[i];
+        }
+        __syncthreads();
+        const MkPhase & D = sm->cur;
+        const int wpr = D.wpr;
+        const int ngroups = GEMV_TEAM_W / wpr;
+        const int group = tw / wpr, wsub = tw % wpr;
+        const int blk = wsub * 32 + lane;
+        const bool valid = blk < D.nblk;
+        // ---------------- activation: stage / quantize into shared memory, then into registers ----------------
+        sa.qs = reinterpret_cast<int8_t *>(act_smem);
+        sa.bsums = reinterpret_cast<int16_t *>(act_smem + D.K);
+        sa.d = reinterpret_cast<float *>(act_smem + D.K + D.K / 8);
+        sa.s = nullptr;
+        if (D.prologue == PRO_NONE) {
+            const int nq = D.K / 16, nb16 = D.K / 128;
+            for (int i = threadIdx.x; i < nq; i += GEMV_THREADS) reinterpret_cast<int4 *>(sa.qs)[i] = __ldcg(reinterpret_cast<const int4 *>(D.act.qs) + i);
+            if ((int) threadIdx.x < nb16) reinterpret_cast<int4 *>(sa.bsums)[threadIdx.x] = __ldcg(reinterpret_cast<const int4 *>(D.act.bsums) + threadIdx.x);
+            if ((int) threadIdx.x < D.nblk) sa.d[threadIdx.x] = __ldcg(D.act.d + threadIdx.x);
+            consumer_bar();
+        } else {
+            GemvParams Q;   // only the prologue fields are read
+            Q.prologue = D.prologue; Q.in0 = D.in0; Q.in1 = D.in1; Q.eps = D.eps; Q.K = D.K; Q.nblk = D.nblk;
+            prologue_load(Q, pr, warp, lane, 0);
+            prologue_compute(Q, ctl, sa, pr, warp, lane);
+        }
+        load_act_regs(r, sa, blk, valid);
+        finish_act_regs(r);
+        // ---------------- consume this CTA's tiles of the phase ----------------
+        const int n_g = sm->cnt[g];
+        for (int i = ((team - base) & 1); i < n_g; i += GEMV_NTEAM) {
+            const int G = base + i;
+            const int s = G % GEMV_NSTAGE;
+            const uint32_t ph = (G / GEMV_NSTAGE) & 1;
+            const int t = (int) blockIdx.x + i * (int) gridDim.x;
+            int m, r0, nrows;
+            tile_info_t(D, t, m, r0, nrows);
+            const GemvMat & M = D.mat[m];
+            const int type = M.type;
+            const int bpb = type == T_Q4_K ? BYTES_Q4_K : (type == T_Q5_K ? BYTES_Q5_K : BYTES_Q6_K);
+            const uint32_t mis = (uint32_t) (((int64_t) r0 * M.row_bytes) & 15);
+            const uint8_t * tile = stages + (size_t) s * GEMV_STAGE_BYTES + mis;
+            mbar_wait(&ctl->full[s], ph);
+            if (wpr == 1) {
+                for (int slot = group; slot < nrows; slot += ngroups) {
+                    const int row = r0 + slot;
+                    float extra = 0.f;
+                    if (lane == 0) {
+                        if (M.bias) extra = M.bias[row];
+                        if (M.resid) extra += __ldcg(M.resid + row);
+                    }
+                    const uint8_t * bp = tile + (size_t) slot * M.row_bytes + (size_t) blk * bpb;
+                    float v = 0.f;
+                    if (valid) {
+                        if (type == T_Q4_K) v = dot_q4K(bp, r);
+                        else if (type == T_Q6_K) v = dot_q6K(bp, r);
+                        else v = dot_q5K(bp, r);
+                    }
+                    if (slot + ngroups >= nrows) {
+                        __syncwarp();
+                        if (lane == 0) mk_release(P, sm, stages, n_phases, g, base, G, pol);
+                    }
+                    v = warp_sum(v);
+                    if (lane == 0) M.y[row] = v + extra;
+                }
+                if (group >= nrows) {
+                    __syncwarp();
+                    if (lane == 0) mk_release(P, sm, stages, n_phases, g, base, G, pol);
+                }
+            } else {
+                const int slot = group;
+                const bool has_row = slot < nrows;
+                const int row = r0 + slot;
+                const bool lead = wsub == 0;
+                float extra = 0.f;
+                if (has_row && lead && lane == 0) {
+                    if (M.bias) extra = M.bias[row];
+                    if (M.resid) extra += __ldcg(M.resid + row);
+                }
+                float v = 0.f;
+                if (has_row && valid) {
+                    const uint8_t * bp = tile + (size_t) slot * M.row_bytes + (size_t) blk * bpb;
+                    if (type == T_Q4_K) v = dot_q4K(bp, r);
+                    else if (type == T_Q6_K) v = dot_q6K(bp, r);
+                    else v = dot_q5K(bp, r);
+                }
+                const uint32_t pph = (puse >> s) & 1u;
+                puse ^= 1u << s;
+                if (!lead) {
+                    __syncwarp();
+                    if (lane == 0) mk_release(P, sm, stages, n_phases, g, base, G, pol);
+                    v = warp_sum(v);
+                    if (lane == 0) {
+                        ctl->part[s][tw] = v;
+                        mbar_arrive(&ctl->pbar[s][group]);
+                    }
+                } else {
+                    v = warp_sum(v);
+                    mbar_wait(&ctl->pbar[s][group], pph);
+                    if (lane == 0) {
+                        float acc = v;
+                        for (int j = 1; j < wpr; j++) acc += ctl->part[s][group * wpr + j];
+                        if (has_row) M.y[row] = acc + extra;
+                        mk_release(P, sm, stages, n_phases, g, base, G, pol);
+                    }
+                }
+            }
+        }
+        base += n_g;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Generic fallback: one warp per row, direct global loads, every supported type (incl. the 32-element block types
 // Q8_0 / Q5_1 that Qwen2.5-72B's ffn_down falls back to, src/llama.cpp:19516-19551), any K.
@@ -567,6 +960,127 @@ int launch_gemv_kquant_fused(const GemvDesc * d, int nmat, int K, const ActQ & a
         if (e) return e;
     }
     return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side of the persistent token kernel
+struct MkHandle {
+    MkParams P{};
+    MkLayer * d_layers = nullptr;
+    unsigned int * d_barrier = nullptr;   // [0] barrier word, [1] error flag
+    int grid = 0;
+};
+
+static bool mk_fill_phase(MkPhase & ph, const MkGemvDesc & g) {
+    if (g.nmat < 1 || g.nmat > GEMV_MAX_MAT || !gemv_fused_prologue_ok(g.K)) return false;
+    const int nblk = g.K / 256;
+    int wpr = 1;
+    while (wpr * 32 < nblk) wpr *= 2;
+    ph.nmat = g.nmat; ph.K = g.K; ph.nblk = nblk; ph.wpr = wpr;
+    ph.prologue = g.pro.kind; ph.in0 = g.pro.in0; ph.in1 = g.pro.in1; ph.eps = g.pro.eps; ph.act = g.act;
+    int tiles = 0;
+    for (int i = 0; i < g.nmat; i++) {
+        GemvMat & M = ph.mat[i];
+        if (!is_kquant(g.d[i].type) || ((uintptr_t) g.d[i].W & 15)) return false;
+        M.W = (const uint8_t *) g.d[i].W; M.y = g.d[i].y; M.bias = g.d[i].bias; M.resid = g.d[i].resid;
+        M.type = g.d[i].type; M.N = g.d[i].N;
+        M.row_bytes = row_bytes(g.d[i].type, g.K);
+        M.total_bytes = M.row_bytes * g.d[i].N;
+        M.rows_per_tile = pick_rows_per_tile(M.row_bytes, GEMV_TEAM_W / wpr, g.d[i].N);
+        if (M.rows_per_tile == 0) return false;
+        M.tile0 = tiles;
+        tiles += (g.d[i].N + M.rows_per_tile - 1) / M.rows_per_tile;
+    }
+    ph.ntiles = tiles;
+    return true;
+}
+
+static int mk_smem_bytes() { return MK_HDR_BYTES + GEMV_NSTAGE * GEMV_STAGE_BYTES + GEMV_ACT_SMEM; }
+
+MkHandle * mk_build(const MkTokenDesc & t, const RopeParams & rp) {
+    if (t.n_layers < 1 || 4 * t.n_layers + 1 > MK_MAX_PHASES || t.n_head > sm_count()) return nullptr;
+    // attention scratch lives in the activation region of shared memory
+    const size_t attn_bytes = ((size_t) ((t.n_ctx + 31) & ~31) + 8 * 128 + 128) * 4 + 2 * 128 * 2 + 8 * 4 + 8 * 8 + 16;
+    if (attn_bytes > (size_t) GEMV_ACT_SMEM) return nullptr;
+    std::vector<MkLayer> L((size_t) t.n_layers);
+    int wsplit = 1;
+    for (int il = 0; il < t.n_layers; il++) {
+        const MkLayerDesc & s = t.layers[il];
+        for (int p = 0; p < 4; p++) {
+            if (!mk_fill_phase(L[il].ph[p], s.ph[p])) return nullptr;
+            const int w = L[il].ph[p].wpr;
+            if (w > 1) { if (wsplit > 1 && w != wsplit) return nullptr; wsplit = w; }
+            if (L[il].ph[p].ntiles / 1 > 65535 * sm_count()) return nullptr;
+        }
+        if (s.F % 256 != 0 || s.F / 256 > sm_count()) return nullptr;
+        L[il].q = s.q; L[il].k = s.k; L[il].v = s.v; L[il].kc = s.kc; L[il].vc = s.vc; L[il].att = s.att;
+        L[il].g = s.g; L[il].u = s.u; L[il].actF = s.actF; L[il].F = s.F;
+    }
+    MkHandle * h = new MkHandle();
+    if (t.with_head) {
+        if (!mk_fill_phase(h->P.head, t.head)) { delete h; return nullptr; }
+        const int w = h->P.head.wpr;
+        if (w > 1 && wsplit > 1 && w != wsplit) { delete h; return nullptr; }
+    }
+    if (cudaMalloc(&h->d_layers, sizeof(MkLayer) * L.size()) != cudaSuccess || cudaMalloc(&h->d_barrier, 256) != cudaSuccess) {
+        cudaGetLastError();
+        mk_free(h);
+        return nullptr;
+    }
+    cudaMemcpy(h->d_layers, L.data(), sizeof(MkLayer) * L.size(), cudaMemcpyHostToDevice);
+    cudaMemset(h->d_barrier, 0, 256);
+    h->P.layers = h->d_layers;
+    h->P.n_layers = t.n_layers;
+    h->P.with_head = t.with_head ? 1 : 0;
+    h->P.pos_dev = t.pos_dev;
+    h->P.rp = rp;
+    h->P.freq_factors = t.freq_factors;
+    h->P.kq_scale = t.kq_scale;
+    h->P.n_head = t.n_head; h->P.n_head_kv = t.n_head_kv; h->P.n_ctx = t.n_ctx;
+    h->P.barrier = h->d_barrier;
+    h->P.error_flag = (int *) (h->d_barrier + 1);
+    h->grid = sm_count();
+    if (cudaFuncSetAttribute(k_token_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, mk_smem_bytes()) != cudaSuccess) {
+        cudaGetLastError();
+        mk_free(h);
+        return nullptr;
+    }
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_token_persistent, GEMV_THREADS, mk_smem_bytes()) != cudaSuccess || per_sm < 1) {
+        cudaGetLastError();
+        mk_free(h);
+        return nullptr;
+    }
+    return h;
+}
+
+int mk_launch(MkHandle * h, cudaStream_t stream) {
+    cudaError_t e = cudaMemsetAsync(h->d_barrier, 0, 4, stream);
+    if (e != cudaSuccess) return (int) e;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(h->grid);
+    cfg.blockDim = dim3(GEMV_THREADS);
+    cfg.dynamicSmemBytes = mk_smem_bytes();
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;   // all CTAs co-resident: the grid barriers cannot deadlock on scheduling
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return (int) cudaLaunchKernelEx(&cfg, k_token_persistent, h->P);
+}
+
+int mk_error(MkHandle * h) {
+    int f = 0;
+    cudaMemcpy(&f, h->d_barrier + 1, 4, cudaMemcpyDeviceToHost);
+    return f;
+}
+
+void mk_free(MkHandle * h) {
+    if (!h) return;
+    if (h->d_layers) cudaFree(h->d_layers);
+    if (h->d_barrier) cudaFree(h->d_barrier);
+    delete h;
 }
 
 int launch_gemv_generic(const GemvDesc & d, int K, const ActQ & act, cudaStream_t stream, bool pdl) {

@@ -37,6 +37,25 @@ int gemv_smem_bytes();
 int launch_gemv_kquant(const GemvDesc * d, int nmat, int K, const ActQ & act, cudaStream_t stream, bool pdl);
 int launch_gemv_kquant_fused(const GemvDesc * d, int nmat, int K, const ActQ & act, const GemvFused & pro, cudaStream_t stream, bool pdl);
 bool gemv_fused_prologue_ok(int K);
+// ---- persistent token kernel (all GEMV phases of a decode step in one cooperative launch; gemv.cu) ----
+struct MkGemvDesc { GemvDesc d[3]; int nmat = 0; int K = 0; GemvFused pro; ActQ act{}; };
+struct MkLayerDesc {
+    MkGemvDesc ph[4];                                   // qkv, wo, gate|up, down
+    const float * q; const float * k; const float * v;  // attention inputs
+    __half * kc; __half * vc; float * att;
+    const float * g; const float * u; ActQ actF; int F;
+};
+struct MkTokenDesc {
+    const MkLayerDesc * layers; int n_layers;
+    MkGemvDesc head; bool with_head;
+    const int32_t * pos_dev; const float * freq_factors; float kq_scale; int n_head, n_head_kv, n_ctx;
+};
+struct MkHandle;
+// returns nullptr when the model / shapes are outside what the persistent kernel handles (caller keeps the multi-kernel path)
+MkHandle * mk_build(const MkTokenDesc & t, const struct RopeParams & rp);
+int mk_launch(MkHandle * h, cudaStream_t stream);     // memset of the grid-barrier word + cooperative launch
+int mk_error(MkHandle * h);                           // 1 if a grid barrier timed out (after synchronising)
+void mk_free(MkHandle * h);
 // any supported type / any K, one warp per row, direct global loads
 int launch_gemv_generic(const GemvDesc & d, int K, const ActQ & act, cudaStream_t stream, bool pdl);
 // picks the right kernel per weight type (all matrices must need the same activation mode)

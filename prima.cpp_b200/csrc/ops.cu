@@ -6,6 +6,7 @@
 // getrows.cu.  Numerics follow the CPU backend (ggml.c:11950, 14143, 13783, 12377), see each kernel.
 #include "launch.h"
 #include "quantize.cuh"
+#include "rope.cuh"
 
 #include <math.h>
 
@@ -137,30 +138,6 @@ __global__ void __launch_bounds__(256) k_rms_norm_rows(const float * __restrict_
 // ------------------------------------------------------------------------------------------------
 // RoPE (ggml.c:14087-14266).  theta for pair i is pos * theta_scale^i computed by i sequential fp32 multiplies, exactly
 // like ggml_rope_cache_init's running product, so the angle is bit-identical to the CPU's.
-__device__ __forceinline__ float rope_yarn_ramp(float low, float high, int i0) {
-    const float y = (i0 / 2 - low) / fmaxf(0.001f, high - low);
-    return 1.0f - fminf(1.0f, fmaxf(0.0f, y));
-}
-__device__ __forceinline__ void rope_cos_sin(const RopeParams & rp, int32_t pos, int pair, const float * freq_factors, float & c, float & s) {
-    float theta = (float) pos;
-    for (int j = 0; j < pair; j++) theta = __fmul_rn(theta, rp.theta_scale);
-    const float ff = freq_factors ? freq_factors[pair] : 1.0f;
-    const float theta_extrap = __fdiv_rn(theta, ff);
-    const float theta_interp = __fmul_rn(rp.freq_scale, theta_extrap);
-    float th = theta_interp, mscale = rp.attn_factor;
-    if (rp.ext_factor != 0.0f) {
-        const float ramp_mix = rope_yarn_ramp(rp.corr_dims[0], rp.corr_dims[1], 2 * pair) * rp.ext_factor;
-        th = theta_interp * (1 - ramp_mix) + theta_extrap * ramp_mix;
-        mscale *= 1.0f + 0.1f * logf(1.0f / rp.freq_scale);
-    }
-    c = __fmul_rn(cosf(th), mscale);
-    s = __fmul_rn(sinf(th), mscale);
-}
-__device__ __forceinline__ void rope_rotate(float x0, float x1, float c, float s, float & y0, float & y1) {
-    y0 = __fsub_rn(__fmul_rn(x0, c), __fmul_rn(x1, s));
-    y1 = __fadd_rn(__fmul_rn(x0, s), __fmul_rn(x1, c));
-}
-
 // grid = n_head + n_head_kv CTAs of D/2 threads: q heads rotate in place; k heads rotate into the f16 K cache and carry
 // the matching v head into the f16 V cache.
 __global__ void k_rope_kvstore(float * __restrict__ q, const float * __restrict__ k, const float * __restrict__ v, __half * __restrict__ kc,
