@@ -363,9 +363,9 @@ constexpr int MK_MAX_PHASES = 4 * 160 + 1;
 struct __align__(16) MkSmem {
     GemvSmemCtl ctl;
     uint16_t cnt[MK_MAX_PHASES + 7];   // tiles of this CTA per phase
-    MkPhase cur;                       // descriptor of the phase being consumed
+    MkPhase desc[4];                   // descriptors of phases g .. g+2 (slot = phase % 4): refills never read global memory
 };
-constexpr int MK_HDR_BYTES = 2560;
+constexpr int MK_HDR_BYTES = 3072;
 static_assert(sizeof(MkSmem) <= MK_HDR_BYTES, "MkSmem header");
 
 __device__ __forceinline__ const MkPhase * mk_phase(const MkParams & P, int g) {
@@ -397,9 +397,18 @@ __device__ __forceinline__ void mk_issue(const MkPhase * ph, GemvSmemCtl * ctl, 
 }
 // issue global iteration G of this CTA (searching forward from phase g whose first iteration is `base`)
 __device__ __forceinline__ void mk_issue_iter(const MkParams & P, MkSmem * sm, uint8_t * stages, int n_phases, int g, int base, int G, uint64_t pol) {
+    const int g0 = g;
     while (g < n_phases && G >= base + (int) sm->cnt[g]) { base += sm->cnt[g]; g++; }
     if (g >= n_phases) return;
-    mk_issue(mk_phase(P, g), &sm->ctl, stages, G % GEMV_NSTAGE, (int) blockIdx.x + (G - base) * (int) gridDim.x, pol);
+    // phases g0 .. g0+2 are cached in shared memory; further look-ahead (only with very few tiles per phase) reads HBM
+    const MkPhase * ph = g <= g0 + 2 ? &sm->desc[g & 3] : mk_phase(P, g);
+    mk_issue(ph, &sm->ctl, stages, G % GEMV_NSTAGE, (int) blockIdx.x + (G - base) * (int) gridDim.x, pol);
+}
+__device__ __forceinline__ void mk_load_desc(const MkParams & P, MkSmem * sm, int g, int n_phases) {
+    if (g >= n_phases) return;
+    const int * src = reinterpret_cast<const int *>(mk_phase(P, g));
+    int * dst = reinterpret_cast<int *>(&sm->desc[g & 3]);
+    for (int i = threadIdx.x; i < (int) (sizeof(MkPhase) / 4); i += GEMV_THREADS) dst[i] = src[i];
 }
 __device__ __forceinline__ void mk_release(const MkParams & P, MkSmem * sm, uint8_t * stages, int n_phases, int g, int base, int G, uint64_t pol) {
     __threadfence_block();
@@ -426,6 +435,14 @@ __device__ __forceinline__ void mk_grid_barrier(const MkParams & P, unsigned & b
         __threadfence();   // gpu-scope fence: invalidates this SM's L1 so plain loads below see the other CTAs' results
     }
     __syncthreads();
+}
+// timeline of layer 1 (phases 4..8): stamp k of phase g -> slot (g-4)*3+k of this CTA's 16-entry trace row
+__device__ __forceinline__ void mk_trace(int g, int k) {
+    if (g_gemv_trace && threadIdx.x == 0 && g >= 4 && g < 9) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_gemv_trace[blockIdx.x * 16 + (g - 4) * 3 + k] = t;
+    }
 }
 __device__ __forceinline__ void bar256() { asm volatile("bar.sync 10, 256;" ::: "memory"); }
 
@@ -563,6 +580,9 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) k_token_persistent(const __gr
         }
         mbar_fence_init();
     }
+    mk_load_desc(P, sm, 0, n_phases);
+    mk_load_desc(P, sm, 1, n_phases);
+    mk_load_desc(P, sm, 2, n_phases);
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int G = 0; G < GEMV_NSTAGE; G++) mk_issue_iter(P, sm, stages, n_phases, 0, 0, G, pol);   // prime the ring
@@ -595,14 +615,11 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) k_token_persistent(const __gr
             }
             mk_grid_barrier(P, bar_idx);
         }
-        // ---------------- descriptor -> shared memory ----------------
-        {
-            const int * src = reinterpret_cast<const int *>(mk_phase(P, g));
-            int * dst = reinterpret_cast<int *>(&sm->cur);
-            for (int i = threadIdx.x; i < (int) (sizeof(MkPhase) / 4); i += GEMV_THREADS) dst[i] = src[i];
-        }
+        // ---------------- descriptors: slot g is resident since phase g-2; fetch g+2 into the slot phase g-2 used ----------------
+        mk_load_desc(P, sm, g + 2, n_phases);   // nobody reads slot (g+2)&3 == (g-2)&3 any more (barrier above)
         __syncthreads();
-        const MkPhase & D = sm->cur;
+        mk_trace(g, 0);
+        const MkPhase & D = sm->desc[g & 3];
         const int wpr = D.wpr;
         const int ngroups = GEMV_TEAM_W / wpr;
         const int group = tw / wpr, wsub = tw % wpr;
@@ -627,6 +644,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) k_token_persistent(const __gr
         }
         load_act_regs(r, sa, blk, valid);
         finish_act_regs(r);
+        mk_trace(g, 1);
         // ---------------- consume this CTA's tiles of the phase ----------------
         const int n_g = sm->cnt[g];
         for (int i = ((team - base) & 1); i < n_g; i += GEMV_NTEAM) {
@@ -708,6 +726,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) k_token_persistent(const __gr
             }
         }
         base += n_g;
+        mk_trace(g, 2);
     }
 }
 

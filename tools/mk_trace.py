@@ -1,0 +1,30 @@
+"""GPU: per-phase timeline of the persistent token kernel (layer 1) on the 70B bench model."""
+import sys, ctypes as C, os
+from pathlib import Path
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
+os.environ["PB200_PERSISTENT"] = "1"
+import numpy as np, torch
+import pkgload
+import bench
+pkg = pkgload.load(); lib = pkg.Lib.get()
+lib.c.pb200_debug_set_trace.argtypes = [C.c_void_p]
+cfg = bench.MODELS["llama3-70b"]
+hp = dict(cfg["hp"], n_ctx=512)
+hp["n_layer"] = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+eng = pkg.Model(pkg.HParams(**hp), 0, (0, hp["n_layer"]), True, True)
+eng.synth(0, 1); eng.finalize()
+tr = torch.zeros(148 * 16, dtype=torch.int64, device="cuda")
+for i in range(140):
+    eng.decode_async(i % 1000, i)
+eng.synchronize()
+lib.check(lib.c.pb200_debug_set_trace(C.c_void_p(tr.data_ptr())), "trace")
+eng.decode_async(5, 140); eng.synchronize()
+a = tr.cpu().numpy().reshape(148, 16).astype(np.float64)
+t0 = a[:, 0].min()
+names = ["qkv", "wo", "gate|up", "down", "qkv(next layer)"]
+print("persistent kernel, layer 1; per phase: [after barrier(s)+desc] [act regs ready] [tiles consumed]; us relative to the first stamp: min / median / max over CTAs")
+for p in range(5):
+    for k, nm in enumerate(("start", "act ready", "done")):
+        col = (a[:, p * 3 + k] - t0) / 1e3
+        print(f"  {names[p]:16s} {nm:10s} {col.min():8.2f} {np.median(col):8.2f} {col.max():8.2f}")
