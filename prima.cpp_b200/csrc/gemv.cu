@@ -38,8 +38,8 @@ __device__ __forceinline__ float silu_f(float x) { return __fdiv_rn(x, 1.0f + ex
 // Warp w owns super-blocks w, w+8, w+16, ... ; lane l owns elements 8l..8l+7 of each.  Blocks are processed four at a
 // time with every global load issued up front, and for PRO_RMSNORM the same registers feed the sum of squares, so the
 // vector is read exactly once (K <= 8192 in one batch; longer vectors loop over batches for the sum, then again to quantize).
-__device__ __forceinline__ void load8(const float * p, float (&v)[8]) {
-    const float4 a0 = *reinterpret_cast<const float4 *>(p), a1 = *reinterpret_cast<const float4 *>(p + 4);
+__device__ __forceinline__ void load8(const float * p, float (&v)[8]) {   // .cg: L2 only (data written by other CTAs of a persistent grid)
+    const float4 a0 = __ldcg(reinterpret_cast<const float4 *>(p)), a1 = __ldcg(reinterpret_cast<const float4 *>(p + 4));
     v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
 }
 // Phase A issues the global loads of the first batch (nothing else), phase B does the arithmetic.  The ring fill is
@@ -73,7 +73,7 @@ __device__ __forceinline__ void prologue_compute(const GemvParams & P, GemvSmemC
                 }
             }
         } else {
-            for (int i = tid; i < P.K; i += GEMV_NW * 32) { const float v = P.in0[i]; sum += (double) __fmul_rn(v, v); }
+            for (int i = tid; i < P.K; i += GEMV_NW * 32) { const float v = __ldcg(P.in0 + i); sum += (double) __fmul_rn(v, v); }
         }
         sum = warp_sum_d(sum);
         if (lane == 0) ctl->red[warp] = sum;
@@ -364,7 +364,10 @@ struct __align__(16) MkSmem {
     GemvSmemCtl ctl;
     uint16_t cnt[MK_MAX_PHASES + 7];   // tiles of this CTA per phase
     MkPhase desc[4];                   // descriptors of phases g .. g+2 (slot = phase % 4): refills never read global memory
+    int xb_count;                      // refills issued across the coming phase boundary
+    int deferred[GEMV_NSTAGE];         // global iterations whose refill waits until the next prologue's loads are out
 };
+constexpr int MK_XB_ALLOWED = 2;       // stages prefetched across a phase boundary before the prologue (one per team)
 constexpr int MK_HDR_BYTES = 3072;
 static_assert(sizeof(MkSmem) <= MK_HDR_BYTES, "MkSmem header");
 
@@ -410,21 +413,35 @@ __device__ __forceinline__ void mk_load_desc(const MkParams & P, MkSmem * sm, in
     int * dst = reinterpret_cast<int *>(&sm->desc[g & 3]);
     for (int i = threadIdx.x; i < (int) (sizeof(MkPhase) / 4); i += GEMV_THREADS) dst[i] = src[i];
 }
+// A refill that belongs to a LATER phase is only issued right away for the first MK_XB_ALLOWED stages: everything an SM has
+// in flight delays its own small dependent loads (measured: 192 KB of bulk copies outstanding per SM add ~4 us to the next
+// prologue's 32-KB activation read, profiles/r1_persistent_timeline.txt), so the rest waits until those loads are out.
 __device__ __forceinline__ void mk_release(const MkParams & P, MkSmem * sm, uint8_t * stages, int n_phases, int g, int base, int G, uint64_t pol) {
     __threadfence_block();
     const int s = G % GEMV_NSTAGE;
     if (atomicAdd(&sm->ctl.cnt[s], 1) == GEMV_TEAM_W - 1) {
         sm->ctl.cnt[s] = 0;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mk_issue_iter(P, sm, stages, n_phases, g, base, G + GEMV_NSTAGE, pol);
+        const int G2 = G + GEMV_NSTAGE;
+        if (G2 >= base + (int) sm->cnt[g]) {                 // crosses into a later phase
+            const int k = atomicAdd(&sm->xb_count, 1);
+            if (k >= MK_XB_ALLOWED) { sm->deferred[k - MK_XB_ALLOWED] = G2; return; }
+        }
+        mk_issue_iter(P, sm, stages, n_phases, g, base, G2, pol);
     }
+}
+// called by thread 0 of the next phase once its prologue loads have been issued
+__device__ __forceinline__ void mk_issue_deferred(const MkParams & P, MkSmem * sm, uint8_t * stages, int n_phases, int g, int base, uint64_t pol) {
+    const int n = sm->xb_count - MK_XB_ALLOWED;
+    for (int i = 0; i < n && i < GEMV_NSTAGE; i++) mk_issue_iter(P, sm, stages, n_phases, g, base, sm->deferred[i], pol);
+    sm->xb_count = 0;
 }
 __device__ __forceinline__ void mk_grid_barrier(const MkParams & P, unsigned & bar_idx) {
     __syncthreads();
     ++bar_idx;
     if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(P.barrier, 1u);
+        // release-add (no return value, no separate membar) then poll with acquire loads
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(P.barrier) : "memory");
         const unsigned target = bar_idx * gridDim.x;
         const long long t0 = clock64();
         unsigned v;
@@ -432,7 +449,6 @@ __device__ __forceinline__ void mk_grid_barrier(const MkParams & P, unsigned & b
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(P.barrier) : "memory");
             if (clock64() - t0 > (1ll << 33)) { *P.error_flag = 1; __trap(); }   // ~4 s: never hang the GPU on a logic error
         } while (v < target);
-        __threadfence();   // gpu-scope fence: invalidates this SM's L1 so plain loads below see the other CTAs' results
     }
     __syncthreads();
 }
@@ -580,6 +596,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) k_token_persistent(const __gr
         }
         mbar_fence_init();
     }
+    if (threadIdx.x == 0) sm->xb_count = 0;
     mk_load_desc(P, sm, 0, n_phases);
     mk_load_desc(P, sm, 1, n_phases);
     mk_load_desc(P, sm, 2, n_phases);
@@ -608,9 +625,11 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) k_token_persistent(const __gr
             const MkLayer & L = P.layers[li];
             const int b = blockIdx.x;
             if (b < L.F / 256 && warp == 0) {
-                float v[8];
+                float v[8], uu[8];
+                load8(L.g + b * 256 + lane * 8, v);
+                load8(L.u + b * 256 + lane * 8, uu);
 #pragma unroll
-                for (int i = 0; i < 8; i++) v[i] = __fmul_rn(silu_f(__ldcg(L.g + b * 256 + lane * 8 + i)), __ldcg(L.u + b * 256 + lane * 8 + i));
+                for (int i = 0; i < 8; i++) v[i] = __fmul_rn(silu_f(v[i]), uu[i]);
                 quantize_warp_q8K(v, lane, b, L.actF);
             }
             mk_grid_barrier(P, bar_idx);
@@ -632,14 +651,29 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) k_token_persistent(const __gr
         sa.s = nullptr;
         if (D.prologue == PRO_NONE) {
             const int nq = D.K / 16, nb16 = D.K / 128;
-            for (int i = threadIdx.x; i < nq; i += GEMV_THREADS) reinterpret_cast<int4 *>(sa.qs)[i] = __ldcg(reinterpret_cast<const int4 *>(D.act.qs) + i);
-            if ((int) threadIdx.x < nb16) reinterpret_cast<int4 *>(sa.bsums)[threadIdx.x] = __ldcg(reinterpret_cast<const int4 *>(D.act.bsums) + threadIdx.x);
-            if ((int) threadIdx.x < D.nblk) sa.d[threadIdx.x] = __ldcg(D.act.d + threadIdx.x);
+            int4 cq[4], cb;
+            float cd = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int i = threadIdx.x + j * GEMV_THREADS;
+                if (i < nq) cq[j] = __ldcg(reinterpret_cast<const int4 *>(D.act.qs) + i);
+            }
+            if ((int) threadIdx.x < nb16) cb = __ldcg(reinterpret_cast<const int4 *>(D.act.bsums) + threadIdx.x);
+            if ((int) threadIdx.x < D.nblk) cd = __ldcg(D.act.d + threadIdx.x);
+            if (threadIdx.x == 0) mk_issue_deferred(P, sm, stages, n_phases, g, base, pol);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int i = threadIdx.x + j * GEMV_THREADS;
+                if (i < nq) reinterpret_cast<int4 *>(sa.qs)[i] = cq[j];
+            }
+            if ((int) threadIdx.x < nb16) reinterpret_cast<int4 *>(sa.bsums)[threadIdx.x] = cb;
+            if ((int) threadIdx.x < D.nblk) sa.d[threadIdx.x] = cd;
             consumer_bar();
         } else {
             GemvParams Q;   // only the prologue fields are read
             Q.prologue = D.prologue; Q.in0 = D.in0; Q.in1 = D.in1; Q.eps = D.eps; Q.K = D.K; Q.nblk = D.nblk;
             prologue_load(Q, pr, warp, lane, 0);
+            if (threadIdx.x == 0) mk_issue_deferred(P, sm, stages, n_phases, g, base, pol);
             prologue_compute(Q, ctl, sa, pr, warp, lane);
         }
         load_act_regs(r, sa, blk, valid);
