@@ -16,7 +16,7 @@ extern std::atomic<uint64_t> g_launches;
 namespace {
 ActQ act_from_ws(void * ws, int64_t k) {
     const int64_t kp = (k + 255) / 256 * 256;
-    ActQ a;
+    ActQ a{};
     uint8_t * p = (uint8_t *) ws;
     a.qs = (int8_t *) p;
     a.d = (float *) (p + kp);

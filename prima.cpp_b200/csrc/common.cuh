@@ -44,7 +44,15 @@ struct ActQ {
     float * d;        // [K/256] or [K/32]
     int16_t * bsums;  // [K/16]        (Q8_K only)
     float * s;        // [K/32]        (Q8_1 only)
+    // per-super-block strides (Q8_K mode): 0 = dense (256 B of qs, 16 bsums).  The shared-memory copy inside the GEMV uses
+    // 272 B / 24 int16 so that 32 lanes reading 32 different super-blocks with 128-bit loads hit 32 different bank groups
+    // (dense 256-B strides are a 32-way bank conflict: measured 4 us per prologue, profiles/r1_persistent_timeline.txt).
+    int qs_stride;    // bytes
+    int bs_stride;    // int16 elements
 };
+__host__ __device__ inline int act_qs_stride(const ActQ & a) { return a.qs_stride ? a.qs_stride : 256; }
+__host__ __device__ inline int act_bs_stride(const ActQ & a) { return a.bs_stride ? a.bs_stride : 16; }
+constexpr int ACT_SMEM_QS_STRIDE = 272, ACT_SMEM_BS_STRIDE = 24;
 enum : int { ACT_Q8_K = 0, ACT_Q8_0 = 1, ACT_Q8_1 = 2 };
 __host__ __device__ inline int act_mode_for(int wtype) { return is_kquant(wtype) ? ACT_Q8_K : (wtype == T_Q8_0 ? ACT_Q8_0 : ACT_Q8_1); }
 

@@ -56,7 +56,7 @@ size_t act_ws_bytes(int64_t k) {
 }
 ActQ act_from_ws(void * ws, int64_t k) {
     const int64_t kp = (k + 255) / 256 * 256;
-    ActQ a;
+    ActQ a{};
     uint8_t * p = (uint8_t *) ws;
     a.qs = (int8_t *) p;
     a.d = (float *) (p + kp);

@@ -4,6 +4,7 @@
 #include "quantize.cuh"
 #include "rope.cuh"
 
+#include <cstdlib>
 #include <vector>
 
 namespace pb {
@@ -78,6 +79,7 @@ __device__ __forceinline__ void prologue_compute(const GemvParams & P, GemvSmemC
         sum = warp_sum_d(sum);
         if (lane == 0) ctl->red[warp] = sum;
         consumer_bar();
+        if (g_gemv_trace && threadIdx.x == 0) { unsigned long long tt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt)); g_gemv_trace[148 * 32 + blockIdx.x] = tt; }
         double t = 0.0;
 #pragma unroll
         for (int i = 0; i < GEMV_NW; i++) t += ctl->red[i];     // every thread: same order, same result
@@ -191,9 +193,11 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) k_gemv_kquant(const __grid_co
     ProRegs pr;
     ActQ sa;   // the CTA's activation in shared memory: qs[K] | bsums[K/16] i16 | d[K/256] f32
     sa.qs = reinterpret_cast<int8_t *>(act_smem);
-    sa.bsums = reinterpret_cast<int16_t *>(act_smem + P.K);
-    sa.d = reinterpret_cast<float *>(act_smem + P.K + P.K / 8);
+    sa.bsums = reinterpret_cast<int16_t *>(act_smem + P.nblk * ACT_SMEM_QS_STRIDE);
+    sa.d = reinterpret_cast<float *>(act_smem + P.nblk * (ACT_SMEM_QS_STRIDE + 2 * ACT_SMEM_BS_STRIDE));
     sa.s = nullptr;
+    sa.qs_stride = ACT_SMEM_QS_STRIDE;
+    sa.bs_stride = ACT_SMEM_BS_STRIDE;
     // 1) request the (small) activation first: ONE coalesced copy per CTA (every warp fetching its own registers from
     //    global memory moved 16x the bytes through L2 and cost ~4 us per launch, profiles/r1_gemv_timeline.md) ...
     int4 cq[4], cb;
@@ -226,9 +230,9 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) k_gemv_kquant(const __grid_co
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const int i = threadIdx.x + j * GEMV_THREADS;
-            if (i < nq) reinterpret_cast<int4 *>(sa.qs)[i] = cq[j];
+            if (i < nq) *reinterpret_cast<int4 *>(sa.qs + (i >> 4) * ACT_SMEM_QS_STRIDE + (i & 15) * 16) = cq[j];
         }
-        if ((int) threadIdx.x < nb16) reinterpret_cast<int4 *>(sa.bsums)[threadIdx.x] = cb;
+        if ((int) threadIdx.x < nb16) *reinterpret_cast<int4 *>(reinterpret_cast<char *>(sa.bsums) + (threadIdx.x >> 1) * (2 * ACT_SMEM_BS_STRIDE) + (threadIdx.x & 1) * 16) = cb;
         if ((int) threadIdx.x < P.nblk) sa.d[threadIdx.x] = cd;
         consumer_bar();
     } else {
@@ -357,6 +361,7 @@ struct MkParams {
     int n_head, n_head_kv, n_ctx;
     unsigned int * barrier;   // zeroed before every launch
     int * error_flag;
+    int xb_allowed;           // stages prefetched across a phase boundary before the next prologue's loads are out
 };
 constexpr int MK_MAX_PHASES = 4 * 160 + 1;
 
@@ -425,14 +430,14 @@ __device__ __forceinline__ void mk_release(const MkParams & P, MkSmem * sm, uint
         const int G2 = G + GEMV_NSTAGE;
         if (G2 >= base + (int) sm->cnt[g]) {                 // crosses into a later phase
             const int k = atomicAdd(&sm->xb_count, 1);
-            if (k >= MK_XB_ALLOWED) { sm->deferred[k - MK_XB_ALLOWED] = G2; return; }
+            if (k >= P.xb_allowed) { sm->deferred[k - P.xb_allowed] = G2; return; }
         }
         mk_issue_iter(P, sm, stages, n_phases, g, base, G2, pol);
     }
 }
 // called by thread 0 of the next phase once its prologue loads have been issued
 __device__ __forceinline__ void mk_issue_deferred(const MkParams & P, MkSmem * sm, uint8_t * stages, int n_phases, int g, int base, uint64_t pol) {
-    const int n = sm->xb_count - MK_XB_ALLOWED;
+    const int n = sm->xb_count - P.xb_allowed;
     for (int i = 0; i < n && i < GEMV_NSTAGE; i++) mk_issue_iter(P, sm, stages, n_phases, g, base, sm->deferred[i], pol);
     sm->xb_count = 0;
 }
@@ -458,6 +463,14 @@ __device__ __forceinline__ void mk_trace(int g, int k) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         g_gemv_trace[blockIdx.x * 16 + (g - 4) * 3 + k] = t;
+    }
+}
+// finer stamps inside the prologue of phases 4 and 7 (qkv, down of layer 1): rows 148.. of the trace buffer
+__device__ __forceinline__ void mk_trace2(int g, int k) {
+    if (g_gemv_trace && threadIdx.x == 0 && (g == 4 || g == 7)) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_gemv_trace[148 * 16 + blockIdx.x * 16 + (g == 4 ? 0 : 8) + k] = t;
     }
 }
 __device__ __forceinline__ void bar256() { asm volatile("bar.sync 10, 256;" ::: "memory"); }
@@ -646,9 +659,11 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) k_token_persistent(const __gr
         const bool valid = blk < D.nblk;
         // ---------------- activation: stage / quantize into shared memory, then into registers ----------------
         sa.qs = reinterpret_cast<int8_t *>(act_smem);
-        sa.bsums = reinterpret_cast<int16_t *>(act_smem + D.K);
-        sa.d = reinterpret_cast<float *>(act_smem + D.K + D.K / 8);
+        sa.bsums = reinterpret_cast<int16_t *>(act_smem + D.nblk * ACT_SMEM_QS_STRIDE);
+        sa.d = reinterpret_cast<float *>(act_smem + D.nblk * (ACT_SMEM_QS_STRIDE + 2 * ACT_SMEM_BS_STRIDE));
         sa.s = nullptr;
+        sa.qs_stride = ACT_SMEM_QS_STRIDE;
+        sa.bs_stride = ACT_SMEM_BS_STRIDE;
         if (D.prologue == PRO_NONE) {
             const int nq = D.K / 16, nb16 = D.K / 128;
             int4 cq[4], cb;
@@ -660,23 +675,31 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) k_token_persistent(const __gr
             }
             if ((int) threadIdx.x < nb16) cb = __ldcg(reinterpret_cast<const int4 *>(D.act.bsums) + threadIdx.x);
             if ((int) threadIdx.x < D.nblk) cd = __ldcg(D.act.d + threadIdx.x);
+            mk_trace2(g, 0);
             if (threadIdx.x == 0) mk_issue_deferred(P, sm, stages, n_phases, g, base, pol);
+            mk_trace2(g, 1);
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const int i = threadIdx.x + j * GEMV_THREADS;
-                if (i < nq) reinterpret_cast<int4 *>(sa.qs)[i] = cq[j];
+                if (i < nq) *reinterpret_cast<int4 *>(sa.qs + (i >> 4) * ACT_SMEM_QS_STRIDE + (i & 15) * 16) = cq[j];
             }
-            if ((int) threadIdx.x < nb16) reinterpret_cast<int4 *>(sa.bsums)[threadIdx.x] = cb;
+            if ((int) threadIdx.x < nb16) *reinterpret_cast<int4 *>(reinterpret_cast<char *>(sa.bsums) + (threadIdx.x >> 1) * (2 * ACT_SMEM_BS_STRIDE) + (threadIdx.x & 1) * 16) = cb;
             if ((int) threadIdx.x < D.nblk) sa.d[threadIdx.x] = cd;
+            mk_trace2(g, 2);
             consumer_bar();
+            mk_trace2(g, 3);
         } else {
             GemvParams Q;   // only the prologue fields are read
             Q.prologue = D.prologue; Q.in0 = D.in0; Q.in1 = D.in1; Q.eps = D.eps; Q.K = D.K; Q.nblk = D.nblk;
+            mk_trace2(g, 0);
             prologue_load(Q, pr, warp, lane, 0);
             if (threadIdx.x == 0) mk_issue_deferred(P, sm, stages, n_phases, g, base, pol);
+            mk_trace2(g, 1);
             prologue_compute(Q, ctl, sa, pr, warp, lane);
+            mk_trace2(g, 3);
         }
         load_act_regs(r, sa, blk, valid);
+        mk_trace2(g, 4);
         finish_act_regs(r);
         mk_trace(g, 1);
         // ---------------- consume this CTA's tiles of the phase ----------------
@@ -944,7 +967,7 @@ uint32_t gemv_tile_bytes(int type, int K, int N) {
     return (uint32_t) (tr * rb);
 }
 
-bool gemv_fused_prologue_ok(int K) { return K % 256 == 0 && K / 256 <= GEMV_MAX_NBLK && K + K / 8 + K / 64 + 64 <= GEMV_ACT_SMEM; }
+bool gemv_fused_prologue_ok(int K) { return K % 256 == 0 && K / 256 <= GEMV_ACT_MAX_NBLK; }
 
 int launch_gemv_kquant_fused(const GemvDesc * d, int nmat, int K, const ActQ & act, const GemvFused & pro, cudaStream_t stream, bool pdl) {
     if (nmat < 1 || nmat > GEMV_MAX_MAT || K % 256 != 0) return (int) cudaErrorInvalidValue;
@@ -1092,6 +1115,9 @@ MkHandle * mk_build(const MkTokenDesc & t, const RopeParams & rp) {
     h->P.n_head = t.n_head; h->P.n_head_kv = t.n_head_kv; h->P.n_ctx = t.n_ctx;
     h->P.barrier = h->d_barrier;
     h->P.error_flag = (int *) (h->d_barrier + 1);
+    h->P.xb_allowed = getenv("PB200_XB") ? atoi(getenv("PB200_XB")) : MK_XB_ALLOWED;
+    if (h->P.xb_allowed < 0) h->P.xb_allowed = 0;
+    if (h->P.xb_allowed > GEMV_NSTAGE) h->P.xb_allowed = GEMV_NSTAGE;
     h->grid = sm_count();
     if (cudaFuncSetAttribute(k_token_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, mk_smem_bytes()) != cudaSuccess) {
         cudaGetLastError();

@@ -30,8 +30,9 @@ constexpr int GEMV_NTEAM = 2;                     // teams alternate stages: tea
 constexpr int GEMV_NW = GEMV_TEAM_W * GEMV_NTEAM;  // consumer warps
 constexpr int GEMV_THREADS = GEMV_NW * 32;        // no producer warp: the last consumer of a stage issues its refill
 constexpr int GEMV_NSTAGE = 4;
-constexpr int GEMV_STAGE_BYTES = 48 * 1024;       // 8 rows of Q4_K/Q5_K or 7 rows of Q6_K @ K=8192; 2 rows @ K=28672
-constexpr int GEMV_ACT_SMEM = 28672 + 28672 / 8 + 28672 / 64 + 64;   // fused-prologue activation (qs | bsums | d), K <= 28 672
+constexpr int GEMV_STAGE_BYTES = 46 * 1024;       // 8 rows of Q4_K/Q5_K or 7 rows of Q6_K @ K=8192; 2 rows @ K=28672 (47 040 B + 16)
+constexpr int GEMV_ACT_MAX_NBLK = 112;            // K <= 28 672 on the fast path
+constexpr int GEMV_ACT_SMEM = GEMV_ACT_MAX_NBLK * (ACT_SMEM_QS_STRIDE + 2 * ACT_SMEM_BS_STRIDE + 4) + 64;   // padded qs | padded bsums | d
 constexpr int GEMV_MAX_MAT = 3;
 constexpr int GEMV_MAX_NBLK = 256;               // K <= 65 536 (8 warps x 32 lanes x one super-block each)
 
@@ -86,13 +87,13 @@ struct ActRegs {
 
 __device__ __forceinline__ void load_act_regs(ActRegs & r, const ActQ & act, int blk, bool valid) {
     if (valid) {
-        const int4 * q = reinterpret_cast<const int4 *>(act.qs + (int64_t) blk * 256);
+        const int4 * q = reinterpret_cast<const int4 *>(act.qs + (int64_t) blk * act_qs_stride(act));
 #pragma unroll
         for (int i = 0; i < 16; i++) {
             int4 v = q[i];
             r.a[4 * i + 0] = v.x; r.a[4 * i + 1] = v.y; r.a[4 * i + 2] = v.z; r.a[4 * i + 3] = v.w;
         }
-        const int4 * b = reinterpret_cast<const int4 *>(act.bsums + (int64_t) blk * 16);
+        const int4 * b = reinterpret_cast<const int4 *>(act.bsums + (int64_t) blk * act_bs_stride(act));
         int4 b0 = b[0], b1 = b[1];
         r.bs[0] = b0.x; r.bs[1] = b0.y; r.bs[2] = b0.z; r.bs[3] = b0.w;
         r.bs[4] = b1.x; r.bs[5] = b1.y; r.bs[6] = b1.z; r.bs[7] = b1.w;

@@ -40,9 +40,9 @@ __device__ __forceinline__ void quantize_warp_q8K(const float (&v)[8], int lane,
         }
         d = __fdiv_rn(1.f, iscale);
     }
-    *reinterpret_cast<uint2 *>(out.qs + blk * 256 + lane * 8) = make_uint2(packed[0], packed[1]);
+    *reinterpret_cast<uint2 *>(out.qs + blk * act_qs_stride(out) + lane * 8) = make_uint2(packed[0], packed[1]);
     int other = __shfl_xor_sync(0xffffffffu, sum, 1);
-    if ((lane & 1) == 0) out.bsums[blk * 16 + (lane >> 1)] = (int16_t)(sum + other);
+    if ((lane & 1) == 0) out.bsums[blk * act_bs_stride(out) + (lane >> 1)] = (int16_t)(sum + other);
     if (lane == 0) out.d[blk] = d;
 }
 

@@ -14,13 +14,16 @@ hp = dict(cfg["hp"], n_ctx=512)
 hp["n_layer"] = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 eng = pkg.Model(pkg.HParams(**hp), 0, (0, hp["n_layer"]), True, True)
 eng.synth(0, 1); eng.finalize()
-tr = torch.zeros(148 * 16, dtype=torch.int64, device="cuda")
+tr = torch.zeros(148 * 34, dtype=torch.int64, device="cuda")
 for i in range(140):
     eng.decode_async(i % 1000, i)
 eng.synchronize()
 lib.check(lib.c.pb200_debug_set_trace(C.c_void_p(tr.data_ptr())), "trace")
 eng.decode_async(5, 140); eng.synchronize()
-a = tr.cpu().numpy().reshape(148, 16).astype(np.float64)
+raw = tr.cpu().numpy().astype(np.float64)
+a = raw[:148 * 16].reshape(148, 16)
+b = raw[148 * 16:148 * 32].reshape(148, 16)
+c = raw[148 * 32:148 * 33]
 t0 = a[:, 0].min()
 names = ["qkv", "wo", "gate|up", "down", "qkv(next layer)"]
 print("persistent kernel, layer 1; per phase: [after barrier(s)+desc] [act regs ready] [tiles consumed]; us relative to the first stamp: min / median / max over CTAs")
@@ -28,3 +31,13 @@ for p in range(5):
     for k, nm in enumerate(("start", "act ready", "done")):
         col = (a[:, p * 3 + k] - t0) / 1e3
         print(f"  {names[p]:16s} {nm:10s} {col.min():8.2f} {np.median(col):8.2f} {col.max():8.2f}")
+
+print("inside the qkv prologue (rmsnorm): stamps rel. to phase start; then the down prologue (staging)")
+for off, base_col, nm in ((0, 0, "qkv"), (8, 9, "down")):
+    st = a[:, base_col]
+    for k, what in enumerate(("loads issued", "deferred refills issued", "smem stored", "after bar / compute", "act regs loaded")):
+        col = (b[:, off + k] - st) / 1e3
+        if (b[:, off + k] > 0).all():
+            print(f"  {nm:5s} {what:26s} {col.min():7.2f} {np.median(col):7.2f} {col.max():7.2f}")
+col = (c - a[:, 12]) / 1e3
+print("  last rmsnorm prologue seen (next-layer qkv): sum-of-squares barrier passed at", np.median(col))
