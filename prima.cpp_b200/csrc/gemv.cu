@@ -372,7 +372,7 @@ struct __align__(16) MkSmem {
     int xb_count;                      // refills issued across the coming phase boundary
     int deferred[GEMV_NSTAGE];         // global iterations whose refill waits until the next prologue's loads are out
 };
-constexpr int MK_XB_ALLOWED = 2;       // stages prefetched across a phase boundary before the prologue (one per team)
+constexpr int MK_XB_ALLOWED = GEMV_NSTAGE;   // measured: deferring buys nothing (the prologue was slow for another reason), keep the ring primed       // stages prefetched across a phase boundary before the prologue (one per team)
 constexpr int MK_HDR_BYTES = 3072;
 static_assert(sizeof(MkSmem) <= MK_HDR_BYTES, "MkSmem header");
 
@@ -521,17 +521,30 @@ __device__ void mk_attention(const MkParams & P, const MkLayer & L, int h, float
         *reinterpret_cast<uint2 *>(L.vc + (int64_t) pos * EK + (int64_t) hk * D + 4 * lane) = *reinterpret_cast<const uint2 *>(v_s + 4 * lane);
     }
     const float q0 = q_s[4 * lane], q1 = q_s[4 * lane + 1], q2 = q_s[4 * lane + 2], q3 = q_s[4 * lane + 3];
-    for (int p = warp; p < n_kv; p += 8) {
-        const __half * krow = p == pos ? k_s : L.kc + (int64_t) p * EK + (int64_t) hk * D;
-        const uint2 kraw = *reinterpret_cast<const uint2 *>(krow + 4 * lane);
-        const float2 k01 = __half22float2(*reinterpret_cast<const __half2 *>(&kraw.x));
-        const float2 k23 = __half22float2(*reinterpret_cast<const __half2 *>(&kraw.y));
-        float s = k01.x * q0;
-        s = fmaf(k01.y, q1, s);
-        s = fmaf(k23.x, q2, s);
-        s = fmaf(k23.y, q3, s);
-        s = warp_sum(s);
-        if (lane == 0) S[p] = __fmul_rn(s, P.kq_scale);
+    for (int p0 = warp; p0 < n_kv; p0 += 32) {     // 4 positions per warp in flight: all K rows requested before any is used
+        uint2 kraw[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int p = p0 + 8 * j;
+            if (p < n_kv) {
+                const __half * krow = p == pos ? k_s : L.kc + (int64_t) p * EK + (int64_t) hk * D;
+                kraw[j] = *reinterpret_cast<const uint2 *>(krow + 4 * lane);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int p = p0 + 8 * j;
+            if (p < n_kv) {
+                const float2 k01 = __half22float2(*reinterpret_cast<const __half2 *>(&kraw[j].x));
+                const float2 k23 = __half22float2(*reinterpret_cast<const __half2 *>(&kraw[j].y));
+                float s = k01.x * q0;
+                s = fmaf(k01.y, q1, s);
+                s = fmaf(k23.x, q2, s);
+                s = fmaf(k23.y, q3, s);
+                s = warp_sum(s);
+                if (lane == 0) S[p] = __fmul_rn(s, P.kq_scale);
+            }
+        }
     }
     bar256();
     float m = -INFINITY;
@@ -563,13 +576,26 @@ __device__ void mk_attention(const MkParams & P, const MkLayer & L, int h, float
     bar256();
     const float inv = s_bc[1];
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    for (int p = warp; p < n_kv; p += 8) {
-        const float w = __half2float(__float2half_rn(__fmul_rn(S[p], inv)));
-        const __half * vrow = p == pos ? v_s : L.vc + (int64_t) p * EK + (int64_t) hk * D;
-        const uint2 vraw = *reinterpret_cast<const uint2 *>(vrow + 4 * lane);
-        const float2 v01 = __half22float2(*reinterpret_cast<const __half2 *>(&vraw.x));
-        const float2 v23 = __half22float2(*reinterpret_cast<const __half2 *>(&vraw.y));
-        a0 = fmaf(v01.x, w, a0); a1 = fmaf(v01.y, w, a1); a2 = fmaf(v23.x, w, a2); a3 = fmaf(v23.y, w, a3);
+    for (int p0 = warp; p0 < n_kv; p0 += 32) {
+        uint2 vraw[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int p = p0 + 8 * j;
+            if (p < n_kv) {
+                const __half * vrow = p == pos ? v_s : L.vc + (int64_t) p * EK + (int64_t) hk * D;
+                vraw[j] = *reinterpret_cast<const uint2 *>(vrow + 4 * lane);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int p = p0 + 8 * j;
+            if (p < n_kv) {
+                const float w = __half2float(__float2half_rn(__fmul_rn(S[p], inv)));
+                const float2 v01 = __half22float2(*reinterpret_cast<const __half2 *>(&vraw[j].x));
+                const float2 v23 = __half22float2(*reinterpret_cast<const __half2 *>(&vraw[j].y));
+                a0 = fmaf(v01.x, w, a0); a1 = fmaf(v01.y, w, a1); a2 = fmaf(v23.x, w, a2); a3 = fmaf(v23.y, w, a3);
+            }
+        }
     }
     *reinterpret_cast<float4 *>(red + warp * 128 + 4 * lane) = make_float4(a0, a1, a2, a3);
     bar256();
