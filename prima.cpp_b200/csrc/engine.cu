@@ -328,7 +328,9 @@ static int prof_end(pb200_model * m) {
 static int64_t tbytes(const Tensor & t) { return (int64_t) t.bytes; }
 
 static void set_next(GemvFused & pro, const Tensor & t, int K) {
-    static const bool on = getenv("PB200_NO_PREFETCH") == nullptr;
+    // measured (profiles/r1_summary.md): pulling the next launch's first tiles into L2 during the tail COSTS 3 % (11.45 vs 11.08 ms):
+    // the prefetch competes with the tail's own refills and the next launch re-reads the lines anyway.  Opt-in only.
+    static const bool on = getenv("PB200_PREFETCH") != nullptr;
     const uint32_t tb = on ? gemv_tile_bytes(t.type, K, (int) t.N) : 0;
     if (tb) { pro.next_W = t.data; pro.next_total_bytes = (int64_t) t.bytes; pro.next_tile_bytes = tb; }
 }
