@@ -128,6 +128,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t * bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// token flavour: the arriving thread gets the phase token and can wait for that phase without tracking a parity bit
+__device__ __forceinline__ uint64_t mbar_arrive_token(uint64_t * bar) {
+    uint64_t st;
+    asm volatile("mbarrier.arrive.shared::cta.b64 %0, [%1];" : "=l"(st) : "r"(smem_u32(bar)) : "memory");
+    return st;
+}
+__device__ __forceinline__ void mbar_wait_token(uint64_t * bar, uint64_t token) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAITT_%=:\n"
+        "mbarrier.try_wait.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONET_%=;\n"
+        "bra WAITT_%=;\n"
+        "DONET_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "l"(token)
+        : "memory");
+}
 // L2 eviction policy for streamed-once weights
 __device__ __forceinline__ uint64_t policy_evict_first() {
     uint64_t p;

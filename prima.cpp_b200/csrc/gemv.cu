@@ -156,7 +156,7 @@ __device__ __forceinline__ void release_stage(const GemvParams & P, GemvSmemCtl 
     }
 }
 
-__global__ void __launch_bounds__(GEMV_THREADS, 1) k_gemv_kquant(const __grid_constant__ GemvParams P) {
+__global__ void __maxnreg__(104) k_gemv_kquant(const __grid_constant__ GemvParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
     GemvSmemCtl * ctl = reinterpret_cast<GemvSmemCtl *>(smem);
     uint8_t * stages = smem + GEMV_CTL_BYTES;
@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) k_gemv_kquant(const __grid_co
             mbar_init(&ctl->full[s], 1);
             ctl->cnt[s] = 0;
 #pragma unroll
-            for (int g = 0; g < 4; g++) mbar_init(&ctl->pbar[s][g], P.wpr > 1 ? P.wpr - 1 : 1);
+            for (int g = 0; g < 4; g++) mbar_init(&ctl->pbar[s][g], P.wpr > 1 ? P.wpr : 1);
         }
         mbar_fence_init();
     }
@@ -187,6 +187,14 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) k_gemv_kquant(const __grid_co
     const bool valid = blk < P.nblk;
 
     pdl_trigger();   // let the next kernel become resident as SMs drain; its own pdl_wait() orders the data
+    if (P.fill_before_wait && threadIdx.x == 0) {
+        // this launch follows a small kernel and is already resident while it runs: stream weights now
+#pragma unroll
+        for (int it = 0; it < GEMV_NSTAGE; it++) {
+            const int t = blockIdx.x + it * gridDim.x;
+            if (t < P.ntiles) issue_tile(P, ctl, stages, it, t, pol);
+        }
+    }
     pdl_wait();      // the activation is produced by the previous kernel in the stream
     trace(1);
     ActRegs r;
@@ -217,7 +225,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) k_gemv_kquant(const __grid_co
     __syncthreads();   // every warp has ISSUED its loads (not waited for them)
     trace(2);
     // 2) ... then start the weight stream: fill the whole ring
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && !P.fill_before_wait) {
 #pragma unroll
         for (int it = 0; it < GEMV_NSTAGE; it++) {
             const int t = blockIdx.x + it * gridDim.x;
@@ -312,7 +320,10 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) k_gemv_kquant(const __grid_co
                 }
             } else {
                 v = warp_sum(v);
-                mbar_wait(&ctl->pbar[s][group], ph);
+                uint64_t tok = 0;
+                if (lane == 0) tok = mbar_arrive_token(&ctl->pbar[s][group]);
+                tok = __shfl_sync(0xffffffffu, tok, 0);
+                mbar_wait_token(&ctl->pbar[s][group], tok);
                 if (lane == 0) {
                     float acc = v;
                     for (int i = 1; i < wpr; i++) acc += ctl->part[s][group * wpr + i];
@@ -635,7 +646,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) k_token_persistent(const __gr
             mbar_init(&ctl->full[s], 1);
             ctl->cnt[s] = 0;
 #pragma unroll
-            for (int gI = 0; gI < 4; gI++) mbar_init(&ctl->pbar[s][gI], wpr_split > 1 ? wpr_split - 1 : 1);
+            for (int gI = 0; gI < 4; gI++) mbar_init(&ctl->pbar[s][gI], wpr_split > 1 ? wpr_split : 1);
         }
         mbar_fence_init();
     }
@@ -651,7 +662,6 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) k_token_persistent(const __gr
     const int team = warp / GEMV_TEAM_W, tw = warp % GEMV_TEAM_W;
     unsigned bar_idx = 0;
     int base = 0;                 // global iteration index of this CTA's first tile of phase g
-    uint32_t puse = 0;            // bit s = parity of completed uses of pbar[s][*]
     ActQ sa;
     ActRegs r;
     ProRegs pr;
@@ -790,8 +800,6 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) k_token_persistent(const __gr
                     else if (type == T_Q6_K) v = dot_q6K(bp, r);
                     else v = dot_q5K(bp, r);
                 }
-                const uint32_t pph = (puse >> s) & 1u;
-                puse ^= 1u << s;
                 if (!lead) {
                     __syncwarp();
                     if (lane == 0) mk_release(P, sm, stages, n_phases, g, base, G, pol);
@@ -802,7 +810,10 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) k_token_persistent(const __gr
                     }
                 } else {
                     v = warp_sum(v);
-                    mbar_wait(&ctl->pbar[s][group], pph);
+                    uint64_t tok = 0;
+                    if (lane == 0) tok = mbar_arrive_token(&ctl->pbar[s][group]);
+                    tok = __shfl_sync(0xffffffffu, tok, 0);
+                    mbar_wait_token(&ctl->pbar[s][group], tok);
                     if (lane == 0) {
                         float acc = v;
                         for (int j = 1; j < wpr; j++) acc += ctl->part[s][group * wpr + j];
@@ -1020,6 +1031,7 @@ int launch_gemv_kquant_fused(const GemvDesc * d, int nmat, int K, const ActQ & a
         P.next_W = (const uint8_t *) pro.next_W;
         P.next_total_bytes = pro.next_total_bytes;
         P.next_tile_bytes = pro.next_tile_bytes;
+        P.fill_before_wait = pro.fill_before_wait ? 1 : 0;
         if (pro.next_W && (((uintptr_t) pro.next_W & 15) || pro.next_tile_bytes == 0)) P.next_W = nullptr;
         int tiles = 0;
         for (int i = 0; i < nmat; i++) {

@@ -29,7 +29,7 @@ constexpr int GEMV_NTEAM = 2;                     // teams alternate stages: tea
                                                   // per-stage latency budget, 4 warps per scheduler instead of 2
 constexpr int GEMV_NW = GEMV_TEAM_W * GEMV_NTEAM;  // consumer warps
 constexpr int GEMV_THREADS = GEMV_NW * 32;        // no producer warp: the last consumer of a stage issues its refill
-constexpr int GEMV_NSTAGE = 4;
+constexpr int GEMV_NSTAGE = 3;                    // 3 x 46 KB: leaves ~50 KB of the SM for the small kernels to co-reside (PDL)
 constexpr int GEMV_STAGE_BYTES = 46 * 1024;       // 8 rows of Q4_K/Q5_K or 7 rows of Q6_K @ K=8192; 2 rows @ K=28672 (47 040 B + 16)
 constexpr int GEMV_ACT_MAX_NBLK = 112;            // K <= 28 672 on the fast path
 constexpr int GEMV_ACT_SMEM = GEMV_ACT_MAX_NBLK * (ACT_SMEM_QS_STRIDE + 2 * ACT_SMEM_BS_STRIDE + 4) + 64;   // padded qs | padded bsums | d
@@ -74,6 +74,7 @@ struct GemvParams {
     const uint8_t * next_W;
     int64_t next_total_bytes;
     uint32_t next_tile_bytes;
+    int fill_before_wait;   // start the weight stream before griddepcontrol.wait (launches that follow a SMALL kernel)
 };
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -26,6 +26,9 @@ struct GemvFused {       // fused activation prologue of the k-quant GEMV (PRO_*
     const void * next_W = nullptr;
     int64_t next_total_bytes = 0;
     uint32_t next_tile_bytes = 0;
+    // this launch follows a small kernel (attention, silu-quant): with PDL its CTAs are resident while that kernel runs, so
+    // the ring is filled BEFORE griddepcontrol.wait and the first ~20 MB of weights stream during the predecessor
+    bool fill_before_wait = false;
 };
 uint32_t gemv_tile_bytes(int type, int K, int N);
 
