@@ -66,6 +66,8 @@ PB200_API int pb200_mul_mat_vec_host(int type, const void * W_dev, int64_t n, in
 
 /* debugging: k_gemv_kquant writes 8 %globaltimer stamps per CTA into dev_buf (u64[grid*8]); NULL disables */
 PB200_API int pb200_debug_set_trace(void * dev_buf);
+/* the in-kernel watchdog never lets a wait spin forever: it gives up after ~0.3 s and records {magic, cta, thread, iteration, parity|token, barrier} */
+PB200_API int pb200_debug_hang_info(unsigned long long * out8);
 
 PB200_API int pb200_rms_norm(const float * x, float * y, int64_t n, int64_t nrows, float eps, void * stream);
 PB200_API int pb200_rope(const float * x, float * y, int64_t n_tokens, int n_head, int head_dim, int n_dims, int mode, const int32_t * pos,

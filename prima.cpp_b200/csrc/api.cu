@@ -120,6 +120,7 @@ int pb200_mul_mat_vec_host(int type, const void * W_dev, int64_t n, int64_t k, c
     return 0;
 }
 
+int pb200_debug_hang_info(unsigned long long * out8) { return gemv_hang_info(out8); }
 int pb200_debug_set_trace(void * dev_buf) { return gemv_set_trace((unsigned long long *) dev_buf); }
 
 int pb200_rms_norm(const float * x, float * y, int64_t n, int64_t nrows, float eps, void * stream) {

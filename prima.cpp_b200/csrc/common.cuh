@@ -115,18 +115,33 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t * bar, uint32_t b
 __device__ __forceinline__ void mbar_arrive(uint64_t * bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t * bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
+// Spin with a watchdog: a logic error must surface as a trap with a diagnostic, never as a hung GPU.
+__device__ unsigned long long g_hang_info[32];
+__device__ const volatile int * g_hang_dump_src = nullptr;   // unused; the per-CTA dump goes through a smem pointer passed by the caller
+__device__ __forceinline__ void mbar_wait(uint64_t * bar, uint32_t parity, int tag = 0, const volatile int * dump = nullptr) {
+    const long long t0 = clock64();
+    while (true) {
+        uint32_t ok;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (ok) return;
+        if (clock64() - t0 > (1ll << 29)) {
+            // give up (results are garbage, the launch still terminates) and leave a diagnostic for pb200_debug_hang_info
+            if (atomicCAS(&g_hang_info[0], 0ull, 0xdead0001ull) == 0ull) {
+                g_hang_info[1] = blockIdx.x; g_hang_info[2] = threadIdx.x; g_hang_info[3] = (unsigned long long) tag;
+                g_hang_info[4] = parity; g_hang_info[5] = smem_u32(bar);
+                if (dump) for (int i = 0; i < 24; i++) g_hang_info[8 + i] = (unsigned long long) (long long) dump[i];
+            }
+            return;
+        }
+    }
 }
 // token flavour: the arriving thread gets the phase token and can wait for that phase without tracking a parity bit
 __device__ __forceinline__ uint64_t mbar_arrive_token(uint64_t * bar) {
@@ -134,18 +149,28 @@ __device__ __forceinline__ uint64_t mbar_arrive_token(uint64_t * bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 %0, [%1];" : "=l"(st) : "r"(smem_u32(bar)) : "memory");
     return st;
 }
-__device__ __forceinline__ void mbar_wait_token(uint64_t * bar, uint64_t token) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAITT_%=:\n"
-        "mbarrier.try_wait.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONET_%=;\n"
-        "bra WAITT_%=;\n"
-        "DONET_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "l"(token)
-        : "memory");
+__device__ __forceinline__ void mbar_wait_token(uint64_t * bar, uint64_t token, int tag = 0) {
+    const long long t0 = clock64();
+    while (true) {
+        uint32_t ok;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "l"(token)
+            : "memory");
+        if (ok) return;
+        if (clock64() - t0 > (1ll << 29)) {
+            if (atomicCAS(&g_hang_info[0], 0ull, 0xdead0002ull) == 0ull) {
+                g_hang_info[1] = blockIdx.x; g_hang_info[2] = threadIdx.x; g_hang_info[3] = (unsigned long long) tag;
+                g_hang_info[4] = token; g_hang_info[5] = smem_u32(bar);
+            }
+            return;
+        }
+    }
 }
 // L2 eviction policy for streamed-once weights
 __device__ __forceinline__ uint64_t policy_evict_first() {

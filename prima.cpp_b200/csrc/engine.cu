@@ -28,6 +28,24 @@ std::atomic<uint64_t> g_launches{0};
         if (_e != 0) return _e;                   \
     } while (0)
 
+static int dbg_sync(cudaStream_t st, const char * what) {
+    static const bool on = getenv("PB200_DEBUG_SYNC") != nullptr;
+    if (!on) return 0;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cs);
+    if (cs != cudaStreamCaptureStatusNone) return 0;
+    fprintf(stderr, "[pb200] launched %s ... ", what);
+    fflush(stderr);
+    cudaError_t e = cudaStreamSynchronize(st);
+    fprintf(stderr, "%s\n", cudaGetErrorString(e));
+    if (e != cudaSuccess) {
+        unsigned long long h[32] = {0};
+        gemv_hang_info(h);
+        fprintf(stderr, "[pb200] watchdog: magic %llx cta %llu thread %llu it %llu parity %llu bar %llx\n", h[0], h[1], h[2], h[3], h[4], h[5]);
+    }
+    return (int) e;
+}
+
 namespace {
 
 struct Tensor {
@@ -346,7 +364,7 @@ static int enqueue_step(pb200_model * m, uint64_t * nlaunch) {
     const int32_t * tok_dev = m->tokpos_dev, * pos_dev = m->tokpos_dev + 1;
     float * x = m->x_in;
     if (m->with_embd) {
-        CK(launch_get_rows(m->tok_embd.data, m->tok_embd.type, E, tok_dev, 1, m->x_a, st, pdl)); n++;
+        CK(launch_get_rows(m->tok_embd.data, m->tok_embd.type, E, tok_dev, 1, m->x_a, st, pdl)); n++; CK(dbg_sync(st, "get_rows"));
         x = m->x_a;
     }
     if (m->use_mk && m->mk && !m->profiling) {
@@ -376,7 +394,7 @@ static int enqueue_step(pb200_model * m, uint64_t * nlaunch) {
             GemvFused pro; pro.kind = 1; pro.in0 = x; pro.in1 = L.attn_norm; pro.eps = hp.rms_eps;
             set_next(pro, L.wo, QD);
             CK(prof_begin(m, tbytes(L.wq) + tbytes(L.wk) + tbytes(L.wv)));
-            CK(launch_gemv_kquant_fused(d, 3, E, m->actE.q, pro, st, pdl)); n++;
+            CK(launch_gemv_kquant_fused(d, 3, E, m->actE.q, pro, st, pdl)); n++; CK(dbg_sync(st, "gemv qkv"));
             CK(prof_end(m));
         } else {
             ActQ none{};
@@ -390,7 +408,7 @@ static int enqueue_step(pb200_model * m, uint64_t * nlaunch) {
                 CK(launch_gemv(&d1, 1, E, m->actE.q, st, pdl)); n++;
             }
         }
-        CK(launch_attn_fused(m->q, m->k, m->v, kc, vc, m->att, H, HK, D, pos_dev, hp.n_ctx, m->rp, m->rope_ff, kq_scale, st, pdl)); n++;
+        CK(launch_attn_fused(m->q, m->k, m->v, kc, vc, m->att, H, HK, D, pos_dev, hp.n_ctx, m->rp, m->rope_ff, kq_scale, st, pdl)); n++; CK(dbg_sync(st, "attn"));
         {
             GemvDesc d1 = {L.wo.data, x1, nullptr, x, L.wo.type, E};   // ffn_inp = wo.att + inpSA
             CK(prof_begin(m, tbytes(L.wo)));
@@ -398,7 +416,7 @@ static int enqueue_step(pb200_model * m, uint64_t * nlaunch) {
                 GemvFused pro; pro.kind = 2; pro.in0 = m->att;
                 pro.fill_before_wait = pdl;   // follows the attention kernel
                 set_next(pro, L.gate, E);
-                CK(launch_gemv_kquant_fused(&d1, 1, QD, m->actQD.q, pro, st, pdl)); n++;
+                CK(launch_gemv_kquant_fused(&d1, 1, QD, m->actQD.q, pro, st, pdl)); n++; CK(dbg_sync(st, "gemv wo"));
             } else {
                 CK(launch_quantize_act(m->att, QD, act_mode_for(L.wo.type), m->actQD.q, st, pdl)); n++;
                 CK(launch_gemv(&d1, 1, QD, m->actQD.q, st, pdl)); n++;
@@ -412,7 +430,7 @@ static int enqueue_step(pb200_model * m, uint64_t * nlaunch) {
             GemvFused pro; pro.kind = 1; pro.in0 = x1; pro.in1 = L.ffn_norm; pro.eps = hp.rms_eps;
             set_next(pro, L.down, F);
             CK(prof_begin(m, tbytes(L.gate) + tbytes(L.up)));
-            CK(launch_gemv_kquant_fused(d, 2, E, m->actE.q, pro, st, pdl)); n++;
+            CK(launch_gemv_kquant_fused(d, 2, E, m->actE.q, pro, st, pdl)); n++; CK(dbg_sync(st, "gemv gate|up"));
             CK(prof_end(m));
         } else {
             ActQ none{};
@@ -434,13 +452,13 @@ static int enqueue_step(pb200_model * m, uint64_t * nlaunch) {
                 GemvFused pro; pro.kind = 3; pro.in0 = m->g; pro.in1 = m->u;
                 CK(launch_gemv_kquant_fused(&d1, 1, F, m->actF.q, pro, st, pdl)); n++;
             } else {
-                CK(launch_silu_mul_quant(m->g, m->u, F, act_mode_for(L.down.type), m->actF.q, nullptr, st, pdl)); n++;
+                CK(launch_silu_mul_quant(m->g, m->u, F, act_mode_for(L.down.type), m->actF.q, nullptr, st, pdl)); n++; CK(dbg_sync(st, "silu"));
                 if (is_kquant(L.down.type)) {
                     GemvFused pro;   // PRO_NONE; only carries the prefetch target: next layer's wq, or the lm_head after the last layer
                     pro.fill_before_wait = pdl;   // follows the silu-quant kernel
                     if (il + 1 < m->l1) set_next(pro, m->layers[il + 1 - m->l0].wq, E);
                     else if (m->with_head) set_next(pro, m->output, E);
-                    CK(launch_gemv_kquant_fused(&d1, 1, F, m->actF.q, pro, st, pdl)); n++;
+                    CK(launch_gemv_kquant_fused(&d1, 1, F, m->actF.q, pro, st, pdl)); n++; CK(dbg_sync(st, "gemv down"));
                 } else {
                     CK(launch_gemv(&d1, 1, F, m->actF.q, st, pdl)); n++;
                 }

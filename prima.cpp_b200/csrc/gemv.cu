@@ -18,6 +18,7 @@ __device__ __forceinline__ void trace(int k) {
         g_gemv_trace[blockIdx.x * 8 + k] = t;
     }
 }
+int gemv_hang_info(unsigned long long * out32) { return (int) cudaMemcpyFromSymbol(out32, g_hang_info, 256); }
 int gemv_set_trace(unsigned long long * dev_buf) { return (int) cudaMemcpyToSymbol(g_gemv_trace, &dev_buf, sizeof(dev_buf)); }
 
 struct __align__(16) GemvSmemCtl {
@@ -27,6 +28,8 @@ struct __align__(16) GemvSmemCtl {
     uint64_t pbar[GEMV_NSTAGE][4];        // wpr > 1: "partials of this stage's row are in shared memory" per warp group
     float part[GEMV_NSTAGE][GEMV_TEAM_W]; // cross-warp partial sums, one slot per stage in flight
     double red[GEMV_NW];                  // rms_norm partial sums of squares
+    int dbg[24];                          // [0..2] copies of cnt, [3..18] iteration each warp is in, [19..21] last refill iteration issued per stage
+    volatile int issued[4];               // highest iteration whose tile has been REQUESTED for the stage (-1: none)
 };
 constexpr int GEMV_CTL_BYTES = 512;
 
@@ -134,12 +137,17 @@ __device__ __forceinline__ void issue_tile(const GemvParams & P, GemvSmemCtl * c
 // called by lane 0 of a consumer warp when the warp no longer needs stage s (iteration it)
 __device__ __forceinline__ void release_stage(const GemvParams & P, GemvSmemCtl * ctl, uint8_t * stages, int s, int it, uint64_t pol) {
     __threadfence_block();
-    if (atomicAdd(&ctl->cnt[s], 1) == GEMV_TEAM_W - 1) {
+    const int old = atomicAdd(&ctl->cnt[s], 1);
+    ctl->dbg[s] = old + 1;
+    if (old == GEMV_TEAM_W - 1) {
         ctl->cnt[s] = 0;
+        ctl->dbg[19 + s] = it + GEMV_NSTAGE;
         const int t = blockIdx.x + (it + GEMV_NSTAGE) * gridDim.x;
         if (t < P.ntiles) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy reads of the stage before the async-proxy refill
             issue_tile(P, ctl, stages, s, t, pol);
+            __threadfence_block();
+            ctl->issued[s] = it + GEMV_NSTAGE;
         } else if (P.next_W) {
             // nothing left to stream for this stage: keep the memory pipe busy with the next launch's first tiles
             const int n_my = (P.ntiles - (int) blockIdx.x + (int) gridDim.x - 1) / (int) gridDim.x;
@@ -171,6 +179,7 @@ __global__ void __maxnreg__(104) k_gemv_kquant(const __grid_constant__ GemvParam
         for (int s = 0; s < GEMV_NSTAGE; s++) {
             mbar_init(&ctl->full[s], 1);
             ctl->cnt[s] = 0;
+            ctl->issued[s] = -1;
 #pragma unroll
             for (int g = 0; g < 4; g++) mbar_init(&ctl->pbar[s][g], P.wpr > 1 ? P.wpr : 1);
         }
@@ -192,7 +201,7 @@ __global__ void __maxnreg__(104) k_gemv_kquant(const __grid_constant__ GemvParam
 #pragma unroll
         for (int it = 0; it < GEMV_NSTAGE; it++) {
             const int t = blockIdx.x + it * gridDim.x;
-            if (t < P.ntiles) issue_tile(P, ctl, stages, it, t, pol);
+            if (t < P.ntiles) { issue_tile(P, ctl, stages, it, t, pol); ctl->issued[it] = it; }
         }
     }
     pdl_wait();      // the activation is produced by the previous kernel in the stream
@@ -229,7 +238,7 @@ __global__ void __maxnreg__(104) k_gemv_kquant(const __grid_constant__ GemvParam
 #pragma unroll
         for (int it = 0; it < GEMV_NSTAGE; it++) {
             const int t = blockIdx.x + it * gridDim.x;
-            if (t < P.ntiles) issue_tile(P, ctl, stages, it, t, pol);
+            if (t < P.ntiles) { issue_tile(P, ctl, stages, it, t, pol); ctl->issued[it] = it; }
         }
     }
     trace(3);
@@ -260,7 +269,14 @@ __global__ void __maxnreg__(104) k_gemv_kquant(const __grid_constant__ GemvParam
         const int bpb = type == T_Q4_K ? BYTES_Q4_K : (type == T_Q5_K ? BYTES_Q5_K : BYTES_Q6_K);
         const uint32_t mis = (uint32_t) (((int64_t) r0 * M.row_bytes) & 15);
         const uint8_t * tile = stages + (size_t) s * GEMV_STAGE_BYTES + mis;
-        mbar_wait(&ctl->full[s], ph);
+        if (lane == 0) ctl->dbg[3 + warp] = it;
+        // With an odd ring depth the previous use of this stage belongs to the OTHER team: a parity wait alone could be
+        // satisfied by the phase before it (ABA).  First make sure this iteration's tile has been requested at all.
+        {
+            const long long w0 = clock64();
+            while (ctl->issued[s] < it) { if (clock64() - w0 > (1ll << 29)) break; }
+        }
+        mbar_wait(&ctl->full[s], ph, it, ctl->dbg);
         if (it == 0) trace(5);
         if (wpr == 1) {
             for (int slot = group; slot < nrows; slot += ngroups) {
@@ -323,7 +339,7 @@ __global__ void __maxnreg__(104) k_gemv_kquant(const __grid_constant__ GemvParam
                 uint64_t tok = 0;
                 if (lane == 0) tok = mbar_arrive_token(&ctl->pbar[s][group]);
                 tok = __shfl_sync(0xffffffffu, tok, 0);
-                mbar_wait_token(&ctl->pbar[s][group], tok);
+                mbar_wait_token(&ctl->pbar[s][group], tok, it);
                 if (lane == 0) {
                     float acc = v;
                     for (int i = 1; i < wpr; i++) acc += ctl->part[s][group * wpr + i];
@@ -422,6 +438,8 @@ __device__ __forceinline__ void mk_issue_iter(const MkParams & P, MkSmem * sm, u
     // phases g0 .. g0+2 are cached in shared memory; further look-ahead (only with very few tiles per phase) reads HBM
     const MkPhase * ph = g <= g0 + 2 ? &sm->desc[g & 3] : mk_phase(P, g);
     mk_issue(ph, &sm->ctl, stages, G % GEMV_NSTAGE, (int) blockIdx.x + (G - base) * (int) gridDim.x, pol);
+    __threadfence_block();
+    sm->ctl.issued[G % GEMV_NSTAGE] = G;
 }
 __device__ __forceinline__ void mk_load_desc(const MkParams & P, MkSmem * sm, int g, int n_phases) {
     if (g >= n_phases) return;
@@ -645,6 +663,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) k_token_persistent(const __gr
         for (int s = 0; s < GEMV_NSTAGE; s++) {
             mbar_init(&ctl->full[s], 1);
             ctl->cnt[s] = 0;
+            ctl->issued[s] = -1;
 #pragma unroll
             for (int gI = 0; gI < 4; gI++) mbar_init(&ctl->pbar[s][gI], wpr_split > 1 ? wpr_split : 1);
         }
@@ -756,7 +775,11 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) k_token_persistent(const __gr
             const int bpb = type == T_Q4_K ? BYTES_Q4_K : (type == T_Q5_K ? BYTES_Q5_K : BYTES_Q6_K);
             const uint32_t mis = (uint32_t) (((int64_t) r0 * M.row_bytes) & 15);
             const uint8_t * tile = stages + (size_t) s * GEMV_STAGE_BYTES + mis;
-            mbar_wait(&ctl->full[s], ph);
+            {
+                const long long w0 = clock64();
+                while (ctl->issued[s] < G) { if (clock64() - w0 > (1ll << 29)) break; }
+            }
+            mbar_wait(&ctl->full[s], ph, G);
             if (wpr == 1) {
                 for (int slot = group; slot < nrows; slot += ngroups) {
                     const int row = r0 + slot;

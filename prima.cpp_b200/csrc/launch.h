@@ -33,7 +33,8 @@ struct GemvFused {       // fused activation prologue of the k-quant GEMV (PRO_*
 uint32_t gemv_tile_bytes(int type, int K, int N);
 
 int sm_count();
-int gemv_set_trace(unsigned long long * dev_buf);   // debugging: per-CTA %globaltimer stamps of k_gemv_kquant
+int gemv_set_trace(unsigned long long * dev_buf);
+int gemv_hang_info(unsigned long long * out8);   // diagnostic written by the mbarrier watchdog before it traps   // debugging: per-CTA %globaltimer stamps of k_gemv_kquant
 int gemv_smem_bytes();
 
 // y_i = W_i . act  for up to 3 k-quant matrices sharing one q8_K activation (TMA-staged persistent kernel)

@@ -215,7 +215,8 @@ def test_full_size_gemv_properties(cuda, lib):
     dequantized weights (get_rows kernel, bit-exact vs the oracle above) times the dequantized q8_K activation in fp64."""
     import gpu_util
     # N large enough that every CTA streams > 4 tiles: exercises the mbarrier ring wrap-around and both parities
-    for t, N, K in ((O.Q4_K, 8192, 8192), (O.Q6_K, 6000, 8192), (O.Q5_K, 6100, 8192), (O.Q4_K, 2500, 28672), (O.Q6_K, 2200, 28672)):
+    for t, N, K in ((O.Q4_K, 8192, 8192), (O.Q6_K, 6000, 8192), (O.Q5_K, 6100, 8192), (O.Q4_K, 2500, 28672), (O.Q6_K, 2200, 28672),
+                    (O.Q6_K, 8192, 28672)):   # 28 tiles per CTA with split rows: caught an mbarrier parity ABA of the 3-stage ring
         W = O.synth_blocks(t, N, K, seed=K + N + t)
         x = np.random.default_rng(t).standard_normal(K).astype(np.float32)
         Wd, xd, ws = dev_u8(W), dev_f32(x), act_ws(lib, K)
