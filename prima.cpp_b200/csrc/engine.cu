@@ -414,7 +414,7 @@ static int enqueue_step(pb200_model * m, uint64_t * nlaunch) {
             CK(prof_begin(m, tbytes(L.wo)));
             if (is_kquant(L.wo.type) && gemv_fused_prologue_ok(QD)) {
                 GemvFused pro; pro.kind = 2; pro.in0 = m->att;
-                pro.fill_before_wait = pdl;   // follows the attention kernel
+                pro.fill_before_wait = pdl && gemv_smem_bytes() < 200 * 1024;   // follows the attention kernel; only pays when both kernels fit on an SM
                 set_next(pro, L.gate, E);
                 CK(launch_gemv_kquant_fused(&d1, 1, QD, m->actQD.q, pro, st, pdl)); n++; CK(dbg_sync(st, "gemv wo"));
             } else {
@@ -455,7 +455,7 @@ static int enqueue_step(pb200_model * m, uint64_t * nlaunch) {
                 CK(launch_silu_mul_quant(m->g, m->u, F, act_mode_for(L.down.type), m->actF.q, nullptr, st, pdl)); n++; CK(dbg_sync(st, "silu"));
                 if (is_kquant(L.down.type)) {
                     GemvFused pro;   // PRO_NONE; only carries the prefetch target: next layer's wq, or the lm_head after the last layer
-                    pro.fill_before_wait = pdl;   // follows the silu-quant kernel
+                    pro.fill_before_wait = pdl && gemv_smem_bytes() < 200 * 1024;   // follows the silu-quant kernel
                     if (il + 1 < m->l1) set_next(pro, m->layers[il + 1 - m->l0].wq, E);
                     else if (m->with_head) set_next(pro, m->output, E);
                     CK(launch_gemv_kquant_fused(&d1, 1, F, m->actF.q, pro, st, pdl)); n++; CK(dbg_sync(st, "gemv down"));

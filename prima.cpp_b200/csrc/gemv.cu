@@ -164,7 +164,7 @@ __device__ __forceinline__ void release_stage(const GemvParams & P, GemvSmemCtl 
     }
 }
 
-__global__ void __maxnreg__(104) k_gemv_kquant(const __grid_constant__ GemvParams P) {
+__global__ void __launch_bounds__(GEMV_THREADS, 1) k_gemv_kquant(const __grid_constant__ GemvParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
     GemvSmemCtl * ctl = reinterpret_cast<GemvSmemCtl *>(smem);
     uint8_t * stages = smem + GEMV_CTL_BYTES;

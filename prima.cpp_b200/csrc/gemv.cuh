@@ -29,7 +29,8 @@ constexpr int GEMV_NTEAM = 2;                     // teams alternate stages: tea
                                                   // per-stage latency budget, 4 warps per scheduler instead of 2
 constexpr int GEMV_NW = GEMV_TEAM_W * GEMV_NTEAM;  // consumer warps
 constexpr int GEMV_THREADS = GEMV_NW * 32;        // no producer warp: the last consumer of a stage issues its refill
-constexpr int GEMV_NSTAGE = 3;                    // 3 x 46 KB: leaves ~50 KB of the SM for the small kernels to co-reside (PDL)
+constexpr int GEMV_NSTAGE = 4;                    // measured: 4 x 46 KB at 128 regs (9.90 ms/token) beats 3 stages at 104 regs with the small
+                                                  // kernels co-resident under PDL (10.09 ms); the ring logic is depth-agnostic
 constexpr int GEMV_STAGE_BYTES = 46 * 1024;       // 8 rows of Q4_K/Q5_K or 7 rows of Q6_K @ K=8192; 2 rows @ K=28672 (47 040 B + 16)
 constexpr int GEMV_ACT_MAX_NBLK = 112;            // K <= 28 672 on the fast path
 constexpr int GEMV_ACT_SMEM = GEMV_ACT_MAX_NBLK * (ACT_SMEM_QS_STRIDE + 2 * ACT_SMEM_BS_STRIDE + 4) + 64;   // padded qs | padded bsums | d
