@@ -31,7 +31,7 @@ struct __align__(16) GemvSmemCtl {
     int dbg[24];                          // [0..2] copies of cnt, [3..18] iteration each warp is in, [19..21] last refill iteration issued per stage
     volatile int issued[4];               // highest iteration whose tile has been REQUESTED for the stage (-1: none)
 };
-constexpr int GEMV_CTL_BYTES = 512;
+constexpr int GEMV_CTL_BYTES = 768;
 
 __device__ __forceinline__ void consumer_bar() {   // the 8 consumer warps only (the producer warp never joins)
     asm volatile("bar.sync 9, %0;" ::"n"(GEMV_NW * 32) : "memory");
@@ -400,7 +400,7 @@ struct __align__(16) MkSmem {
     int deferred[GEMV_NSTAGE];         // global iterations whose refill waits until the next prologue's loads are out
 };
 constexpr int MK_XB_ALLOWED = GEMV_NSTAGE;   // measured: deferring buys nothing (the prologue was slow for another reason), keep the ring primed       // stages prefetched across a phase boundary before the prologue (one per team)
-constexpr int MK_HDR_BYTES = 3072;
+constexpr int MK_HDR_BYTES = 3328;
 static_assert(sizeof(MkSmem) <= MK_HDR_BYTES, "MkSmem header");
 
 __device__ __forceinline__ const MkPhase * mk_phase(const MkParams & P, int g) {
