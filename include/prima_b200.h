@@ -16,6 +16,8 @@
  *   pb200_soft_max          ggml_cuda_op_soft_max softmax.cu:170-206; CPU ggml.c:13783-13880
  *   pb200_attn_decode       FA-off attention chain: ggml_cuda_mul_mat_batched_cublas x2 + soft_max + cont,
  *                           ggml-cuda.cu:1737-1881; graph src/llama.cpp:10032-10165
+ *   pb200_mul_mat_q         ggml_cuda_op_mul_mat_q mmq.cu:3-98 -> mul_mat_q<type,...> mmq.cuh:2583-2650 (+ quantize_mmq_q8_1_cuda
+ *                           quantize.cu:143-169): the batched / prefill product, here on tcgen05 + TMEM
  *   pb200_get_rows          ggml_cuda_op_get_rows getrows.cu (k-quant rows are unsupported there, ggml-cuda.cu:3033-3047)
  *   pb200_model_* / pb200_decode*   the per-token loop ggml_backend_cuda_graph_compute ggml-cuda.cu:2508-2778 over the
  *                           graph of build_llama / build_qwen2 (src/llama.cpp:11000-11216, 12736-12916) — one fused,
@@ -84,6 +86,14 @@ PB200_API int pb200_copy_strided(const void * src_f32, void * dst, int dst_is_f1
 /* d[i0,i1,i2,i3] = sum_k a_f16[k,i0,i2/r2,i3/r3] * f16(b[k,i1,i2,i3]) — the FA-off KQ / KQV products (ggml-cuda.cu:1737-1881), byte strides */
 PB200_API int pb200_mul_mat_f16(const void * a_f16, const float * b_f32, float * d, int64_t k, const int64_t * ne, int64_t r2, int64_t r3,
                                 const int64_t * a_strides, const int64_t * b_strides, const int64_t * d_strides, void * stream);
+/* batched (prefill) product: dst[t][n] = sum_k W[n][k] * x[t][k] (+ bias[n]); W: n rows of k-quant blocks (Q4_K/Q5_K/Q6_K,
+ * k % 256 == 0), x: t rows of ldx floats, dst: t rows of n floats.  Activations are quantized to q8_K like the CPU backend,
+ * then both operands run as fp16 on the tensor cores with fp32 accumulation.  ws: pb200_mul_mat_q_workspace_bytes(k, t). */
+PB200_API size_t pb200_mul_mat_q_workspace_bytes(int64_t k, int64_t t);
+PB200_API int pb200_mul_mat_q(int type, const void * W, int64_t n, int64_t k, const float * x, int64_t ldx, int64_t t, float * dst,
+                              const float * bias, void * ws, void * stream);
+/* 1 if any pb200_mul_mat_q launch gave up on a stuck pipeline (results invalid); sticky, debugging aid */
+PB200_API int pb200_mul_mat_q_aborted(void);
 PB200_API int pb200_get_rows(int type, const void * table, int64_t k, const int32_t * ids, int64_t n_ids, float * y, void * stream);
 /* decode attention over an f16 KV cache laid out [n_ctx][n_head_kv*head_dim]; n_kv = *pos_dev + 1 */
 PB200_API int pb200_attn_decode(const float * q, const void * k_cache_f16, const void * v_cache_f16, float * out, int n_head, int n_head_kv,

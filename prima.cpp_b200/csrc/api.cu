@@ -181,6 +181,16 @@ int pb200_mul_mat_f16(const void * a_f16, const float * b_f32, float * d, int64_
     return launch_mul_mat_f16(a_f16, b_f32, d, k, ne, r2, r3, a_strides, b_strides, d_strides, (cudaStream_t) stream);
 }
 
+size_t pb200_mul_mat_q_workspace_bytes(int64_t k, int64_t t) { return (k > 0 && t > 0) ? mmq_workspace_bytes(k, t) : 0; }
+int pb200_mul_mat_q(int type, const void * W, int64_t n, int64_t k, const float * x, int64_t ldx, int64_t t, float * dst, const float * bias, void * ws,
+                    void * stream) {
+    if (!W || !x || !dst || !ws || n <= 0 || t <= 0 || ldx < k) return PB200_EINVAL;
+    if (!mmq_supported(type, k)) return PB200_ENOTSUP;
+    g_launches += 2;
+    return (int) launch_mmq(type, W, n, k, x, ldx, t, dst, bias, ws, (cudaStream_t) stream);
+}
+int pb200_mul_mat_q_aborted(void) { return mmq_aborted(); }
+
 int pb200_get_rows(int type, const void * table, int64_t k, const int32_t * ids, int64_t n_ids, float * y, void * stream) {
     if (!table || !ids || !y || k <= 0 || n_ids <= 0) return PB200_EINVAL;
     if (!(type_ok(type) || type == T_F32 || type == T_F16)) return PB200_ENOTSUP;

@@ -506,6 +506,13 @@ __device__ __forceinline__ void mk_trace2(int g, int k) {
         g_gemv_trace[148 * 16 + blockIdx.x * 16 + (g == 4 ? 0 : 8) + k] = t;
     }
 }
+__device__ __forceinline__ void mk_trace3(int slot) {
+    if (g_gemv_trace && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_gemv_trace[148 * 16 + blockIdx.x * 16 + slot] = t;
+    }
+}
 __device__ __forceinline__ void bar256() { asm volatile("bar.sync 10, 256;" ::: "memory"); }
 
 // RoPE + KV store + attention for q head h by warps 0..7 (256 threads); same arithmetic as k_attn_fused (ops.cu)
@@ -688,11 +695,15 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) k_token_persistent(const __gr
     for (int g = 0; g < n_phases; g++) {
         const int li = g >> 2, pi = g < 4 * P.n_layers ? (g & 3) : 4;
         // ---------------- dependencies of this phase ----------------
+        if (g == 5) mk_trace3(5);
         if (g > 0) mk_grid_barrier(P, bar_idx);                       // previous GEMV phase complete everywhere
+        if (g == 5) mk_trace3(6);
         if (pi == 1) {                                                // wo needs the attention output
             const MkLayer & L = P.layers[li];
             if ((int) blockIdx.x < P.n_head && warp < 8) mk_attention(P, L, blockIdx.x, reinterpret_cast<float *>(act_smem), warp, lane);
+            if (g == 5) mk_trace3(7);
             mk_grid_barrier(P, bar_idx);
+            if (g == 5) mk_trace3(13);
         } else if (pi == 3) {                                         // ffn_down needs silu(g)*u quantized
             const MkLayer & L = P.layers[li];
             const int b = blockIdx.x;

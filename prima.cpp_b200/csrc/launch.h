@@ -107,6 +107,12 @@ int launch_soft_max(const float * x, const float * mask, float * y, int ncols, i
                     cudaStream_t stream);
 
 // get_rows on a quantized / f16 / f32 table: y[i][:] = dequant(table[ids[i]])   (getrows.cu; ggml.c get_rows_q)
+// batched k-quant mat-mul on tcgen05 (mmq.cu): dst[T][N] = X[T][K] . W[N][K]^T (+ bias[N]); ws from mmq_workspace_bytes
+size_t mmq_workspace_bytes(int64_t K, int64_t T);
+bool mmq_supported(int type, int64_t K);
+int mmq_aborted();
+cudaError_t launch_mmq(int type, const void * W, int64_t N, int64_t K, const float * x, int64_t ldx, int64_t T, float * dst, const float * bias,
+                       void * ws, cudaStream_t st);
 int launch_get_rows(const void * table, int type, int K, const int32_t * ids, int n_ids, float * y, cudaStream_t stream, bool pdl);
 
 // element-wise helpers for the plugin

@@ -1,0 +1,123 @@
+"""-m gpu: the batched (prefill) k-quant product pb200_mul_mat_q — tcgen05 tensor cores — against the CPU oracle.
+
+Numerics bar (floating point, stated here): the kernel quantizes every activation row to q8_K exactly as the CPU backend
+does, expands the weights with the reference's dequantization formulas, rounds BOTH operands to fp16 and accumulates in
+fp32 on the tensor pipe.  Versus the oracle's integer dot products that leaves two fp16 roundings per product:
+    |err[t,n]| <= 2^-10 * sum_k |W[n,k]| * |x_q[t,k]|      (checked element-wise, rigorous bound + fp32 summation slack)
+    NMSE <= 1e-6                                          (the reference's own MUL_MAT bar is 5e-4, test-backend-ops.cpp:1639)
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import oracle_lib as O
+from gpu_util import dev_f32, dev_u8, ptr, sync
+
+pytestmark = pytest.mark.gpu
+KQ = [O.Q4_K, O.Q5_K, O.Q6_K]
+
+
+def run_mmq(lib, t, W, N, K, X, bias=None, ldx=None):
+    T = X.shape[0]
+    ldx = ldx or K
+    Xp = np.zeros((T, ldx), np.float32)
+    Xp[:, :K] = X
+    Wd, xd = dev_u8(W), dev_f32(Xp)
+    y = torch.full((T, N), float("nan"), dtype=torch.float32, device="cuda")
+    ws = torch.zeros(lib.c.pb200_mul_mat_q_workspace_bytes(K, T) + 64, dtype=torch.uint8, device="cuda")
+    bd = dev_f32(bias) if bias is not None else None
+    lib.check(lib.c.pb200_mul_mat_q(t, ptr(Wd), N, K, ptr(xd), ldx, T, ptr(y), ptr(bd) if bd is not None else None, ptr(ws), None), "mul_mat_q")
+    sync()
+    assert lib.c.pb200_mul_mat_q_aborted() == 0, "tcgen05 pipeline gave up (watchdog)"
+    return y.cpu().numpy()
+
+
+def oracle(port, t, W, N, K, X):
+    return np.stack([port.mul_mat(t, W, N, K, X[i]).reshape(-1) for i in range(X.shape[0])])
+
+
+def check(got, want, Wf, X):
+    assert np.isfinite(got).all()
+    err = np.abs(got - want)
+    bound = 2.0 ** -10 * (np.abs(X) @ np.abs(Wf).T) * 1.05 + 1e-6
+    assert (err <= bound).all(), f"max err {err.max():.3e} exceeds the two-roundings bound (worst ratio {(err / bound).max():.2f})"
+    nmse = float(np.sum((got - want) ** 2) / max(np.sum(want ** 2), 1e-30))
+    assert nmse <= 1e-6, f"NMSE {nmse:.3e}"
+
+
+@pytest.mark.parametrize("t", KQ, ids=lambda t: O.TYPE_NAME[t])
+@pytest.mark.parametrize("N,K,T", [(128, 256, 16), (256, 512, 33), (384, 1024, 128), (200, 768, 7), (128, 2048, 300)])
+def test_mmq_vs_oracle(cuda, lib, port, t, N, K, T):
+    rng = np.random.default_rng(1000 * t + N + K + T)
+    W = O.synth_blocks(t, N, K, seed=17 * t + N)
+    X = rng.standard_normal((T, K)).astype(np.float32)
+    X[0] = 0.0                      # an all-zero row quantizes to d = 0
+    if T > 2:
+        X[2] *= 1e-3
+    got = run_mmq(lib, t, W, N, K, X)
+    want = oracle(port, t, W, N, K, X)
+    Wf = port.dequantize(t, W, N * K).reshape(N, K)
+    check(got, want, Wf, X)
+    assert np.all(got[0] == 0.0)
+
+
+def test_mmq_integer_exact(cuda, lib, port):
+    """Small-integer activations and Q4_K blocks whose scales make every weight an exact fp16 integer: the tensor-core
+    result must then equal the oracle bit for bit (a layout / swizzle / descriptor error cannot hide behind a tolerance)."""
+    N, K, T = 256, 1024, 64
+    rng = np.random.default_rng(5)
+    nb = N * K // 256
+    blk = np.zeros((nb, 144), np.uint8)
+    blk[:, 0:2] = np.array([1.0], np.float16).view(np.uint8)        # d = 1
+    blk[:, 2:4] = np.array([1.0], np.float16).view(np.uint8)        # dmin = 1
+    sc = rng.integers(1, 4, size=(nb, 8)).astype(np.uint8)          # 6-bit scales 1..3, mins 0..7 (j < 4 and j >= 4 packing)
+    mn = rng.integers(0, 8, size=(nb, 8)).astype(np.uint8)
+    s12 = np.zeros((nb, 12), np.uint8)
+    s12[:, 0:4] = sc[:, 0:4]
+    s12[:, 4:8] = mn[:, 0:4]
+    s12[:, 8:12] = (sc[:, 4:8] & 0xF) | ((mn[:, 4:8] & 0xF) << 4)
+    blk[:, 4:16] = s12
+    blk[:, 16:] = rng.integers(0, 256, size=(nb, 128)).astype(np.uint8)
+    W = blk.reshape(-1)
+    # activations: integers in [-127, 127] with the extreme present in every 256-block, so q8_K reproduces them exactly
+    X = rng.integers(-20, 21, size=(T, K)).astype(np.float32)
+    X[:, ::256] = -127.0
+    got = run_mmq(lib, O.Q4_K, W, N, K, X)
+    want = oracle(port, O.Q4_K, W, N, K, X)
+    assert np.array_equal(got, want)
+
+
+def test_mmq_bias_ragged_rows_and_strided_input(cuda, lib, port):
+    t, N, K, T = O.Q6_K, 200, 512, 40        # N not a multiple of the 128-row tile, ldx > K
+    rng = np.random.default_rng(9)
+    W = O.synth_blocks(t, N, K, seed=3)
+    X = rng.standard_normal((T, K)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    got = run_mmq(lib, t, W, N, K, X, bias=bias, ldx=K + 64)
+    want = oracle(port, t, W, N, K, X) + bias[None, :]
+    Wf = port.dequantize(t, W, N * K).reshape(N, K)
+    check(got, want, Wf, X)
+
+
+def test_mmq_matches_gemv_columnwise_full_width(cuda, lib):
+    """Size-independent property at a 70B shape: every column of the batched product agrees with the decode GEMV (which is
+    bit-exact with the oracle) within the two-roundings bound."""
+    t, N, K, T = O.Q4_K, 8192, 8192, 512
+    g = torch.Generator(device="cuda").manual_seed(1)
+    W = O.synth_blocks(t, 256, K, seed=11)                  # 256 distinct rows, tiled to N
+    Wfull = np.tile(W.reshape(256, -1), (N // 256, 1)).reshape(-1)
+    X = torch.randn((T, K), generator=g, device="cuda", dtype=torch.float32).cpu().numpy()
+    got = run_mmq(lib, t, Wfull, N, K, X)
+    assert np.array_equal(got[:, :256], got[:, 256:512])    # identical weight rows -> identical outputs
+    Wd = dev_u8(Wfull)
+    ws = torch.zeros(lib.c.pb200_act_workspace_bytes(K) + 64, dtype=torch.uint8, device="cuda")
+    for col in (0, 1, 255, 256, 511):
+        xd = dev_f32(X[col])
+        y = torch.zeros(N, dtype=torch.float32, device="cuda")
+        lib.check(lib.c.pb200_mul_mat_vec(t, ptr(Wd), N, K, ptr(xd), ptr(y), ptr(ws), None), "mul_mat_vec")
+        sync()
+        ref = y.cpu().numpy()
+        nmse = float(np.sum((got[col] - ref) ** 2) / np.sum(ref ** 2))
+        assert nmse <= 1e-6, f"column {col}: NMSE {nmse:.3e}"

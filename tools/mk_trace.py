@@ -41,3 +41,9 @@ for off, base_col, nm in ((0, 0, "qkv"), (8, 9, "down")):
             print(f"  {nm:5s} {what:26s} {col.min():7.2f} {np.median(col):7.2f} {col.max():7.2f}")
 col = (c - a[:, 12]) / 1e3
 print("  last rmsnorm prologue seen (next-layer qkv): sum-of-squares barrier passed at", np.median(col))
+
+print("attention block of layer 1 (rel. to qkv phase start): phase-4 done / barrier A passed / attention done / barrier B passed")
+for slot, nm in ((5, "qkv tiles done"), (6, "barrier A passed"), (7, "attention done (or skipped)"), (13, "barrier B passed")):
+    col = (b[:, slot] - a[:, 0].min()) / 1e3
+    attn = col[:64]; rest = col[64:]
+    print(f"  {nm:28s} attention CTAs {attn.min():7.2f} {np.median(attn):7.2f} {attn.max():7.2f} | other CTAs {rest.min():7.2f} {np.median(rest):7.2f} {rest.max():7.2f}")
