@@ -4,20 +4,24 @@
 // tiles with __syncthreads ping-pong) and quantize_mmq_q8_1_cuda (quantize.cu:143-169), SURVEY §8 row a-4.
 // Numerics follow the CPU backend the oracle restates: every activation row is quantized to q8_K exactly as
 // quantize_row_q8_K_ref does (ggml-quants.c:3785-3822) and the weights are expanded with the dequantize_row_q{4,5,6}_K
-// formulas (ggml-quants.c:2040-2065, 2390-2420, 2690-2725); both are then rounded to fp16 and multiplied on the tensor
-// pipe with fp32 accumulation.  The result differs from the integer-dot CPU value only by those two fp16 roundings
-// (NMSE ~1e-7; tests/test_gpu_mmq.py states the bound).
+// formulas (ggml-quants.c:2040-2065, 2390-2420, 2690-2725) evaluated in fp16 (exact integer q, fp16 sub-block scale and
+// offset, one fused multiply-add); both operands are fp16 on the tensor pipe with fp32 accumulation.  The result differs
+// from the integer-dot CPU value by a few fp16 roundings per product (NMSE ~1e-6; tests/test_gpu_mmq.py states the bound).
 //
 //   dst[t][n] = sum_k W[n][k] * X[t][k]        W: N x K k-quant rows, X: T x K f32, dst: T x N f32 (ggml layout)
 //
-// One CTA owns a 128-row x BN-column tile of dst (BN <= 256 tokens) and walks K in 64-element steps:
-//   warp 0      producer: cp.async.bulk of the raw quantized blocks (one per row per 256-K super-block) into a 2-deep ring,
-//               and of the pre-tiled fp16 activation chunk (BN x 128 B, already in the UMMA swizzle-128B image) per step
-//   warp 1      owns TMEM; one lane issues 4 x tcgen05.mma (M=128, N=BN, K=16, kind::f16) per step and commits to mbarriers
-//   warps 2..9  expand 128 x 64 weights per step to fp16 straight into the swizzled A stage (generic-proxy stores +
-//               fence.proxy.async); afterwards warps 2..5 read the accumulator out of TMEM (tcgen05.ld 32x32b) and store dst
+// One CTA owns 128 weight rows x (1 or 2) token tiles of BN <= 256 columns — two accumulators (all 512 TMEM columns) share
+// every expanded weight stage when T is large enough — and walks K in 64-element steps:
+//   warp 0      owns TMEM; one lane issues 4 x tcgen05.mma (M=128, N=BN, K=16, kind::f16) per step and accumulator, one commit per step
+//   warp 1      activation producer: one cp.async.bulk per step of the pre-tiled fp16 chunk (BN x 128 B, already in the
+//               UMMA swizzle-128B image), 4-deep ring
+//   warps 2..9  fetch their own rows' raw quantized blocks (16-byte cp.async pieces, 3 super-blocks deep, completion through
+//               cp.async.mbarrier.arrive) and expand 128 x 64 weights per step to fp16 straight into the swizzled A stage (generic-proxy stores +
+//               fence.proxy.async), 2 stages; afterwards warps 2..5 read the accumulator out of TMEM (tcgen05.ld 32x32b) and store dst
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+
+#include <cstdlib>
 
 #include "common.cuh"
 #include "launch.h"
@@ -26,9 +30,11 @@ namespace pb {
 
 constexpr int MMQ_BM = 128;
 constexpr int MMQ_BK = 64;
-constexpr int MMQ_NSTAGE = 3;
+constexpr int MMQ_A_NST = 2;      // expanded-weight stages (filled by compute, no latency to hide)
+constexpr int MMQ_B_NST = 4;      // activation stages (L2 loads: the deep ring)
 constexpr int MMQ_DQ_WARPS = 8;
-constexpr int MMQ_THREADS = (2 + MMQ_DQ_WARPS) * 32;
+constexpr int MMQ_DQ_WARP0 = 2;   // warps 0,1 = MMA issuer (owns TMEM), activation producer
+constexpr int MMQ_THREADS = (MMQ_DQ_WARP0 + MMQ_DQ_WARPS) * 32;
 constexpr int MMQ_A_BYTES = MMQ_BM * 128;   // one A stage: 128 rows x 64 fp16
 constexpr int MMQ_CTL_BYTES = 256;
 
@@ -38,13 +44,16 @@ struct MmqParams {
     float * dst;           // [T][N]
     const float * bias;    // [N] or null
     int64_t row_bytes, total_bytes;
-    int type, N, K, T, BN, bpb, slot;   // slot: bytes reserved per row in a raw stage (16-B aligned window around one block)
+    int nraw, b_nst;       // ring depths chosen at launch from the shared-memory budget
+    int nacc, ttiles;      // accumulators (token tiles) per CTA, number of token tiles
+    int N, K, T, BN, bpb, slot;   // slot: bytes reserved per row in a raw stage (16-B aligned window around one block)
     uint32_t tmem_cols, idesc;
 };
 
 struct MmqCtl {
-    uint64_t raw_full[2], raw_empty[2];
-    uint64_t a_ready[MMQ_NSTAGE], b_full[MMQ_NSTAGE], stage_free[MMQ_NSTAGE];
+    uint64_t raw_full[3], raw_empty[3];
+    uint64_t a_ready[MMQ_A_NST], b_full[MMQ_B_NST];
+    uint64_t step_done[MMQ_B_NST];   // one tcgen05.commit per step: step u arrives on step_done[u % 4]; frees A stage u % 2 and B stage u % b_nst
     uint64_t acc_ready;
     uint32_t tmem_base;
     int abort;
@@ -68,6 +77,7 @@ __device__ __forceinline__ bool mmq_try(uint64_t * bar, uint32_t parity) {
 }
 // bounded wait: a broken pipeline must end the launch (and report through pb200_mmq_aborted), never hang the device
 __device__ __forceinline__ bool mmq_wait(MmqCtl * ctl, uint64_t * bar, uint32_t parity) {
+    if (mmq_try(bar, parity)) return true;          // the common case costs one try_wait
     const long long t0 = clock64();
     int spins = 0;
     while (!mmq_try(bar, parity)) {
@@ -125,101 +135,113 @@ __device__ __forceinline__ uint32_t lds32_u2(const uint8_t * p) {
 }
 
 // ---- weight expansion: thread (row, h) produces K elements [64c + 32h, 64c + 32h + 32) of its row as 16 half2 ----
-__device__ __forceinline__ void expand_q4K(const uint8_t * blk, int c, int h, uint32_t (&out)[16]) {
-    const float d = __half2float(*reinterpret_cast<const __half *>(blk));
-    const float dmin = __half2float(*reinterpret_cast<const __half *>(blk + 2));
-    const uint8_t * sc = blk + 4;
-    const int j = 2 * c + h;
-    int s, m;
-    if (j < 4) { s = sc[j] & 63; m = sc[j + 4] & 63; }
-    else { s = (sc[j + 4] & 0xF) | ((sc[j - 4] >> 6) << 4); m = (sc[j + 4] >> 4) | ((sc[j] >> 6) << 4); }
-    const float d1 = __fmul_rn(d, (float) s), m1 = __fmul_rn(dmin, (float) m);
-    const uint4 * q = reinterpret_cast<const uint4 *>(blk + 16 + 32 * c);
-    const uint4 qa = q[0], qb = q[1];
-    const uint32_t w[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        const uint32_t v = (w[i] >> (4 * h)) & 0x0F0F0F0Fu;
-        const float f0 = __fsub_rn(__fmul_rn(d1, (float) (v & 0xFF)), m1);
-        const float f1 = __fsub_rn(__fmul_rn(d1, (float) ((v >> 8) & 0xFF)), m1);
-        const float f2 = __fsub_rn(__fmul_rn(d1, (float) ((v >> 16) & 0xFF)), m1);
-        const float f3 = __fsub_rn(__fmul_rn(d1, (float) (v >> 24)), m1);
-        out[2 * i] = pack_h2(f0, f1);
-        out[2 * i + 1] = pack_h2(f2, f3);
-    }
+// The integer q of every weight is made an EXACT fp16 with the exponent trick (0x6400 | q == 1024 + q, minus 1024 + zero),
+// then one half2 FMA applies the sub-block scale and offset (both rounded to fp16).  A 32-bit word holds 4 consecutive-k
+// bytes; the two half2 come out as (k0,k2) and (k1,k3): the activation tiles use the same within-4 order (k_mmq_prep).
+__device__ __forceinline__ __half2 bits_h2(uint32_t v) { return *reinterpret_cast<__half2 *>(&v); }
+__device__ __forceinline__ uint32_t h2_bits(__half2 v) { return *reinterpret_cast<uint32_t *>(&v); }
+__device__ __forceinline__ uint32_t and_or(uint32_t a, uint32_t mask, uint32_t magic) {   // (a & mask) | magic in one LOP3
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "r"(mask), "r"(magic));
+    return d;
 }
-__device__ __forceinline__ void expand_q5K(const uint8_t * blk, int c, int h, uint32_t (&out)[16]) {
-    const float d = __half2float(*reinterpret_cast<const __half *>(blk));
-    const float dmin = __half2float(*reinterpret_cast<const __half *>(blk + 2));
-    const uint8_t * sc = blk + 4;
-    const int j = 2 * c + h;
-    int s, m;
-    if (j < 4) { s = sc[j] & 63; m = sc[j + 4] & 63; }
-    else { s = (sc[j + 4] & 0xF) | ((sc[j - 4] >> 6) << 4); m = (sc[j + 4] >> 4) | ((sc[j] >> 6) << 4); }
-    const float d1 = __fmul_rn(d, (float) s), m1 = __fmul_rn(dmin, (float) m);
-    const uint4 * qh4 = reinterpret_cast<const uint4 *>(blk + 16);
-    const uint4 * q = reinterpret_cast<const uint4 *>(blk + 48 + 32 * c);
-    const uint4 qa = q[0], qb = q[1], ha = qh4[0], hb = qh4[1];
-    const uint32_t w[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
-    const uint32_t hh[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        const uint32_t v = ((w[i] >> (4 * h)) & 0x0F0F0F0Fu) | (((hh[i] >> j) & 0x01010101u) << 4);
-        const float f0 = __fsub_rn(__fmul_rn(d1, (float) (v & 0xFF)), m1);
-        const float f1 = __fsub_rn(__fmul_rn(d1, (float) ((v >> 8) & 0xFF)), m1);
-        const float f2 = __fsub_rn(__fmul_rn(d1, (float) ((v >> 16) & 0xFF)), m1);
-        const float f3 = __fsub_rn(__fmul_rn(d1, (float) (v >> 24)), m1);
-        out[2 * i] = pack_h2(f0, f1);
-        out[2 * i + 1] = pack_h2(f2, f3);
-    }
+template <uint32_t MASK>
+__device__ __forceinline__ void expand_word(uint32_t t, __half2 bias, __half2 scale, __half2 off, uint32_t & o02, uint32_t & o13) {
+    const uint32_t p02 = and_or(t, MASK, 0x64006400u);
+    const uint32_t p13 = and_or(t >> 8, MASK, 0x64006400u);
+    o02 = h2_bits(__hfma2(__hadd2(bits_h2(p02), bias), scale, off));
+    o13 = h2_bits(__hfma2(__hadd2(bits_h2(p13), bias), scale, off));
 }
-__device__ __forceinline__ void expand_q6K(const uint8_t * blk, int c, int h, uint32_t (&out)[16]) {
-    // blk is 2-byte aligned only (210-byte blocks)
-    const float d = __half2float(*reinterpret_cast<const __half *>(blk + 208));
-    const int n = c >> 1, p = c & 1;
-    const uint8_t * ql = blk + 64 * n + 32 * h;
-    const uint8_t * qh = blk + 128 + 32 * n;
-    const int8_t * sc = reinterpret_cast<const int8_t *>(blk + 192 + 8 * n + 2 * h + 4 * p);
-    const float d0 = __fmul_rn(d, (float) sc[0]), d1 = __fmul_rn(d, (float) sc[1]);
+__device__ __forceinline__ void scale_min_k4(const uint8_t * sc, int j, int & s, int & m) {   // get_scale_min_k4, ggml-quants.c:1950-1958
+    // branch-free: both packings are computed, j selects
+    const int lo_s = sc[j & 3], lo_m = sc[(j & 3) + 4], hi = sc[(j & 3) + 8];
+    const int s0 = lo_s & 63, m0 = lo_m & 63;
+    const int s1 = (hi & 0xF) | ((lo_s >> 6) << 4), m1 = (hi >> 4) | ((lo_m >> 6) << 4);
+    s = j < 4 ? s0 : s1;
+    m = j < 4 ? m0 : m1;
+}
+template <int TYPE>
+__device__ __forceinline__ void expand(const uint8_t * blk, int c, int h, uint32_t (&out)[16]) {
+    if (TYPE == T_Q4_K || TYPE == T_Q5_K) {
+        const float d = __half2float(*reinterpret_cast<const __half *>(blk));
+        const float dmin = __half2float(*reinterpret_cast<const __half *>(blk + 2));
+        const int j = 2 * c + h;
+        int s, m;
+        scale_min_k4(blk + 4, j, s, m);
+        const __half2 scale = __float2half2_rn(__fmul_rn(d, (float) s)), off = __float2half2_rn(-__fmul_rn(dmin, (float) m));
+        const __half2 bias = __float2half2_rn(-1024.f);
+        const uint4 * q = reinterpret_cast<const uint4 *>(blk + (TYPE == T_Q4_K ? 16 : 48) + 32 * c);
+        const uint4 qa = q[0], qb = q[1];
+        const uint32_t w[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+        if (TYPE == T_Q4_K) {
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-        const uint32_t lw = lds32_u2(ql + 4 * i), hw = lds32_u2(qh + 4 * i);
-        const uint32_t v = ((lw >> (4 * p)) & 0x0F0F0F0Fu) | (((hw >> (4 * p + 2 * h)) & 0x03030303u) << 4);
-        const float dd = i < 4 ? d0 : d1;
-        const float f0 = __fmul_rn(dd, (float) ((int) (v & 0xFF) - 32));
-        const float f1 = __fmul_rn(dd, (float) ((int) ((v >> 8) & 0xFF) - 32));
-        const float f2 = __fmul_rn(dd, (float) ((int) ((v >> 16) & 0xFF) - 32));
-        const float f3 = __fmul_rn(dd, (float) ((int) (v >> 24) - 32));
-        out[2 * i] = pack_h2(f0, f1);
-        out[2 * i + 1] = pack_h2(f2, f3);
+            for (int i = 0; i < 8; i++) expand_word<0x000F000Fu>(w[i] >> (4 * h), bias, scale, off, out[2 * i], out[2 * i + 1]);
+        } else {
+            const uint4 * qh4 = reinterpret_cast<const uint4 *>(blk + 16);
+            const uint4 ha = qh4[0], hb = qh4[1];
+            const uint32_t hh[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                expand_word<0x001F001Fu>(((w[i] >> (4 * h)) & 0x0F0F0F0Fu) | (((hh[i] >> j) << 4) & 0x10101010u), bias, scale, off, out[2 * i],
+                                         out[2 * i + 1]);
+        }
+    } else {
+        // Q6_K: blk is 2-byte aligned only (210-byte blocks): words are fetched as aligned pairs and funnel-shifted
+        const float d = __half2float(*reinterpret_cast<const __half *>(blk + 208));
+        const int n = c >> 1, p = c & 1;
+        const uint8_t * ql = blk + 64 * n + 32 * h;
+        const uint8_t * qh = blk + 128 + 32 * n;
+        const int8_t * sc = reinterpret_cast<const int8_t *>(blk + 192 + 8 * n + 2 * h + 4 * p);
+        const __half2 s0 = __float2half2_rn(__fmul_rn(d, (float) sc[0])), s1 = __float2half2_rn(__fmul_rn(d, (float) sc[1]));
+        const __half2 bias = __float2half2_rn(-1056.f), zero = __float2half2_rn(0.f);
+        const uint32_t shl = (uint32_t) (reinterpret_cast<uintptr_t>(blk) & 2) * 8;     // 0 or 16 (ql and qh share blk's alignment)
+        const uint32_t * lw = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(ql) & ~(uintptr_t) 3);
+        const uint32_t * hw = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(qh) & ~(uintptr_t) 3);
+        uint32_t lprev = lw[0], hprev = hw[0];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint32_t lnext = lw[i + 1], hnext = hw[i + 1];
+            const uint32_t l = __funnelshift_r(lprev, lnext, shl), hq = __funnelshift_r(hprev, hnext, shl);
+            lprev = lnext; hprev = hnext;
+            const uint32_t t = ((l >> (4 * p)) & 0x0F0F0F0Fu) | (((hq >> (4 * p + 2 * h)) << 4) & 0x30303030u);
+            expand_word<0x003F003Fu>(t, bias, i < 4 ? s0 : s1, zero, out[2 * i], out[2 * i + 1]);
+        }
     }
 }
 
+__device__ __forceinline__ void cp_async16(void * smem_dst, const void * gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+
+template <int TYPE>
 __global__ void __launch_bounds__(MMQ_THREADS, 1) k_mmq_tc(const __grid_constant__ MmqParams P) {
     extern __shared__ uint8_t smem_raw[];
     // the swizzle-128B atoms (A and B stages) need 1024-byte alignment in the shared window
     uint8_t * smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int BN = P.BN;
-    const int b_bytes = BN * 128;
-    uint8_t * a_st = smem;                                       // [NSTAGE][16 KB]
-    uint8_t * b_st = a_st + MMQ_NSTAGE * MMQ_A_BYTES;            // [NSTAGE][BN*128]
-    uint8_t * raw = b_st + MMQ_NSTAGE * b_bytes;                 // [2][128 * slot]
-    MmqCtl * ctl = reinterpret_cast<MmqCtl *>(raw + 2 * MMQ_BM * P.slot);
+    const int b1 = BN * 128;                                     // one token tile's chunk
+    const int b_bytes = P.nacc * b1;                             // one B stage
+    uint8_t * a_st = smem;                                       // [A_NST][16 KB]
+    uint8_t * b_st = a_st + MMQ_A_NST * MMQ_A_BYTES;             // [b_nst][nacc][BN*128]
+    uint8_t * raw = b_st + P.b_nst * b_bytes;                    // [nraw][128 * slot]
+    MmqCtl * ctl = reinterpret_cast<MmqCtl *>(raw + P.nraw * MMQ_BM * P.slot);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row0 = blockIdx.x * MMQ_BM;
-    const int ttile = blockIdx.y;
+    const int tt0 = blockIdx.y * P.nacc;                         // first token tile of this CTA
+    const int nacc = min(P.nacc, P.ttiles - tt0);                // the last CTA of an odd count has one
     const int nsb = P.K / 256;
     const int nchunk = nsb * 4;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; i++) { mbar_init(&ctl->raw_full[i], 1); mbar_init(&ctl->raw_empty[i], MMQ_DQ_WARPS); }
-        for (int i = 0; i < MMQ_NSTAGE; i++) { mbar_init(&ctl->a_ready[i], MMQ_DQ_WARPS); mbar_init(&ctl->b_full[i], 1); mbar_init(&ctl->stage_free[i], 1); }
+        for (int i = 0; i < 3; i++) { mbar_init(&ctl->raw_full[i], MMQ_DQ_WARPS * 32); mbar_init(&ctl->raw_empty[i], MMQ_DQ_WARPS); }
+        for (int i = 0; i < MMQ_A_NST; i++) mbar_init(&ctl->a_ready[i], MMQ_DQ_WARPS);
+        for (int i = 0; i < MMQ_B_NST; i++) { mbar_init(&ctl->b_full[i], 1); mbar_init(&ctl->step_done[i], 1); }
         mbar_init(&ctl->acc_ready, 1);
         ctl->abort = 0;
         mbar_fence_init();
     }
-    if (warp == 1) {
+    if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl->tmem_base)), "r"(P.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -229,120 +251,122 @@ __global__ void __launch_bounds__(MMQ_THREADS, 1) k_mmq_tc(const __grid_constant
     const uint32_t tmem = *(volatile uint32_t *) &ctl->tmem_base;
 
     if (warp == 0) {
-        // ================= producer =================
-        const uint8_t * Bt = P.B + (size_t) ttile * (P.K / MMQ_BK) * b_bytes;
-        const int64_t lim = (P.total_bytes + 15) & ~(int64_t) 15;
-        for (int sb = 0; sb < nsb; sb++) {
-            const int rs = sb & 1, rr = sb >> 1;
-            bool ok = true;
-            if (rr > 0) ok = mmq_wait(ctl, &ctl->raw_empty[rs], (rr - 1) & 1);
-            if (!ok) break;
-            // one 16-B aligned window per row around its block of super-block sb
-            uint32_t my_bytes = 0;
-            int64_t a0[4];
-            uint32_t nb[4];
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const int r = lane + 32 * i;
-                const int gr = min(row0 + r, P.N - 1);
-                const int64_t g0 = (int64_t) gr * P.row_bytes + (int64_t) sb * P.bpb;
-                a0[i] = g0 & ~(int64_t) 15;
-                int64_t a1 = (g0 + P.bpb + 15) & ~(int64_t) 15;
-                if (a1 > lim) a1 = lim;
-                nb[i] = (uint32_t) (a1 - a0[i]);
-                my_bytes += nb[i];
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) my_bytes += __shfl_xor_sync(0xffffffffu, my_bytes, o);
-            if (lane == 0) mbar_arrive_expect_tx(&ctl->raw_full[rs], my_bytes);
-            __syncwarp();
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const int r = lane + 32 * i;
-                bulk_g2s_plain(raw + (size_t) (rs * MMQ_BM + r) * P.slot, P.W + a0[i], nb[i], &ctl->raw_full[rs]);
-            }
-            // the 4 activation chunks of this super-block
-            if (lane == 0) {
-                for (int c = 0; c < 4; c++) {
-                    const int u = sb * 4 + c, s = u % MMQ_NSTAGE, round = u / MMQ_NSTAGE;
-                    if (round > 0 && !mmq_wait(ctl, &ctl->stage_free[s], (round - 1) & 1)) { ok = false; break; }
-                    mbar_arrive_expect_tx(&ctl->b_full[s], (uint32_t) b_bytes);
-                    bulk_g2s_plain(b_st + (size_t) s * b_bytes, Bt + (size_t) u * b_bytes, (uint32_t) b_bytes, &ctl->b_full[s]);
-                }
-            }
-            ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
-            if (!ok) break;
-        }
-    } else if (warp == 1) {
         // ================= MMA issuer =================
         if (lane == 0) {
             for (int u = 0; u < nchunk; u++) {
-                const int s = u % MMQ_NSTAGE, round = u / MMQ_NSTAGE;
-                if (!mmq_wait(ctl, &ctl->a_ready[s], round & 1)) break;
-                if (!mmq_wait(ctl, &ctl->b_full[s], round & 1)) break;
+                const int sa = u % MMQ_A_NST, ra = u / MMQ_A_NST, sb = u % P.b_nst, rb = u / P.b_nst;
+                if (!mmq_wait(ctl, &ctl->b_full[sb], rb & 1)) break;
+                if (!mmq_wait(ctl, &ctl->a_ready[sa], ra & 1)) break;
                 tc_fence_after();
-                const uint64_t da = umma_desc_sw128(smem_u32(a_st + (size_t) s * MMQ_A_BYTES));
-                const uint64_t db = umma_desc_sw128(smem_u32(b_st + (size_t) s * b_bytes));
+                const uint64_t da = umma_desc_sw128(smem_u32(a_st + (size_t) sa * MMQ_A_BYTES));
+                const uint64_t db = umma_desc_sw128(smem_u32(b_st + (size_t) sb * b_bytes));
+                const uint64_t db2 = umma_desc_sw128(smem_u32(b_st + (size_t) sb * b_bytes + b1));
 #pragma unroll
-                for (int k = 0; k < MMQ_BK / 16; k++) umma_f16(tmem, da + 2 * k, db + 2 * k, P.idesc, (u | k) != 0);
-                umma_commit(&ctl->stage_free[s]);
+                for (int k = 0; k < MMQ_BK / 16; k++) {
+                    umma_f16(tmem, da + 2 * k, db + 2 * k, P.idesc, (u | k) != 0);
+                    if (nacc == 2) umma_f16(tmem + 256, da + 2 * k, db2 + 2 * k, P.idesc, (u | k) != 0);
+                }
+                umma_commit(&ctl->step_done[u % MMQ_B_NST]);
             }
             umma_commit(&ctl->acc_ready);
         }
         __syncwarp();
+    } else if (warp == 1) {
+        // ================= activation producer: runs up to b_nst steps ahead of the tensor core =================
+        if (lane == 0) {
+            const size_t tile_stride = (size_t) (P.K / MMQ_BK) * b1;
+            const uint8_t * Bt = P.B + (size_t) tt0 * tile_stride;
+            for (int u = 0; u < nchunk; u++) {
+                const int sb = u % P.b_nst, rb = u / P.b_nst;
+                if (rb > 0) {   // step u - b_nst consumed this stage
+                    const int f = u - P.b_nst;
+                    if (!mmq_wait(ctl, &ctl->step_done[f % MMQ_B_NST], (f / MMQ_B_NST) & 1)) break;
+                }
+                mbar_arrive_expect_tx(&ctl->b_full[sb], (uint32_t) (nacc * b1));
+                for (int a = 0; a < nacc; a++)
+                    bulk_g2s_plain(b_st + (size_t) sb * b_bytes + (size_t) a * b1, Bt + (size_t) a * tile_stride + (size_t) u * b1, (uint32_t) b1,
+                                   &ctl->b_full[sb]);
+            }
+        }
+        __syncwarp();
     } else {
         // ================= weight expansion =================
-        const int dt = threadIdx.x - 64;        // 0..255
+        const int dt = threadIdx.x - MMQ_DQ_WARP0 * 32;        // 0..255
         const int r = dt >> 1, h = dt & 1;
         const int gr = min(row0 + r, P.N - 1);
         bool ok = true;
+        // this thread fetches its own half of the row's block: 16-byte cp.async pieces of the 16-B aligned window around it
+        const int64_t lim = (P.total_bytes + 15) & ~(int64_t) 15;
+        const int cpr = P.slot >> 4, p_lo = h ? (cpr + 1) / 2 : 0, p_hi = h ? cpr : (cpr + 1) / 2;
+        auto fetch = [&](int x) {
+            const int64_t src0 = ((int64_t) gr * P.row_bytes + (int64_t) x * P.bpb) & ~(int64_t) 15;
+            uint8_t * dst0 = raw + ((size_t) (x % P.nraw) * MMQ_BM + r) * P.slot;
+            for (int pc = p_lo; pc < p_hi; pc++)
+                if (src0 + pc * 16 + 16 <= lim) cp_async16(dst0 + pc * 16, P.W + src0 + pc * 16);
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&ctl->raw_full[x % P.nraw])) : "memory");
+        };
+        for (int x = 0; x < P.nraw - 1 && x < nsb; x++) fetch(x);
+        // the four 16-byte pieces this thread writes per step, already swizzled
+        const uint32_t arow = r * 128;
+        const uint32_t o0 = arow + (((4 * h + 0) ^ (r & 7)) << 4), o1 = arow + (((4 * h + 1) ^ (r & 7)) << 4);
+        const uint32_t o2 = arow + (((4 * h + 2) ^ (r & 7)) << 4), o3 = arow + (((4 * h + 3) ^ (r & 7)) << 4);
+        int u = 0;
         for (int sb = 0; sb < nsb && ok; sb++) {
-            const int rs = sb & 1, rr = sb >> 1;
+            const int rs = sb % P.nraw, rr = sb / P.nraw;
+            {   // refill the slot super-block sb-1 used, once every expansion warp has left it
+                const int x = sb + P.nraw - 1;
+                if (x < nsb) {
+                    if (sb > 0 && !mmq_wait(ctl, &ctl->raw_empty[(sb - 1) % P.nraw], ((sb - 1) / P.nraw) & 1)) { ok = false; break; }
+                    fetch(x);
+                }
+            }
             if (!mmq_wait(ctl, &ctl->raw_full[rs], rr & 1)) { ok = false; break; }
             const int64_t g0 = (int64_t) gr * P.row_bytes + (int64_t) sb * P.bpb;
             const uint8_t * blk = raw + (size_t) (rs * MMQ_BM + r) * P.slot + (g0 & 15);
-            for (int c = 0; c < 4; c++) {
-                const int u = sb * 4 + c, s = u % MMQ_NSTAGE, round = u / MMQ_NSTAGE;
-                uint32_t v[16];
-                if (P.type == T_Q4_K) expand_q4K(blk, c, h, v);
-                else if (P.type == T_Q5_K) expand_q5K(blk, c, h, v);
-                else expand_q6K(blk, c, h, v);
-                if (round > 0 && !mmq_wait(ctl, &ctl->stage_free[s], (round - 1) & 1)) { ok = false; break; }
-                uint8_t * arow = a_st + (size_t) s * MMQ_A_BYTES + r * 128;
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const int chunk = (4 * h + j) ^ (r & 7);
-                    *reinterpret_cast<uint4 *>(arow + chunk * 16) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            for (int c = 0; c < 4; c++, u++) {
+                uint32_t v[16];
+                expand<TYPE>(blk, c, h, v);
+                if (u >= MMQ_A_NST) {   // step u - 2 has consumed this A stage
+                    const int f = u - MMQ_A_NST;
+                    if (!mmq_wait(ctl, &ctl->step_done[f % MMQ_B_NST], (f / MMQ_B_NST) & 1)) { ok = false; break; }
                 }
+                uint8_t * as = a_st + (size_t) (u % MMQ_A_NST) * MMQ_A_BYTES;
+                *reinterpret_cast<uint4 *>(as + o0) = make_uint4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<uint4 *>(as + o1) = make_uint4(v[4], v[5], v[6], v[7]);
+                *reinterpret_cast<uint4 *>(as + o2) = make_uint4(v[8], v[9], v[10], v[11]);
+                *reinterpret_cast<uint4 *>(as + o3) = make_uint4(v[12], v[13], v[14], v[15]);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core's async proxy
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&ctl->a_ready[s]);
+                if (lane == 0) mbar_arrive(&ctl->a_ready[u % MMQ_A_NST]);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&ctl->raw_empty[rs]);
         }
-        // ================= epilogue: warps 2..5 cover the four 32-lane quadrants of TMEM =================
-        if (warp < 6) {
+        // ================= epilogue: four consecutive warps cover the four 32-lane quadrants of TMEM =================
+        if (warp < MMQ_DQ_WARP0 + 4) {
             const bool acc_ok = mmq_wait(ctl, &ctl->acc_ready, 0);
             tc_fence_after();
             const int quad = warp & 3;
             const int n = row0 + quad * 32 + lane;
             const float bias = (P.bias && n < P.N) ? P.bias[n] : 0.f;
-            for (int c0 = 0; c0 < BN; c0 += 16) {
-                uint32_t v[16];
-                const uint32_t taddr = tmem + ((uint32_t) (quad * 32) << 16) + (uint32_t) c0;
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-                      "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                    : "r"(taddr)
-                    : "memory");
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (acc_ok && n < P.N) {
+            for (int a = 0; a < nacc; a++) {
+                for (int c0 = 0; c0 < BN; c0 += 16) {
+                    uint32_t v[16];
+                    const uint32_t taddr = tmem + ((uint32_t) (quad * 32) << 16) + (uint32_t) (a * 256 + c0);
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                        : "r"(taddr)
+                        : "memory");
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (acc_ok && n < P.N) {
 #pragma unroll
-                    for (int i = 0; i < 16; i++) {
-                        const int t = ttile * BN + c0 + i;
-                        if (t < P.T) P.dst[(size_t) t * P.N + n] = __fadd_rn(__uint_as_float(v[i]), bias);
+                        for (int i = 0; i < 16; i++) {
+                            const int t = (tt0 + a) * BN + c0 + i;
+                            if (t < P.T) P.dst[(size_t) t * P.N + n] = __fadd_rn(__uint_as_float(v[i]), bias);
+                        }
                     }
                 }
             }
@@ -350,7 +374,7 @@ __global__ void __launch_bounds__(MMQ_THREADS, 1) k_mmq_tc(const __grid_constant
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == 0) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(P.tmem_cols) : "memory");
     }
@@ -398,7 +422,8 @@ __global__ void __launch_bounds__(256) k_mmq_prep(const float * __restrict__ x, 
                 f[i] = __fmul_rn(d, (float) q);
             }
 #pragma unroll
-            for (int i = 0; i < 4; i++) h[i] = pack_h2(f[2 * i], f[2 * i + 1]);
+            // within every 4 consecutive k the order is (0,2,1,3): the weight expansion produces its half2 pairs that way
+            h[0] = pack_h2(f[0], f[2]); h[1] = pack_h2(f[1], f[3]); h[2] = pack_h2(f[4], f[6]); h[3] = pack_h2(f[5], f[7]);
         }
         const int k = b * 256 + lane * 8;
         const int kc = k >> 6, j = (k & 63) >> 3;
@@ -426,6 +451,18 @@ int mmq_aborted() {
     return v;
 }
 
+template <int TYPE>
+static cudaError_t mmq_launch_typed(const MmqParams & P, dim3 grid, size_t smem, cudaStream_t st) {
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_mmq_tc<TYPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    k_mmq_tc<TYPE><<<grid, MMQ_THREADS, smem, st>>>(P);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_mmq(int type, const void * W, int64_t N, int64_t K, const float * x, int64_t ldx, int64_t T, float * dst, const float * bias,
                        void * ws, cudaStream_t st) {
     if (!mmq_supported(type, K) || N <= 0 || T <= 0) return cudaErrorInvalidValue;
@@ -442,28 +479,37 @@ cudaError_t launch_mmq(int type, const void * W, int64_t N, int64_t K, const flo
     P.bias = bias;
     P.row_bytes = row_bytes(type, K);
     P.total_bytes = P.row_bytes * N;
-    P.type = type;
     P.N = (int) N;
     P.K = (int) K;
     P.T = (int) T;
     P.BN = BN;
     P.bpb = type == T_Q4_K ? BYTES_Q4_K : (type == T_Q5_K ? BYTES_Q5_K : BYTES_Q6_K);
     P.slot = type == T_Q6_K ? 240 : P.bpb;
+    P.ttiles = tpad / BN;
+    const int rtiles = (int) ((N + MMQ_BM - 1) / MMQ_BM);
+    // two accumulators per CTA halve the weight-expansion work per FLOP; worth it once that still fills most of the SMs
+    static const int force_nacc = getenv("PB200_MMQ_NACC") ? atoi(getenv("PB200_MMQ_NACC")) : 0;
+    P.nacc = (P.ttiles >= 2 && (int64_t) rtiles * ((P.ttiles + 1) / 2) >= (sm_count() * 4) / 5) ? 2 : 1;
+    if (force_nacc == 1 || (force_nacc == 2 && P.ttiles >= 2)) P.nacc = force_nacc;
     uint32_t cols = 32;
     while ((int) cols < BN) cols <<= 1;
-    P.tmem_cols = cols;
+    P.tmem_cols = P.nacc == 2 ? 512 : cols;
     // kind::f16 instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): D=f32, A=B=f16, both K-major, N>>3, M>>4
     P.idesc = (1u << 4) | ((uint32_t) (BN >> 3) << 17) | ((uint32_t) (MMQ_BM >> 4) << 24);
-    const size_t smem = 1024 + (size_t) MMQ_NSTAGE * (MMQ_A_BYTES + BN * 128) + 2 * (size_t) MMQ_BM * P.slot + MMQ_CTL_BYTES;
-    static size_t configured = 0;
-    if (smem > configured) {
-        e = cudaFuncSetAttribute(k_mmq_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
-    dim3 grid((unsigned) ((N + MMQ_BM - 1) / MMQ_BM), (unsigned) (tpad / BN));
-    k_mmq_tc<<<grid, MMQ_THREADS, smem, st>>>(P);
-    return cudaGetLastError();
+    // ring depths: 3 raw super-block slots (HBM latency) if they fit, and as many activation stages (2..4) as the 227 KB budget leaves
+    auto smem_for = [&](int nraw, int b_nst) {
+        return 1024 + (size_t) MMQ_A_NST * MMQ_A_BYTES + (size_t) b_nst * P.nacc * BN * 128 + (size_t) nraw * MMQ_BM * P.slot + MMQ_CTL_BYTES;
+    };
+    P.nraw = 3;
+    if (smem_for(3, 2) > 232448) P.nraw = 2;
+    P.b_nst = MMQ_B_NST;
+    while (P.b_nst > 2 && smem_for(P.nraw, P.b_nst) > 232448) P.b_nst--;
+    const size_t smem = smem_for(P.nraw, P.b_nst);
+    if (smem > 232448) return cudaErrorInvalidConfiguration;
+    dim3 grid((unsigned) rtiles, (unsigned) ((P.ttiles + P.nacc - 1) / P.nacc));
+    if (type == T_Q4_K) return mmq_launch_typed<T_Q4_K>(P, grid, smem, st);
+    if (type == T_Q5_K) return mmq_launch_typed<T_Q5_K>(P, grid, smem, st);
+    return mmq_launch_typed<T_Q6_K>(P, grid, smem, st);
 }
 
 }  // namespace pb

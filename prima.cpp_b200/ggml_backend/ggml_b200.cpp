@@ -45,6 +45,8 @@ struct b200_backend_ctx {
     cudaStream_t stream = nullptr;
     void * act_ws = nullptr;       // quantized-activation workspace (grown on demand)
     size_t act_ws_bytes = 0;
+    void * mmq_ws = nullptr;       // fp16 activation tiles for the tensor-core path (grown on demand)
+    size_t mmq_ws_bytes = 0;
     std::string name;
 };
 struct b200_buffer_ctx {
@@ -52,6 +54,8 @@ struct b200_buffer_ctx {
     void * base;
 };
 
+static const int64_t MMQ_MIN_COLS = 8;
+static bool mmq_type(enum ggml_type t) { return t == GGML_TYPE_Q4_K || t == GGML_TYPE_Q5_K || t == GGML_TYPE_Q6_K; }
 static bool type_is_quant(enum ggml_type t) {
     return t == GGML_TYPE_Q4_K || t == GGML_TYPE_Q5_K || t == GGML_TYPE_Q6_K || t == GGML_TYPE_Q8_0 || t == GGML_TYPE_Q5_1;
 }
@@ -177,9 +181,11 @@ static bool b200_supports_op(ggml_backend_dev_t, const ggml_tensor * op) {
             if (a->ne[2] == 0 || a->ne[3] == 0 || b->ne[2] % a->ne[2] || b->ne[3] % a->ne[3]) return false;
             if (a->type == GGML_TYPE_F16) return a->nb[0] == sizeof(ggml_fp16_t) && b->nb[0] == sizeof(float) && op->nb[0] == sizeof(float);
             if (!type_is_quant(a->type)) return false;
-            // quantized weights: rows of src1 must be dense; the decode GEMV handles one activation column per launch
-            return ggml_is_contiguous(a) && b->nb[0] == sizeof(float) && ggml_is_contiguous(op) && a->ne[0] % ggml_blck_size(a->type) == 0 &&
-                   b->ne[1] * b->ne[2] * b->ne[3] <= 64;
+            // quantized weights: rows of src1 must be dense.  The decode GEMV handles one activation column per launch; k-quant
+            // weights with K % 256 == 0 take the tensor-core path (pb200_mul_mat_q) for any number of columns.
+            if (!(ggml_is_contiguous(a) && b->nb[0] == sizeof(float) && ggml_is_contiguous(op) && a->ne[0] % ggml_blck_size(a->type) == 0)) return false;
+            if (mmq_type(a->type) && a->ne[0] % 256 == 0 && b->nb[1] % 16 == 0) return true;
+            return b->ne[1] * b->ne[2] * b->ne[3] <= 64;
         }
         case GGML_OP_ROPE: {
             const int mode = ((const int32_t *) op->op_params)[2];
@@ -250,6 +256,23 @@ static bool b200_compute_node(b200_backend_ctx * ctx, ggml_tensor * dst) {
                 ctx->act_ws_bytes = need;
             }
             const int64_t r2 = b->ne[2] / a->ne[2], r3 = b->ne[3] / a->ne[3];
+            if (b->ne[1] >= MMQ_MIN_COLS && mmq_type(a->type) && K % 256 == 0 && b->nb[1] % 16 == 0) {
+                // batched / prefill: the reference switches to mul_mat_q above 8 columns as well (ggml-cuda/mmq.cu:137-139)
+                const size_t need_q = pb200_mul_mat_q_workspace_bytes(K, b->ne[1]);
+                if (need_q > ctx->mmq_ws_bytes) {
+                    if (ctx->mmq_ws) { CUDA_OK(cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->mmq_ws); }
+                    CUDA_OK(cudaMalloc(&ctx->mmq_ws, need_q + 256));
+                    ctx->mmq_ws_bytes = need_q;
+                }
+                for (int64_t i3 = 0; i3 < b->ne[3]; i3++)
+                    for (int64_t i2 = 0; i2 < b->ne[2]; i2++) {
+                        const char * w = (const char *) a->data + (i2 / r2) * a->nb[2] + (i3 / r3) * a->nb[3];
+                        const float * x = (const float *) ((const char *) b->data + i2 * b->nb[2] + i3 * b->nb[3]);
+                        float * y = (float *) ((char *) dst->data + i2 * dst->nb[2] + i3 * dst->nb[3]);
+                        PB_OK(pb200_mul_mat_q((int) a->type, w, N, K, x, (int64_t) (b->nb[1] / sizeof(float)), b->ne[1], y, nullptr, ctx->mmq_ws, st));
+                    }
+                return true;
+            }
             for (int64_t i3 = 0; i3 < b->ne[3]; i3++)
                 for (int64_t i2 = 0; i2 < b->ne[2]; i2++)
                     for (int64_t i1 = 0; i1 < b->ne[1]; i1++) {
@@ -315,6 +338,7 @@ static void b200_backend_free(ggml_backend_t backend) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->act_ws) cudaFree(ctx->act_ws);
+    if (ctx->mmq_ws) cudaFree(ctx->mmq_ws);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     delete backend;

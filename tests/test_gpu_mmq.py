@@ -1,10 +1,13 @@
 """-m gpu: the batched (prefill) k-quant product pb200_mul_mat_q — tcgen05 tensor cores — against the CPU oracle.
 
 Numerics bar (floating point, stated here): the kernel quantizes every activation row to q8_K exactly as the CPU backend
-does, expands the weights with the reference's dequantization formulas, rounds BOTH operands to fp16 and accumulates in
-fp32 on the tensor pipe.  Versus the oracle's integer dot products that leaves two fp16 roundings per product:
-    |err[t,n]| <= 2^-10 * sum_k |W[n,k]| * |x_q[t,k]|      (checked element-wise, rigorous bound + fp32 summation slack)
-    NMSE <= 1e-6                                          (the reference's own MUL_MAT bar is 5e-4, test-backend-ops.cpp:1639)
+does and expands the weights with the reference's dequantization formulas evaluated in fp16: the integer q is exact, the
+sub-block scale d*sc and offset dmin*m are rounded to fp16, one fused multiply-add, fp16 result; activations d*q8 are
+rounded to fp16; products accumulate in fp32 on the tensor pipe.  Versus the oracle's integer dot products that is at most
+four fp16 roundings (2^-11 each) on terms no larger than the sub-block's largest weight:
+    |err[t,n]| <= 2^-9 * sum_k (|W[n,k]| + max_{32-sub-block}|W[n,.]|) * |x[t,k]|      (checked element-wise)
+    NMSE <= 4e-6                              (the reference's own MUL_MAT bar is 5e-4, test-backend-ops.cpp:1639)
+Integer-valued inputs with exactly representable scales must come out bit-exact (test_mmq_integer_exact).
 """
 import ctypes as C
 
@@ -41,10 +44,12 @@ def oracle(port, t, W, N, K, X):
 def check(got, want, Wf, X):
     assert np.isfinite(got).all()
     err = np.abs(got - want)
-    bound = 2.0 ** -10 * (np.abs(X) @ np.abs(Wf).T) * 1.05 + 1e-6
-    assert (err <= bound).all(), f"max err {err.max():.3e} exceeds the two-roundings bound (worst ratio {(err / bound).max():.2f})"
+    N, K = Wf.shape
+    sub = np.repeat(np.abs(Wf).reshape(N, K // 32, 32).max(axis=2), 32, axis=1)
+    bound = 2.0 ** -9 * (np.abs(X) @ (np.abs(Wf) + sub).T) + 1e-6
+    assert (err <= bound).all(), f"max err {err.max():.3e} exceeds the fp16-roundings bound (worst ratio {(err / bound).max():.2f})"
     nmse = float(np.sum((got - want) ** 2) / max(np.sum(want ** 2), 1e-30))
-    assert nmse <= 1e-6, f"NMSE {nmse:.3e}"
+    assert nmse <= 4e-6, f"NMSE {nmse:.3e}"
 
 
 @pytest.mark.parametrize("t", KQ, ids=lambda t: O.TYPE_NAME[t])
@@ -102,9 +107,9 @@ def test_mmq_bias_ragged_rows_and_strided_input(cuda, lib, port):
 
 
 def test_mmq_matches_gemv_columnwise_full_width(cuda, lib):
-    """Size-independent property at a 70B shape: every column of the batched product agrees with the decode GEMV (which is
-    bit-exact with the oracle) within the two-roundings bound."""
-    t, N, K, T = O.Q4_K, 8192, 8192, 512
+    """Size-independent property at a 70B shape (also the dual-accumulator configuration): every column of the batched product agrees with the decode GEMV (which is
+    bit-exact with the oracle) to NMSE <= 4e-6."""
+    t, N, K, T = O.Q4_K, 8192, 8192, 700     # 3 token tiles: two accumulators per CTA, the last CTA column has one; ragged last tile
     g = torch.Generator(device="cuda").manual_seed(1)
     W = O.synth_blocks(t, 256, K, seed=11)                  # 256 distinct rows, tiled to N
     Wfull = np.tile(W.reshape(256, -1), (N // 256, 1)).reshape(-1)
@@ -113,11 +118,11 @@ def test_mmq_matches_gemv_columnwise_full_width(cuda, lib):
     assert np.array_equal(got[:, :256], got[:, 256:512])    # identical weight rows -> identical outputs
     Wd = dev_u8(Wfull)
     ws = torch.zeros(lib.c.pb200_act_workspace_bytes(K) + 64, dtype=torch.uint8, device="cuda")
-    for col in (0, 1, 255, 256, 511):
+    for col in (0, 1, 255, 256, 511, 512, 600, 699):
         xd = dev_f32(X[col])
         y = torch.zeros(N, dtype=torch.float32, device="cuda")
         lib.check(lib.c.pb200_mul_mat_vec(t, ptr(Wd), N, K, ptr(xd), ptr(y), ptr(ws), None), "mul_mat_vec")
         sync()
         ref = y.cpu().numpy()
         nmse = float(np.sum((got[col] - ref) ** 2) / np.sum(ref ** 2))
-        assert nmse <= 1e-6, f"column {col}: NMSE {nmse:.3e}"
+        assert nmse <= 4e-6, f"column {col}: NMSE {nmse:.3e}"

@@ -27,23 +27,8 @@ def run(t, W, N, K, X):
     return rc, y.cpu().numpy()
 
 
-for (t, N, K, T) in [(O.Q4_K, 128, 256, 16), (O.Q4_K, 256, 512, 33), (O.Q5_K, 256, 512, 64), (O.Q6_K, 256, 512, 64), (O.Q4_K, 384, 1024, 300)]:
-    rng = np.random.default_rng(N + K + T)
-    W = O.synth_blocks(t, N, K, seed=t)
-    X = rng.standard_normal((T, K)).astype(np.float32)
-    rc, got = run(t, W, N, K, X)
-    want = np.stack([port.mul_mat(t, W, N, K, X[i]).reshape(-1) for i in range(T)])
-    nmse = float(np.sum((got - want) ** 2) / np.sum(want ** 2)) if np.isfinite(got).all() else float("nan")
-    print(f"type {O.TYPE_NAME[t]} N {N} K {K} T {T}: rc {rc} aborted {lib.c.pb200_mul_mat_q_aborted()} nan {int(np.isnan(got).sum())} "
-          f"NMSE {nmse:.3e} maxerr {np.nanmax(np.abs(got - want)):.3e} |want| {np.abs(want).max():.2f}", flush=True)
-    if not (nmse < 1e-5):
-        # help locate layout errors: which rows / columns are wrong
-        bad = ~np.isclose(got, want, rtol=2e-2, atol=2e-2)
-        print("  bad fraction", bad.mean(), "bad cols(n) sample", np.unique(np.where(bad)[1])[:20], "bad rows(t) sample", np.unique(np.where(bad)[0])[:20])
-        print("  got[0,:8]", got[0, :8], "\n  want[0,:8]", want[0, :8])
-
 # timing at 70B shapes
-for (t, N, K, T) in [(O.Q4_K, 8192, 8192, 512), (O.Q4_K, 28672, 8192, 512), (O.Q6_K, 8192, 28672, 512), (O.Q4_K, 8192, 8192, 128), (O.Q4_K, 28672, 8192, 2048)]:
+for (t, N, K, T) in [(O.Q4_K, 8192, 8192, 512), (O.Q4_K, 28672, 8192, 512), (O.Q6_K, 8192, 28672, 512), (O.Q4_K, 8192, 8192, 128), (O.Q4_K, 28672, 8192, 2048), (O.Q4_K, 8192, 8192, 2048), (O.Q6_K, 8192, 28672, 2048), (O.Q5_K, 8192, 8192, 2048)]:
     rb = lib.c.pb200_row_bytes(t, K)
     Wd = torch.randint(0, 255, (N * rb + 64,), dtype=torch.uint8, device="cuda")
     xd = torch.randn((T, K), device="cuda")
