@@ -47,6 +47,26 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def tensor_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        if "bf16_tflops" in d:
+            return float(d["bf16_tflops"]), "measured (MEASURED_PEAKS.json bf16_tflops: cuBLAS bf16 8192^3 burst; the prefill batch is timed alone)"
+    return 2250.0, "fallback (B200_PROFILING.md 2.25 PFLOP/s dense bf16/fp16)"
+
+
+def prefill_flops(hp, T):
+    """Algorithmic FLOPs of one prompt batch: 2 * sum(N*K) * T over the per-layer mat-muls, causal attention
+    4 * T^2/2 * n_embd per layer, lm_head for the last token only."""
+    E, F, D = hp["n_embd"], hp["n_ff"], 128
+    QD, EK = hp["n_head"] * D, hp["n_head_kv"] * D
+    p_mm = E * QD + 2 * E * EK + QD * E + 3 * E * F
+    mm = 2.0 * p_mm * T * hp["n_layer"]
+    att = 4.0 * (T * (T + 1) / 2) * QD * hp["n_layer"]
+    return mm, att, 2.0 * E * hp["n_vocab"]
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
@@ -189,6 +209,7 @@ def main():
     ap.add_argument("--n-ctx", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--prompt", type=int, default=PROMPT, help="untimed prompt tokens decoded before the timed region")
+    ap.add_argument("--pp", type=int, default=512, help="prompt-processing batch measured after the decode run (0 = skip; single GPU only)")
     ap.add_argument("--ncu", action="store_true", help="bracket the timed region with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     args = ap.parse_args()
     PROMPT = args.prompt
@@ -375,6 +396,26 @@ def main():
         out["pipeline"] = {"stages": world, "hand_offs_per_token": world, "sum_of_stage_ms": stage_ms, "pipelined_ms_per_token": ms_step,
                            "exposed_handoff_ms": max(0.0, ms_step - stage_ms), "exposed_frac": max(0.0, ms_step - stage_ms) / ms_step,
                            "note": "b=1 decode is serial across stages (SURVEY H7): N GPUs hold N x the model, they do not cut the token latency"}
+    if world == 1 and args.pp > 0 and args.pp <= args.n_ctx:
+        # prompt processing (prefill) of one ubatch through pb200_prefill: tensor-core mat-muls, batched attention
+        toks = np.array([token_at(i, nv) for i in range(args.pp)], dtype=np.int32)
+        eng.kv_clear()
+        eng.prefill(toks, 0, logits_host)                      # warm-up (allocates the batch buffers)
+        reps, best = 3, None
+        for _ in range(reps):
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            eng.prefill(toks, 0, logits_host)                  # tokens from host memory in, last-token logits out: end to end
+            dt = time.perf_counter() - t1
+            best = dt if best is None else min(best, dt)
+        mm, att, head = prefill_flops(hp, args.pp)
+        tpeak, tsrc = tensor_peak()
+        out["prefill"] = {"metric": f"prompt tokens/s, {cfg['name']}, one ubatch of {args.pp} tokens (llama-bench pp{args.pp})", "tokens": args.pp,
+                          "ms": best * 1e3, "value": args.pp / best, "unit": "tokens/s", "timing": f"host wall clock around pb200_prefill (synchronous), best of {reps}",
+                          "roofline": {"bound": "tensor", "achieved": (mm + att + head) / best / 1e12, "peak": tpeak, "unit": "TFLOP/s",
+                                       "frac": (mm + att + head) / best / 1e12 / tpeak, "peak_source": tsrc,
+                                       "algorithmic_flops": {"matmul": mm, "attention_causal": att, "lm_head_last_token": head},
+                                       "kernel": "k_mmq_tc (tcgen05 k-quant mat-mul); attention still runs on CUDA cores (k_attn_decode over a head x token grid)"}}
     if not args.no_cpu_baseline:
         try:
             out["cpu_baseline"] = cpu_reference(args.model, 4, 1)

@@ -86,12 +86,12 @@ PB200_API int pb200_copy_strided(const void * src_f32, void * dst, int dst_is_f1
 /* d[i0,i1,i2,i3] = sum_k a_f16[k,i0,i2/r2,i3/r3] * f16(b[k,i1,i2,i3]) — the FA-off KQ / KQV products (ggml-cuda.cu:1737-1881), byte strides */
 PB200_API int pb200_mul_mat_f16(const void * a_f16, const float * b_f32, float * d, int64_t k, const int64_t * ne, int64_t r2, int64_t r3,
                                 const int64_t * a_strides, const int64_t * b_strides, const int64_t * d_strides, void * stream);
-/* batched (prefill) product: dst[t][n] = sum_k W[n][k] * x[t][k] (+ bias[n]); W: n rows of k-quant blocks (Q4_K/Q5_K/Q6_K,
- * k % 256 == 0), x: t rows of ldx floats, dst: t rows of n floats.  Activations are quantized to q8_K like the CPU backend,
+/* batched (prefill) product: dst[t][n] = sum_k W[n][k] * x[t][k] (+ bias[n]) (+ resid[t][n]); W: n rows of k-quant blocks
+ * (Q4_K/Q5_K/Q6_K, k % 256 == 0), x: t rows of ldx floats, dst / resid: t rows of n floats, resid must not alias dst.  Activations are quantized to q8_K like the CPU backend,
  * then both operands run as fp16 on the tensor cores with fp32 accumulation.  ws: pb200_mul_mat_q_workspace_bytes(k, t). */
 PB200_API size_t pb200_mul_mat_q_workspace_bytes(int64_t k, int64_t t);
 PB200_API int pb200_mul_mat_q(int type, const void * W, int64_t n, int64_t k, const float * x, int64_t ldx, int64_t t, float * dst,
-                              const float * bias, void * ws, void * stream);
+                              const float * bias, const float * resid, void * ws, void * stream);
 /* 1 if any pb200_mul_mat_q launch gave up on a stuck pipeline (results invalid); sticky, debugging aid */
 PB200_API int pb200_mul_mat_q_aborted(void);
 PB200_API int pb200_get_rows(int type, const void * table, int64_t k, const int32_t * ids, int64_t n_ids, float * y, void * stream);
@@ -122,6 +122,12 @@ PB200_API int pb200_model_set_tensor(pb200_model * m, const char * name, int typ
 PB200_API int pb200_model_synth(pb200_model * m, int ftype, uint64_t seed);
 PB200_API int pb200_model_finalize(pb200_model * m);     /* allocate KV cache + activations, capture the CUDA graph */
 PB200_API int64_t pb200_model_weight_bytes(const pb200_model * m);    /* algorithmic bytes read per decoded token on this shard */
+/* Prompt processing (prefill): n_tokens tokens at positions pos0 .. pos0+n_tokens-1 through all layers as one batch — the
+ * reference's llama_decode with a multi-token ubatch (ne11 > 1: ggml_cuda_op_mul_mat_q, mmq.cu:3-98; attention
+ * ggml-cuda.cu:1737-1881).  Mat-muls on the tensor cores (pb200_mul_mat_q), attention over the K/V rows just stored.  The KV
+ * cache is left exactly as n_tokens pb200_decode calls would leave it up to fp16-rounding differences in the mat-muls;
+ * logits of the LAST token go to logits_host (may be NULL).  Models created with with_embd and first_layer == 0 only. */
+PB200_API int pb200_prefill(pb200_model * m, const int32_t * tokens_host, int32_t n_tokens, int32_t pos0, float * logits_host);
 PB200_API int pb200_kv_clear(pb200_model * m);
 
 /* one decode step, HOST in/out (the llama_decode-equivalent call): token id + position in, n_vocab logits out.

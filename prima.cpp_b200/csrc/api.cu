@@ -182,12 +182,12 @@ int pb200_mul_mat_f16(const void * a_f16, const float * b_f32, float * d, int64_
 }
 
 size_t pb200_mul_mat_q_workspace_bytes(int64_t k, int64_t t) { return (k > 0 && t > 0) ? mmq_workspace_bytes(k, t) : 0; }
-int pb200_mul_mat_q(int type, const void * W, int64_t n, int64_t k, const float * x, int64_t ldx, int64_t t, float * dst, const float * bias, void * ws,
-                    void * stream) {
-    if (!W || !x || !dst || !ws || n <= 0 || t <= 0 || ldx < k) return PB200_EINVAL;
+int pb200_mul_mat_q(int type, const void * W, int64_t n, int64_t k, const float * x, int64_t ldx, int64_t t, float * dst, const float * bias,
+                    const float * resid, void * ws, void * stream) {
+    if (!W || !x || !dst || !ws || n <= 0 || t <= 0 || ldx < k || resid == dst) return PB200_EINVAL;
     if (!mmq_supported(type, k)) return PB200_ENOTSUP;
     g_launches += 2;
-    return (int) launch_mmq(type, W, n, k, x, ldx, t, dst, bias, ws, (cudaStream_t) stream);
+    return (int) launch_mmq(type, W, n, k, x, ldx, t, dst, bias, resid, ws, (cudaStream_t) stream);
 }
 int pb200_mul_mat_q_aborted(void) { return mmq_aborted(); }
 

@@ -7,6 +7,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdio>
@@ -109,6 +110,14 @@ struct pb200_model {
     MkHandle * mk = nullptr;          // persistent token kernel (all GEMV phases in one cooperative launch)
     bool use_mk = false;
     float * mk_final_x = nullptr;
+    // prompt-processing (prefill) scratch, grown on demand
+    struct Prefill {
+        int T = 0;
+        float *x0 = nullptr, *x1 = nullptr, *xn = nullptr, *q = nullptr, *k = nullptr, *v = nullptr, *att = nullptr, *g = nullptr, *u = nullptr;
+        void * ws = nullptr;
+        int32_t *tok = nullptr, *pos = nullptr;
+        std::vector<void *> allocs;
+    } pf;
     std::vector<cudaEvent_t> prof_ev;
     std::vector<int64_t> prof_bytes;
     size_t prof_n = 0;
@@ -240,6 +249,7 @@ void pb200_model_free(pb200_model * m) {
     if (m->graph_exec) cudaGraphExecDestroy(m->graph_exec);
     if (m->mk) mk_free(m->mk);
     for (void * p : m->allocs) cudaFree(p);
+    for (void * p : m->pf.allocs) cudaFree(p);
     if (m->tokpos_host) cudaFreeHost(m->tokpos_host);
     if (m->logits_host) cudaFreeHost(m->logits_host);
     cudaStreamDestroy(m->stream);
@@ -620,6 +630,123 @@ int pb200_model_finalize(pb200_model * m) {
 
 int64_t pb200_model_weight_bytes(const pb200_model * m) { return m ? m->weight_bytes : 0; }
 
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+// Prompt processing: all T tokens through every layer as one batch.  Same graph as enqueue_step (build_llama / build_qwen2,
+// src/llama.cpp:11000-11216, 12736-12916) with ne11 = T: the mat-muls run on the tensor cores (mmq.cu), attention is the
+// decode kernel over a (head, token) grid reading the K/V rows just written to the cache (causal: token t sees rows <= pos_t).
+static int pf_reserve(pb200_model * m, int T) {
+    pb200_model::Prefill & P = m->pf;
+    if (T <= P.T) return 0;
+    CK(cudaStreamSynchronize(m->stream));
+    for (void * p : P.allocs) cudaFree(p);
+    P.allocs.clear();
+    P.T = 0;
+    const pb200_hparams & hp = m->hp;
+    const size_t E = hp.n_embd, QD = (size_t) hp.n_head * hp.head_dim, EK = (size_t) hp.n_head_kv * hp.head_dim, F = hp.n_ff;
+    auto grab = [&](void ** p, size_t bytes) -> int {
+        cudaError_t e = cudaMalloc(p, (bytes + 255) / 256 * 256);
+        if (e != cudaSuccess) return (int) e;
+        P.allocs.push_back(*p);
+        return 0;
+    };
+    CK(grab((void **) &P.x0, T * E * 4)); CK(grab((void **) &P.x1, T * E * 4)); CK(grab((void **) &P.xn, T * std::max(E, QD) * 4));
+    CK(grab((void **) &P.q, T * QD * 4)); CK(grab((void **) &P.k, T * EK * 4)); CK(grab((void **) &P.v, T * EK * 4));
+    CK(grab((void **) &P.att, T * QD * 4)); CK(grab((void **) &P.g, T * F * 4)); CK(grab((void **) &P.u, T * F * 4));
+    CK(grab(&P.ws, mmq_workspace_bytes((int64_t) std::max(std::max(E, QD), F), T) + 256));
+    CK(grab((void **) &P.tok, (size_t) T * 4)); CK(grab((void **) &P.pos, (size_t) T * 4));
+    P.T = T;
+    return 0;
+}
+
+// y[t][:] = W . x[t][:] (+ bias): tensor-core path when the type / K allow it, otherwise the decode GEMV row by row
+static int pf_matmul(pb200_model * m, const Tensor & W, const float * x, int T, float * y, const float * bias, const float * resid, uint64_t & n) {
+    cudaStream_t st = m->stream;
+    if (mmq_supported(W.type, W.K) && T >= 8) {
+        n += 2;
+        return (int) launch_mmq(W.type, W.data, W.N, W.K, x, W.K, T, y, bias, resid, m->pf.ws, st);
+    }
+    ActQ act = act_from_ws(m->actF.base, W.K);
+    for (int t = 0; t < T; t++) {
+        CK(launch_quantize_act(x + (size_t) t * W.K, (int) W.K, act_mode_for(W.type), act, st, false));
+        GemvDesc d1 = {W.data, y + (size_t) t * W.N, bias, resid ? resid + (size_t) t * W.N : nullptr, W.type, (int) W.N};
+        CK(launch_gemv(&d1, 1, (int) W.K, act, st, false));
+        n += 2;
+    }
+    return 0;
+}
+
+__global__ void k_iota_pos(int32_t * pos, int pos0, int T) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < T) pos[i] = pos0 + i;
+}
+
+extern "C" int pb200_prefill(pb200_model * m, const int32_t * tokens_host, int32_t T, int32_t pos0, float * logits_host) {
+    if (!m || !m->finalized) return PB200_ESTATE;
+    if (!tokens_host || T <= 0 || pos0 < 0 || pos0 + T > m->hp.n_ctx) return PB200_EINVAL;
+    if (!m->with_embd || m->l0 != 0) return PB200_ENOTSUP;   // batched prompt processing starts at the embedding (single-process models)
+    for (int t = 0; t < T; t++)
+        if (tokens_host[t] < 0 || tokens_host[t] >= m->hp.n_vocab) return PB200_EINVAL;
+    cudaSetDevice(m->device);
+    CK(pf_reserve(m, T));
+    pb200_model::Prefill & P = m->pf;
+    const pb200_hparams & hp = m->hp;
+    const int E = hp.n_embd, H = hp.n_head, HK = hp.n_head_kv, D = hp.head_dim, F = hp.n_ff;
+    const int QD = H * D, EK = HK * D;
+    cudaStream_t st = m->stream;
+    uint64_t n = 0;
+    CK(cudaMemcpyAsync(P.tok, tokens_host, (size_t) T * 4, cudaMemcpyHostToDevice, st));
+    k_iota_pos<<<(T + 255) / 256, 256, 0, st>>>(P.pos, pos0, T); n++;
+    CK(cudaGetLastError());
+    CK(launch_get_rows(m->tok_embd.data, m->tok_embd.type, E, P.tok, T, P.x0, st, false)); n++;
+    const float kq_scale = 1.0f / sqrtf((float) D);
+    float * x = P.x0, * y = P.x1;
+    for (int il = m->l0; il < m->l1; il++) {
+        Layer & L = m->layers[il - m->l0];
+        __half * kc = m->kcache + (size_t) (il - m->l0) * hp.n_ctx * EK;
+        __half * vc = m->vcache + (size_t) (il - m->l0) * hp.n_ctx * EK;
+        // --- attention block ---
+        CK(launch_rms_norm(x, P.xn, E, T, hp.rms_eps, st, L.attn_norm)); n++;
+        CK(pf_matmul(m, L.wq, P.xn, T, P.q, L.bq, nullptr, n));
+        CK(pf_matmul(m, L.wk, P.xn, T, P.k, L.bk, nullptr, n));
+        CK(pf_matmul(m, L.wv, P.xn, T, P.v, L.bv, nullptr, n));
+        CK(launch_rope(P.q, P.q, T, H, D, QD, D, P.pos, m->rp, m->rope_ff, st)); n++;
+        CK(launch_rope(P.k, P.k, T, HK, D, EK, D, P.pos, m->rp, m->rope_ff, st)); n++;
+        CK(launch_cpy_f32_f16(P.k, kc + (size_t) pos0 * EK, (int64_t) T * EK, st)); n++;
+        CK(launch_cpy_f32_f16(P.v, vc + (size_t) pos0 * EK, (int64_t) T * EK, st)); n++;
+        CK(launch_attn_batch(P.q, kc, vc, P.att, H, HK, D, P.pos, T, pos0 + T, kq_scale, st)); n++;
+        CK(pf_matmul(m, L.wo, P.att, T, y, nullptr, x, n));                  // ffn_inp = wo.att + inpSA (residual in the epilogue)
+        // --- FFN block ---
+        CK(launch_rms_norm(y, P.xn, E, T, hp.rms_eps, st, L.ffn_norm)); n++;
+        CK(pf_matmul(m, L.gate, P.xn, T, P.g, nullptr, nullptr, n));
+        CK(pf_matmul(m, L.up, P.xn, T, P.u, nullptr, nullptr, n));
+        CK(launch_silu_mul(P.g, P.u, P.g, (int64_t) T * F, st)); n++;
+        CK(pf_matmul(m, L.down, P.g, T, x, nullptr, y, n));                  // l_out = down.act + ffn_inp   (x is free: y holds ffn_inp)
+    }
+    // hidden state of the last token -> the decode path's output head
+    CK(cudaMemcpyAsync(m->x_b, x + (size_t) (T - 1) * E, (size_t) E * 4, cudaMemcpyDeviceToDevice, st));
+    if (m->with_head) {
+        GemvDesc d1 = {m->output.data, m->logits, nullptr, nullptr, m->output.type, hp.n_vocab};
+        if (is_kquant(m->output.type) && gemv_fused_prologue_ok(E)) {
+            GemvFused pro; pro.kind = 1; pro.in0 = m->x_b; pro.in1 = m->output_norm; pro.eps = hp.rms_eps;
+            CK(launch_gemv_kquant_fused(&d1, 1, E, m->actE.q, pro, st, false)); n++;
+        } else {
+            CK(launch_rmsnorm_quant(m->x_b, m->output_norm, E, hp.rms_eps, act_mode_for(m->output.type), m->actE.q, nullptr, st, false)); n++;
+            CK(launch_gemv(&d1, 1, E, m->actE.q, st, false)); n++;
+        }
+    }
+    g_launches += n;
+    if (m->with_head && logits_host) {
+        CK(cudaMemcpyAsync(m->logits_host, m->logits, (size_t) hp.n_vocab * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        memcpy(logits_host, m->logits_host, (size_t) hp.n_vocab * 4);
+        return 0;
+    }
+    return (int) cudaStreamSynchronize(st);
+}
+
+extern "C" {
 int pb200_kv_clear(pb200_model * m) {
     if (!m || !m->finalized) return PB200_ESTATE;
     cudaSetDevice(m->device);

@@ -72,7 +72,7 @@ int launch_silu_mul_quant(const float * gate, const float * up, int K, int mode,
 // out = quant( rms_norm(x) * w ), optional f32 copy  [llm_build_norm, src/llama.cpp:9772-9802; ggml.c:11950-11996]
 int launch_rmsnorm_quant(const float * x, const float * w, int n, float eps, int mode, const ActQ & out, float * f32_out, cudaStream_t stream, bool pdl);
 // plain ops for the ggml-backend plugin (rows x n)
-int launch_rms_norm(const float * x, float * y, int n, int64_t nrows, float eps, cudaStream_t stream);
+int launch_rms_norm(const float * x, float * y, int n, int64_t nrows, float eps, cudaStream_t stream, const float * w = nullptr);   // w: fused MUL by the norm weight
 
 struct RopeParams {
     int n_dims, mode, n_ctx_orig;
@@ -97,6 +97,9 @@ int launch_rope(const float * x, float * y, int64_t ntok, int n_head, int D, int
 int launch_attn_decode(const float * q, const __half * kcache, const __half * vcache, float * out, int n_head, int n_head_kv, int D,
                        const int32_t * pos_dev, int n_ctx, float scale, float * scratch, cudaStream_t stream, bool pdl);
 int attn_scratch_floats(int n_head, int n_ctx);
+// batched form for prompt processing: token t (q row t, out row t) attends to cache rows [0, pos_dev[t]]
+int launch_attn_batch(const float * q, const __half * kcache, const __half * vcache, float * out, int n_head, int n_head_kv, int D,
+                      const int32_t * pos_dev, int n_tok, int n_kv_max, float scale, cudaStream_t stream);
 // rope(q), rope(k) -> f16 K row, v -> f16 V row, cache store and attention in one launch (the engine's per-token path)
 int launch_attn_fused(const float * q, const float * k, const float * v, __half * kcache, __half * vcache, float * out, int n_head, int n_head_kv,
                       int D, const int32_t * pos_dev, int n_ctx, const RopeParams & rp, const float * freq_factors, float scale, cudaStream_t stream,
@@ -112,12 +115,13 @@ size_t mmq_workspace_bytes(int64_t K, int64_t T);
 bool mmq_supported(int type, int64_t K);
 int mmq_aborted();
 cudaError_t launch_mmq(int type, const void * W, int64_t N, int64_t K, const float * x, int64_t ldx, int64_t T, float * dst, const float * bias,
-                       void * ws, cudaStream_t st);
+                       const float * resid, void * ws, cudaStream_t st);   // resid: [T][N] added in the epilogue (must not alias dst)
 int launch_get_rows(const void * table, int type, int K, const int32_t * ids, int n_ids, float * y, cudaStream_t stream, bool pdl);
 
 // element-wise helpers for the plugin
 int launch_binary(int op /*0 add, 1 mul*/, const float * a, const float * b, float * y, int64_t n, int64_t nb /*b broadcast period*/, cudaStream_t stream);
 int launch_silu(const float * x, float * y, int64_t n, cudaStream_t stream);
+int launch_silu_mul(const float * g, const float * u, float * y, int64_t n, cudaStream_t stream);   // y = silu(g) * u
 int launch_cpy_f32_f16(const float * x, __half * y, int64_t n, cudaStream_t stream);
 int launch_copy_strided(const void * src, void * dst, int dst_is_f16, const int64_t ne[4], const int64_t sb[4], const int64_t db[4], cudaStream_t stream);
 int launch_mul_mat_f16(const void * A, const void * B, void * D, int64_t K, const int64_t ne[4], int64_t r2, int64_t r3, const int64_t ab[4],

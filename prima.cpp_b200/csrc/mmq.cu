@@ -43,9 +43,11 @@ struct MmqParams {
     const uint8_t * B;     // activations, fp16, tiled [T/BN][K/64][BN x 128 B swizzled]
     float * dst;           // [T][N]
     const float * bias;    // [N] or null
+    const float * resid;   // [T][N] or null: residual added in the epilogue
     int64_t row_bytes, total_bytes;
     int nraw, b_nst;       // ring depths chosen at launch from the shared-memory budget
     int nacc, ttiles;      // accumulators (token tiles) per CTA, number of token tiles
+    int ksplit;            // 1, or 2: blockIdx.z takes half of K and the halves meet in dst by atomic add (dst pre-zeroed)
     int N, K, T, BN, bpb, slot;   // slot: bytes reserved per row in a raw stage (16-B aligned window around one block)
     uint32_t tmem_cols, idesc;
 };
@@ -230,7 +232,8 @@ __global__ void __launch_bounds__(MMQ_THREADS, 1) k_mmq_tc(const __grid_constant
     const int row0 = blockIdx.x * MMQ_BM;
     const int tt0 = blockIdx.y * P.nacc;                         // first token tile of this CTA
     const int nacc = min(P.nacc, P.ttiles - tt0);                // the last CTA of an odd count has one
-    const int nsb = P.K / 256;
+    const int nsb = P.K / 256 / P.ksplit;                        // super-blocks this CTA walks ...
+    const int sb0 = blockIdx.z * nsb;                            // ... starting here
     const int nchunk = nsb * 4;
 
     if (threadIdx.x == 0) {
@@ -275,7 +278,7 @@ __global__ void __launch_bounds__(MMQ_THREADS, 1) k_mmq_tc(const __grid_constant
         // ================= activation producer: runs up to b_nst steps ahead of the tensor core =================
         if (lane == 0) {
             const size_t tile_stride = (size_t) (P.K / MMQ_BK) * b1;
-            const uint8_t * Bt = P.B + (size_t) tt0 * tile_stride;
+            const uint8_t * Bt = P.B + (size_t) tt0 * tile_stride + (size_t) sb0 * 4 * b1;
             for (int u = 0; u < nchunk; u++) {
                 const int sb = u % P.b_nst, rb = u / P.b_nst;
                 if (rb > 0) {   // step u - b_nst consumed this stage
@@ -299,7 +302,7 @@ __global__ void __launch_bounds__(MMQ_THREADS, 1) k_mmq_tc(const __grid_constant
         const int64_t lim = (P.total_bytes + 15) & ~(int64_t) 15;
         const int cpr = P.slot >> 4, p_lo = h ? (cpr + 1) / 2 : 0, p_hi = h ? cpr : (cpr + 1) / 2;
         auto fetch = [&](int x) {
-            const int64_t src0 = ((int64_t) gr * P.row_bytes + (int64_t) x * P.bpb) & ~(int64_t) 15;
+            const int64_t src0 = ((int64_t) gr * P.row_bytes + (int64_t) (sb0 + x) * P.bpb) & ~(int64_t) 15;
             uint8_t * dst0 = raw + ((size_t) (x % P.nraw) * MMQ_BM + r) * P.slot;
             for (int pc = p_lo; pc < p_hi; pc++)
                 if (src0 + pc * 16 + 16 <= lim) cp_async16(dst0 + pc * 16, P.W + src0 + pc * 16);
@@ -321,7 +324,7 @@ __global__ void __launch_bounds__(MMQ_THREADS, 1) k_mmq_tc(const __grid_constant
                 }
             }
             if (!mmq_wait(ctl, &ctl->raw_full[rs], rr & 1)) { ok = false; break; }
-            const int64_t g0 = (int64_t) gr * P.row_bytes + (int64_t) sb * P.bpb;
+            const int64_t g0 = (int64_t) gr * P.row_bytes + (int64_t) (sb0 + sb) * P.bpb;
             const uint8_t * blk = raw + (size_t) (rs * MMQ_BM + r) * P.slot + (g0 & 15);
 #pragma unroll
             for (int c = 0; c < 4; c++, u++) {
@@ -349,7 +352,7 @@ __global__ void __launch_bounds__(MMQ_THREADS, 1) k_mmq_tc(const __grid_constant
             tc_fence_after();
             const int quad = warp & 3;
             const int n = row0 + quad * 32 + lane;
-            const float bias = (P.bias && n < P.N) ? P.bias[n] : 0.f;
+            const float bias = (P.bias && n < P.N && blockIdx.z == 0) ? P.bias[n] : 0.f;
             for (int a = 0; a < nacc; a++) {
                 for (int c0 = 0; c0 < BN; c0 += 16) {
                     uint32_t v[16];
@@ -365,7 +368,12 @@ __global__ void __launch_bounds__(MMQ_THREADS, 1) k_mmq_tc(const __grid_constant
 #pragma unroll
                         for (int i = 0; i < 16; i++) {
                             const int t = (tt0 + a) * BN + c0 + i;
-                            if (t < P.T) P.dst[(size_t) t * P.N + n] = __fadd_rn(__uint_as_float(v[i]), bias);
+                            if (t < P.T) {
+                                float y = __fadd_rn(__uint_as_float(v[i]), bias);
+                                if (P.resid && blockIdx.z == 0) y = __fadd_rn(y, P.resid[(size_t) t * P.N + n]);
+                                if (P.ksplit == 1) P.dst[(size_t) t * P.N + n] = y;
+                                else atomicAdd(&P.dst[(size_t) t * P.N + n], y);   // two addends onto 0: order-independent
+                            }
                         }
                     }
                 }
@@ -381,8 +389,11 @@ __global__ void __launch_bounds__(MMQ_THREADS, 1) k_mmq_tc(const __grid_constant
 }
 
 // ---- activation rows -> q8_K (exactly as the CPU backend quantizes them) -> fp16, written in the tiled UMMA image ----
-__global__ void __launch_bounds__(256) k_mmq_prep(const float * __restrict__ x, int64_t ldx, int T, int K, int BN, uint8_t * __restrict__ out) {
+__global__ void __launch_bounds__(256) k_mmq_prep(const float * __restrict__ x, int64_t ldx, int T, int K, int BN, uint8_t * __restrict__ out,
+                                                  float * __restrict__ zero_dst, int N) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (zero_dst && (int) blockIdx.x < T)   // split-K launches accumulate into dst
+        for (int i = threadIdx.x; i < N; i += 256) zero_dst[(size_t) blockIdx.x * N + i] = 0.f;
     const int nblk = K / 256;
     const int t = blockIdx.x;                       // 0 .. Tpad-1
     const int b_bytes = BN * 128;
@@ -464,19 +475,17 @@ static cudaError_t mmq_launch_typed(const MmqParams & P, dim3 grid, size_t smem,
 }
 
 cudaError_t launch_mmq(int type, const void * W, int64_t N, int64_t K, const float * x, int64_t ldx, int64_t T, float * dst, const float * bias,
-                       void * ws, cudaStream_t st) {
+                       const float * resid, void * ws, cudaStream_t st) {
     if (!mmq_supported(type, K) || N <= 0 || T <= 0) return cudaErrorInvalidValue;
     const int BN = mmq_pick_bn((int) T);
     const int tpad = (int) ((T + BN - 1) / BN * BN);
-    k_mmq_prep<<<tpad, 256, 0, st>>>(x, ldx, (int) T, (int) K, BN, (uint8_t *) ws);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
 
     MmqParams P{};
     P.W = (const uint8_t *) W;
     P.B = (const uint8_t *) ws;
     P.dst = dst;
     P.bias = bias;
+    P.resid = resid;
     P.row_bytes = row_bytes(type, K);
     P.total_bytes = P.row_bytes * N;
     P.N = (int) N;
@@ -487,10 +496,28 @@ cudaError_t launch_mmq(int type, const void * W, int64_t N, int64_t K, const flo
     P.slot = type == T_Q6_K ? 240 : P.bpb;
     P.ttiles = tpad / BN;
     const int rtiles = (int) ((N + MMQ_BM - 1) / MMQ_BM);
-    // two accumulators per CTA halve the weight-expansion work per FLOP; worth it once that still fills most of the SMs
+    // Configuration: two accumulators per CTA halve the weight-expansion work per FLOP (measured 1040 vs 590 TFLOP/s at full
+    // occupancy); splitting K in two doubles the CTA count for small N x T but costs ~20 % (zeroing, atomics, activations read
+    // twice).  Pick the best estimated (efficiency x SM occupancy).
     static const int force_nacc = getenv("PB200_MMQ_NACC") ? atoi(getenv("PB200_MMQ_NACC")) : 0;
-    P.nacc = (P.ttiles >= 2 && (int64_t) rtiles * ((P.ttiles + 1) / 2) >= (sm_count() * 4) / 5) ? 2 : 1;
-    if (force_nacc == 1 || (force_nacc == 2 && P.ttiles >= 2)) P.nacc = force_nacc;
+    static const int force_ks = getenv("PB200_MMQ_KSPLIT") ? atoi(getenv("PB200_MMQ_KSPLIT")) : 0;
+    const int nsm = sm_count(), nsb_all = (int) (K / 256);
+    double best = -1.0;
+    P.nacc = 1; P.ksplit = 1;
+    for (int nacc = 1; nacc <= 2; nacc++)
+        for (int ks = 1; ks <= 2; ks++) {
+            if (nacc == 2 && P.ttiles < 2) continue;
+            if (ks == 2 && (nsb_all % 2 != 0 || nsb_all < 8)) continue;
+            if (force_nacc && nacc != force_nacc && !(force_nacc == 2 && P.ttiles < 2)) continue;
+            if (force_ks && ks != force_ks && !(ks == 1 && (nsb_all % 2 != 0 || nsb_all < 8))) continue;
+            const int64_t ctas = (int64_t) rtiles * ((P.ttiles + nacc - 1) / nacc) * ks;
+            const double occ = (double) ctas / (double) ((ctas + nsm - 1) / nsm * nsm);
+            const double score = occ * (nacc == 2 ? 1.0 : 0.57) * (ks == 2 ? 0.80 : 1.0);
+            if (score > best) { best = score; P.nacc = nacc; P.ksplit = ks; }
+        }
+    k_mmq_prep<<<tpad, 256, 0, st>>>(x, ldx, (int) T, (int) K, BN, (uint8_t *) ws, P.ksplit > 1 ? dst : nullptr, (int) N);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
     uint32_t cols = 32;
     while ((int) cols < BN) cols <<= 1;
     P.tmem_cols = P.nacc == 2 ? 512 : cols;
@@ -506,7 +533,7 @@ cudaError_t launch_mmq(int type, const void * W, int64_t N, int64_t K, const flo
     while (P.b_nst > 2 && smem_for(P.nraw, P.b_nst) > 232448) P.b_nst--;
     const size_t smem = smem_for(P.nraw, P.b_nst);
     if (smem > 232448) return cudaErrorInvalidConfiguration;
-    dim3 grid((unsigned) rtiles, (unsigned) ((P.ttiles + P.nacc - 1) / P.nacc));
+    dim3 grid((unsigned) rtiles, (unsigned) ((P.ttiles + P.nacc - 1) / P.nacc), (unsigned) P.ksplit);
     if (type == T_Q4_K) return mmq_launch_typed<T_Q4_K>(P, grid, smem, st);
     if (type == T_Q5_K) return mmq_launch_typed<T_Q5_K>(P, grid, smem, st);
     return mmq_launch_typed<T_Q6_K>(P, grid, smem, st);

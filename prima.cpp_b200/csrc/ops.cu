@@ -113,7 +113,8 @@ __global__ void __launch_bounds__(1024) k_rmsnorm_quant(const float * __restrict
 }
 
 // plain row-wise rms_norm for the plugin (no weight): one CTA per row
-__global__ void __launch_bounds__(256) k_rms_norm_rows(const float * __restrict__ x, float * __restrict__ y, int n, float eps) {
+__global__ void __launch_bounds__(256) k_rms_norm_rows(const float * __restrict__ x, float * __restrict__ y, int n, float eps,
+                                                       const float * __restrict__ w) {
     __shared__ double red[8];
     __shared__ float s_scale;
     const float * xr = x + (int64_t) blockIdx.x * n;
@@ -132,7 +133,11 @@ __global__ void __launch_bounds__(256) k_rms_norm_rows(const float * __restrict_
     }
     __syncthreads();
     const float scale = s_scale;
-    for (int i = threadIdx.x; i < n; i += 256) yr[i] = __fmul_rn(xr[i], scale);
+    if (w) {   // the following MUL node by the norm weight (src/llama.cpp:9772-9802), same two roundings as the separate kernels
+        for (int i = threadIdx.x; i < n; i += 256) yr[i] = __fmul_rn(__fmul_rn(xr[i], scale), w[i]);
+    } else {
+        for (int i = threadIdx.x; i < n; i += 256) yr[i] = __fmul_rn(xr[i], scale);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -202,11 +207,14 @@ __global__ void k_rope(const float * __restrict__ x, float * __restrict__ y, int
 //   o[d] = sum_p f32(V16[p][d]) * f32(f16(w[p]))            (second mul_mat, probabilities rounded to f16)
 __global__ void __launch_bounds__(256) k_attn_decode(const float * __restrict__ q, const __half * __restrict__ kc, const __half * __restrict__ vc,
                                                      float * __restrict__ out, int n_head, int n_head_kv, int D, const int32_t * __restrict__ pos_dev,
-                                                     float scale) {
+                                                     float scale, int64_t q_tok_stride, int64_t out_tok_stride) {
     extern __shared__ float sm[];   // S[n_kv_pad] | red[8][128]
     pdl_trigger();   // dependents may launch now; they still wait for this grid's completion in their own pdl_wait()
     pdl_wait();
-    const int n_kv = *pos_dev + 1;
+    // blockIdx.y = token of a batch (prefill): its own position, q row and out row; K/V rows [0, pos] are already in the cache
+    const int n_kv = pos_dev[blockIdx.y] + 1;
+    q += (int64_t) blockIdx.y * q_tok_stride;
+    out += (int64_t) blockIdx.y * out_tok_stride;
     const int h = blockIdx.x, hk = h / (n_head / n_head_kv);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t EK = (int64_t) n_head_kv * D;
@@ -275,6 +283,81 @@ __global__ void __launch_bounds__(256) k_attn_decode(const float * __restrict__ 
 #pragma unroll
         for (int i = 0; i < 8; i++) t += red[i * 128 + threadIdx.x];
         out[(int64_t) h * D + threadIdx.x] = t;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Prompt-processing attention, same arithmetic per (head, token) row as k_attn_decode (f16-rounded q and probabilities, double
+// softmax sum) but one CTA per (kv head, token): its warps are the q heads of the GQA group, so the K/V rows of the kv head
+// come out of L2 once per CTA and are shared through L1 (the per-head grid re-read them gqa x: measured L2-bound, 7 TB/s).
+// Each warp walks all n_kv rows of its head alone: no cross-warp reduction, scores in the warp's shared-memory strip.
+__global__ void __launch_bounds__(256) k_attn_prefill(const float * __restrict__ q, const __half * __restrict__ kc, const __half * __restrict__ vc,
+                                                      float * __restrict__ out, int n_head, int n_head_kv, const int32_t * __restrict__ pos_dev,
+                                                      float scale, int n_kv_pad) {
+    constexpr int D = 128;
+    extern __shared__ float sm[];   // [8 warps][n_kv_pad]
+    const int tok = blockIdx.y, hk = blockIdx.x;
+    const int n_kv = pos_dev[tok] + 1;
+    const int gqa = n_head / n_head_kv;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t EK = (int64_t) n_head_kv * D;
+    float * S = sm + (size_t) warp * n_kv_pad;
+    const __half * kbase = kc + (int64_t) hk * D + 4 * lane;
+    const __half * vbase = vc + (int64_t) hk * D + 4 * lane;
+    for (int hh = warp; hh < gqa; hh += 8) {
+        const int h = hk * gqa + hh;
+        const float4 qv = *reinterpret_cast<const float4 *>(q + ((int64_t) tok * n_head + h) * D + 4 * lane);
+        const float q0 = __half2float(__float2half_rn(qv.x)), q1 = __half2float(__float2half_rn(qv.y));
+        const float q2 = __half2float(__float2half_rn(qv.z)), q3 = __half2float(__float2half_rn(qv.w));
+        float m = -INFINITY;
+        for (int p0 = 0; p0 < n_kv; p0 += 4) {
+            uint2 kraw[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (p0 + j < n_kv) kraw[j] = *reinterpret_cast<const uint2 *>(kbase + (int64_t) (p0 + j) * EK);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (p0 + j < n_kv) {
+                    const float2 k01 = __half22float2(*reinterpret_cast<const __half2 *>(&kraw[j].x));
+                    const float2 k23 = __half22float2(*reinterpret_cast<const __half2 *>(&kraw[j].y));
+                    float s = k01.x * q0;
+                    s = fmaf(k01.y, q1, s);
+                    s = fmaf(k23.x, q2, s);
+                    s = fmaf(k23.y, q3, s);
+                    s = __fmul_rn(warp_sum(s), scale);
+                    m = fmaxf(m, s);
+                    if (lane == 0) S[p0 + j] = s;
+                }
+            }
+        }
+        __syncwarp();
+        double dsum = 0.0;
+        for (int p = lane; p < n_kv; p += 32) {
+            const float e = expf(__fsub_rn(S[p], m));
+            S[p] = e;
+            dsum += (double) e;
+        }
+        dsum = warp_sum_d(dsum);
+        const float inv = (float) (1.0 / dsum);
+        __syncwarp();
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        for (int p0 = 0; p0 < n_kv; p0 += 4) {
+            uint2 vraw[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (p0 + j < n_kv) vraw[j] = *reinterpret_cast<const uint2 *>(vbase + (int64_t) (p0 + j) * EK);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (p0 + j < n_kv) {
+                    const float w = __half2float(__float2half_rn(__fmul_rn(S[p0 + j], inv)));
+                    const float2 v01 = __half22float2(*reinterpret_cast<const __half2 *>(&vraw[j].x));
+                    const float2 v23 = __half22float2(*reinterpret_cast<const __half2 *>(&vraw[j].y));
+                    a0 = fmaf(v01.x, w, a0); a1 = fmaf(v01.y, w, a1); a2 = fmaf(v23.x, w, a2); a3 = fmaf(v23.y, w, a3);
+                }
+            }
+        }
+        *reinterpret_cast<float4 *>(out + ((int64_t) tok * n_head + h) * D + 4 * lane) = make_float4(a0, a1, a2, a3);
+        __syncwarp();
     }
 }
 
@@ -538,6 +621,10 @@ __global__ void k_silu(const float * __restrict__ x, float * __restrict__ y, int
     const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) y[i] = silu_f32(x[i]);
 }
+__global__ void k_silu_mul(const float * __restrict__ g, const float * __restrict__ u, float * __restrict__ y, int64_t n) {
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = __fmul_rn(silu_f32(g[i]), u[i]);
+}
 __global__ void k_cpy_f32_f16(const float * __restrict__ x, __half * __restrict__ y, int64_t n) {
     const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) y[i] = __float2half_rn(x[i]);
@@ -624,8 +711,8 @@ int launch_rmsnorm_quant(const float * x, const float * w, int n, float eps, int
     launch_cfg(cfg, attr, dim3(1), dim3(1024), 0, stream, pdl);
     return (int) cudaLaunchKernelEx(&cfg, k_rmsnorm_quant, x, w, n, eps, mode, out, f32_out);
 }
-int launch_rms_norm(const float * x, float * y, int n, int64_t nrows, float eps, cudaStream_t stream) {
-    k_rms_norm_rows<<<(unsigned) nrows, 256, 0, stream>>>(x, y, n, eps);
+int launch_rms_norm(const float * x, float * y, int n, int64_t nrows, float eps, cudaStream_t stream, const float * w) {
+    k_rms_norm_rows<<<(unsigned) nrows, 256, 0, stream>>>(x, y, n, eps, w);
     return (int) cudaGetLastError();
 }
 
@@ -669,7 +756,36 @@ int launch_attn_decode(const float * q, const __half * kcache, const __half * vc
     }
     cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1];
     launch_cfg(cfg, attr, dim3(n_head), dim3(256), smem, stream, pdl);
-    return (int) cudaLaunchKernelEx(&cfg, k_attn_decode, q, kcache, vcache, out, n_head, n_head_kv, D, pos_dev, scale);
+    return (int) cudaLaunchKernelEx(&cfg, k_attn_decode, q, kcache, vcache, out, n_head, n_head_kv, D, pos_dev, scale, (int64_t) 0, (int64_t) 0);
+}
+// prefill: n_tok query rows (strides in floats), token t attends to cache rows [0, pos_dev[t]]
+int launch_attn_batch(const float * q, const __half * kcache, const __half * vcache, float * out, int n_head, int n_head_kv, int D,
+                      const int32_t * pos_dev, int n_tok, int n_kv_max, float scale, cudaStream_t stream) {
+    if (D != 128 || n_tok <= 0 || n_tok > 65535) return (int) cudaErrorInvalidValue;
+    {   // GQA-shared kernel: 8 score strips of n_kv_max floats must fit in shared memory
+        const int n_kv_pad = (n_kv_max + 31) & ~31;
+        const size_t smem_p = (size_t) 8 * n_kv_pad * sizeof(float);
+        static int configured = 0;
+        if (smem_p <= 200 * 1024) {
+            if ((int) smem_p > configured && smem_p > 40 * 1024) {
+                cudaError_t e = cudaFuncSetAttribute(k_attn_prefill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_p);
+                if (e != cudaSuccess) return (int) e;
+                configured = (int) smem_p;
+            }
+            k_attn_prefill<<<dim3(n_head_kv, n_tok), 256, smem_p, stream>>>(q, kcache, vcache, out, n_head, n_head_kv, pos_dev, scale, n_kv_pad);
+            return (int) cudaGetLastError();
+        }
+    }
+    const size_t smem = ((size_t) ((n_kv_max + 31) & ~31) + 8 * 128) * sizeof(float);
+    if ((int) smem > g_attn_smem_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_attn_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        if (e != cudaSuccess) return (int) e;
+        g_attn_smem_set = (int) smem;
+    }
+    cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1];
+    launch_cfg(cfg, attr, dim3(n_head, n_tok), dim3(256), smem, stream, false);
+    return (int) cudaLaunchKernelEx(&cfg, k_attn_decode, q, kcache, vcache, out, n_head, n_head_kv, D, pos_dev, scale, (int64_t) n_head * D,
+                                    (int64_t) n_head * D);
 }
 
 static int g_attnf_smem_set = 0;
@@ -711,6 +827,10 @@ int launch_binary(int op, const float * a, const float * b, float * y, int64_t n
 }
 int launch_silu(const float * x, float * y, int64_t n, cudaStream_t stream) {
     k_silu<<<(unsigned) ((n + 255) / 256), 256, 0, stream>>>(x, y, n);
+    return (int) cudaGetLastError();
+}
+int launch_silu_mul(const float * g, const float * u, float * y, int64_t n, cudaStream_t stream) {
+    k_silu_mul<<<(unsigned) ((n + 255) / 256), 256, 0, stream>>>(g, u, y, n);
     return (int) cudaGetLastError();
 }
 int launch_cpy_f32_f16(const float * x, __half * y, int64_t n, cudaStream_t stream) {

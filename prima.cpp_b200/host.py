@@ -65,7 +65,7 @@ class Lib:
         c.pb200_get_rows.argtypes = [C.c_int, vp, i64, vp, i64, vp, vp]
         c.pb200_mul_mat_q_workspace_bytes.restype = C.c_size_t
         c.pb200_mul_mat_q_workspace_bytes.argtypes = [i64, i64]
-        c.pb200_mul_mat_q.argtypes = [C.c_int, vp, i64, i64, vp, i64, i64, vp, vp, vp, vp]
+        c.pb200_mul_mat_q.argtypes = [C.c_int, vp, i64, i64, vp, i64, i64, vp, vp, vp, vp, vp]
         c.pb200_attn_decode.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, f32, vp]
         c.pb200_model_create.restype = vp
         c.pb200_model_create.argtypes = [C.POINTER(HParams), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
@@ -77,6 +77,7 @@ class Lib:
         c.pb200_model_weight_bytes.argtypes = [vp]
         c.pb200_kv_clear.argtypes = [vp]
         c.pb200_decode.argtypes = [vp, i32, i32, vp]
+        c.pb200_prefill.argtypes = [vp, vp, i32, i32, vp]
         c.pb200_decode_async.argtypes = [vp, i32, i32]
         c.pb200_synchronize.argtypes = [vp]
         for n in ("pb200_logits_device", "pb200_hidden_in_device", "pb200_hidden_out_device", "pb200_stream"):
@@ -134,6 +135,15 @@ class Model:
         ptr = None if logits_out is None else logits_out.ctypes.data_as(C.c_void_p)
         self.lib.check(self.lib.c.pb200_decode(self.h, token, pos, ptr), "decode")
         return logits_out
+
+    def prefill(self, tokens, pos0: int = 0, logits_out=None):
+        """Prompt processing: all tokens as one batch (tensor-core mat-muls); returns the last token's logits."""
+        import numpy as np
+        toks = np.ascontiguousarray(tokens, dtype=np.int32)
+        out = logits_out if logits_out is not None else np.empty(self.hp.n_vocab, dtype=np.float32)
+        self.lib.check(self.lib.c.pb200_prefill(self.h, toks.ctypes.data_as(C.c_void_p), int(toks.size), int(pos0), out.ctypes.data_as(C.c_void_p)),
+                       "prefill")
+        return out
 
     def decode_async(self, token: int, pos: int) -> None:
         self.lib.check(self.lib.c.pb200_decode_async(self.h, token, pos), "decode_async")

@@ -22,7 +22,7 @@ pytestmark = pytest.mark.gpu
 KQ = [O.Q4_K, O.Q5_K, O.Q6_K]
 
 
-def run_mmq(lib, t, W, N, K, X, bias=None, ldx=None):
+def run_mmq(lib, t, W, N, K, X, bias=None, ldx=None, resid=None):
     T = X.shape[0]
     ldx = ldx or K
     Xp = np.zeros((T, ldx), np.float32)
@@ -31,7 +31,9 @@ def run_mmq(lib, t, W, N, K, X, bias=None, ldx=None):
     y = torch.full((T, N), float("nan"), dtype=torch.float32, device="cuda")
     ws = torch.zeros(lib.c.pb200_mul_mat_q_workspace_bytes(K, T) + 64, dtype=torch.uint8, device="cuda")
     bd = dev_f32(bias) if bias is not None else None
-    lib.check(lib.c.pb200_mul_mat_q(t, ptr(Wd), N, K, ptr(xd), ldx, T, ptr(y), ptr(bd) if bd is not None else None, ptr(ws), None), "mul_mat_q")
+    rd = dev_f32(resid) if resid is not None else None
+    lib.check(lib.c.pb200_mul_mat_q(t, ptr(Wd), N, K, ptr(xd), ldx, T, ptr(y), ptr(bd) if bd is not None else None,
+                                    ptr(rd) if rd is not None else None, ptr(ws), None), "mul_mat_q")
     sync()
     assert lib.c.pb200_mul_mat_q_aborted() == 0, "tcgen05 pipeline gave up (watchdog)"
     return y.cpu().numpy()
@@ -94,22 +96,24 @@ def test_mmq_integer_exact(cuda, lib, port):
     assert np.array_equal(got, want)
 
 
-def test_mmq_bias_ragged_rows_and_strided_input(cuda, lib, port):
-    t, N, K, T = O.Q6_K, 200, 512, 40        # N not a multiple of the 128-row tile, ldx > K
+def test_mmq_bias_residual_ragged_rows_and_strided_input(cuda, lib, port):
+    t, N, K, T = O.Q6_K, 200, 2048, 40       # N not a multiple of the 128-row tile, ldx > K, split-K (bias added once)
     rng = np.random.default_rng(9)
     W = O.synth_blocks(t, N, K, seed=3)
     X = rng.standard_normal((T, K)).astype(np.float32)
     bias = rng.standard_normal(N).astype(np.float32)
-    got = run_mmq(lib, t, W, N, K, X, bias=bias, ldx=K + 64)
-    want = oracle(port, t, W, N, K, X) + bias[None, :]
+    resid = rng.standard_normal((T, N)).astype(np.float32)
+    got = run_mmq(lib, t, W, N, K, X, bias=bias, ldx=K + 64, resid=resid)
+    want = (oracle(port, t, W, N, K, X) + bias[None, :]) + resid
     Wf = port.dequantize(t, W, N * K).reshape(N, K)
     check(got, want, Wf, X)
 
 
-def test_mmq_matches_gemv_columnwise_full_width(cuda, lib):
+@pytest.mark.parametrize("T", [700, 512])   # 700: two accumulators per CTA + a ragged third tile; 512: two accumulators + split-K
+def test_mmq_matches_gemv_columnwise_full_width(cuda, lib, T):
     """Size-independent property at a 70B shape (also the dual-accumulator configuration): every column of the batched product agrees with the decode GEMV (which is
     bit-exact with the oracle) to NMSE <= 4e-6."""
-    t, N, K, T = O.Q4_K, 8192, 8192, 700     # 3 token tiles: two accumulators per CTA, the last CTA column has one; ragged last tile
+    t, N, K = O.Q4_K, 8192, 8192
     g = torch.Generator(device="cuda").manual_seed(1)
     W = O.synth_blocks(t, 256, K, seed=11)                  # 256 distinct rows, tiled to N
     Wfull = np.tile(W.reshape(256, -1), (N // 256, 1)).reshape(-1)
@@ -119,6 +123,8 @@ def test_mmq_matches_gemv_columnwise_full_width(cuda, lib):
     Wd = dev_u8(Wfull)
     ws = torch.zeros(lib.c.pb200_act_workspace_bytes(K) + 64, dtype=torch.uint8, device="cuda")
     for col in (0, 1, 255, 256, 511, 512, 600, 699):
+        if col >= T:
+            continue
         xd = dev_f32(X[col])
         y = torch.zeros(N, dtype=torch.float32, device="cuda")
         lib.check(lib.c.pb200_mul_mat_vec(t, ptr(Wd), N, K, ptr(xd), ptr(y), ptr(ws), None), "mul_mat_vec")

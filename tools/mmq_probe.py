@@ -22,7 +22,7 @@ def run(t, W, N, K, X):
     Wd, xd = dev_u8(W), dev_f32(X)
     y = torch.full((T, N), float("nan"), dtype=torch.float32, device="cuda")
     ws = torch.zeros(lib.c.pb200_mul_mat_q_workspace_bytes(K, T) + 64, dtype=torch.uint8, device="cuda")
-    rc = lib.c.pb200_mul_mat_q(t, ptr(Wd), N, K, ptr(xd), K, T, ptr(y), None, ptr(ws), None)
+    rc = lib.c.pb200_mul_mat_q(t, ptr(Wd), N, K, ptr(xd), K, T, ptr(y), None, None, ptr(ws), None)
     sync()
     return rc, y.cpu().numpy()
 
@@ -35,13 +35,13 @@ for (t, N, K, T) in [(O.Q4_K, 8192, 8192, 512), (O.Q4_K, 28672, 8192, 512), (O.Q
     y = torch.zeros((T, N), device="cuda")
     ws = torch.zeros(lib.c.pb200_mul_mat_q_workspace_bytes(K, T) + 64, dtype=torch.uint8, device="cuda")
     for _ in range(2):
-        lib.c.pb200_mul_mat_q(t, ptr(Wd), N, K, ptr(xd), K, T, ptr(y), None, ptr(ws), None)
+        lib.c.pb200_mul_mat_q(t, ptr(Wd), N, K, ptr(xd), K, T, ptr(y), None, None, ptr(ws), None)
     sync()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     reps = 5
     for _ in range(reps):
-        lib.c.pb200_mul_mat_q(t, ptr(Wd), N, K, ptr(xd), K, T, ptr(y), None, ptr(ws), None)
+        lib.c.pb200_mul_mat_q(t, ptr(Wd), N, K, ptr(xd), K, T, ptr(y), None, None, ptr(ws), None)
     e1.record(); sync()
     ms = e0.elapsed_time(e1) / reps
     print(f"perf {O.TYPE_NAME[t]} N {N} K {K} T {T}: {ms:.3f} ms  {2.0 * N * K * T / ms / 1e9:.1f} TFLOP/s aborted {lib.c.pb200_mul_mat_q_aborted()}", flush=True)
