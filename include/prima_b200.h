@@ -98,6 +98,10 @@ PB200_API int pb200_get_rows(int type, const void * table, int64_t k, const int3
 /* decode attention over an f16 KV cache laid out [n_ctx][n_head_kv*head_dim]; n_kv = *pos_dev + 1 */
 PB200_API int pb200_attn_decode(const float * q, const void * k_cache_f16, const void * v_cache_f16, float * out, int n_head, int n_head_kv,
                                 int head_dim, const int32_t * pos_dev, int n_ctx, float scale, void * stream);
+/* prompt-processing attention: n_tok query rows q[t][n_head][head_dim]; token t attends to cache rows [0, pos_dev[t]] (its own
+ * K/V row already stored); n_kv_max >= max(pos_dev) + 1.  Same FA-off arithmetic per row as pb200_attn_decode. */
+PB200_API int pb200_attn_prefill(const float * q, const void * k_cache_f16, const void * v_cache_f16, float * out, int n_head, int n_head_kv,
+                                 int head_dim, const int32_t * pos_dev, int n_tok, int n_kv_max, float scale, void * stream);
 
 /* ---- decode engine (one model shard per process / GPU) ---- */
 typedef struct pb200_hparams {

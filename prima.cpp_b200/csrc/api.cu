@@ -206,4 +206,13 @@ int pb200_attn_decode(const float * q, const void * k_cache_f16, const void * v_
                               nullptr, (cudaStream_t) stream, false);
 }
 
+int pb200_attn_prefill(const float * q, const void * k_cache_f16, const void * v_cache_f16, float * out, int n_head, int n_head_kv, int head_dim,
+                       const int32_t * pos_dev, int n_tok, int n_kv_max, float scale, void * stream) {
+    if (!q || !k_cache_f16 || !v_cache_f16 || !out || !pos_dev || head_dim != 128 || n_head_kv <= 0 || n_head % n_head_kv || n_tok <= 0 || n_kv_max <= 0)
+        return PB200_EINVAL;
+    g_launches++;
+    return launch_attn_batch(q, (const __half *) k_cache_f16, (const __half *) v_cache_f16, out, n_head, n_head_kv, head_dim, pos_dev, n_tok, n_kv_max,
+                             scale, (cudaStream_t) stream);
+}
+
 }  // extern "C"

@@ -682,7 +682,21 @@ __global__ void k_iota_pos(int32_t * pos, int pos0, int T) {
     if (i < T) pos[i] = pos0 + i;
 }
 
+static int prefill_ubatch(pb200_model * m, const int32_t * tokens_host, int32_t T, int32_t pos0, float * logits_host);
+static const int PB200_N_UBATCH = 512;   // the reference's default n_ubatch (common/common.h): longer prompts go through in slices
+
 extern "C" int pb200_prefill(pb200_model * m, const int32_t * tokens_host, int32_t T, int32_t pos0, float * logits_host) {
+    if (!m || !m->finalized) return PB200_ESTATE;
+    if (!tokens_host || T <= 0 || pos0 < 0 || pos0 + T > m->hp.n_ctx) return PB200_EINVAL;
+    for (int32_t done = 0; done < T; done += PB200_N_UBATCH) {
+        const int32_t n = std::min<int32_t>(PB200_N_UBATCH, T - done);
+        const int rc = prefill_ubatch(m, tokens_host + done, n, pos0 + done, done + n == T ? logits_host : nullptr);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+static int prefill_ubatch(pb200_model * m, const int32_t * tokens_host, int32_t T, int32_t pos0, float * logits_host) {
     if (!m || !m->finalized) return PB200_ESTATE;
     if (!tokens_host || T <= 0 || pos0 < 0 || pos0 + T > m->hp.n_ctx) return PB200_EINVAL;
     if (!m->with_embd || m->l0 != 0) return PB200_ENOTSUP;   // batched prompt processing starts at the embedding (single-process models)

@@ -287,77 +287,125 @@ __global__ void __launch_bounds__(256) k_attn_decode(const float * __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Prompt-processing attention, same arithmetic per (head, token) row as k_attn_decode (f16-rounded q and probabilities, double
-// softmax sum) but one CTA per (kv head, token): its warps are the q heads of the GQA group, so the K/V rows of the kv head
-// come out of L2 once per CTA and are shared through L1 (the per-head grid re-read them gqa x: measured L2-bound, 7 TB/s).
-// Each warp walks all n_kv rows of its head alone: no cross-warp reduction, scores in the warp's shared-memory strip.
-__global__ void __launch_bounds__(256) k_attn_prefill(const float * __restrict__ q, const __half * __restrict__ kc, const __half * __restrict__ vc,
-                                                      float * __restrict__ out, int n_head, int n_head_kv, const int32_t * __restrict__ pos_dev,
-                                                      float scale, int n_kv_pad) {
+// Tiled prompt-processing attention: one CTA per (kv head, ATT_TQ consecutive tokens; 4, or 2 / 1 for long contexts).  Warp w =
+// q head w of the GQA group (loops when gqa > 8) for those tokens; K and V stream through shared memory in 32-position tiles and every tile is used by all
+// gqa x 4 query rows (a per-(head, token) grid re-reads K/V for every row: measured L2-bound at 7 TB/s, 0.6 ms per 70B layer at T = 512).  Numerics are the CPU
+// graph's (FA off): q and the probabilities rounded to f16, softmax sum in double; scores of all rows live in shared memory,
+// so this kernel serves n_kv up to ATTN_TILED_MAX_KV and the launcher falls back beyond that.
+constexpr int ATT_TK = 32, ATT_KSTRIDE = 130;   // halves per K row in smem: 65 words => conflict-free column walks
+template <int ATT_TQ>
+__global__ void __launch_bounds__(256) k_attn_prefill_tiled(const float * __restrict__ q, const __half * __restrict__ kc,
+                                                            const __half * __restrict__ vc, float * __restrict__ out, int n_head, int n_head_kv,
+                                                            const int32_t * __restrict__ pos_dev, int n_tok, float scale, int n_kv_pad) {
     constexpr int D = 128;
-    extern __shared__ float sm[];   // [8 warps][n_kv_pad]
-    const int tok = blockIdx.y, hk = blockIdx.x;
-    const int n_kv = pos_dev[tok] + 1;
+    extern __shared__ __align__(16) uint8_t att_smem[];
     const int gqa = n_head / n_head_kv;
+    const int hk = blockIdx.x, t0 = blockIdx.y * ATT_TQ;
+    const int ntq = min(ATT_TQ, n_tok - t0);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t EK = (int64_t) n_head_kv * D;
-    float * S = sm + (size_t) warp * n_kv_pad;
-    const __half * kbase = kc + (int64_t) hk * D + 4 * lane;
-    const __half * vbase = vc + (int64_t) hk * D + 4 * lane;
-    for (int hh = warp; hh < gqa; hh += 8) {
-        const int h = hk * gqa + hh;
-        const float4 qv = *reinterpret_cast<const float4 *>(q + ((int64_t) tok * n_head + h) * D + 4 * lane);
-        const float q0 = __half2float(__float2half_rn(qv.x)), q1 = __half2float(__float2half_rn(qv.y));
-        const float q2 = __half2float(__float2half_rn(qv.z)), q3 = __half2float(__float2half_rn(qv.w));
-        float m = -INFINITY;
-        for (int p0 = 0; p0 < n_kv; p0 += 4) {
-            uint2 kraw[4];
+    float * S = reinterpret_cast<float *>(att_smem);                           // [gqa * TQ][n_kv_pad]
+    float * q_s = S + (size_t) gqa * ATT_TQ * n_kv_pad;                        // [gqa * TQ][128]   f16-rounded q as f32
+    __half * kv_s = reinterpret_cast<__half *>(q_s + (size_t) gqa * ATT_TQ * D);   // [TK][KSTRIDE]
+    __shared__ int s_nkv[ATT_TQ];
+    if (threadIdx.x < ATT_TQ) s_nkv[threadIdx.x] = threadIdx.x < ntq ? pos_dev[t0 + threadIdx.x] + 1 : 0;
+    for (int i = threadIdx.x; i < gqa * ATT_TQ * D; i += 256) {
+        const int row = i / D, d = i - row * D, hh = row / ATT_TQ, tq = row - hh * ATT_TQ;
+        q_s[i] = tq < ntq ? __half2float(__float2half_rn(q[((int64_t) (t0 + tq) * n_head + hk * gqa + hh) * D + d])) : 0.f;
+    }
+    __syncthreads();
+    int n_kv_max = 0;
 #pragma unroll
-            for (int j = 0; j < 4; j++)
-                if (p0 + j < n_kv) kraw[j] = *reinterpret_cast<const uint2 *>(kbase + (int64_t) (p0 + j) * EK);
+    for (int i = 0; i < ATT_TQ; i++) n_kv_max = max(n_kv_max, s_nkv[i]);
+
+    // ---- scores: S[row][p] = scale * q_row . K[p] ----
+    for (int p0 = 0; p0 < n_kv_max; p0 += ATT_TK) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < ATT_TK * (D / 8); i += 256) {            // 16-byte pieces: 32 rows x 16
+            const int r = i >> 4, c = i & 15;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (p0 + r < n_kv_max) v = *reinterpret_cast<const uint4 *>(kc + (int64_t) (p0 + r) * EK + (int64_t) hk * D + c * 8);
+            uint32_t * dst = reinterpret_cast<uint32_t *>(kv_s + r * ATT_KSTRIDE + c * 8);   // rows are only 4-byte aligned (260 B stride)
+            dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+        }
+        __syncthreads();
+        for (int hh = warp; hh < gqa; hh += 8) {
+            const __half2 * krow = reinterpret_cast<const __half2 *>(kv_s + lane * ATT_KSTRIDE);   // lane = position p0 + lane
+            const float * qh = q_s + (size_t) hh * ATT_TQ * D;
+            float a[ATT_TQ];
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                if (p0 + j < n_kv) {
-                    const float2 k01 = __half22float2(*reinterpret_cast<const __half2 *>(&kraw[j].x));
-                    const float2 k23 = __half22float2(*reinterpret_cast<const __half2 *>(&kraw[j].y));
-                    float s = k01.x * q0;
-                    s = fmaf(k01.y, q1, s);
-                    s = fmaf(k23.x, q2, s);
-                    s = fmaf(k23.y, q3, s);
-                    s = __fmul_rn(warp_sum(s), scale);
-                    m = fmaxf(m, s);
-                    if (lane == 0) S[p0 + j] = s;
+            for (int tq = 0; tq < ATT_TQ; tq++) a[tq] = 0.f;
+#pragma unroll 8
+            for (int d2 = 0; d2 < D / 2; d2++) {
+                const float2 k2 = __half22float2(krow[d2]);
+#pragma unroll
+                for (int tq = 0; tq < ATT_TQ; tq++) {
+                    const float2 qq = *reinterpret_cast<const float2 *>(qh + tq * D + 2 * d2);
+                    a[tq] = fmaf(k2.x, qq.x, a[tq]);
+                    a[tq] = fmaf(k2.y, qq.y, a[tq]);
                 }
             }
+            float * Sr = S + (size_t) hh * ATT_TQ * n_kv_pad + p0 + lane;
+#pragma unroll
+            for (int tq = 0; tq < ATT_TQ; tq++) Sr[(size_t) tq * n_kv_pad] = __fmul_rn(a[tq], scale);
         }
-        __syncwarp();
+    }
+    __syncthreads();
+    // ---- softmax per row (warp per row): p = f16(exp(s - max) * float(1 / double sum)), causal length per token ----
+    for (int row = warp; row < gqa * ATT_TQ; row += 8) {
+        const int n_kv = s_nkv[row % ATT_TQ];
+        float * Sr = S + (size_t) row * n_kv_pad;
+        float m = -INFINITY;
+        for (int p = lane; p < n_kv; p += 32) m = fmaxf(m, Sr[p]);
+        m = warp_max(m);
         double dsum = 0.0;
         for (int p = lane; p < n_kv; p += 32) {
-            const float e = expf(__fsub_rn(S[p], m));
-            S[p] = e;
+            const float e = expf(__fsub_rn(Sr[p], m));
+            Sr[p] = e;
             dsum += (double) e;
         }
         dsum = warp_sum_d(dsum);
-        const float inv = (float) (1.0 / dsum);
-        __syncwarp();
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        for (int p0 = 0; p0 < n_kv; p0 += 4) {
-            uint2 vraw[4];
+        const float inv = n_kv > 0 ? (float) (1.0 / dsum) : 0.f;
+        for (int p = lane; p < n_kv_pad; p += 32) Sr[p] = p < n_kv ? __half2float(__float2half_rn(__fmul_rn(Sr[p], inv))) : 0.f;
+    }
+    // ---- out[row][:] = sum_p P[row][p] * V[p][:]   (lane owns 4 of the 128 dims) ----
+    float acc[1][ATT_TQ][4];
+    for (int hbase = 0; hbase < gqa; hbase += 8) {
+        const int hh = hbase + warp;
 #pragma unroll
-            for (int j = 0; j < 4; j++)
-                if (p0 + j < n_kv) vraw[j] = *reinterpret_cast<const uint2 *>(vbase + (int64_t) (p0 + j) * EK);
+        for (int tq = 0; tq < ATT_TQ; tq++) { acc[0][tq][0] = acc[0][tq][1] = acc[0][tq][2] = acc[0][tq][3] = 0.f; }
+        for (int p0 = 0; p0 < n_kv_max; p0 += ATT_TK) {
+            __syncthreads();
+            for (int i = threadIdx.x; i < ATT_TK * (D / 8); i += 256) {
+                const int r = i >> 4, c = i & 15;
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (p0 + r < n_kv_max) v = *reinterpret_cast<const uint4 *>(vc + (int64_t) (p0 + r) * EK + (int64_t) hk * D + c * 8);
+                *reinterpret_cast<uint4 *>(kv_s + r * D + c * 8) = v;             // V tile dense: rows of 256 B
+            }
+            __syncthreads();
+            if (hh < gqa) {
+                const float * Pr = S + (size_t) hh * ATT_TQ * n_kv_pad + p0;
+                const int np = min(ATT_TK, n_kv_max - p0);
+                for (int j = 0; j < np; j++) {
+                    const uint2 vraw = *reinterpret_cast<const uint2 *>(kv_s + j * D + 4 * lane);
+                    const float2 v01 = __half22float2(*reinterpret_cast<const __half2 *>(&vraw.x));
+                    const float2 v23 = __half22float2(*reinterpret_cast<const __half2 *>(&vraw.y));
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                if (p0 + j < n_kv) {
-                    const float w = __half2float(__float2half_rn(__fmul_rn(S[p0 + j], inv)));
-                    const float2 v01 = __half22float2(*reinterpret_cast<const __half2 *>(&vraw[j].x));
-                    const float2 v23 = __half22float2(*reinterpret_cast<const __half2 *>(&vraw[j].y));
-                    a0 = fmaf(v01.x, w, a0); a1 = fmaf(v01.y, w, a1); a2 = fmaf(v23.x, w, a2); a3 = fmaf(v23.y, w, a3);
+                    for (int tq = 0; tq < ATT_TQ; tq++) {
+                        const float w = Pr[(size_t) tq * n_kv_pad + j];
+                        acc[0][tq][0] = fmaf(v01.x, w, acc[0][tq][0]); acc[0][tq][1] = fmaf(v01.y, w, acc[0][tq][1]);
+                        acc[0][tq][2] = fmaf(v23.x, w, acc[0][tq][2]); acc[0][tq][3] = fmaf(v23.y, w, acc[0][tq][3]);
+                    }
                 }
             }
         }
-        *reinterpret_cast<float4 *>(out + ((int64_t) tok * n_head + h) * D + 4 * lane) = make_float4(a0, a1, a2, a3);
-        __syncwarp();
+        if (hh < gqa) {
+#pragma unroll
+            for (int tq = 0; tq < ATT_TQ; tq++)
+                if (tq < ntq)
+                    *reinterpret_cast<float4 *>(out + ((int64_t) (t0 + tq) * n_head + hk * gqa + hh) * D + 4 * lane) =
+                        make_float4(acc[0][tq][0], acc[0][tq][1], acc[0][tq][2], acc[0][tq][3]);
+        }
     }
 }
 
@@ -762,17 +810,25 @@ int launch_attn_decode(const float * q, const __half * kcache, const __half * vc
 int launch_attn_batch(const float * q, const __half * kcache, const __half * vcache, float * out, int n_head, int n_head_kv, int D,
                       const int32_t * pos_dev, int n_tok, int n_kv_max, float scale, cudaStream_t stream) {
     if (D != 128 || n_tok <= 0 || n_tok > 65535) return (int) cudaErrorInvalidValue;
-    {   // GQA-shared kernel: 8 score strips of n_kv_max floats must fit in shared memory
+    static const int attn_mode = getenv("PB200_ATTN_MODE") ? atoi(getenv("PB200_ATTN_MODE")) : 0;   // A/B switch: 1 = the per-(head, token) grid of k_attn_decode
+    if (attn_mode == 0 && n_head % n_head_kv == 0) {   // tiled kernel: all score rows of gqa x TQ queries in shared memory
+        const int gqa = n_head / n_head_kv;
         const int n_kv_pad = (n_kv_max + 31) & ~31;
-        const size_t smem_p = (size_t) 8 * n_kv_pad * sizeof(float);
-        static int configured = 0;
-        if (smem_p <= 200 * 1024) {
-            if ((int) smem_p > configured && smem_p > 40 * 1024) {
-                cudaError_t e = cudaFuncSetAttribute(k_attn_prefill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_p);
+        auto smem_for = [&](int tq) { return (size_t) gqa * tq * n_kv_pad * 4 + (size_t) gqa * tq * D * 4 + (size_t) ATT_TK * ATT_KSTRIDE * 2; };
+        const int tq = smem_for(4) <= 200 * 1024 ? 4 : (smem_for(2) <= 200 * 1024 ? 2 : (smem_for(1) <= 200 * 1024 ? 1 : 0));
+        if (tq) {
+            const size_t smem_t = smem_for(tq);
+            static int configured_t[5] = {0, 0, 0, 0, 0};
+            const void * fn = tq == 4 ? (const void *) k_attn_prefill_tiled<4> : (tq == 2 ? (const void *) k_attn_prefill_tiled<2> : (const void *) k_attn_prefill_tiled<1>);
+            if ((int) smem_t > configured_t[tq] && smem_t > 40 * 1024) {
+                cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_t);
                 if (e != cudaSuccess) return (int) e;
-                configured = (int) smem_p;
+                configured_t[tq] = (int) smem_t;
             }
-            k_attn_prefill<<<dim3(n_head_kv, n_tok), 256, smem_p, stream>>>(q, kcache, vcache, out, n_head, n_head_kv, pos_dev, scale, n_kv_pad);
+            const dim3 grid(n_head_kv, (n_tok + tq - 1) / tq);
+            if (tq == 4) k_attn_prefill_tiled<4><<<grid, 256, smem_t, stream>>>(q, kcache, vcache, out, n_head, n_head_kv, pos_dev, n_tok, scale, n_kv_pad);
+            else if (tq == 2) k_attn_prefill_tiled<2><<<grid, 256, smem_t, stream>>>(q, kcache, vcache, out, n_head, n_head_kv, pos_dev, n_tok, scale, n_kv_pad);
+            else k_attn_prefill_tiled<1><<<grid, 256, smem_t, stream>>>(q, kcache, vcache, out, n_head, n_head_kv, pos_dev, n_tok, scale, n_kv_pad);
             return (int) cudaGetLastError();
         }
     }

@@ -67,6 +67,7 @@ class Lib:
         c.pb200_mul_mat_q_workspace_bytes.argtypes = [i64, i64]
         c.pb200_mul_mat_q.argtypes = [C.c_int, vp, i64, i64, vp, i64, i64, vp, vp, vp, vp, vp]
         c.pb200_attn_decode.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, f32, vp]
+        c.pb200_attn_prefill.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, f32, vp]
         c.pb200_model_create.restype = vp
         c.pb200_model_create.argtypes = [C.POINTER(HParams), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         c.pb200_model_free.argtypes = [vp]

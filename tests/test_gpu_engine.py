@@ -194,6 +194,23 @@ def test_prefill_chunked_equals_whole(cuda, pkg):
     assert a.argmax() == b.argmax()
 
 
+def test_prefill_longer_than_one_ubatch(cuda, pkg):
+    """600 tokens = one 512-token slice + 88 (the engine's internal n_ubatch) against two 300-token calls: the second slice attends
+    over the first one's K/V rows (n_kv up to 600: the tiled attention kernel with longer score rows)."""
+    tm = TinyModel(n_layer=2, n_embd=512, n_head=4, n_head_kv=2, n_ff=1024, n_vocab=256, n_ctx=640, arch="llama", ftype="q4_K_M",
+                   freq_factors=False, seed=6, branch_scale=0.1)
+    toks = [(i * 31 + 7) % 256 for i in range(600)]
+    eng = tm.load_engine(pkg)
+    a = eng.prefill(toks, 0).copy()
+    eng.kv_clear()
+    eng.prefill(toks[:300], 0)
+    b = eng.prefill(toks[300:], 300).copy()
+    eng.close()
+    assert np.isfinite(a).all()
+    assert float(np.sum((a - b) ** 2) / np.sum(a ** 2)) < 1e-4
+    assert b[a.argmax()] >= b.max() - 0.1
+
+
 def test_prefill_argument_errors(cuda, pkg):
     tm = TinyModel(n_layer=1, n_embd=256, n_head=2, n_head_kv=1, n_ff=512, n_vocab=64, n_ctx=16, arch="llama", ftype="q4_K_M",
                    freq_factors=False, seed=1)

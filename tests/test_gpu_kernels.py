@@ -210,6 +210,32 @@ def test_attn_decode(cuda, lib, port, n_kv):
     assert np.mean(np.abs(out.cpu().numpy() - want)) < 2e-5
 
 
+@pytest.mark.parametrize("H,HK,n_tok,pos0", [(8, 2, 21, 5), (64, 8, 9, 120), (16, 2, 6, 1790), (16, 2, 3, 6390)],
+                         ids=["tiled-gqa4-ragged", "tiled-gqa8-70B-heads", "tiled-2-tokens-per-cta-long-context", "per-head-fallback-very-long"])
+def test_attn_prefill_vs_oracle(cuda, lib, port, H, HK, n_tok, pos0):
+    """Prompt-processing attention: every (token, head) row against the oracle's decode attention at that token's causal length.
+    Covers the tiled kernel (K/V tiles shared by the GQA group x 4 / 2 tokens) and the per-(head, token) fallback."""
+    rng = np.random.default_rng(H + n_tok)
+    D = 128
+    n_ctx = pos0 + n_tok
+    q = rng.standard_normal((n_tok, H * D)).astype(np.float32)
+    Kc = (rng.standard_normal((n_ctx, HK * D)) * 0.5).astype(np.float16)
+    Vc = rng.standard_normal((n_ctx, HK * D)).astype(np.float16)
+    pos_h = (pos0 + np.arange(n_tok)).astype(np.int32)
+    out = torch.full((n_tok, H * D), float("nan"), device="cuda")
+    pos = torch.from_numpy(pos_h).cuda()
+    qd, kd, vd = dev_f32(q), torch.from_numpy(Kc).cuda(), torch.from_numpy(Vc).cuda()
+    scale = 1.0 / np.sqrt(D)
+    lib.check(lib.c.pb200_attn_prefill(ptr(qd), ptr(kd), ptr(vd), ptr(out), H, HK, D, ptr(pos), n_tok, n_ctx, scale, None), "attn_prefill")
+    sync()
+    got = out.cpu().numpy()
+    assert np.isfinite(got).all()
+    for t in range(n_tok):
+        want = port.attention_decode(q[t], Kc.view(np.uint16), Vc.view(np.uint16), H, HK, D, int(pos_h[t]) + 1, scale)
+        assert np.max(np.abs(got[t] - want)) < 3e-4, (t, np.max(np.abs(got[t] - want)))
+        assert np.mean(np.abs(got[t] - want)) < 2e-5
+
+
 def test_full_size_gemv_properties(cuda, lib):
     """BASELINE sizes (Llama-3-70B shapes): the fused TMA kernel must agree with an independent evaluation —
     dequantized weights (get_rows kernel, bit-exact vs the oracle above) times the dequantized q8_K activation in fp64."""
