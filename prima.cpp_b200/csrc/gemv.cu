@@ -999,6 +999,105 @@ __global__ void __launch_bounds__(256) k_gemv_generic(const __grid_constant__ Ge
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Streaming GEMV for the 32-element block types (Q8_0 34 B, Q5_1 24 B per block): Qwen2.5-72B's ffn_down (K = 29 568, not a
+// multiple of 256) falls back to them (src/llama.cpp:19516-19551) and they are a third of that model's bytes.
+// The activation (q8_0 / q8_1) is staged once per CTA in shared memory; every warp streams whole rows through its own 4-deep
+// cp.async ring of 32-block chunks (8-byte pieces, all lanes issue, ~100 KB in flight per SM at 3 CTAs/SM); lane l owns block
+// l of every chunk, i.e. the same blocks and the same per-lane order as k_gemv_generic => bit-identical results.
+constexpr int B32_NST = 4;
+struct GemvB32Params {
+    const uint8_t * W;
+    float * y;
+    const float * bias;
+    const float * resid;
+    int64_t row_bytes;
+    int type, N, K, nb, bpb;
+    ActQ act;
+};
+__global__ void __launch_bounds__(256) k_gemv_blk32(const __grid_constant__ GemvB32Params P) {
+    extern __shared__ __align__(16) uint8_t b32_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kp = (P.K + 15) & ~15;
+    int8_t * a_qs = reinterpret_cast<int8_t *>(b32_smem);                        // [K]
+    float * a_d = reinterpret_cast<float *>(b32_smem + kp);                      // [nb]
+    float * a_s = a_d + P.nb;                                                    // [nb]  (Q5_1 only)
+    const int cb = 32 * P.bpb;                                                   // chunk bytes: 1088 / 768
+    uint8_t * ring = b32_smem + ((kp + 8 * P.nb + 15) & ~15) + (size_t) warp * B32_NST * 1088;
+    pdl_trigger();
+    pdl_wait();
+    for (int i = threadIdx.x; i < P.K / 16; i += 256) reinterpret_cast<int4 *>(a_qs)[i] = reinterpret_cast<const int4 *>(P.act.qs)[i];
+    for (int i = threadIdx.x; i < P.nb; i += 256) { a_d[i] = P.act.d[i]; if (P.type == T_Q5_1) a_s[i] = P.act.s[i]; }
+    __syncthreads();
+    const int nchunk = (P.nb + 31) / 32;
+    const int pieces = cb / 8;
+    for (int row = blockIdx.x * 8 + warp; row < P.N; row += gridDim.x * 8) {
+        const uint8_t * wrow = P.W + (int64_t) row * P.row_bytes;
+        auto issue = [&](int c) {
+            if (c < nchunk) {
+                const int64_t off = (int64_t) c * cb;
+                uint8_t * dst = ring + (size_t) (c % B32_NST) * 1088;
+                for (int pc = lane; pc < pieces; pc += 32)
+                    if (off + pc * 8 + 8 <= P.row_bytes)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst + pc * 8)), "l"(wrow + off + pc * 8) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        for (int c = 0; c < B32_NST - 1; c++) issue(c);
+        float acc = 0.f;
+        for (int c = 0; c < nchunk; c++) {
+            issue(c + B32_NST - 1);
+            asm volatile("cp.async.wait_group %0;" ::"n"(B32_NST - 1) : "memory");
+            __syncwarp();
+            const int b = c * 32 + lane;
+            if (b < P.nb) {
+                const uint8_t * bp = ring + (size_t) (c % B32_NST) * 1088 + lane * P.bpb;
+                const int4 * a = reinterpret_cast<const int4 *>(a_qs + (int64_t) b * 32);
+                const int4 a0 = a[0], a1 = a[1];
+                const int av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                int sumi = 0;
+                if (P.type == T_Q8_0) {
+                    // 34-byte blocks are only 2-byte aligned: read the 9 aligned words around the block; qs (offset 2) is either
+                    // word-aligned already (block at 4k+2) or straddles two words (block at 4k): one PRMT per word, selector per lane
+                    const uint32_t * wp = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(bp) & ~(uintptr_t) 3);
+                    const bool odd = (reinterpret_cast<uintptr_t>(bp) & 2) != 0;
+                    const uint32_t sel = odd ? 0x7654u : 0x5432u;
+                    uint32_t w[9];
+#pragma unroll
+                    for (int i = 0; i < 9; i++) w[i] = wp[i];
+                    const float d = __half2float(__ushort_as_half((unsigned short) ((w[0] >> (odd ? 16 : 0)) & 0xffff)));
+#pragma unroll
+                    for (int i = 0; i < 8; i++) sumi = dp4a_ss((int) __byte_perm(w[i], w[i + 1], sel), av[i], sumi);
+                    acc += (float) sumi * (d * a_d[b]);
+                } else {
+                    const uint32_t dmw = *reinterpret_cast<const uint32_t *>(bp);
+                    const float d = __half2float(__ushort_as_half((unsigned short) (dmw & 0xffff)));
+                    const float mm = __half2float(__ushort_as_half((unsigned short) (dmw >> 16)));
+                    const uint32_t qh = *reinterpret_cast<const uint32_t *>(bp + 4);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const uint32_t w = *reinterpret_cast<const uint32_t *>(bp + 8 + 4 * i);
+                        // bit k of a nibble of qh -> bit 4 of byte k: x * 0x00204081 puts bit k at 8k (no carries), then << 4
+                        const uint32_t hb_lo = ((((qh >> (4 * i)) & 0xFu) * 0x00204081u) & 0x01010101u) << 4;
+                        const uint32_t hb_hi = ((((qh >> (4 * i + 16)) & 0xFu) * 0x00204081u) & 0x01010101u) << 4;
+                        sumi = dp4a_us((w & 0x0f0f0f0fu) | hb_lo, av[i], sumi);
+                        sumi = dp4a_us(((w >> 4) & 0x0f0f0f0fu) | hb_hi, av[4 + i], sumi);
+                    }
+                    acc += (d * a_d[b]) * (float) sumi + mm * a_s[b];
+                }
+            }
+            __syncwarp();   // the slot is refilled by the next issue()
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        acc = warp_sum(acc);
+        if (lane == 0) {
+            if (P.bias) acc += P.bias[row];
+            if (P.resid) acc += P.resid[row];
+            P.y[row] = acc;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 static int pick_rows_per_tile(int64_t row_bytes, int ngroups, int N);
 bool gemv_fused_prologue_ok(int K);
 static int g_sm_count = 0;
@@ -1238,7 +1337,47 @@ void mk_free(MkHandle * h) {
     delete h;
 }
 
+static int launch_gemv_blk32(const GemvDesc & d, int K, const ActQ & act, cudaStream_t stream, bool pdl) {
+    GemvB32Params P{};
+    P.W = (const uint8_t *) d.W;
+    P.y = d.y;
+    P.bias = d.bias;
+    P.resid = d.resid;
+    P.type = d.type;
+    P.N = d.N;
+    P.K = K;
+    P.nb = K / 32;
+    P.bpb = d.type == T_Q8_0 ? BYTES_Q8_0 : BYTES_Q5_1;
+    P.row_bytes = row_bytes(d.type, K);
+    P.act = act;
+    const int kp = (K + 15) & ~15;
+    const size_t smem = (size_t) ((kp + 8 * P.nb + 15) & ~15) + (size_t) 8 * B32_NST * 1088;
+    static size_t configured = 0;
+    if (smem > configured && smem > 40 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_gemv_blk32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        if (e != cudaSuccess) return (int) e;
+        configured = smem;
+    }
+    const int per_sm = (int) std::max<size_t>(1, std::min<size_t>(4, (224 * 1024) / (smem + 1024)));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(std::min((d.N + 7) / 8, sm_count() * per_sm));
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return (int) cudaLaunchKernelEx(&cfg, k_gemv_blk32, P);
+}
+
 int launch_gemv_generic(const GemvDesc & d, int K, const ActQ & act, cudaStream_t stream, bool pdl) {
+    // 32-element block types with 8-byte aligned rows and an activation that fits in shared memory: the streaming kernel
+    static const bool no_b32 = getenv("PB200_NO_BLK32") != nullptr;
+    if (!no_b32 && (d.type == T_Q8_0 || d.type == T_Q5_1) && K % 32 == 0 && row_bytes(d.type, K) % 8 == 0 && K % 16 == 0 && K <= 131072 &&
+        ((uintptr_t) d.W & 7) == 0)
+        return launch_gemv_blk32(d, K, act, stream, pdl);
     GemvGenericParams P{};
     P.W = (const uint8_t *) d.W;
     P.y = d.y;

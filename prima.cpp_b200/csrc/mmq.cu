@@ -9,6 +9,8 @@
 // from the integer-dot CPU value by a few fp16 roundings per product (NMSE ~1e-6; tests/test_gpu_mmq.py states the bound).
 //
 //   dst[t][n] = sum_k W[n][k] * X[t][k]        W: N x K k-quant rows, X: T x K f32, dst: T x N f32 (ggml layout)
+// Also the 32-element block types Q8_0 / Q5_1 (K % 64 == 0; activations quantized per 32 values like their CPU dot): Qwen2.5-72B's
+// ffn_down, whose K = 29 568 rules the k-quants out (src/llama.cpp:19516-19551).
 //
 // One CTA owns 128 weight rows x (1 or 2) token tiles of BN <= 256 columns — two accumulators (all 512 TMEM columns) share
 // every expanded weight stage when T is large enough — and walks K in 64-element steps:
@@ -164,7 +166,39 @@ __device__ __forceinline__ void scale_min_k4(const uint8_t * sc, int j, int & s,
 }
 template <int TYPE>
 __device__ __forceinline__ void expand(const uint8_t * blk, int c, int h, uint32_t (&out)[16]) {
-    if (TYPE == T_Q4_K || TYPE == T_Q5_K) {
+    if (TYPE == T_Q8_0) {
+        // 32-element blocks, 34 B each ([d f16][32 x i8]); blk = the group of 8 blocks covering 256 K, this thread's block is 2c + h.
+        // Blocks are 2-byte aligned: qs (offset 2) is either word-aligned or straddles words -> one PRMT per word.
+        const uint8_t * bb = blk + (2 * c + h) * BYTES_Q8_0;
+        const uint32_t * wp = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(bb) & ~(uintptr_t) 3);
+        const bool odd = (reinterpret_cast<uintptr_t>(bb) & 2) != 0;
+        const uint32_t sel = odd ? 0x7654u : 0x5432u;
+        uint32_t w[9];
+#pragma unroll
+        for (int i = 0; i < 9; i++) w[i] = wp[i];
+        const __half dh = __ushort_as_half((unsigned short) ((w[0] >> (odd ? 16 : 0)) & 0xffff));
+        const __half2 scale = __half2half2(dh), bias = __float2half2_rn(-1152.f), zero = __float2half2_rn(0.f);
+#pragma unroll
+        for (int i = 0; i < 8; i++)   // q + 128 as an unsigned byte, 0x6400 | u = 1024 + u, minus 1152 = q exactly
+            expand_word<0x00FF00FFu>(__byte_perm(w[i], w[i + 1], sel) ^ 0x80808080u, bias, scale, zero, out[2 * i], out[2 * i + 1]);
+    } else if (TYPE == T_Q5_1) {
+        // 24 B blocks ([d f16][m f16][qh u32][16 x 2 nibbles]), 8-byte aligned; element j < 16 = low nibble of qs[j] | bit j of qh << 4,
+        // element j + 16 = high nibble | bit j + 16
+        const uint8_t * bb = blk + (2 * c + h) * BYTES_Q5_1;
+        const uint2 hd = *reinterpret_cast<const uint2 *>(bb);
+        const __half2 dm = bits_h2(hd.x);
+        const __half2 scale = __half2half2(__low2half(dm)), off = __half2half2(__high2half(dm)), bias = __float2half2_rn(-1024.f);
+        const uint32_t qh = hd.y;
+        const uint2 qa = *reinterpret_cast<const uint2 *>(bb + 8), qb = *reinterpret_cast<const uint2 *>(bb + 16);
+        const uint32_t w[4] = {qa.x, qa.y, qb.x, qb.y};
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint32_t hb_lo = ((((qh >> (4 * i)) & 0xFu) * 0x00204081u) & 0x01010101u) << 4;
+            const uint32_t hb_hi = ((((qh >> (4 * i + 16)) & 0xFu) * 0x00204081u) & 0x01010101u) << 4;
+            expand_word<0x001F001Fu>((w[i] & 0x0F0F0F0Fu) | hb_lo, bias, scale, off, out[2 * i], out[2 * i + 1]);
+            expand_word<0x001F001Fu>(((w[i] >> 4) & 0x0F0F0F0Fu) | hb_hi, bias, scale, off, out[8 + 2 * i], out[8 + 2 * i + 1]);
+        }
+    } else if (TYPE == T_Q4_K || TYPE == T_Q5_K) {
         const float d = __half2float(*reinterpret_cast<const __half *>(blk));
         const float dmin = __half2float(*reinterpret_cast<const __half *>(blk + 2));
         const int j = 2 * c + h;
@@ -232,9 +266,10 @@ __global__ void __launch_bounds__(MMQ_THREADS, 1) k_mmq_tc(const __grid_constant
     const int row0 = blockIdx.x * MMQ_BM;
     const int tt0 = blockIdx.y * P.nacc;                         // first token tile of this CTA
     const int nacc = min(P.nacc, P.ttiles - tt0);                // the last CTA of an odd count has one
-    const int nsb = P.K / 256 / P.ksplit;                        // super-blocks this CTA walks ...
+    const int nstep_all = P.K / MMQ_BK;                          // 64-element steps; a 256-K group (4 steps) is one raw fetch
+    const int nsb = ((nstep_all + 3) / 4) / P.ksplit;            // groups this CTA walks (ksplit > 1 only when they divide evenly) ...
     const int sb0 = blockIdx.z * nsb;                            // ... starting here
-    const int nchunk = nsb * 4;
+    const int nchunk = min(nsb * 4, nstep_all - sb0 * 4);        // the last group of a K % 256 != 0 row (32-element block types) is short
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 3; i++) { mbar_init(&ctl->raw_full[i], MMQ_DQ_WARPS * 32); mbar_init(&ctl->raw_empty[i], MMQ_DQ_WARPS); }
@@ -328,6 +363,7 @@ __global__ void __launch_bounds__(MMQ_THREADS, 1) k_mmq_tc(const __grid_constant
             const uint8_t * blk = raw + (size_t) (rs * MMQ_BM + r) * P.slot + (g0 & 15);
 #pragma unroll
             for (int c = 0; c < 4; c++, u++) {
+                if (u >= nchunk) break;
                 uint32_t v[16];
                 expand<TYPE>(blk, c, h, v);
                 if (u >= MMQ_A_NST) {   // step u - 2 has consumed this A stage
@@ -389,17 +425,20 @@ __global__ void __launch_bounds__(MMQ_THREADS, 1) k_mmq_tc(const __grid_constant
 }
 
 // ---- activation rows -> q8_K (exactly as the CPU backend quantizes them) -> fp16, written in the tiled UMMA image ----
+// blk32: the weight type is Q8_0 / Q5_1, whose CPU dot quantizes the activation per 32 values (q8_0 / q8_1: d = amax / 127 stored
+// as f16, q = round-half-even(x * 127 / amax), quantize_row_q8_0 ggml-quants.c:943-1010) instead of per 256 (q8_K).
 __global__ void __launch_bounds__(256) k_mmq_prep(const float * __restrict__ x, int64_t ldx, int T, int K, int BN, uint8_t * __restrict__ out,
-                                                  float * __restrict__ zero_dst, int N) {
+                                                  float * __restrict__ zero_dst, int N, int blk32) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (zero_dst && (int) blockIdx.x < T)   // split-K launches accumulate into dst
         for (int i = threadIdx.x; i < N; i += 256) zero_dst[(size_t) blockIdx.x * N + i] = 0.f;
-    const int nblk = K / 256;
+    const int nblk = (K + 255) / 256;
     const int t = blockIdx.x;                       // 0 .. Tpad-1
     const int b_bytes = BN * 128;
     for (int b = warp; b < nblk; b += 8) {
         float v[8];
-        if (t < T) {
+        const bool live = b * 256 + lane * 8 < K;   // K % 32 == 0: a 4-lane group (one 32-block) is live or dead as a whole
+        if (t < T && live) {
             const float4 * p = reinterpret_cast<const float4 *>(x + (size_t) t * ldx + (size_t) b * 256 + lane * 8);
             const float4 a = p[0], c = p[1];
             v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
@@ -422,7 +461,19 @@ __global__ void __launch_bounds__(256) k_mmq_prep(const float * __restrict__ x, 
             if (oa > amax || (oa == amax && oi < idx)) { amax = oa; vmax = ov; idx = oi; }
         }
         uint32_t h[4] = {0u, 0u, 0u, 0u};
-        if (amax != 0.f) {
+        if (blk32) {
+            float am = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; i++) am = fmaxf(am, fabsf(v[i]));
+            am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, 1));
+            am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, 2));
+            const float d = __half2float(__float2half_rn(__fdiv_rn(am, 127.f)));
+            const float id = am != 0.f ? __fdiv_rn(127.f, am) : 0.f;
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) f[i] = __fmul_rn(d, (float) __float2int_rn(__fmul_rn(v[i], id)));
+            h[0] = pack_h2(f[0], f[2]); h[1] = pack_h2(f[1], f[3]); h[2] = pack_h2(f[4], f[6]); h[3] = pack_h2(f[5], f[7]);
+        } else if (amax != 0.f) {
             const float iscale = __fdiv_rn(-127.f, vmax);
             const float d = __fdiv_rn(1.f, iscale);
             float f[8];
@@ -440,7 +491,7 @@ __global__ void __launch_bounds__(256) k_mmq_prep(const float * __restrict__ x, 
         const int kc = k >> 6, j = (k & 63) >> 3;
         const int tt = t / BN, tl = t % BN;
         uint8_t * dstp = out + ((size_t) tt * (K / 64) + kc) * b_bytes + (size_t) tl * 128 + (size_t) ((j ^ (tl & 7)) << 4);
-        *reinterpret_cast<uint4 *>(dstp) = make_uint4(h[0], h[1], h[2], h[3]);
+        if (live) *reinterpret_cast<uint4 *>(dstp) = make_uint4(h[0], h[1], h[2], h[3]);
     }
 }
 
@@ -454,7 +505,10 @@ size_t mmq_workspace_bytes(int64_t K, int64_t T) {
     const int64_t tpad = (T + BN - 1) / BN * BN;
     return (size_t) (tpad * K * 2);
 }
-bool mmq_supported(int type, int64_t K) { return is_kquant(type) && K % 256 == 0 && K >= 256; }
+bool mmq_supported(int type, int64_t K) {
+    if (is_kquant(type)) return K % 256 == 0 && K >= 256;
+    return (type == T_Q8_0 || type == T_Q5_1) && K % 64 == 0 && K >= 256;   // 32-element blocks: two per 64-element step
+}
 
 int mmq_aborted() {
     int v = 0;
@@ -492,8 +546,9 @@ cudaError_t launch_mmq(int type, const void * W, int64_t N, int64_t K, const flo
     P.K = (int) K;
     P.T = (int) T;
     P.BN = BN;
-    P.bpb = type == T_Q4_K ? BYTES_Q4_K : (type == T_Q5_K ? BYTES_Q5_K : BYTES_Q6_K);
-    P.slot = type == T_Q6_K ? 240 : P.bpb;
+    // bytes of one 256-K group of a row, and the 16-byte aligned window reserved for it (Q6_K and Q8_0 rows are not 16-B aligned)
+    P.bpb = type == T_Q4_K ? BYTES_Q4_K : type == T_Q5_K ? BYTES_Q5_K : type == T_Q6_K ? BYTES_Q6_K : type == T_Q8_0 ? 8 * BYTES_Q8_0 : 8 * BYTES_Q5_1;
+    P.slot = type == T_Q6_K ? 240 : (type == T_Q8_0 ? 288 : P.bpb);
     P.ttiles = tpad / BN;
     const int rtiles = (int) ((N + MMQ_BM - 1) / MMQ_BM);
     // Configuration: two accumulators per CTA halve the weight-expansion work per FLOP (measured 1040 vs 590 TFLOP/s at full
@@ -501,7 +556,7 @@ cudaError_t launch_mmq(int type, const void * W, int64_t N, int64_t K, const flo
     // twice).  Pick the best estimated (efficiency x SM occupancy).
     static const int force_nacc = getenv("PB200_MMQ_NACC") ? atoi(getenv("PB200_MMQ_NACC")) : 0;
     static const int force_ks = getenv("PB200_MMQ_KSPLIT") ? atoi(getenv("PB200_MMQ_KSPLIT")) : 0;
-    const int nsm = sm_count(), nsb_all = (int) (K / 256);
+    const int nsm = sm_count(), nsb_all = (int) (K % 256 == 0 ? K / 256 : 1);   // no split-K for a short last group
     double best = -1.0;
     P.nacc = 1; P.ksplit = 1;
     for (int nacc = 1; nacc <= 2; nacc++)
@@ -515,7 +570,7 @@ cudaError_t launch_mmq(int type, const void * W, int64_t N, int64_t K, const flo
             const double score = occ * (nacc == 2 ? 1.0 : 0.57) * (ks == 2 ? 0.80 : 1.0);
             if (score > best) { best = score; P.nacc = nacc; P.ksplit = ks; }
         }
-    k_mmq_prep<<<tpad, 256, 0, st>>>(x, ldx, (int) T, (int) K, BN, (uint8_t *) ws, P.ksplit > 1 ? dst : nullptr, (int) N);
+    k_mmq_prep<<<tpad, 256, 0, st>>>(x, ldx, (int) T, (int) K, BN, (uint8_t *) ws, P.ksplit > 1 ? dst : nullptr, (int) N, is_kquant(type) ? 0 : 1);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     uint32_t cols = 32;
@@ -536,7 +591,9 @@ cudaError_t launch_mmq(int type, const void * W, int64_t N, int64_t K, const flo
     dim3 grid((unsigned) rtiles, (unsigned) ((P.ttiles + P.nacc - 1) / P.nacc), (unsigned) P.ksplit);
     if (type == T_Q4_K) return mmq_launch_typed<T_Q4_K>(P, grid, smem, st);
     if (type == T_Q5_K) return mmq_launch_typed<T_Q5_K>(P, grid, smem, st);
-    return mmq_launch_typed<T_Q6_K>(P, grid, smem, st);
+    if (type == T_Q6_K) return mmq_launch_typed<T_Q6_K>(P, grid, smem, st);
+    if (type == T_Q8_0) return mmq_launch_typed<T_Q8_0>(P, grid, smem, st);
+    return mmq_launch_typed<T_Q5_1>(P, grid, smem, st);
 }
 
 }  // namespace pb

@@ -55,7 +55,10 @@ struct b200_buffer_ctx {
 };
 
 static const int64_t MMQ_MIN_COLS = 8;
-static bool mmq_type(enum ggml_type t) { return t == GGML_TYPE_Q4_K || t == GGML_TYPE_Q5_K || t == GGML_TYPE_Q6_K; }
+static bool mmq_ok(enum ggml_type t, int64_t k) {   // mirrors mmq_supported() of the library
+    if (t == GGML_TYPE_Q4_K || t == GGML_TYPE_Q5_K || t == GGML_TYPE_Q6_K) return k % 256 == 0;
+    return (t == GGML_TYPE_Q8_0 || t == GGML_TYPE_Q5_1) && k % 64 == 0 && k >= 256;
+}
 static bool type_is_quant(enum ggml_type t) {
     return t == GGML_TYPE_Q4_K || t == GGML_TYPE_Q5_K || t == GGML_TYPE_Q6_K || t == GGML_TYPE_Q8_0 || t == GGML_TYPE_Q5_1;
 }
@@ -184,7 +187,7 @@ static bool b200_supports_op(ggml_backend_dev_t, const ggml_tensor * op) {
             // quantized weights: rows of src1 must be dense.  The decode GEMV handles one activation column per launch; k-quant
             // weights with K % 256 == 0 take the tensor-core path (pb200_mul_mat_q) for any number of columns.
             if (!(ggml_is_contiguous(a) && b->nb[0] == sizeof(float) && ggml_is_contiguous(op) && a->ne[0] % ggml_blck_size(a->type) == 0)) return false;
-            if (mmq_type(a->type) && a->ne[0] % 256 == 0 && b->nb[1] % 16 == 0) return true;
+            if (mmq_ok(a->type, a->ne[0]) && b->nb[1] % 16 == 0) return true;
             return b->ne[1] * b->ne[2] * b->ne[3] <= 64;
         }
         case GGML_OP_ROPE: {
@@ -256,7 +259,7 @@ static bool b200_compute_node(b200_backend_ctx * ctx, ggml_tensor * dst) {
                 ctx->act_ws_bytes = need;
             }
             const int64_t r2 = b->ne[2] / a->ne[2], r3 = b->ne[3] / a->ne[3];
-            if (b->ne[1] >= MMQ_MIN_COLS && mmq_type(a->type) && K % 256 == 0 && b->nb[1] % 16 == 0) {
+            if (b->ne[1] >= MMQ_MIN_COLS && mmq_ok(a->type, K) && b->nb[1] % 16 == 0) {
                 // batched / prefill: the reference switches to mul_mat_q above 8 columns as well (ggml-cuda/mmq.cu:137-139)
                 const size_t need_q = pb200_mul_mat_q_workspace_bytes(K, b->ne[1]);
                 if (need_q > ctx->mmq_ws_bytes) {

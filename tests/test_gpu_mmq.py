@@ -70,6 +70,22 @@ def test_mmq_vs_oracle(cuda, lib, port, t, N, K, T):
     assert np.all(got[0] == 0.0)
 
 
+@pytest.mark.parametrize("t", [O.Q8_0, O.Q5_1], ids=lambda t: O.TYPE_NAME[t])
+@pytest.mark.parametrize("N,K,T", [(256, 448, 33), (128, 1984, 64), (200, 512, 9), (128, 29568, 24)])
+def test_mmq_small_block_types_vs_oracle(cuda, lib, port, t, N, K, T):
+    """Q8_0 / Q5_1 (32-element blocks; the CPU dot quantizes the activation per 32 values): K % 64 == 0 is enough, so rows that are
+    not 16-byte aligned and a short last 256-K group are the norm here; the last case is Qwen2.5-72B's ffn_down K."""
+    rng = np.random.default_rng(100 * t + N + K + T)
+    W = O.synth_blocks(t, N, K, seed=5 * t + N)
+    X = rng.standard_normal((T, K)).astype(np.float32)
+    X[0] = 0.0
+    got = run_mmq(lib, t, W, N, K, X)
+    want = oracle(port, t, W, N, K, X)
+    Wf = port.dequantize(t, W, N * K).reshape(N, K)
+    check(got, want, Wf, X)
+    assert np.all(got[0] == 0.0)
+
+
 def test_mmq_integer_exact(cuda, lib, port):
     """Small-integer activations and Q4_K blocks whose scales make every weight an exact fp16 integer: the tensor-core
     result must then equal the oracle bit for bit (a layout / swizzle / descriptor error cannot hide behind a tolerance)."""
