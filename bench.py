@@ -12,6 +12,8 @@ layer ranges per rank, hidden state handed off with one NCCL send/recv per stage
 
 Prints ONE JSON line (rank 0).  `value`: device-resident steps (token id via kernel argument, logits stay in HBM);
 `e2e`: the llama_decode-equivalent host call (token id + position H2D from pinned memory, logits D2H every step).
+At N=1 the line also carries `prefill`: one --pp (512) token prompt batch through pb200_prefill (tensor-core mat-muls) with its
+own tensor-pipe roofline — extra information next to the headline metric, measured after it, never part of `value`.
 """
 import argparse
 import ctypes as C
@@ -397,25 +399,29 @@ def main():
                            "exposed_handoff_ms": max(0.0, ms_step - stage_ms), "exposed_frac": max(0.0, ms_step - stage_ms) / ms_step,
                            "note": "b=1 decode is serial across stages (SURVEY H7): N GPUs hold N x the model, they do not cut the token latency"}
     if world == 1 and args.pp > 0 and args.pp <= args.n_ctx:
-        # prompt processing (prefill) of one ubatch through pb200_prefill: tensor-core mat-muls, batched attention
-        toks = np.array([token_at(i, nv) for i in range(args.pp)], dtype=np.int32)
-        eng.kv_clear()
-        eng.prefill(toks, 0, logits_host)                      # warm-up (allocates the batch buffers)
-        reps, best = 3, None
-        for _ in range(reps):
-            torch.cuda.synchronize()
-            t1 = time.perf_counter()
-            eng.prefill(toks, 0, logits_host)                  # tokens from host memory in, last-token logits out: end to end
-            dt = time.perf_counter() - t1
-            best = dt if best is None else min(best, dt)
-        mm, att, head = prefill_flops(hp, args.pp)
-        tpeak, tsrc = tensor_peak()
-        out["prefill"] = {"metric": f"prompt tokens/s, {cfg['name']}, one ubatch of {args.pp} tokens (llama-bench pp{args.pp})", "tokens": args.pp,
-                          "ms": best * 1e3, "value": args.pp / best, "unit": "tokens/s", "timing": f"host wall clock around pb200_prefill (synchronous), best of {reps}",
-                          "roofline": {"bound": "tensor", "achieved": (mm + att + head) / best / 1e12, "peak": tpeak, "unit": "TFLOP/s",
-                                       "frac": (mm + att + head) / best / 1e12 / tpeak, "peak_source": tsrc,
-                                       "algorithmic_flops": {"matmul": mm, "attention_causal": att, "lm_head_last_token": head},
-                                       "kernel": "k_mmq_tc (tcgen05 k-quant mat-mul); attention still runs on CUDA cores (k_attn_decode over a head x token grid)"}}
+        try:
+            # prompt processing (prefill) of one ubatch through pb200_prefill: tensor-core mat-muls, batched attention
+            toks = np.array([token_at(i, nv) for i in range(args.pp)], dtype=np.int32)
+            eng.kv_clear()
+            eng.prefill(toks, 0, logits_host)                      # warm-up (allocates the batch buffers)
+            reps, best = 3, None
+            for _ in range(reps):
+                torch.cuda.synchronize()
+                t1 = time.perf_counter()
+                eng.prefill(toks, 0, logits_host)                  # tokens from host memory in, last-token logits out: end to end
+                dt = time.perf_counter() - t1
+                best = dt if best is None else min(best, dt)
+            mm, att, head = prefill_flops(hp, args.pp)
+            tpeak, tsrc = tensor_peak()
+            out["prefill"] = {"metric": f"prompt tokens/s, {cfg['name']}, one ubatch of {args.pp} tokens (llama-bench pp{args.pp})", "tokens": args.pp,
+                              "ms": best * 1e3, "value": args.pp / best, "unit": "tokens/s", "timing": f"host wall clock around pb200_prefill (synchronous), best of {reps}",
+                              "roofline": {"bound": "tensor", "achieved": (mm + att + head) / best / 1e12, "peak": tpeak, "unit": "TFLOP/s",
+                                           "frac": (mm + att + head) / best / 1e12 / tpeak, "peak_source": tsrc,
+                                           "algorithmic_flops": {"matmul": mm, "attention_causal": att, "lm_head_last_token": head},
+                                           "kernel": "k_mmq_tc (tcgen05 k-quant mat-mul); attention on CUDA cores (k_attn_prefill_tiled: K/V tiles shared by the GQA group x 4 tokens)"}}
+        except Exception as ex:   # the extra measurement must never take the headline line down
+            out["prefill"] = {"value": None, "unit": "tokens/s", "error": repr(ex)}
+
     if not args.no_cpu_baseline:
         try:
             out["cpu_baseline"] = cpu_reference(args.model, 4, 1)
