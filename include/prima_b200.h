@@ -40,7 +40,7 @@ extern "C" {
 /* enum ggml_type values used on this path (ggml/include/ggml.h:356-395) */
 enum { PB200_TYPE_F32 = 0, PB200_TYPE_F16 = 1, PB200_TYPE_Q5_1 = 7, PB200_TYPE_Q8_0 = 8, PB200_TYPE_Q4_K = 12, PB200_TYPE_Q5_K = 13, PB200_TYPE_Q6_K = 14 };
 
-enum { PB200_EINVAL = -1, PB200_ENOMEM = -2, PB200_ENOTSUP = -3, PB200_ESTATE = -4 };
+enum { PB200_EINVAL = -1, PB200_ENOMEM = -2, PB200_ENOTSUP = -3, PB200_ESTATE = -4, PB200_EABORTED = -5 };
 
 /* ---- library ---- */
 PB200_API const char * pb200_version(void);

@@ -38,6 +38,7 @@ const char * pb200_error_string(int code) {
         case PB200_ENOMEM: return "out of memory";
         case PB200_ENOTSUP: return "unsupported tensor type or shape on this path";
         case PB200_ESTATE: return "model not in the right state (missing tensors / not finalized)";
+        case PB200_EABORTED: return "a kernel's pipeline watchdog gave up (results invalid; see pb200_mul_mat_q_aborted)";
     }
     return code > 0 ? cudaGetErrorString((cudaError_t) code) : "unknown error";
 }

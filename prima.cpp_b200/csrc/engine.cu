@@ -751,13 +751,11 @@ static int prefill_ubatch(pb200_model * m, const int32_t * tokens_host, int32_t 
         }
     }
     g_launches += n;
-    if (m->with_head && logits_host) {
-        CK(cudaMemcpyAsync(m->logits_host, m->logits, (size_t) hp.n_vocab * 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        memcpy(logits_host, m->logits_host, (size_t) hp.n_vocab * 4);
-        return 0;
-    }
-    return (int) cudaStreamSynchronize(st);
+    if (m->with_head && logits_host) CK(cudaMemcpyAsync(m->logits_host, m->logits, (size_t) hp.n_vocab * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (mmq_aborted()) return PB200_EABORTED;   // a tensor-core launch gave up on a stuck pipeline: the batch's results are invalid
+    if (m->with_head && logits_host) memcpy(logits_host, m->logits_host, (size_t) hp.n_vocab * 4);
+    return 0;
 }
 
 extern "C" {

@@ -31,6 +31,7 @@ def test_row_bytes_and_workspace(lib):
     assert c.pb200_row_bytes(7, 29568) == 29568 // 32 * 24
     assert c.pb200_act_workspace_bytes(8192) == 8192 + 8192 // 32 * 8 + 8192 // 16 * 2
     assert c.pb200_error_string(-3).decode().startswith("unsupported")
+    assert "watchdog" in c.pb200_error_string(-5).decode()
 
 
 def test_argument_validation_no_gpu(lib, pkg):
