@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <cstdint>
 #include <cstring>
 #include <mutex>
 
@@ -186,6 +187,7 @@ size_t pb200_mul_mat_q_workspace_bytes(int64_t k, int64_t t) { return (k > 0 && 
 int pb200_mul_mat_q(int type, const void * W, int64_t n, int64_t k, const float * x, int64_t ldx, int64_t t, float * dst, const float * bias,
                     const float * resid, void * ws, void * stream) {
     if (!W || !x || !dst || !ws || n <= 0 || t <= 0 || ldx < k || resid == dst) return PB200_EINVAL;
+    if (((uintptr_t) x & 15) || (ldx & 3) || ((uintptr_t) W & 15)) return PB200_EINVAL;   // rows are read as float4, weights as 16-byte pieces
     if (!mmq_supported(type, k)) return PB200_ENOTSUP;
     g_launches += 2;
     return (int) launch_mmq(type, W, n, k, x, ldx, t, dst, bias, resid, ws, (cudaStream_t) stream);
