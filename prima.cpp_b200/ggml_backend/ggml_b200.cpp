@@ -259,7 +259,8 @@ static bool b200_compute_node(b200_backend_ctx * ctx, ggml_tensor * dst) {
                 ctx->act_ws_bytes = need;
             }
             const int64_t r2 = b->ne[2] / a->ne[2], r3 = b->ne[3] / a->ne[3];
-            if (b->ne[1] >= MMQ_MIN_COLS && mmq_ok(a->type, K) && b->nb[1] % 16 == 0 && (uintptr_t) b->data % 16 == 0 && b->nb[2] % 16 == 0 && b->nb[3] % 16 == 0) {   // the prep kernel reads rows as float4
+            if (b->ne[1] >= MMQ_MIN_COLS && mmq_ok(a->type, K) && b->nb[1] % 16 == 0 && (uintptr_t) b->data % 16 == 0 && b->nb[2] % 16 == 0 && b->nb[3] % 16 == 0 &&
+                (uintptr_t) a->data % 16 == 0 && a->nb[2] % 16 == 0 && a->nb[3] % 16 == 0) {   // the prep kernel reads rows as float4
                 // batched / prefill: the reference switches to mul_mat_q above 8 columns as well (ggml-cuda/mmq.cu:137-139)
                 const size_t need_q = pb200_mul_mat_q_workspace_bytes(K, b->ne[1]);
                 if (need_q > ctx->mmq_ws_bytes) {
