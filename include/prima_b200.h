@@ -55,7 +55,10 @@ PB200_API uint64_t     pb200_kernel_launches(void);       /* kernels launched by
 PB200_API size_t pb200_act_workspace_bytes(int64_t k);
 /* x[k] f32 -> activation workspace in the format the CPU backend uses for weight type wtype (q8_K / q8_0 / q8_1) */
 PB200_API int pb200_quantize_act(int wtype, const float * x, int64_t k, void * act_ws, void * stream);
-/* y[n] = W[n][k] . x   with W raw GGUF blocks of `type`; act_ws from pb200_quantize_act(type, x, k) */
+/* y[n] = W[n][k] . x   with W raw GGUF blocks of `type`; act_ws from pb200_quantize_act(type, x, k).
+ * W must be 16-byte aligned and its allocation padded to a multiple of 16 bytes (+16): the kernel moves whole 16-byte units and
+ * may read up to 15 bytes past the last row (Q6_K / Q8_0 rows are not multiples of 16 bytes).  ggml-backend buffers of the B200
+ * plugin and pb200_model_set_tensor pad for you. */
 PB200_API int pb200_mul_mat_vec_q(int type, const void * W, int64_t n, int64_t k, const void * act_ws, float * y,
                                   const float * bias, const float * resid, void * stream);
 /* convenience: quantize + mul_mat_vec in one call (what ggml_cuda_mul_mat does for ne11 == 1) */
@@ -66,10 +69,16 @@ PB200_API int pb200_mul_mat_vec_fused(int nmat, const int * types, const void * 
 /* HOST buffers end to end (H2D of x, quantize, GEMV, D2H of y, synchronised): W must already be on the device */
 PB200_API int pb200_mul_mat_vec_host(int type, const void * W_dev, int64_t n, int64_t k, const float * x_host, float * y_host);
 
-/* debugging: k_gemv_kquant writes 8 %globaltimer stamps per CTA into dev_buf (u64[grid*8]); NULL disables */
-PB200_API int pb200_debug_set_trace(void * dev_buf);
-/* the in-kernel watchdog never lets a wait spin forever: it gives up after ~0.3 s and records {magic, cta, thread, iteration, parity|token, barrier} */
-PB200_API int pb200_debug_hang_info(unsigned long long * out8);
+/* profiling: while a buffer is set, k_gemv_kquant runs its instrumented instantiation: launch i writes row (i % slots) of
+ * dev_buf (rows of 4096 u64), CTA c its 8 entries [8c .. 8c+7]: [0..5] %globaltimer (ns) at CTA start / ring fill issued /
+ * dependency resolved (griddepcontrol.wait returned) / activation in registers / first tile landed / done, [6], [7] clock64 at
+ * the first and last stamp.  NULL or slots = 0 switches back to the uninstrumented kernel. */
+PB200_API int pb200_debug_set_trace(void * dev_buf, int slots);
+/* Every in-kernel wait is bounded (~1 s of SM clocks).  A wait that gives up ends its launch quickly with invalid results and
+ * the call that synchronises on it (pb200_decode, pb200_synchronize, pb200_prefill) returns PB200_EABORTED once; the flag
+ * re-arms, later calls are unaffected.  Callers that only use the single-op entry points on their own streams poll this after
+ * synchronising: returns 1 (and clears the flag) if any launch of this process gave up since the last call. */
+PB200_API int pb200_aborted(void);
 
 PB200_API int pb200_rms_norm(const float * x, float * y, int64_t n, int64_t nrows, float eps, void * stream);
 PB200_API int pb200_rope(const float * x, float * y, int64_t n_tokens, int n_head, int head_dim, int n_dims, int mode, const int32_t * pos,
@@ -92,8 +101,6 @@ PB200_API int pb200_mul_mat_f16(const void * a_f16, const float * b_f32, float *
 PB200_API size_t pb200_mul_mat_q_workspace_bytes(int64_t k, int64_t t);
 PB200_API int pb200_mul_mat_q(int type, const void * W, int64_t n, int64_t k, const float * x, int64_t ldx, int64_t t, float * dst,
                               const float * bias, const float * resid, void * ws, void * stream);
-/* 1 if any pb200_mul_mat_q launch gave up on a stuck pipeline (results invalid); sticky, debugging aid */
-PB200_API int pb200_mul_mat_q_aborted(void);
 PB200_API int pb200_get_rows(int type, const void * table, int64_t k, const int32_t * ids, int64_t n_ids, float * y, void * stream);
 /* decode attention over an f16 KV cache laid out [n_ctx][n_head_kv*head_dim]; n_kv = *pos_dev + 1 */
 PB200_API int pb200_attn_decode(const float * q, const void * k_cache_f16, const void * v_cache_f16, float * out, int n_head, int n_head_kv,
@@ -150,10 +157,6 @@ PB200_API int pb200_get_hidden(pb200_model * m, float * hidden_host);   /* copie
 PB200_API int pb200_profile_step(pb200_model * m, int32_t token, int32_t pos, double * gemv_ms, int64_t * gemv_bytes, int32_t * gemv_launches, double * step_ms);
 PB200_API int pb200_set_hidden(pb200_model * m, const float * hidden_host);   /* host -> hidden_in (tests, host-staged hand-off) */
 PB200_API int pb200_debug_read(pb200_model * m, const char * name, float * host, int64_t n);   /* white-box tests: q,k,v,att,g,u,x_a,x_b,xn,logits */
-/* persistent token kernel (one cooperative launch per token, PB200_PERSISTENT=1 at finalize makes it the captured default);
- * toggling after finalize switches to direct launches.  _error: 1 if a grid barrier ever timed out. */
-PB200_API int pb200_set_persistent(pb200_model * m, int on);
-PB200_API int pb200_persistent_error(pb200_model * m);
 PB200_API int pb200_set_use_graph(pb200_model * m, int on);             /* CUDA-graph replay on/off (default on) */
 
 #ifdef __cplusplus

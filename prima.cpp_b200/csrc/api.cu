@@ -39,7 +39,7 @@ const char * pb200_error_string(int code) {
         case PB200_ENOMEM: return "out of memory";
         case PB200_ENOTSUP: return "unsupported tensor type or shape on this path";
         case PB200_ESTATE: return "model not in the right state (missing tensors / not finalized)";
-        case PB200_EABORTED: return "a kernel's pipeline watchdog gave up (results invalid; see pb200_mul_mat_q_aborted)";
+        case PB200_EABORTED: return "a kernel's wait watchdog gave up: the results of this call are invalid (later calls are unaffected)";
     }
     return code > 0 ? cudaGetErrorString((cudaError_t) code) : "unknown error";
 }
@@ -97,7 +97,10 @@ int pb200_mul_mat_vec_host(int type, const void * W_dev, int64_t n, int64_t k, c
     static thread_local Stage S;
     if (!S.st && cudaStreamCreateWithFlags(&S.st, cudaStreamNonBlocking) != cudaSuccess) return (int) cudaGetLastError();
     if (k > S.k) {
-        if (S.hx) { cudaFreeHost(S.hx); cudaFree(S.dx); cudaFree(S.ws); }
+        if (S.hx) cudaFreeHost(S.hx);
+        if (S.dx) cudaFree(S.dx);
+        if (S.ws) cudaFree(S.ws);
+        S.hx = S.dx = nullptr; S.ws = nullptr; S.k = 0;     // a failed re-allocation below must not leave dangling pointers behind
         cudaError_t e;
         if ((e = cudaMallocHost((void **) &S.hx, (size_t) k * 4)) != cudaSuccess) return (int) e;
         if ((e = cudaMalloc((void **) &S.dx, (size_t) k * 4)) != cudaSuccess) return (int) e;
@@ -105,7 +108,9 @@ int pb200_mul_mat_vec_host(int type, const void * W_dev, int64_t n, int64_t k, c
         S.k = k;
     }
     if (n > S.n) {
-        if (S.hy) { cudaFreeHost(S.hy); cudaFree(S.dy); }
+        if (S.hy) cudaFreeHost(S.hy);
+        if (S.dy) cudaFree(S.dy);
+        S.hy = S.dy = nullptr; S.n = 0;
         cudaError_t e;
         if ((e = cudaMallocHost((void **) &S.hy, (size_t) n * 4)) != cudaSuccess) return (int) e;
         if ((e = cudaMalloc((void **) &S.dy, (size_t) n * 4)) != cudaSuccess) return (int) e;
@@ -122,8 +127,7 @@ int pb200_mul_mat_vec_host(int type, const void * W_dev, int64_t n, int64_t k, c
     return 0;
 }
 
-int pb200_debug_hang_info(unsigned long long * out8) { return gemv_hang_info(out8); }
-int pb200_debug_set_trace(void * dev_buf) { return gemv_set_trace((unsigned long long *) dev_buf); }
+int pb200_debug_set_trace(void * dev_buf, int slots) { return gemv_set_trace((unsigned long long *) dev_buf, slots); }
 
 int pb200_rms_norm(const float * x, float * y, int64_t n, int64_t nrows, float eps, void * stream) {
     if (!x || !y || n <= 0 || nrows <= 0) return PB200_EINVAL;
@@ -192,7 +196,7 @@ int pb200_mul_mat_q(int type, const void * W, int64_t n, int64_t k, const float 
     g_launches += 2;
     return (int) launch_mmq(type, W, n, k, x, ldx, t, dst, bias, resid, ws, (cudaStream_t) stream);
 }
-int pb200_mul_mat_q_aborted(void) { return mmq_aborted(); }
+int pb200_aborted(void) { return check_clear_abort(); }
 
 int pb200_get_rows(int type, const void * table, int64_t k, const int32_t * ids, int64_t n_ids, float * y, void * stream) {
     if (!table || !ids || !y || k <= 0 || n_ids <= 0) return PB200_EINVAL;
@@ -203,7 +207,7 @@ int pb200_get_rows(int type, const void * table, int64_t k, const int32_t * ids,
 
 int pb200_attn_decode(const float * q, const void * k_cache_f16, const void * v_cache_f16, float * out, int n_head, int n_head_kv, int head_dim,
                       const int32_t * pos_dev, int n_ctx, float scale, void * stream) {
-    if (!q || !k_cache_f16 || !v_cache_f16 || !out || !pos_dev || head_dim != 128 || n_head % n_head_kv) return PB200_EINVAL;
+    if (!q || !k_cache_f16 || !v_cache_f16 || !out || !pos_dev || head_dim != 128 || n_head_kv <= 0 || n_head <= 0 || n_head % n_head_kv) return PB200_EINVAL;
     g_launches++;
     return launch_attn_decode(q, (const __half *) k_cache_f16, (const __half *) v_cache_f16, out, n_head, n_head_kv, head_dim, pos_dev, n_ctx, scale,
                               nullptr, (cudaStream_t) stream, false);

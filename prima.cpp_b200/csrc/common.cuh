@@ -115,31 +115,49 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t * bar, uint32_t b
 __device__ __forceinline__ void mbar_arrive(uint64_t * bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// Spin with a watchdog: a logic error must surface as a trap with a diagnostic, never as a hung GPU.
-__device__ unsigned long long g_hang_info[32];
-__device__ const volatile int * g_hang_dump_src = nullptr;   // unused; the per-CTA dump goes through a smem pointer passed by the caller
-__device__ __forceinline__ void mbar_wait(uint64_t * bar, uint32_t parity, int tag = 0, const volatile int * dump = nullptr) {
+// Bounded waits.  A wait that exceeds ~1 s of SM clocks (a logic error, never load: the longest legitimate wait is one HBM
+// round trip) raises the CTA-wide `cta_abort` word and the process-wide host-mapped `abort_flag`, after which every wait of
+// the CTA returns at once: the launch terminates quickly with invalid results and the host reports PB200_EABORTED for the
+// call that synchronises on it (engine.cu / api.cu check and clear the flag).  Nothing hangs, nothing fails silently.
+constexpr long long PB_WAIT_TIMEOUT_CYCLES = 1ll << 31;
+__device__ __forceinline__ bool mbar_try_parity(uint64_t * bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ bool mbar_try_token(uint64_t * bar, uint64_t token) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "l"(token)
+        : "memory");
+    return ok != 0;
+}
+static __device__ __noinline__ void wait_gave_up(volatile int * cta_abort, int * abort_flag) {
+    *cta_abort = 1;
+    if (abort_flag) { *(volatile int *) abort_flag = 1; __threadfence_system(); }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t * bar, uint32_t parity, volatile int * cta_abort, int * abort_flag) {
+    if (mbar_try_parity(bar, parity)) return;       // the common case costs one try_wait (which itself suspends for a while)
     const long long t0 = clock64();
-    while (true) {
-        uint32_t ok;
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(ok)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-        if (ok) return;
-        if (clock64() - t0 > (1ll << 29)) {
-            // give up (results are garbage, the launch still terminates) and leave a diagnostic for pb200_debug_hang_info
-            if (atomicCAS(&g_hang_info[0], 0ull, 0xdead0001ull) == 0ull) {
-                g_hang_info[1] = blockIdx.x; g_hang_info[2] = threadIdx.x; g_hang_info[3] = (unsigned long long) tag;
-                g_hang_info[4] = parity; g_hang_info[5] = smem_u32(bar);
-                if (dump) for (int i = 0; i < 24; i++) g_hang_info[8 + i] = (unsigned long long) (long long) dump[i];
-            }
-            return;
+    int spins = 0;
+    while (!mbar_try_parity(bar, parity)) {
+        if ((++spins & 63) == 0) {
+            if (*cta_abort) return;
+            if (clock64() - t0 > PB_WAIT_TIMEOUT_CYCLES) { wait_gave_up(cta_abort, abort_flag); return; }
         }
     }
 }
@@ -149,26 +167,14 @@ __device__ __forceinline__ uint64_t mbar_arrive_token(uint64_t * bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 %0, [%1];" : "=l"(st) : "r"(smem_u32(bar)) : "memory");
     return st;
 }
-__device__ __forceinline__ void mbar_wait_token(uint64_t * bar, uint64_t token, int tag = 0) {
+__device__ __forceinline__ void mbar_wait_token(uint64_t * bar, uint64_t token, volatile int * cta_abort, int * abort_flag) {
+    if (mbar_try_token(bar, token)) return;
     const long long t0 = clock64();
-    while (true) {
-        uint32_t ok;
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(ok)
-            : "r"(smem_u32(bar)), "l"(token)
-            : "memory");
-        if (ok) return;
-        if (clock64() - t0 > (1ll << 29)) {
-            if (atomicCAS(&g_hang_info[0], 0ull, 0xdead0002ull) == 0ull) {
-                g_hang_info[1] = blockIdx.x; g_hang_info[2] = threadIdx.x; g_hang_info[3] = (unsigned long long) tag;
-                g_hang_info[4] = token; g_hang_info[5] = smem_u32(bar);
-            }
-            return;
+    int spins = 0;
+    while (!mbar_try_token(bar, token)) {
+        if ((++spins & 63) == 0) {
+            if (*cta_abort) return;
+            if (clock64() - t0 > PB_WAIT_TIMEOUT_CYCLES) { wait_gave_up(cta_abort, abort_flag); return; }
         }
     }
 }

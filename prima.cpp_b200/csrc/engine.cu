@@ -39,11 +39,6 @@ static int dbg_sync(cudaStream_t st, const char * what) {
     fflush(stderr);
     cudaError_t e = cudaStreamSynchronize(st);
     fprintf(stderr, "%s\n", cudaGetErrorString(e));
-    if (e != cudaSuccess) {
-        unsigned long long h[32] = {0};
-        gemv_hang_info(h);
-        fprintf(stderr, "[pb200] watchdog: magic %llx cta %llu thread %llu it %llu parity %llu bar %llx\n", h[0], h[1], h[2], h[3], h[4], h[5]);
-    }
     return (int) e;
 }
 
@@ -96,7 +91,7 @@ struct pb200_model {
     std::vector<Layer> layers;   // index il - l0
     __half *kcache = nullptr, *vcache = nullptr;
     float *x_in = nullptr, *x_a = nullptr, *x_b = nullptr, *q = nullptr, *k = nullptr, *v = nullptr, *att = nullptr, *g = nullptr, *u = nullptr,
-          *xn = nullptr, *logits = nullptr;
+          *xn = nullptr, *x_out = nullptr, *logits = nullptr;
     ActBuf actE, actQD, actF;
     int32_t * tokpos_dev = nullptr;    // [0] token, [1] pos
     int32_t * tokpos_host = nullptr;   // pinned
@@ -107,9 +102,6 @@ struct pb200_model {
     int64_t weight_bytes = 0;
     std::vector<void *> allocs;
     bool profiling = false;
-    MkHandle * mk = nullptr;          // persistent token kernel (all GEMV phases in one cooperative launch)
-    bool use_mk = false;
-    float * mk_final_x = nullptr;
     // prompt-processing (prefill) scratch, grown on demand
     struct Prefill {
         int T = 0;
@@ -228,6 +220,7 @@ extern "C" {
 
 pb200_model * pb200_model_create(const pb200_hparams * hp, int device, int layer_begin, int layer_end, int with_embd, int with_head) {
     if (!hp || layer_begin < 0 || layer_end > hp->n_layer || layer_begin > layer_end) return nullptr;
+    if (hp->n_head_kv <= 0 || hp->n_head <= 0 || hp->n_ff <= 0 || hp->n_vocab <= 0 || hp->n_ctx <= 0 || hp->n_embd <= 0) return nullptr;
     if (hp->head_dim != 128 || hp->n_head % hp->n_head_kv != 0 || hp->n_embd % 256 != 0) return nullptr;
     if (cudaSetDevice(device) != cudaSuccess) return nullptr;
     pb200_model * m = new pb200_model();
@@ -247,7 +240,6 @@ void pb200_model_free(pb200_model * m) {
     cudaSetDevice(m->device);
     cudaStreamSynchronize(m->stream);
     if (m->graph_exec) cudaGraphExecDestroy(m->graph_exec);
-    if (m->mk) mk_free(m->mk);
     for (void * p : m->allocs) cudaFree(p);
     for (void * p : m->pf.allocs) cudaFree(p);
     if (m->tokpos_host) cudaFreeHost(m->tokpos_host);
@@ -355,14 +347,6 @@ static int prof_end(pb200_model * m) {
 }
 static int64_t tbytes(const Tensor & t) { return (int64_t) t.bytes; }
 
-static void set_next(GemvFused & pro, const Tensor & t, int K) {
-    // measured (profiles/r1_summary.md): pulling the next launch's first tiles into L2 during the tail COSTS 3 % (11.45 vs 11.08 ms):
-    // the prefetch competes with the tail's own refills and the next launch re-reads the lines anyway.  Opt-in only.
-    static const bool on = getenv("PB200_PREFETCH") != nullptr;
-    const uint32_t tb = on ? gemv_tile_bytes(t.type, K, (int) t.N) : 0;
-    if (tb) { pro.next_W = t.data; pro.next_total_bytes = (int64_t) t.bytes; pro.next_tile_bytes = tb; }
-}
-
 // one decode step enqueued on m->stream (captured into the CUDA graph by finalize)
 static int enqueue_step(pb200_model * m, uint64_t * nlaunch) {
     const pb200_hparams & hp = m->hp;
@@ -377,13 +361,6 @@ static int enqueue_step(pb200_model * m, uint64_t * nlaunch) {
         CK(launch_get_rows(m->tok_embd.data, m->tok_embd.type, E, tok_dev, 1, m->x_a, st, pdl)); n++; CK(dbg_sync(st, "get_rows"));
         x = m->x_a;
     }
-    if (m->use_mk && m->mk && !m->profiling) {
-        // whole token = embedding gather + ONE cooperative launch (+ a 32-KB copy that keeps hidden_out at a stable address)
-        CK(mk_launch(m->mk, st)); n++;
-        if (m->mk_final_x != m->x_b) CK(cudaMemcpyAsync(m->x_b, m->mk_final_x, (size_t) E * 4, cudaMemcpyDeviceToDevice, st));
-        if (nlaunch) *nlaunch = n;
-        return 0;
-    }
     const float kq_scale = 1.0f / sqrtf((float) D);
     // three rotating hidden-state buffers so that a residual source is never overwritten by its consumer
     float * bufs[3] = {m->x_a, m->x_b, m->xn};
@@ -394,6 +371,7 @@ static int enqueue_step(pb200_model * m, uint64_t * nlaunch) {
         float * x1 = nullptr, * x2 = nullptr;
         for (int i = 0; i < 3 && (!x1 || !x2); i++)
             if (bufs[i] != x) { if (!x1) x1 = bufs[i]; else x2 = bufs[i]; }
+        if (il + 1 == m->l1) x2 = m->x_out;   // the last layer writes hidden_out in place (a copy node would break the PDL chain)
         // --- attention block ---
         const bool qkv_k = is_kquant(L.wq.type) && is_kquant(L.wk.type) && is_kquant(L.wv.type) && gemv_fused_prologue_ok(E);
         if (qkv_k) {
@@ -402,7 +380,6 @@ static int enqueue_step(pb200_model * m, uint64_t * nlaunch) {
                              {L.wk.data, m->k, L.bk, nullptr, L.wk.type, EK},
                              {L.wv.data, m->v, L.bv, nullptr, L.wv.type, EK}};
             GemvFused pro; pro.kind = 1; pro.in0 = x; pro.in1 = L.attn_norm; pro.eps = hp.rms_eps;
-            set_next(pro, L.wo, QD);
             CK(prof_begin(m, tbytes(L.wq) + tbytes(L.wk) + tbytes(L.wv)));
             CK(launch_gemv_kquant_fused(d, 3, E, m->actE.q, pro, st, pdl)); n++; CK(dbg_sync(st, "gemv qkv"));
             CK(prof_end(m));
@@ -424,8 +401,6 @@ static int enqueue_step(pb200_model * m, uint64_t * nlaunch) {
             CK(prof_begin(m, tbytes(L.wo)));
             if (is_kquant(L.wo.type) && gemv_fused_prologue_ok(QD)) {
                 GemvFused pro; pro.kind = 2; pro.in0 = m->att;
-                pro.fill_before_wait = pdl && gemv_smem_bytes() < 200 * 1024;   // follows the attention kernel; only pays when both kernels fit on an SM
-                set_next(pro, L.gate, E);
                 CK(launch_gemv_kquant_fused(&d1, 1, QD, m->actQD.q, pro, st, pdl)); n++; CK(dbg_sync(st, "gemv wo"));
             } else {
                 CK(launch_quantize_act(m->att, QD, act_mode_for(L.wo.type), m->actQD.q, st, pdl)); n++;
@@ -438,7 +413,6 @@ static int enqueue_step(pb200_model * m, uint64_t * nlaunch) {
         if (gu_k) {
             GemvDesc d[2] = {{L.gate.data, m->g, nullptr, nullptr, L.gate.type, F}, {L.up.data, m->u, nullptr, nullptr, L.up.type, F}};
             GemvFused pro; pro.kind = 1; pro.in0 = x1; pro.in1 = L.ffn_norm; pro.eps = hp.rms_eps;
-            set_next(pro, L.down, F);
             CK(prof_begin(m, tbytes(L.gate) + tbytes(L.up)));
             CK(launch_gemv_kquant_fused(d, 2, E, m->actE.q, pro, st, pdl)); n++; CK(dbg_sync(st, "gemv gate|up"));
             CK(prof_end(m));
@@ -456,96 +430,35 @@ static int enqueue_step(pb200_model * m, uint64_t * nlaunch) {
         {
             GemvDesc d1 = {L.down.data, x2, nullptr, x1, L.down.type, E};   // l_out = down.act + ffn_inp
             CK(prof_begin(m, tbytes(L.down)));
-            if (false && is_kquant(L.down.type) && gemv_fused_prologue_ok(F)) {
-                // measured (profiles/r1_launches.md): recomputing silu(g)*u in all 148 CTAs costs +17 us per layer, the separate
-                // 14-CTA kernel 5 us -> keep the kernel; the fused path stays available for the persistent design
-                GemvFused pro; pro.kind = 3; pro.in0 = m->g; pro.in1 = m->u;
-                CK(launch_gemv_kquant_fused(&d1, 1, F, m->actF.q, pro, st, pdl)); n++;
+            // silu(g)*u -> q8_K stays a separate small kernel: under PDL the down GEMV's CTAs are already resident and fill their
+            // rings while it runs (recomputing it in every GEMV CTA cost +17 us per layer, profiles/r1_summary.md)
+            CK(launch_silu_mul_quant(m->g, m->u, F, act_mode_for(L.down.type), m->actF.q, nullptr, st, pdl)); n++; CK(dbg_sync(st, "silu"));
+            if (is_kquant(L.down.type)) {
+                GemvFused pro;   // PRO_NONE
+                CK(launch_gemv_kquant_fused(&d1, 1, F, m->actF.q, pro, st, pdl)); n++; CK(dbg_sync(st, "gemv down"));
             } else {
-                CK(launch_silu_mul_quant(m->g, m->u, F, act_mode_for(L.down.type), m->actF.q, nullptr, st, pdl)); n++; CK(dbg_sync(st, "silu"));
-                if (is_kquant(L.down.type)) {
-                    GemvFused pro;   // PRO_NONE; only carries the prefetch target: next layer's wq, or the lm_head after the last layer
-                    pro.fill_before_wait = pdl && gemv_smem_bytes() < 200 * 1024;   // follows the silu-quant kernel
-                    if (il + 1 < m->l1) set_next(pro, m->layers[il + 1 - m->l0].wq, E);
-                    else if (m->with_head) set_next(pro, m->output, E);
-                    CK(launch_gemv_kquant_fused(&d1, 1, F, m->actF.q, pro, st, pdl)); n++; CK(dbg_sync(st, "gemv down"));
-                } else {
-                    CK(launch_gemv(&d1, 1, F, m->actF.q, st, pdl)); n++;
-                }
+                CK(launch_gemv(&d1, 1, F, m->actF.q, st, pdl)); n++;
             }
             CK(prof_end(m));
         }
         x = x2;
     }
-    // hidden_out: keep a stable address for the next pipeline stage / tests
-    if (x != m->x_b) { CK(cudaMemcpyAsync(m->x_b, x, (size_t) E * 4, cudaMemcpyDeviceToDevice, st)); }
+    // hidden_out has a stable address for the next pipeline stage / tests (a stage without layers forwards its input)
+    if (x != m->x_out) { CK(cudaMemcpyAsync(m->x_out, x, (size_t) E * 4, cudaMemcpyDeviceToDevice, st)); }
     if (m->with_head) {
         GemvDesc d1 = {m->output.data, m->logits, nullptr, nullptr, m->output.type, hp.n_vocab};
         CK(prof_begin(m, tbytes(m->output)));
         if (is_kquant(m->output.type) && gemv_fused_prologue_ok(E)) {
-            GemvFused pro; pro.kind = 1; pro.in0 = m->x_b; pro.in1 = m->output_norm; pro.eps = hp.rms_eps;
-            CK(launch_gemv_kquant_fused(&d1, 1, E, m->actE.q, pro, st, false)); n++;
+            GemvFused pro; pro.kind = 1; pro.in0 = m->x_out; pro.in1 = m->output_norm; pro.eps = hp.rms_eps;
+            CK(launch_gemv_kquant_fused(&d1, 1, E, m->actE.q, pro, st, pdl && m->l1 > m->l0)); n++;
         } else {
-            CK(launch_rmsnorm_quant(m->x_b, m->output_norm, E, hp.rms_eps, act_mode_for(m->output.type), m->actE.q, nullptr, st, false)); n++;
+            CK(launch_rmsnorm_quant(m->x_out, m->output_norm, E, hp.rms_eps, act_mode_for(m->output.type), m->actE.q, nullptr, st, pdl && m->l1 > m->l0)); n++;
             CK(launch_gemv(&d1, 1, E, m->actE.q, st, pdl)); n++;
         }
         CK(prof_end(m));
     }
     if (nlaunch) *nlaunch = n;
     return 0;
-}
-
-// descriptors of the persistent token kernel: same dataflow as enqueue_step (buffer rotation included)
-static void build_mk(pb200_model * m) {
-    const pb200_hparams & hp = m->hp;
-    const int E = hp.n_embd, H = hp.n_head, HK = hp.n_head_kv, D = hp.head_dim, F = hp.n_ff;
-    const int QD = H * D, EK = HK * D;
-    const size_t nl = m->layers.size();
-    if (nl == 0) return;
-    std::vector<MkLayerDesc> L(nl);
-    float * x = m->with_embd ? m->x_a : m->x_in;
-    float * bufs[3] = {m->x_a, m->x_b, m->xn};
-    for (size_t i = 0; i < nl; i++) {
-        Layer & Ly = m->layers[i];
-        const Tensor * all[7] = {&Ly.wq, &Ly.wk, &Ly.wv, &Ly.wo, &Ly.gate, &Ly.up, &Ly.down};
-        for (const Tensor * t : all) if (!is_kquant(t->type)) return;
-        float * x1 = nullptr, * x2 = nullptr;
-        for (int j = 0; j < 3 && (!x1 || !x2); j++)
-            if (bufs[j] != x) { if (!x1) x1 = bufs[j]; else x2 = bufs[j]; }
-        MkLayerDesc & d = L[i];
-        d.ph[0].nmat = 3; d.ph[0].K = E;
-        d.ph[0].d[0] = {Ly.wq.data, m->q, Ly.bq, nullptr, Ly.wq.type, QD};
-        d.ph[0].d[1] = {Ly.wk.data, m->k, Ly.bk, nullptr, Ly.wk.type, EK};
-        d.ph[0].d[2] = {Ly.wv.data, m->v, Ly.bv, nullptr, Ly.wv.type, EK};
-        d.ph[0].pro.kind = 1; d.ph[0].pro.in0 = x; d.ph[0].pro.in1 = Ly.attn_norm; d.ph[0].pro.eps = hp.rms_eps;
-        d.ph[1].nmat = 1; d.ph[1].K = QD;
-        d.ph[1].d[0] = {Ly.wo.data, x1, nullptr, x, Ly.wo.type, E};
-        d.ph[1].pro.kind = 2; d.ph[1].pro.in0 = m->att;
-        d.ph[2].nmat = 2; d.ph[2].K = E;
-        d.ph[2].d[0] = {Ly.gate.data, m->g, nullptr, nullptr, Ly.gate.type, F};
-        d.ph[2].d[1] = {Ly.up.data, m->u, nullptr, nullptr, Ly.up.type, F};
-        d.ph[2].pro.kind = 1; d.ph[2].pro.in0 = x1; d.ph[2].pro.in1 = Ly.ffn_norm; d.ph[2].pro.eps = hp.rms_eps;
-        d.ph[3].nmat = 1; d.ph[3].K = F;
-        d.ph[3].d[0] = {Ly.down.data, x2, nullptr, x1, Ly.down.type, E};
-        d.ph[3].pro.kind = 0; d.ph[3].act = m->actF.q;
-        d.q = m->q; d.k = m->k; d.v = m->v;
-        d.kc = m->kcache + i * (size_t) hp.n_ctx * EK; d.vc = m->vcache + i * (size_t) hp.n_ctx * EK; d.att = m->att;
-        d.g = m->g; d.u = m->u; d.actF = m->actF.q; d.F = F;
-        x = x2;
-    }
-    MkTokenDesc T{};
-    T.layers = L.data(); T.n_layers = (int) nl;
-    T.with_head = m->with_head;
-    if (m->with_head) {
-        if (!is_kquant(m->output.type)) return;
-        T.head.nmat = 1; T.head.K = E;
-        T.head.d[0] = {m->output.data, m->logits, nullptr, nullptr, m->output.type, hp.n_vocab};
-        T.head.pro.kind = 1; T.head.pro.in0 = x; T.head.pro.in1 = m->output_norm; T.head.pro.eps = hp.rms_eps;
-    }
-    T.pos_dev = m->tokpos_dev + 1; T.freq_factors = m->rope_ff; T.kq_scale = 1.0f / sqrtf((float) D);
-    T.n_head = H; T.n_head_kv = HK; T.n_ctx = hp.n_ctx;
-    m->mk = mk_build(T, m->rp);
-    m->mk_final_x = x;
 }
 
 int pb200_model_finalize(pb200_model * m) {
@@ -582,6 +495,7 @@ int pb200_model_finalize(pb200_model * m) {
     CK(m->alloc((void **) &m->x_a, E * 4));
     CK(m->alloc((void **) &m->x_b, E * 4));
     CK(m->alloc((void **) &m->xn, E * 4));
+    CK(m->alloc((void **) &m->x_out, E * 4));
     CK(m->alloc((void **) &m->q, QD * 4));
     CK(m->alloc((void **) &m->k, EK * 4));
     CK(m->alloc((void **) &m->v, EK * 4));
@@ -604,8 +518,6 @@ int pb200_model_finalize(pb200_model * m) {
     CK(cudaMallocHost((void **) &m->tokpos_host, 16));
     if (m->with_head) CK(cudaMallocHost((void **) &m->logits_host, (size_t) hp.n_vocab * 4));
     rope_params_init(m->rp, hp.head_dim, hp.rope_mode, hp.n_ctx_orig, hp.rope_freq_base, hp.rope_freq_scale, 0.0f, 1.0f, 32.0f, 1.0f);
-    build_mk(m);
-    m->use_mk = m->mk != nullptr && getenv("PB200_PERSISTENT") != nullptr && atoi(getenv("PB200_PERSISTENT")) != 0;
     CK(cudaDeviceSynchronize());
 
     // warm-up (sets kernel attributes outside of capture), then capture the whole token as one graph
@@ -739,21 +651,21 @@ static int prefill_ubatch(pb200_model * m, const int32_t * tokens_host, int32_t 
         CK(pf_matmul(m, L.down, P.g, T, x, nullptr, y, n));                  // l_out = down.act + ffn_inp   (x is free: y holds ffn_inp)
     }
     // hidden state of the last token -> the decode path's output head
-    CK(cudaMemcpyAsync(m->x_b, x + (size_t) (T - 1) * E, (size_t) E * 4, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(m->x_out, x + (size_t) (T - 1) * E, (size_t) E * 4, cudaMemcpyDeviceToDevice, st));
     if (m->with_head) {
         GemvDesc d1 = {m->output.data, m->logits, nullptr, nullptr, m->output.type, hp.n_vocab};
         if (is_kquant(m->output.type) && gemv_fused_prologue_ok(E)) {
-            GemvFused pro; pro.kind = 1; pro.in0 = m->x_b; pro.in1 = m->output_norm; pro.eps = hp.rms_eps;
+            GemvFused pro; pro.kind = 1; pro.in0 = m->x_out; pro.in1 = m->output_norm; pro.eps = hp.rms_eps;
             CK(launch_gemv_kquant_fused(&d1, 1, E, m->actE.q, pro, st, false)); n++;
         } else {
-            CK(launch_rmsnorm_quant(m->x_b, m->output_norm, E, hp.rms_eps, act_mode_for(m->output.type), m->actE.q, nullptr, st, false)); n++;
+            CK(launch_rmsnorm_quant(m->x_out, m->output_norm, E, hp.rms_eps, act_mode_for(m->output.type), m->actE.q, nullptr, st, false)); n++;
             CK(launch_gemv(&d1, 1, E, m->actE.q, st, false)); n++;
         }
     }
     g_launches += n;
     if (m->with_head && logits_host) CK(cudaMemcpyAsync(m->logits_host, m->logits, (size_t) hp.n_vocab * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    if (mmq_aborted()) return PB200_EABORTED;   // a tensor-core launch gave up on a stuck pipeline: the batch's results are invalid
+    if (check_clear_abort()) return PB200_EABORTED;   // a kernel's wait watchdog gave up: this batch's results are invalid (flag re-armed)
     if (m->with_head && logits_host) memcpy(logits_host, m->logits_host, (size_t) hp.n_vocab * 4);
     return 0;
 }
@@ -798,26 +710,29 @@ int pb200_decode(pb200_model * m, int32_t token, int32_t pos, float * logits_hos
     if (m->with_head && logits_host) {
         CK(cudaMemcpyAsync(m->logits_host, m->logits, (size_t) m->hp.n_vocab * 4, cudaMemcpyDeviceToHost, m->stream));
         CK(cudaStreamSynchronize(m->stream));
+        if (check_clear_abort()) return PB200_EABORTED;   // a wait watchdog fired inside this step: its logits are invalid
         memcpy(logits_host, m->logits_host, (size_t) m->hp.n_vocab * 4);
         return 0;
     }
-    return (int) cudaStreamSynchronize(m->stream);
+    CK(cudaStreamSynchronize(m->stream));
+    return check_clear_abort() ? PB200_EABORTED : 0;
 }
 
 int pb200_synchronize(pb200_model * m) {
     if (!m) return PB200_EINVAL;
     cudaSetDevice(m->device);
-    return (int) cudaStreamSynchronize(m->stream);
+    CK(cudaStreamSynchronize(m->stream));
+    return check_clear_abort() ? PB200_EABORTED : 0;
 }
 float * pb200_logits_device(pb200_model * m) { return m ? m->logits : nullptr; }
 float * pb200_hidden_in_device(pb200_model * m) { return m ? m->x_in : nullptr; }
-float * pb200_hidden_out_device(pb200_model * m) { return m ? m->x_b : nullptr; }
+float * pb200_hidden_out_device(pb200_model * m) { return m ? m->x_out : nullptr; }
 void * pb200_stream(pb200_model * m) { return m ? (void *) m->stream : nullptr; }
 int pb200_get_hidden(pb200_model * m, float * hidden_host) {
     if (!m || !m->finalized || !hidden_host) return PB200_EINVAL;
     cudaSetDevice(m->device);
     CK(cudaStreamSynchronize(m->stream));
-    return (int) cudaMemcpy(hidden_host, m->x_b, (size_t) m->hp.n_embd * 4, cudaMemcpyDeviceToHost);
+    return (int) cudaMemcpy(hidden_host, m->x_out, (size_t) m->hp.n_embd * 4, cudaMemcpyDeviceToHost);
 }
 int pb200_profile_step(pb200_model * m, int32_t token, int32_t pos, double * gemv_ms, int64_t * gemv_bytes, int32_t * gemv_launches, double * step_ms) {
     if (!m || !m->finalized) return PB200_ESTATE;
@@ -864,18 +779,10 @@ int pb200_debug_read(pb200_model * m, const char * name, float * host, int64_t n
     CK(cudaStreamSynchronize(m->stream));
     const std::string s(name);
     const float * p = s == "q" ? m->q : s == "k" ? m->k : s == "v" ? m->v : s == "att" ? m->att : s == "g" ? m->g : s == "u" ? m->u :
-                      s == "x_a" ? m->x_a : s == "x_b" ? m->x_b : s == "xn" ? m->xn : s == "x_in" ? m->x_in : s == "logits" ? m->logits : nullptr;
+                      s == "x_a" ? m->x_a : s == "x_b" ? m->x_b : s == "x_out" ? m->x_out : s == "xn" ? m->xn : s == "x_in" ? m->x_in : s == "logits" ? m->logits : nullptr;
     if (!p) return PB200_EINVAL;
     return (int) cudaMemcpy(host, p, (size_t) n * 4, cudaMemcpyDeviceToHost);
 }
-int pb200_set_persistent(pb200_model * m, int on) {
-    if (!m) return PB200_EINVAL;
-    if (on && !m->mk) return PB200_ENOTSUP;
-    // the captured graph contains whichever path was active at finalize: switch to direct launches when toggled
-    if ((on != 0) != m->use_mk) { m->use_mk = on != 0; m->use_graph = false; }
-    return 0;
-}
-int pb200_persistent_error(pb200_model * m) { return (m && m->mk) ? mk_error(m->mk) : 0; }
 int pb200_set_use_graph(pb200_model * m, int on) {
     if (!m) return PB200_EINVAL;
     m->use_graph = on != 0;

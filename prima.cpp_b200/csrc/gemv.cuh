@@ -6,36 +6,39 @@
 // is q8_K, every integer sub-result is exact, only the order of the final fp32 adds differs.
 //
 // B200 design (memory-bound, no tensor cores):
-//   * persistent grid, one CTA per SM; row tiles of raw blocks stream HBM -> shared memory with cp.async.bulk (1-D TMA,
-//     SASS UBLKCP) into a 4-deep ring (up to ~192 KB in flight per SM).  There is no producer warp: the consumer warp
-//     that finishes a stage last re-arms its mbarrier and issues the refill itself (zero polling latency, 512 threads
-//     = 128 registers each);
-//   * 16 consumer warps in two teams that alternate ring stages; ONE LANE OWNS ONE SUPER-BLOCK COLUMN: lane l of sub-warp s keeps the 256 int8 activations of
+//   * persistent grid of TWO 256-thread CTAs per SM (<= 113 KB of shared memory and 128 registers each).  Two CTAs per SM is
+//     what lets consecutive kernels of the token overlap under programmatic dependent launch: when a CTA of launch A exits,
+//     a CTA of launch B becomes resident on that SM and streams its first weight tiles (they never depend on A) while the
+//     rest of A drains; a small kernel between two GEMVs (attention, silu-quant) runs while the next GEMV's rings fill.
+//     Round 1's single 512-thread / 227-KB CTA per SM serialised every launch boundary: 9.25 us fixed cost per launch
+//     (profiles/r1_gemv_microbench.txt) x 321 launches = 3 ms of a 10-ms token;
+//   * row tiles of raw blocks stream HBM -> shared memory with cp.async.bulk (1-D TMA, SASS UBLKCP) into an nstage-deep ring
+//     (4-8 stages of ~16-24 KB chosen per launch; ~185 KB in flight per SM).  There is no producer warp: the consumer warp
+//     that finishes a stage last re-arms its mbarrier and issues the refill itself;
+//   * 8 consumer warps; ONE LANE OWNS ONE SUPER-BLOCK COLUMN: lane l of sub-warp s keeps the 256 int8 activations of
 //     super-block (32 s + l) plus its bsums and scale in registers for the whole kernel, so shared memory is read
 //     exactly once per weight byte (128-bit LDS, conflict-free at 144/176-B strides) and the activation costs no
 //     bandwidth at all after the prologue;
+//   * rows of a stage are dealt to the warp groups round-robin ACROSS stages (row j of the CTA's sequence -> group j mod
+//     ngroups), so any number of rows per stage keeps all warps busy and several stages are consumed concurrently;
 //   * per row: integer dp4a/dp2a dot, one fp32 scale, a 5-step shuffle reduction; rows longer than 32 super-blocks
-//     are split over 2/4/8 warps and combined through a few floats of shared memory in a fixed order
+//     are split over 2/4 warps and combined through a few floats of shared memory in a fixed order
 //     (deterministic, no atomics);
-//   * several matrices that share one activation (q|k|v, gate|up) run as ONE launch (tile list over matrices);
-//   * griddepcontrol (PDL): the weight stream starts before the producing kernel has finished.
+//   * several matrices that share one activation (q|k|v, gate|up) run as ONE launch (tile list over matrices).
 #pragma once
 #include "common.cuh"
 
 namespace pb {
 
-constexpr int GEMV_TEAM_W = 8;                    // consumer warps that share one stage (a "team")
-constexpr int GEMV_NTEAM = 2;                     // teams alternate stages: team t consumes iterations t, t+2, ... — twice the
-                                                  // per-stage latency budget, 4 warps per scheduler instead of 2
-constexpr int GEMV_NW = GEMV_TEAM_W * GEMV_NTEAM;  // consumer warps
-constexpr int GEMV_THREADS = GEMV_NW * 32;        // no producer warp: the last consumer of a stage issues its refill
-constexpr int GEMV_NSTAGE = 4;                    // measured: 4 x 46 KB at 128 regs (9.90 ms/token) beats 3 stages at 104 regs with the small
-                                                  // kernels co-resident under PDL (10.09 ms); the ring logic is depth-agnostic
-constexpr int GEMV_STAGE_BYTES = 46 * 1024;       // 8 rows of Q4_K/Q5_K or 7 rows of Q6_K @ K=8192; 2 rows @ K=28672 (47 040 B + 16)
+constexpr int GEMV_NW = 8;                        // consumer warps per CTA
+constexpr int GEMV_THREADS = GEMV_NW * 32;
+constexpr int GEMV_CTAS_PER_SM = 2;
+constexpr int GEMV_MAX_STAGE = 8;
+constexpr int GEMV_SMEM_LIMIT = 113 * 1024;       // 2 x (113 KB + 1 KB reserved per CTA) = the 228 KB of an SM
+constexpr int GEMV_STAGE_TARGET = 20 * 1024;      // bytes per ring stage aimed for (rows per stage = target / row bytes)
 constexpr int GEMV_ACT_MAX_NBLK = 112;            // K <= 28 672 on the fast path
-constexpr int GEMV_ACT_SMEM = GEMV_ACT_MAX_NBLK * (ACT_SMEM_QS_STRIDE + 2 * ACT_SMEM_BS_STRIDE + 4) + 64;   // padded qs | padded bsums | d
 constexpr int GEMV_MAX_MAT = 3;
-constexpr int GEMV_MAX_NBLK = 256;               // K <= 65 536 (8 warps x 32 lanes x one super-block each)
+__host__ __device__ inline int gemv_act_smem_bytes(int nblk) { return nblk * (ACT_SMEM_QS_STRIDE + 2 * ACT_SMEM_BS_STRIDE + 4) + 64; }   // padded qs | padded bsums | d
 
 struct GemvMat {
     const uint8_t * W;     // raw GGUF blocks, row-major [N][K/256 blocks]
@@ -50,8 +53,8 @@ struct GemvMat {
     int tile0;             // index of this matrix' first tile in the launch-wide tile list
 };
 
-// Fused prologue: every CTA produces the q8_K activation itself (redundantly, from L2) while its producer warp is already
-// streaming weights, instead of a separate tiny kernel + launch in front of each GEMV:
+// Fused prologue: every CTA produces the q8_K activation itself (redundantly, from L2) while its ring is already
+// filling, instead of a separate tiny kernel + launch in front of each GEMV:
 //   PRO_NONE     activation already quantized in HBM (`act`)
 //   PRO_RMSNORM  act = q8_K( rms_norm(in0) * in1 )          llm_build_norm + quantize_row_q8_K   (in1 = norm weight)
 //   PRO_QUANT    act = q8_K( in0 )                          attention output -> wo
@@ -63,19 +66,17 @@ struct GemvParams {
     int nmat;
     int ntiles;
     int K;
-    int nblk;      // K / 256
-    int wpr;       // warps per row: 1, 2, 4 or 8
-    ActQ act;      // q8_K activation (PRO_NONE)
+    int nblk;          // K / 256
+    int wpr;           // warps per row: 1, 2 or 4
+    int nstage;        // ring depth of this launch
+    int stage_bytes;   // bytes reserved per stage (multiple of 128)
+    ActQ act;          // q8_K activation (PRO_NONE)
     int prologue;
     const float * in0;
     const float * in1;
     float eps;
-    // cross-kernel prefetch: when this CTA's ring stops refilling (its last tiles are in flight) it pulls the tiles the NEXT
-    // GEMV launch will request first (tile c, c+G, c+2G, c+3G of its first matrix) into L2, so that launch's ramp-up reads L2
-    const uint8_t * next_W;
-    int64_t next_total_bytes;
-    uint32_t next_tile_bytes;
-    int fill_before_wait;   // start the weight stream before griddepcontrol.wait (launches that follow a SMALL kernel)
+    int * abort_flag;              // host-mapped: set by the wait watchdog (never on a healthy run)
+    unsigned long long * trace;    // per-CTA %globaltimer stamps (TRACE instantiation only)
 };
 
 // ---------------------------------------------------------------------------------------------------------------

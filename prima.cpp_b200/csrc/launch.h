@@ -22,44 +22,27 @@ struct GemvFused {       // fused activation prologue of the k-quant GEMV (PRO_*
     const float * in0 = nullptr;
     const float * in1 = nullptr;
     float eps = 0.f;
-    // optional: first matrix of the NEXT k-quant GEMV launch in the stream (cross-kernel L2 prefetch of its first tiles)
-    const void * next_W = nullptr;
-    int64_t next_total_bytes = 0;
-    uint32_t next_tile_bytes = 0;
-    // this launch follows a small kernel (attention, silu-quant): with PDL its CTAs are resident while that kernel runs, so
-    // the ring is filled BEFORE griddepcontrol.wait and the first ~20 MB of weights stream during the predecessor
-    bool fill_before_wait = false;
 };
-uint32_t gemv_tile_bytes(int type, int K, int N);
 
-int sm_count();
-int gemv_set_trace(unsigned long long * dev_buf);
-int gemv_hang_info(unsigned long long * out8);   // diagnostic written by the mbarrier watchdog before it traps   // debugging: per-CTA %globaltimer stamps of k_gemv_kquant
-int gemv_smem_bytes();
+// ---- per-device host state (gemv.cu): cudaFuncSetAttribute / SM count are per device, one process may drive several ----
+constexpr int PB_MAX_DEV = 64;
+struct FuncAttrCache { size_t bytes[PB_MAX_DEV] = {0}; };
+int cur_device();
+int sm_count();                       // of the current device
+// raise a kernel's dynamic shared-memory limit on the current device if needed (max_carveout: also prefer the full 228 KB carve-out)
+cudaError_t ensure_dyn_smem(FuncAttrCache & c, const void * fn, size_t bytes, bool max_carveout);
+// wait watchdogs (common.cuh): host-mapped flag every kernel with a bounded wait gets a pointer to; check_clear_abort() returns 1
+// once per abort and re-arms — the C ABI reports PB200_EABORTED for the call that synchronised on the aborted launch
+int * abort_flag();
+int check_clear_abort();
+
+int gemv_set_trace(unsigned long long * dev_buf, int slots);   // profiling: per-CTA stamps of k_gemv_kquant, launch i -> row i % slots of u64[4096]; NULL = off
+int gemv_smem_bytes(int type, int K, int N);        // dynamic shared memory of the fast kernel for this shape (0: generic kernel)
 
 // y_i = W_i . act  for up to 3 k-quant matrices sharing one q8_K activation (TMA-staged persistent kernel)
 int launch_gemv_kquant(const GemvDesc * d, int nmat, int K, const ActQ & act, cudaStream_t stream, bool pdl);
 int launch_gemv_kquant_fused(const GemvDesc * d, int nmat, int K, const ActQ & act, const GemvFused & pro, cudaStream_t stream, bool pdl);
 bool gemv_fused_prologue_ok(int K);
-// ---- persistent token kernel (all GEMV phases of a decode step in one cooperative launch; gemv.cu) ----
-struct MkGemvDesc { GemvDesc d[3]; int nmat = 0; int K = 0; GemvFused pro; ActQ act{}; };
-struct MkLayerDesc {
-    MkGemvDesc ph[4];                                   // qkv, wo, gate|up, down
-    const float * q; const float * k; const float * v;  // attention inputs
-    __half * kc; __half * vc; float * att;
-    const float * g; const float * u; ActQ actF; int F;
-};
-struct MkTokenDesc {
-    const MkLayerDesc * layers; int n_layers;
-    MkGemvDesc head; bool with_head;
-    const int32_t * pos_dev; const float * freq_factors; float kq_scale; int n_head, n_head_kv, n_ctx;
-};
-struct MkHandle;
-// returns nullptr when the model / shapes are outside what the persistent kernel handles (caller keeps the multi-kernel path)
-MkHandle * mk_build(const MkTokenDesc & t, const struct RopeParams & rp);
-int mk_launch(MkHandle * h, cudaStream_t stream);     // memset of the grid-barrier word + cooperative launch
-int mk_error(MkHandle * h);                           // 1 if a grid barrier timed out (after synchronising)
-void mk_free(MkHandle * h);
 // any supported type / any K, one warp per row, direct global loads
 int launch_gemv_generic(const GemvDesc & d, int K, const ActQ & act, cudaStream_t stream, bool pdl);
 // picks the right kernel per weight type (all matrices must need the same activation mode)
@@ -113,7 +96,6 @@ int launch_soft_max(const float * x, const float * mask, float * y, int ncols, i
 // batched k-quant mat-mul on tcgen05 (mmq.cu): dst[T][N] = X[T][K] . W[N][K]^T (+ bias[N]); ws from mmq_workspace_bytes
 size_t mmq_workspace_bytes(int64_t K, int64_t T);
 bool mmq_supported(int type, int64_t K);
-int mmq_aborted();
 cudaError_t launch_mmq(int type, const void * W, int64_t N, int64_t K, const float * x, int64_t ldx, int64_t T, float * dst, const float * bias,
                        const float * resid, void * ws, cudaStream_t st);   // resid: [T][N] added in the epilogue (must not alias dst)
 int launch_get_rows(const void * table, int type, int K, const int32_t * ids, int n_ids, float * y, cudaStream_t stream, bool pdl);

@@ -41,6 +41,7 @@ constexpr int MMQ_A_BYTES = MMQ_BM * 128;   // one A stage: 128 rows x 64 fp16
 constexpr int MMQ_CTL_BYTES = 256;
 
 struct MmqParams {
+    int * abort_flag;      // host-mapped, raised by the wait watchdog
     const uint8_t * W;
     const uint8_t * B;     // activations, fp16, tiled [T/BN][K/64][BN x 128 B swizzled]
     float * dst;           // [T][N]
@@ -60,11 +61,10 @@ struct MmqCtl {
     uint64_t step_done[MMQ_B_NST];   // one tcgen05.commit per step: step u arrives on step_done[u % 4]; frees A stage u % 2 and B stage u % b_nst
     uint64_t acc_ready;
     uint32_t tmem_base;
-    int abort;
+    volatile int abort;
 };
 static_assert(sizeof(MmqCtl) <= MMQ_CTL_BYTES, "ctl");
 
-__device__ int g_mmq_abort;
 
 __device__ __forceinline__ bool mmq_try(uint64_t * bar, uint32_t parity) {
     uint32_t ok;
@@ -80,22 +80,22 @@ __device__ __forceinline__ bool mmq_try(uint64_t * bar, uint32_t parity) {
     return ok != 0;
 }
 // bounded wait: a broken pipeline must end the launch (and report through pb200_mmq_aborted), never hang the device
-__device__ __forceinline__ bool mmq_wait(MmqCtl * ctl, uint64_t * bar, uint32_t parity) {
+__device__ __forceinline__ bool mmq_wait_(MmqCtl * ctl, uint64_t * bar, uint32_t parity, int * abort_flag) {
     if (mmq_try(bar, parity)) return true;          // the common case costs one try_wait
     const long long t0 = clock64();
     int spins = 0;
     while (!mmq_try(bar, parity)) {
         if ((++spins & 255) == 0) {
-            if (*(volatile int *) &ctl->abort) return false;
-            if (clock64() - t0 > (1ll << 27)) {
-                *(volatile int *) &ctl->abort = 1;
-                atomicExch(&g_mmq_abort, 1);
+            if (ctl->abort) return false;
+            if (clock64() - t0 > PB_WAIT_TIMEOUT_CYCLES) {
+                wait_gave_up(&ctl->abort, abort_flag);
                 return false;
             }
         }
     }
     return true;
 }
+#define mmq_wait(ctl, bar, parity) mmq_wait_(ctl, bar, parity, P.abort_flag)
 __device__ __forceinline__ void bulk_g2s_plain(void * smem_dst, const void * gsrc, uint32_t bytes, uint64_t * bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)), "l"(gsrc),
                  "r"(bytes), "r"(smem_u32(bar))
@@ -510,20 +510,11 @@ bool mmq_supported(int type, int64_t K) {
     return (type == T_Q8_0 || type == T_Q5_1) && K % 64 == 0 && K >= 256;   // 32-element blocks: two per 64-element step
 }
 
-int mmq_aborted() {
-    int v = 0;
-    cudaMemcpyFromSymbol(&v, g_mmq_abort, sizeof(int));
-    return v;
-}
-
 template <int TYPE>
 static cudaError_t mmq_launch_typed(const MmqParams & P, dim3 grid, size_t smem, cudaStream_t st) {
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_mmq_tc<TYPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
+    static FuncAttrCache attr_cache;
+    cudaError_t e = ensure_dyn_smem(attr_cache, (const void *) k_mmq_tc<TYPE>, smem, false);
+    if (e != cudaSuccess) return e;
     k_mmq_tc<TYPE><<<grid, MMQ_THREADS, smem, st>>>(P);
     return cudaGetLastError();
 }
@@ -535,6 +526,7 @@ cudaError_t launch_mmq(int type, const void * W, int64_t N, int64_t K, const flo
     const int tpad = (int) ((T + BN - 1) / BN * BN);
 
     MmqParams P{};
+    P.abort_flag = abort_flag();
     P.W = (const uint8_t *) W;
     P.B = (const uint8_t *) ws;
     P.dst = dst;

@@ -792,15 +792,14 @@ int launch_rope(const float * x, float * y, int64_t ntok, int n_head, int D, int
 }
 
 int attn_scratch_floats(int, int) { return 0; }
-static int g_attn_smem_set = 0;
+static FuncAttrCache g_attn_attr;
 int launch_attn_decode(const float * q, const __half * kcache, const __half * vcache, float * out, int n_head, int n_head_kv, int D,
                        const int32_t * pos_dev, int n_ctx, float scale, float *, cudaStream_t stream, bool pdl) {
     if (D != 128) return (int) cudaErrorInvalidValue;
     const size_t smem = ((size_t) ((n_ctx + 31) & ~31) + 8 * 128) * sizeof(float);
-    if ((int) smem > g_attn_smem_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_attn_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    {
+        cudaError_t e = ensure_dyn_smem(g_attn_attr, (const void *) k_attn_decode, smem, false);
         if (e != cudaSuccess) return (int) e;
-        g_attn_smem_set = (int) smem;
     }
     cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1];
     launch_cfg(cfg, attr, dim3(n_head), dim3(256), smem, stream, pdl);
@@ -818,12 +817,11 @@ int launch_attn_batch(const float * q, const __half * kcache, const __half * vca
         const int tq = smem_for(4) <= 200 * 1024 ? 4 : (smem_for(2) <= 200 * 1024 ? 2 : (smem_for(1) <= 200 * 1024 ? 1 : 0));
         if (tq) {
             const size_t smem_t = smem_for(tq);
-            static int configured_t[5] = {0, 0, 0, 0, 0};
+            static FuncAttrCache attr_t[5];
             const void * fn = tq == 4 ? (const void *) k_attn_prefill_tiled<4> : (tq == 2 ? (const void *) k_attn_prefill_tiled<2> : (const void *) k_attn_prefill_tiled<1>);
-            if ((int) smem_t > configured_t[tq] && smem_t > 40 * 1024) {
-                cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_t);
+            {
+                cudaError_t e = ensure_dyn_smem(attr_t[tq], fn, smem_t, false);
                 if (e != cudaSuccess) return (int) e;
-                configured_t[tq] = (int) smem_t;
             }
             const dim3 grid(n_head_kv, (n_tok + tq - 1) / tq);
             if (tq == 4) k_attn_prefill_tiled<4><<<grid, 256, smem_t, stream>>>(q, kcache, vcache, out, n_head, n_head_kv, pos_dev, n_tok, scale, n_kv_pad);
@@ -833,10 +831,9 @@ int launch_attn_batch(const float * q, const __half * kcache, const __half * vca
         }
     }
     const size_t smem = ((size_t) ((n_kv_max + 31) & ~31) + 8 * 128) * sizeof(float);
-    if ((int) smem > g_attn_smem_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_attn_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    {
+        cudaError_t e = ensure_dyn_smem(g_attn_attr, (const void *) k_attn_decode, smem, false);
         if (e != cudaSuccess) return (int) e;
-        g_attn_smem_set = (int) smem;
     }
     cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1];
     launch_cfg(cfg, attr, dim3(n_head, n_tok), dim3(256), smem, stream, false);
@@ -844,16 +841,15 @@ int launch_attn_batch(const float * q, const __half * kcache, const __half * vca
                                     (int64_t) n_head * D);
 }
 
-static int g_attnf_smem_set = 0;
+static FuncAttrCache g_attnf_attr;
 int launch_attn_fused(const float * q, const float * k, const float * v, __half * kcache, __half * vcache, float * out, int n_head, int n_head_kv,
                       int D, const int32_t * pos_dev, int n_ctx, const RopeParams & rp, const float * freq_factors, float scale, cudaStream_t stream,
                       bool pdl) {
     if (D != 128) return (int) cudaErrorInvalidValue;
     const size_t smem = ((size_t) ((n_ctx + 31) & ~31) + 8 * 128) * sizeof(float);
-    if ((int) smem > g_attnf_smem_set && smem > 40 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(k_attn_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    {
+        cudaError_t e = ensure_dyn_smem(g_attnf_attr, (const void *) k_attn_fused, smem, false);
         if (e != cudaSuccess) return (int) e;
-        g_attnf_smem_set = (int) smem;
     }
     cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1];
     launch_cfg(cfg, attr, dim3(n_head), dim3(256), smem, stream, pdl);
@@ -863,8 +859,9 @@ int launch_attn_fused(const float * q, const float * k, const float * v, __half 
 int launch_soft_max(const float * x, const float * mask, float * y, int ncols, int64_t nrows, int64_t rows_per_mask_cycle, float scale,
                     cudaStream_t stream) {
     const size_t smem = (size_t) ncols * sizeof(float);
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(k_soft_max, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    static FuncAttrCache sm_attr;
+    {
+        cudaError_t e = ensure_dyn_smem(sm_attr, (const void *) k_soft_max, smem, false);
         if (e != cudaSuccess) return (int) e;
     }
     k_soft_max<<<(unsigned) nrows, 256, smem, stream>>>(x, mask, y, ncols, rows_per_mask_cycle, scale);

@@ -89,8 +89,6 @@ class Lib:
         c.pb200_debug_read.argtypes = [vp, C.c_char_p, vp, i64]
         c.pb200_profile_step.argtypes = [vp, i32, i32, C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(i32), C.POINTER(C.c_double)]
         c.pb200_set_use_graph.argtypes = [vp, C.c_int]
-        c.pb200_set_persistent.argtypes = [vp, C.c_int]
-        c.pb200_persistent_error.argtypes = [vp]
 
     @classmethod
     def get(cls) -> "Lib":
@@ -173,12 +171,6 @@ class Model:
         import numpy as np
         a = np.ascontiguousarray(h, dtype=np.float32)
         self.lib.check(self.lib.c.pb200_set_hidden(self.h, a.ctypes.data_as(C.c_void_p)), "set_hidden")
-
-    def set_persistent(self, on: bool) -> int:
-        return self.lib.c.pb200_set_persistent(self.h, int(on))
-
-    def persistent_error(self) -> int:
-        return self.lib.c.pb200_persistent_error(self.h)
 
     def set_use_graph(self, on: bool) -> None:
         self.lib.c.pb200_set_use_graph(self.h, int(on))

@@ -120,29 +120,6 @@ def test_pipeline_stages_bit_identical(cuda, pkg):
         e.close()
 
 
-@pytest.mark.parametrize("arch", ["llama", "qwen2"])
-def test_persistent_token_kernel_bit_identical(cuda, pkg, arch):
-    """One cooperative launch per token (persistent ring across phases, grid barriers) must reproduce the multi-kernel path
-    bit for bit: same dot code, same reduction orders, same fused prologues."""
-    tm = TinyModel(n_layer=3, n_embd=1024, n_head=8, n_head_kv=2, n_ff=2816, n_vocab=384, n_ctx=96, arch=arch, seed=21, branch_scale=0.3)
-    toks = [(i * 7919 + 13) % 384 for i in range(20)]
-    eng = tm.load_engine(pkg)
-    want = np.zeros((len(toks), 384), np.float32)
-    for i, t in enumerate(toks):
-        eng.decode(int(t), i, want[i])
-    rc = eng.set_persistent(True)
-    if rc != 0:
-        eng.close()
-        pytest.skip("persistent kernel not applicable to this model")
-    eng.kv_clear()
-    got = np.zeros_like(want)
-    for i, t in enumerate(toks):
-        eng.decode(int(t), i, got[i])
-    assert eng.persistent_error() == 0
-    assert np.array_equal(got, want), float(np.max(np.abs(got - want)))
-    eng.close()
-
-
 # Prompt processing (pb200_prefill): the batch goes through the tensor-core mat-mul (fp16 operands, see tests/test_gpu_mmq.py
 # for its bound) instead of the integer-dot GEMV, so it is NOT bit-identical with token-by-token decoding; the bar is the
 # reference's own whole-block bar (NMSE 2e-3, tests/test-backend-ops.cpp:3000) with a much tighter expectation on the prompt's
