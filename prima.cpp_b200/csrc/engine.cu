@@ -354,6 +354,8 @@ static int enqueue_step(pb200_model * m, uint64_t * nlaunch) {
     const int QD = H * D, EK = HK * D;
     cudaStream_t st = m->stream;
     static const bool pdl = getenv("PB200_NO_PDL") == nullptr;   // programmatic dependent launch on every kernel of the step
+    static const bool attn_v2 = getenv("PB200_ATTN_V1") == nullptr;   // A/B: round 1's attention kernel + quantize prologue in wo
+    static const bool fuse_norm = getenv("PB200_FUSE_NORM") != nullptr && atoi(getenv("PB200_FUSE_NORM")) != 0;   // A/B: rms-norm in every GEMV CTA's prologue
     uint64_t n = 0;
     const int32_t * tok_dev = m->tokpos_dev, * pos_dev = m->tokpos_dev + 1;
     float * x = m->x_in;
@@ -380,6 +382,10 @@ static int enqueue_step(pb200_model * m, uint64_t * nlaunch) {
                              {L.wk.data, m->k, L.bk, nullptr, L.wk.type, EK},
                              {L.wv.data, m->v, L.bv, nullptr, L.wv.type, EK}};
             GemvFused pro; pro.kind = 1; pro.in0 = x; pro.in1 = L.attn_norm; pro.eps = hp.rms_eps;
+            if (!fuse_norm) {   // rms_norm * w -> q8_K once, by one CTA; the GEMV (already resident, ring filling) only stages the result
+                CK(launch_rmsnorm_quant(x, L.attn_norm, E, hp.rms_eps, ACT_Q8_K, m->actE.q, nullptr, st, pdl)); n++;
+                pro = GemvFused{};
+            }
             CK(prof_begin(m, tbytes(L.wq) + tbytes(L.wk) + tbytes(L.wv)));
             CK(launch_gemv_kquant_fused(d, 3, E, m->actE.q, pro, st, pdl)); n++; CK(dbg_sync(st, "gemv qkv"));
             CK(prof_end(m));
@@ -395,12 +401,20 @@ static int enqueue_step(pb200_model * m, uint64_t * nlaunch) {
                 CK(launch_gemv(&d1, 1, E, m->actE.q, st, pdl)); n++;
             }
         }
-        CK(launch_attn_fused(m->q, m->k, m->v, kc, vc, m->att, H, HK, D, pos_dev, hp.n_ctx, m->rp, m->rope_ff, kq_scale, st, pdl)); n++; CK(dbg_sync(st, "attn"));
+        const bool wo_k = is_kquant(L.wo.type) && gemv_fused_prologue_ok(QD);
+        bool att_quantized = false;
+        if (wo_k && attn_v2) {   // clustered attention writes the q8_K activation of wo itself
+            const int rc = launch_attn_fused2(m->q, m->k, m->v, kc, vc, m->att, m->actQD.q, H, HK, D, pos_dev, hp.n_ctx, m->rp, m->rope_ff, kq_scale, st, pdl);
+            if (rc == 0) { att_quantized = true; n++; }
+            else if (rc != (int) cudaErrorNotSupported) return rc;
+        }
+        if (!att_quantized) { CK(launch_attn_fused(m->q, m->k, m->v, kc, vc, m->att, H, HK, D, pos_dev, hp.n_ctx, m->rp, m->rope_ff, kq_scale, st, pdl)); n++; }
+        CK(dbg_sync(st, "attn"));
         {
             GemvDesc d1 = {L.wo.data, x1, nullptr, x, L.wo.type, E};   // ffn_inp = wo.att + inpSA
             CK(prof_begin(m, tbytes(L.wo)));
-            if (is_kquant(L.wo.type) && gemv_fused_prologue_ok(QD)) {
-                GemvFused pro; pro.kind = 2; pro.in0 = m->att;
+            if (wo_k) {
+                GemvFused pro; pro.kind = att_quantized ? 0 : 2; pro.in0 = m->att;
                 CK(launch_gemv_kquant_fused(&d1, 1, QD, m->actQD.q, pro, st, pdl)); n++; CK(dbg_sync(st, "gemv wo"));
             } else {
                 CK(launch_quantize_act(m->att, QD, act_mode_for(L.wo.type), m->actQD.q, st, pdl)); n++;
@@ -413,6 +427,10 @@ static int enqueue_step(pb200_model * m, uint64_t * nlaunch) {
         if (gu_k) {
             GemvDesc d[2] = {{L.gate.data, m->g, nullptr, nullptr, L.gate.type, F}, {L.up.data, m->u, nullptr, nullptr, L.up.type, F}};
             GemvFused pro; pro.kind = 1; pro.in0 = x1; pro.in1 = L.ffn_norm; pro.eps = hp.rms_eps;
+            if (!fuse_norm) {
+                CK(launch_rmsnorm_quant(x1, L.ffn_norm, E, hp.rms_eps, ACT_Q8_K, m->actE.q, nullptr, st, pdl)); n++;
+                pro = GemvFused{};
+            }
             CK(prof_begin(m, tbytes(L.gate) + tbytes(L.up)));
             CK(launch_gemv_kquant_fused(d, 2, E, m->actE.q, pro, st, pdl)); n++; CK(dbg_sync(st, "gemv gate|up"));
             CK(prof_end(m));
@@ -450,7 +468,13 @@ static int enqueue_step(pb200_model * m, uint64_t * nlaunch) {
         CK(prof_begin(m, tbytes(m->output)));
         if (is_kquant(m->output.type) && gemv_fused_prologue_ok(E)) {
             GemvFused pro; pro.kind = 1; pro.in0 = m->x_out; pro.in1 = m->output_norm; pro.eps = hp.rms_eps;
-            CK(launch_gemv_kquant_fused(&d1, 1, E, m->actE.q, pro, st, pdl && m->l1 > m->l0)); n++;
+            bool head_pdl = pdl && m->l1 > m->l0;
+            if (!fuse_norm) {
+                CK(launch_rmsnorm_quant(m->x_out, m->output_norm, E, hp.rms_eps, ACT_Q8_K, m->actE.q, nullptr, st, head_pdl)); n++;
+                pro = GemvFused{};
+                head_pdl = pdl;
+            }
+            CK(launch_gemv_kquant_fused(&d1, 1, E, m->actE.q, pro, st, head_pdl)); n++;
         } else {
             CK(launch_rmsnorm_quant(m->x_out, m->output_norm, E, hp.rms_eps, act_mode_for(m->output.type), m->actE.q, nullptr, st, pdl && m->l1 > m->l0)); n++;
             CK(launch_gemv(&d1, 1, E, m->actE.q, st, pdl)); n++;

@@ -149,12 +149,27 @@ __device__ __forceinline__ float dot_block(int type, const uint8_t * bp, const A
     return dot_q5K(bp, r);
 }
 
+// split rows (wpr > 1): the leader warp's row whose partials are still being collected
+struct PendingRow { bool active; int s, it; uint64_t tok; float v, extra; float * y; };
+__device__ __forceinline__ void finish_split_row(const GemvParams & P, GemvSmemCtl * ctl, uint8_t * stages, const PendingRow & pr, int group, int wpr,
+                                                 int lane, uint64_t pol) {
+    const uint64_t tok = __shfl_sync(0xffffffffu, pr.tok, 0);
+    mbar_wait_token(&ctl->pbar[pr.s][group], tok, &ctl->aborted, P.abort_flag);
+    if (lane == 0) {
+        float acc = pr.v;
+        for (int i = 1; i < wpr; i++) acc += ctl->part[pr.s][group * wpr + i];
+        *pr.y = acc + pr.extra;
+        release_stage(P, ctl, stages, pr.s, pr.it, pol);   // last: part[s] cannot be overwritten before it was read
+    }
+}
+
 template <bool TRACE>
 __global__ void __launch_bounds__(GEMV_THREADS, GEMV_CTAS_PER_SM) k_gemv_kquant(const __grid_constant__ GemvParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
     GemvSmemCtl * ctl = reinterpret_cast<GemvSmemCtl *>(smem);
     uint8_t * stages = smem + GEMV_CTL_BYTES;
-    uint8_t * act_smem = stages + (size_t) P.nstage * P.stage_bytes;
+    // the activation staging area is dead once every lane holds its super-block in registers: it doubles as the last ring stages
+    uint8_t * act_smem = stages + (size_t) P.nstage_init * P.stage_bytes;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     stamp<TRACE>(P, 0);
@@ -174,7 +189,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_CTAS_PER_SM) k_gemv_kquant(
     // Weights never depend on the previous kernel: start streaming BEFORE griddepcontrol.wait.  Under PDL this CTA is resident
     // while the tail of the previous GEMV (or a whole small kernel: attention, silu-quant) still runs on other SMs.
     if (threadIdx.x == 0) {
-        for (int it = 0; it < P.nstage; it++) {
+        for (int it = 0; it < P.nstage_init; it++) {
             const int t = blockIdx.x + it * gridDim.x;
             if (t < P.ntiles) issue_tile(P, ctl, stages, it, t, pol);
         }
@@ -225,10 +240,22 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_CTAS_PER_SM) k_gemv_kquant(
     }
     load_act_regs(r, sa, blk, valid);
     finish_act_regs(r);
+    if (P.nstage_init < P.nstage) {
+        __syncthreads();   // every warp has its registers: hand the staging area to the ring
+        if (threadIdx.x == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            for (int it = P.nstage_init; it < P.nstage; it++) {
+                const int t = blockIdx.x + it * gridDim.x;
+                if (t < P.ntiles) issue_tile(P, ctl, stages, it, t, pol);
+            }
+        }
+    }
     stamp<TRACE>(P, 3);
 
     // Every warp visits every iteration in order (so a parity wait can never be satisfied by an older phase of the same stage);
     // row `slot` of iteration `it` belongs to warp group (it * rows_per_tile + slot) mod ngroups.
+    PendingRow pend;
+    pend.active = false;
     int s = 0;
     uint32_t ph = 0;
     for (int it = 0, t = blockIdx.x; t < P.ntiles; t += gridDim.x, it++, s = (s + 1 == P.nstage ? 0 : s + 1), ph ^= (s == 0 ? 1u : 0u)) {
@@ -240,6 +267,8 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_CTAS_PER_SM) k_gemv_kquant(
         const uint32_t mis = (uint32_t) (((int64_t) r0 * M.row_bytes) & 15);
         const uint8_t * tile = stages + (size_t) s * P.stage_bytes + mis;
         const int first = (group - it * M.rows_per_tile) & (ngroups - 1);                     // this group's first slot in the stage
+        // a pending split row pins its stage: never let it get a full ring behind (the refill this wait needs could depend on it)
+        if (pend.active && it - pend.it >= P.nstage - 1) { finish_split_row(P, ctl, stages, pend, group, wpr, lane, pol); pend.active = false; }
         mbar_wait(&ctl->full[s], ph, &ctl->aborted, P.abort_flag);
         if (TRACE && it == 0) stamp<TRACE>(P, 4);
         if (wpr == 1) {
@@ -293,20 +322,17 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_CTAS_PER_SM) k_gemv_kquant(
                     mbar_arrive(&ctl->pbar[s][group]);   // release semantics: the partial is visible to the waiter
                 }
             } else {
+                // The leader finishes row i only after it has issued its own dot of row i+1 (one row of latency hidden per group:
+                // with a single row in flight the arrive -> wait -> combine chain capped ffn_down at ~4.5 TB/s).
                 v = warp_sum(v);
                 uint64_t tok = 0;
                 if (lane == 0) tok = mbar_arrive_token(&ctl->pbar[s][group]);
-                tok = __shfl_sync(0xffffffffu, tok, 0);
-                mbar_wait_token(&ctl->pbar[s][group], tok, &ctl->aborted, P.abort_flag);
-                if (lane == 0) {
-                    float acc = v;
-                    for (int i = 1; i < wpr; i++) acc += ctl->part[s][group * wpr + i];
-                    M.y[row] = acc + extra;
-                    release_stage(P, ctl, stages, s, it, pol);
-                }
+                if (pend.active) finish_split_row(P, ctl, stages, pend, group, wpr, lane, pol);
+                pend.active = true; pend.s = s; pend.it = it; pend.tok = tok; pend.v = v; pend.extra = extra; pend.y = M.y + row;
             }
         }
     }
+    if (pend.active) finish_split_row(P, ctl, stages, pend, group, wpr, lane, pol);
     stamp<TRACE>(P, 5);
 }
 
@@ -611,7 +637,15 @@ int gemv_set_trace(unsigned long long * dev_buf, int slots) {
 bool gemv_fused_prologue_ok(int K) { return K > 0 && K % 256 == 0 && K / 256 <= GEMV_ACT_MAX_NBLK; }
 
 // ring geometry of one launch: rows per tile of each matrix, stage size, depth — everything that must fit 2 CTAs on an SM
-struct GemvPlan { int wpr, nstage, stage_bytes, smem, rows[GEMV_MAX_MAT]; };
+struct GemvPlan { int wpr, nstage, nstage_init, stage_bytes, smem, rows[GEMV_MAX_MAT]; };
+// tunables (environment, read once): ring geometry experiments without a rebuild
+struct GemvTune { int stage_target, max_stage; };
+static const GemvTune tune = [] {
+    GemvTune t{GEMV_STAGE_TARGET, GEMV_MAX_STAGE};
+    if (const char * e = getenv("PB200_GEMV_STAGE_KB")) t.stage_target = std::max(4, atoi(e)) * 1024;
+    if (const char * e = getenv("PB200_GEMV_MAX_STAGE")) t.max_stage = std::min(GEMV_MAX_STAGE, std::max(2, atoi(e)));
+    return t;
+}();
 static bool gemv_plan(const int * types, const int * Ns, int nmat, int K, GemvPlan & pl) {
     if (!gemv_fused_prologue_ok(K)) return false;
     const int nblk = K / 256;
@@ -622,7 +656,7 @@ static bool gemv_plan(const int * types, const int * Ns, int nmat, int K, GemvPl
     for (int i = 0; i < nmat; i++) {
         if (!is_kquant(types[i]) || Ns[i] < 1) return false;
         const int64_t rb = row_bytes(types[i], K);
-        int R = (int) std::max<int64_t>(1, GEMV_STAGE_TARGET / rb);
+        int R = (int) std::max<int64_t>(1, tune.stage_target / rb);
         if (wpr > 1) R = std::min(R, ngroups);     // split rows: at most one row per warp group and stage
         R = std::min(R, Ns[i]);
         pl.rows[i] = R;
@@ -630,11 +664,14 @@ static bool gemv_plan(const int * types, const int * Ns, int nmat, int K, GemvPl
     }
     pl.wpr = wpr;
     pl.stage_bytes = (int) ((biggest + 16 + 127) / 128 * 128);
+    // the activation staging area overlays the last stages of the ring (they are filled once the activation is in registers)
     const int act = gemv_act_smem_bytes(nblk);
-    const int budget = GEMV_SMEM_LIMIT - GEMV_CTL_BYTES - act;
-    pl.nstage = std::min(GEMV_MAX_STAGE, budget / pl.stage_bytes);
-    if (pl.nstage < 2) return false;
-    pl.smem = GEMV_CTL_BYTES + pl.nstage * pl.stage_bytes + act;
+    const int act_stages = (act + pl.stage_bytes - 1) / pl.stage_bytes;
+    pl.nstage = std::min(tune.max_stage, (GEMV_SMEM_LIMIT - GEMV_CTL_BYTES) / pl.stage_bytes);
+    pl.nstage_init = pl.nstage - act_stages;
+    if (pl.nstage_init < 2) return false;
+    if (wpr > 1 && pl.nstage < 4) return false;     // the deferred leader holds one extra stage per group
+    pl.smem = GEMV_CTL_BYTES + pl.nstage * pl.stage_bytes;
     return true;
 }
 int gemv_smem_bytes(int type, int K, int N) {
@@ -673,6 +710,7 @@ int launch_gemv_kquant_fused(const GemvDesc * d, int nmat, int K, const ActQ & a
     P.K = K;
     P.nmat = nmat;
     P.nstage = pl.nstage;
+    P.nstage_init = pl.nstage_init;
     P.stage_bytes = pl.stage_bytes;
     P.act = act;
     P.prologue = pro.kind;

@@ -88,6 +88,12 @@ int launch_attn_fused(const float * q, const float * k, const float * v, __half 
                       int D, const int32_t * pos_dev, int n_ctx, const RopeParams & rp, const float * freq_factors, float scale, cudaStream_t stream,
                       bool pdl);
 
+// latency-restructured version that also writes the q8_K-quantized output (clusters of 2 CTAs = one super-block); returns
+// cudaErrorNotSupported for shapes it does not handle (odd n_head, very long n_ctx): fall back to launch_attn_fused
+int launch_attn_fused2(const float * q, const float * k, const float * v, __half * kcache, __half * vcache, float * out, const ActQ & outq, int n_head,
+                       int n_head_kv, int D, const int32_t * pos_dev, int n_ctx, const RopeParams & rp, const float * freq_factors, float scale,
+                       cudaStream_t stream, bool pdl);
+
 // soft_max_ext for the plugin: y[r][:] = softmax(x[r][:]*scale + mask[r % mask_rows][:])  (softmax.cu:14-116)
 int launch_soft_max(const float * x, const float * mask, float * y, int ncols, int64_t nrows, int64_t rows_per_mask_cycle, float scale,
                     cudaStream_t stream);

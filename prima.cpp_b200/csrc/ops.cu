@@ -57,8 +57,16 @@ __global__ void __launch_bounds__(256) k_silu_mul_quant(const float * __restrict
     const int64_t base = blk * 256 + lane * 8;
     if (blk * 256 >= K) return;
     float v[8];
+    if (base + 8 <= K && ((((uintptr_t) g) | ((uintptr_t) u)) & 15) == 0) {   // both operands in flight before either is used
+        const float4 g0 = __ldcg(reinterpret_cast<const float4 *>(g + base)), g1 = __ldcg(reinterpret_cast<const float4 *>(g + base + 4));
+        const float4 u0 = __ldcg(reinterpret_cast<const float4 *>(u + base)), u1 = __ldcg(reinterpret_cast<const float4 *>(u + base + 4));
+        const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, uv[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
 #pragma unroll
-    for (int i = 0; i < 8; i++) v[i] = base + i < K ? __fmul_rn(silu_f32(g[base + i]), u[base + i]) : 0.f;
+        for (int i = 0; i < 8; i++) v[i] = __fmul_rn(silu_f32(gv[i]), uv[i]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = base + i < K ? __fmul_rn(silu_f32(g[base + i]), u[base + i]) : 0.f;
+    }
     if (f32_out) {
 #pragma unroll
         for (int i = 0; i < 8; i++)
@@ -109,6 +117,56 @@ __global__ void __launch_bounds__(1024) k_rmsnorm_quant(const float * __restrict
             v[i] = t;
         }
         if (out.qs) quantize_warp(mode, v, lane, gidx, out);
+    }
+}
+
+// Decode-path variant: q8_K( rms_norm(x) * w ) of one vector, ONE CTA of 16 warps.  The vector is read once (128-bit loads, all
+// issued before anything is used) and stays in registers between the sum of squares and the quantization.  Under PDL the GEMV
+// that consumes the result is already resident and streaming its weights while this runs; doing the same work in the prologue
+// of each of its 296 CTAs cost ~7 us per launch (profiles/r2_token_trace_v1.txt: 19 MB of redundant L2 reads).
+constexpr int RQ_WARPS = 16;   // RQ_B super-blocks per warp in registers: 2 (n <= 8192, ~64 registers: fits beside a resident GEMV CTA) or 4
+template <int RQ_B>
+__global__ void __launch_bounds__(RQ_WARPS * 32) k_rmsnorm_q8K(const float * __restrict__ x, const float * __restrict__ w, int n, float eps, ActQ out) {
+    __shared__ double red[RQ_WARPS];
+    pdl_trigger();
+    pdl_wait();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nblk = n / 256;
+    float xv[RQ_B][8], wv[RQ_B][8];
+#pragma unroll
+    for (int j = 0; j < RQ_B; j++) {
+        const int b = warp + j * RQ_WARPS;
+        if (b < nblk) {
+            const float4 a0 = __ldcg(reinterpret_cast<const float4 *>(x + b * 256 + lane * 8)), a1 = __ldcg(reinterpret_cast<const float4 *>(x + b * 256 + lane * 8 + 4));
+            xv[j][0] = a0.x; xv[j][1] = a0.y; xv[j][2] = a0.z; xv[j][3] = a0.w; xv[j][4] = a1.x; xv[j][5] = a1.y; xv[j][6] = a1.z; xv[j][7] = a1.w;
+            const float4 w0 = *reinterpret_cast<const float4 *>(w + b * 256 + lane * 8), w1 = *reinterpret_cast<const float4 *>(w + b * 256 + lane * 8 + 4);
+            wv[j][0] = w0.x; wv[j][1] = w0.y; wv[j][2] = w0.z; wv[j][3] = w0.w; wv[j][4] = w1.x; wv[j][5] = w1.y; wv[j][6] = w1.z; wv[j][7] = w1.w;
+        }
+    }
+    double sum = 0.0;   // float products widened to double: exact partial sums, grouping does not matter (ggml.c:11976-11984)
+#pragma unroll
+    for (int j = 0; j < RQ_B; j++) {
+        if (warp + j * RQ_WARPS < nblk) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) sum += (double) __fmul_rn(xv[j][i], xv[j][i]);
+        }
+    }
+    sum = warp_sum_d(sum);
+    if (lane == 0) red[warp] = sum;
+    __syncthreads();
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < RQ_WARPS; i++) t += red[i];
+    const float mean = (float) (t / (double) n);
+    const float scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, eps)));
+#pragma unroll
+    for (int j = 0; j < RQ_B; j++) {
+        const int b = warp + j * RQ_WARPS;
+        if (b < nblk) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) xv[j][i] = __fmul_rn(__fmul_rn(xv[j][i], scale), wv[j][i]);
+            quantize_warp_q8K(xv[j], lane, b, out);
+        }
     }
 }
 
@@ -555,6 +613,274 @@ __global__ void __launch_bounds__(256) k_attn_fused(const float * __restrict__ q
 }
 
 // ------------------------------------------------------------------------------------------------
+// Decode attention v2 (the engine's per-token path): same arithmetic as k_attn_fused, restructured for LATENCY — under PDL this
+// kernel sits between the q|k|v GEMV and the wo GEMV, and every microsecond of it is a bubble in the weight stream:
+//   * one CTA of 16 warps per q head, launched as CLUSTERS OF 2 (heads 2j, 2j+1 = one 256-value q8_K super-block of the output):
+//     the pair agrees on the block's arg-max through distributed shared memory and writes the QUANTIZED activation itself,
+//     so the wo GEMV needs no quantize prologue (4 us per layer in profiles/r2_token_trace_v1.txt);
+//   * everything that does not depend on the q|k|v GEMV happens BEFORE griddepcontrol.wait: the position, the RoPE angles and
+//     the K/V cache rows [0, pos) (written by earlier tokens) — up to 256 rows each are in flight as cp.async copies into
+//     shared memory (completion on mbarriers) while the GEMV drains.  Round 1's kernel chained ~10 dependent L2 round trips
+//     (pos -> q -> K rows 4 at a time -> V rows 4 at a time);
+//   * longer contexts stream further 128-row chunks through the same two buffers per tensor.
+constexpr int A2_THREADS = 512, A2_WARPS = 16, A2_CHUNK = 128;
+struct Attn2Smem {   // fixed part; dynamic tail: S[n_ctx padded to 32] floats
+    uint64_t kbar[2], vbar[2];
+    float cand[4];                 // this CTA's arg-max candidate {amax, vmax, idx, -} for the cluster exchange
+    float q_s[128];
+    float o_s[128];
+    float cs[64][2];
+    __half k_s[128], v_s[128];
+    float s_red[A2_WARPS];
+    double s_redd[A2_WARPS];
+    float s_bc[2];
+    float red[A2_WARPS][128];
+    __half kbuf[2][A2_CHUNK][128];
+    __half vbuf[2][A2_CHUNK][128];
+};
+__device__ __forceinline__ void a2_issue_chunk(__half (*dst)[128], const __half * cache, int64_t EK, int hk, int c, int n_cache, uint64_t * bar) {
+    const int r0 = c * A2_CHUNK;
+    const int nrows = min(A2_CHUNK, n_cache - r0);
+    const int pieces = nrows * 16;                      // 16-byte pieces: 16 per 256-byte row
+    for (int i = threadIdx.x; i < pieces; i += A2_THREADS) {
+        const int r = i >> 4, cpart = i & 15;
+        const __half * src = cache + (int64_t) (r0 + r) * EK + (int64_t) hk * 128 + cpart * 8;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(&dst[r][cpart * 8])), "l"(src) : "memory");
+    }
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");   // fires when this thread's copies have landed
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float ld_dsmem_f32(const float * local_addr, uint32_t cta_rank) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local_addr)), "r"(cta_rank));
+    float v;
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(A2_THREADS, 1) k_attn_fused2(const float * __restrict__ q, const float * __restrict__ k, const float * __restrict__ v,
+                                                               __half * __restrict__ kc, __half * __restrict__ vc, float * __restrict__ out, ActQ outq,
+                                                               int n_head, int n_head_kv, const int32_t * __restrict__ pos_dev, RopeParams rp,
+                                                               const float * __restrict__ freq_factors, float scale, int * abort_flag) {
+    constexpr int D = 128;
+    extern __shared__ __align__(128) uint8_t a2_raw[];
+    Attn2Smem * sm = reinterpret_cast<Attn2Smem *>(a2_raw);
+    float * S = reinterpret_cast<float *>(a2_raw + sizeof(Attn2Smem));
+    __shared__ volatile int cta_abort;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gqa = n_head / n_head_kv;
+    const int h = blockIdx.x, hk = h / gqa;
+    const int64_t EK = (int64_t) n_head_kv * D;
+    if (threadIdx.x == 0) {
+        mbar_init(&sm->kbar[0], A2_THREADS); mbar_init(&sm->kbar[1], A2_THREADS);
+        mbar_init(&sm->vbar[0], A2_THREADS); mbar_init(&sm->vbar[1], A2_THREADS);
+        cta_abort = 0;
+        mbar_fence_init();
+    }
+    __syncthreads();
+    pdl_trigger();
+    // ---- independent of the producing GEMV: position (written before this token's first kernel), cache rows of earlier tokens
+    const int pos = *pos_dev;
+    const int n_kv = pos + 1, n_cache = pos;                   // row `pos` itself comes from shared memory (k_s / v_s)
+    const int nchunks = (n_cache + A2_CHUNK - 1) / A2_CHUNK;
+    if (nchunks > 0) a2_issue_chunk(sm->kbuf[0], kc, EK, hk, 0, n_cache, &sm->kbar[0]);
+    if (nchunks > 1) a2_issue_chunk(sm->kbuf[1], kc, EK, hk, 1, n_cache, &sm->kbar[1]);
+    if (nchunks > 0) a2_issue_chunk(sm->vbuf[0], vc, EK, hk, 0, n_cache, &sm->vbar[0]);
+    if (nchunks > 1) a2_issue_chunk(sm->vbuf[1], vc, EK, hk, 1, n_cache, &sm->vbar[1]);
+    const int half_dims = rp.n_dims / 2;
+    const bool neox = rp.mode & 2;
+    if (threadIdx.x < 64 && (int) threadIdx.x < half_dims) {
+        float c, s;
+        rope_cos_sin(rp, pos, threadIdx.x, freq_factors, c, s);
+        sm->cs[threadIdx.x][0] = c; sm->cs[threadIdx.x][1] = s;
+    }
+    pdl_wait();
+    // ---- q / k / v of this token (f32, just produced): RoPE in shared memory, f16 rounding identical to the cache store
+    float x0 = 0.f, x1 = 0.f, vv = 0.f;
+    {
+        const int t = threadIdx.x;
+        if (t < 128) {
+            const int pair = t & 63;
+            const float * src = t < 64 ? q + (int64_t) h * D : k + (int64_t) hk * D;
+            if (pair < half_dims) {
+                const int i0 = neox ? pair : 2 * pair, i1 = neox ? pair + half_dims : 2 * pair + 1;
+                x0 = __ldcg(src + i0); x1 = __ldcg(src + i1);
+            }
+        } else if (t < 256) {
+            vv = __ldcg(v + (int64_t) hk * D + (t - 128));
+        }
+    }
+    __syncthreads();   // cs[] visible
+    {
+        const int t = threadIdx.x;
+        if (t < 128) {
+            const int pair = t & 63;
+            const bool is_q = t < 64;
+            const float * src = is_q ? q + (int64_t) h * D : k + (int64_t) hk * D;
+            if (pair < half_dims) {
+                const int i0 = neox ? pair : 2 * pair, i1 = neox ? pair + half_dims : 2 * pair + 1;
+                float y0, y1;
+                rope_rotate(x0, x1, sm->cs[pair][0], sm->cs[pair][1], y0, y1);
+                if (is_q) { sm->q_s[i0] = __half2float(__float2half_rn(y0)); sm->q_s[i1] = __half2float(__float2half_rn(y1)); }
+                else { sm->k_s[i0] = __float2half_rn(y0); sm->k_s[i1] = __float2half_rn(y1); }
+            }
+            for (int i = rp.n_dims + pair; i < D; i += 64) {   // un-rotated tail when n_dims < D
+                if (is_q) sm->q_s[i] = __half2float(__float2half_rn(__ldcg(src + i)));
+                else sm->k_s[i] = __float2half_rn(__ldcg(src + i));
+            }
+        } else if (t < 256) {
+            sm->v_s[t - 128] = __float2half_rn(vv);
+        }
+    }
+    __syncthreads();
+    if (h % gqa == 0 && threadIdx.x < 32) {   // one CTA per kv head publishes the fresh row (8 B per lane, coalesced)
+        *reinterpret_cast<uint2 *>(kc + (int64_t) pos * EK + (int64_t) hk * D + 4 * lane) = *reinterpret_cast<const uint2 *>(sm->k_s + 4 * lane);
+        *reinterpret_cast<uint2 *>(vc + (int64_t) pos * EK + (int64_t) hk * D + 4 * lane) = *reinterpret_cast<const uint2 *>(sm->v_s + 4 * lane);
+    }
+    const float q0 = sm->q_s[4 * lane], q1 = sm->q_s[4 * lane + 1], q2 = sm->q_s[4 * lane + 2], q3 = sm->q_s[4 * lane + 3];
+    auto score_row = [&](const __half * krow) -> float {
+        const uint2 kraw = *reinterpret_cast<const uint2 *>(krow + 4 * lane);
+        const float2 k01 = __half22float2(*reinterpret_cast<const __half2 *>(&kraw.x));
+        const float2 k23 = __half22float2(*reinterpret_cast<const __half2 *>(&kraw.y));
+        float s = k01.x * q0;
+        s = fmaf(k01.y, q1, s);
+        s = fmaf(k23.x, q2, s);
+        s = fmaf(k23.y, q3, s);
+        return warp_sum(s);
+    };
+    // ---- scores
+    for (int c = 0; c < nchunks; c++) {
+        const int b = c & 1;
+        mbar_wait(&sm->kbar[b], (uint32_t) ((c >> 1) & 1), &cta_abort, abort_flag);
+        const int r0 = c * A2_CHUNK, nrows = min(A2_CHUNK, n_cache - r0);
+        for (int r = warp; r < nrows; r += A2_WARPS) {
+            const float s = score_row(sm->kbuf[b][r]);
+            if (lane == 0) S[r0 + r] = __fmul_rn(s, scale);
+        }
+        if (c + 2 < nchunks) {
+            __syncthreads();   // every warp is done with this buffer
+            a2_issue_chunk(sm->kbuf[b], kc, EK, hk, c + 2, n_cache, &sm->kbar[b]);
+        }
+    }
+    if (warp == 0) {
+        const float s = score_row(sm->k_s);
+        if (lane == 0) S[pos] = __fmul_rn(s, scale);
+    }
+    __syncthreads();
+    // ---- softmax (ggml.c:13783: max, expf, double sum, p = e * float(1/sum))
+    float m = -INFINITY;
+    for (int p = threadIdx.x; p < n_kv; p += A2_THREADS) m = fmaxf(m, S[p]);
+    m = warp_max(m);
+    if (lane == 0) sm->s_red[warp] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = sm->s_red[0];
+        for (int i = 1; i < A2_WARPS; i++) t = fmaxf(t, sm->s_red[i]);
+        sm->s_bc[0] = t;
+    }
+    __syncthreads();
+    const float mx = sm->s_bc[0];
+    double dsum = 0.0;
+    for (int p = threadIdx.x; p < n_kv; p += A2_THREADS) {
+        const float e = expf(__fsub_rn(S[p], mx));
+        S[p] = e;
+        dsum += (double) e;
+    }
+    dsum = warp_sum_d(dsum);
+    if (lane == 0) sm->s_redd[warp] = dsum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0;
+        for (int i = 0; i < A2_WARPS; i++) t += sm->s_redd[i];
+        sm->s_bc[1] = (float) (1.0 / t);
+    }
+    __syncthreads();
+    const float inv = sm->s_bc[1];
+    // ---- P.V with f16-rounded probabilities
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    auto pv_row = [&](const __half * vrow, int p) {
+        const float w = __half2float(__float2half_rn(__fmul_rn(S[p], inv)));
+        const uint2 vraw = *reinterpret_cast<const uint2 *>(vrow + 4 * lane);
+        const float2 v01 = __half22float2(*reinterpret_cast<const __half2 *>(&vraw.x));
+        const float2 v23 = __half22float2(*reinterpret_cast<const __half2 *>(&vraw.y));
+        a0 = fmaf(v01.x, w, a0); a1 = fmaf(v01.y, w, a1); a2 = fmaf(v23.x, w, a2); a3 = fmaf(v23.y, w, a3);
+    };
+    for (int c = 0; c < nchunks; c++) {
+        const int b = c & 1;
+        mbar_wait(&sm->vbar[b], (uint32_t) ((c >> 1) & 1), &cta_abort, abort_flag);
+        const int r0 = c * A2_CHUNK, nrows = min(A2_CHUNK, n_cache - r0);
+        for (int r = warp; r < nrows; r += A2_WARPS) pv_row(sm->vbuf[b][r], r0 + r);
+        if (c + 2 < nchunks) {
+            __syncthreads();
+            a2_issue_chunk(sm->vbuf[b], vc, EK, hk, c + 2, n_cache, &sm->vbar[b]);
+        }
+    }
+    if (warp == (pos % A2_WARPS)) pv_row(sm->v_s, pos);
+    *reinterpret_cast<float4 *>(&sm->red[warp][4 * lane]) = make_float4(a0, a1, a2, a3);
+    __syncthreads();
+    if (threadIdx.x < 128) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < A2_WARPS; i++) t += sm->red[i][threadIdx.x];
+        out[(int64_t) h * D + threadIdx.x] = t;
+        sm->o_s[threadIdx.x] = t;
+    }
+    // ---- q8_K of the output: heads (2j, 2j+1) = cluster ranks (0, 1) = super-block j  (quantize_row_q8_K_ref, ggml-quants.c:3785-3822)
+    if (outq.qs) {
+        __syncthreads();
+        const uint32_t rank = h & 1u;
+        float xv[4];
+        float amax = 0.f, vmax = 0.f;
+        int idx = 0x7fffffff;
+        if (warp == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                xv[i] = sm->o_s[4 * lane + i];
+                const float ax = fabsf(xv[i]);
+                if (ax > amax) { amax = ax; vmax = xv[i]; idx = (int) rank * 128 + 4 * lane + i; }   // strict '>': first occurrence
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float oa = __shfl_xor_sync(0xffffffffu, amax, o), ov = __shfl_xor_sync(0xffffffffu, vmax, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+                if (oa > amax || (oa == amax && oi < idx)) { amax = oa; vmax = ov; idx = oi; }
+            }
+            if (lane == 0) { sm->cand[0] = amax; sm->cand[1] = vmax; sm->cand[2] = __int_as_float(idx); }
+        }
+        cluster_sync_all();
+        if (warp == 0) {
+            const float oa = ld_dsmem_f32(&sm->cand[0], rank ^ 1u), ov = ld_dsmem_f32(&sm->cand[1], rank ^ 1u);
+            const int oi = __float_as_int(ld_dsmem_f32(&sm->cand[2], rank ^ 1u));
+            if (oa > amax || (oa == amax && oi < idx)) { amax = oa; vmax = ov; idx = oi; }
+            const int64_t blk = h >> 1;
+            uint32_t packed = 0u;
+            int sum = 0;
+            float d = 0.f;
+            if (amax != 0.f) {
+                const float iscale = __fdiv_rn(-127.f, vmax);
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    int qv = nearest_int_magic(__fmul_rn(iscale, xv[i]));
+                    qv = qv < 127 ? qv : 127;
+                    sum += qv;
+                    packed |= (uint32_t) (qv & 0xff) << (8 * i);
+                }
+                d = __fdiv_rn(1.f, iscale);
+            }
+            *reinterpret_cast<uint32_t *>(outq.qs + blk * act_qs_stride(outq) + rank * 128 + 4 * lane) = packed;
+            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+            if ((lane & 3) == 0) outq.bsums[blk * act_bs_stride(outq) + rank * 8 + (lane >> 2)] = (int16_t) sum;
+            if (rank == 0 && lane == 0) outq.d[blk] = d;
+        }
+        cluster_sync_all();   // the partner may still be reading this CTA's candidate
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // soft_max_ext rows (plugin): y = softmax(x*scale + mask)
 __global__ void __launch_bounds__(256) k_soft_max(const float * __restrict__ x, const float * __restrict__ mask, float * __restrict__ y, int ncols,
                                                   int64_t rows_per_mask_cycle, float scale) {
@@ -756,6 +1082,11 @@ int launch_silu_mul_quant(const float * gate, const float * up, int K, int mode,
 }
 int launch_rmsnorm_quant(const float * x, const float * w, int n, float eps, int mode, const ActQ & out, float * f32_out, cudaStream_t stream, bool pdl) {
     cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1];
+    if (mode == ACT_Q8_K && w && !f32_out && out.qs && n % 256 == 0 && n / 256 <= RQ_WARPS * 4 && ((uintptr_t) x & 15) == 0 && ((uintptr_t) w & 15) == 0) {
+        launch_cfg(cfg, attr, dim3(1), dim3(RQ_WARPS * 32), 0, stream, pdl);
+        if (n / 256 <= RQ_WARPS * 2) return (int) cudaLaunchKernelEx(&cfg, k_rmsnorm_q8K<2>, x, w, n, eps, out);
+        return (int) cudaLaunchKernelEx(&cfg, k_rmsnorm_q8K<4>, x, w, n, eps, out);
+    }
     launch_cfg(cfg, attr, dim3(1), dim3(1024), 0, stream, pdl);
     return (int) cudaLaunchKernelEx(&cfg, k_rmsnorm_quant, x, w, n, eps, mode, out, f32_out);
 }
@@ -854,6 +1185,32 @@ int launch_attn_fused(const float * q, const float * k, const float * v, __half 
     cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1];
     launch_cfg(cfg, attr, dim3(n_head), dim3(256), smem, stream, pdl);
     return (int) cudaLaunchKernelEx(&cfg, k_attn_fused, q, k, v, kcache, vcache, out, n_head, n_head_kv, pos_dev, rp, freq_factors, scale);
+}
+
+// v2: returns cudaErrorNotSupported when the shape is outside what the clustered kernel handles (caller uses launch_attn_fused + a quantize prologue)
+int launch_attn_fused2(const float * q, const float * k, const float * v, __half * kcache, __half * vcache, float * out, const ActQ & outq, int n_head,
+                       int n_head_kv, int D, const int32_t * pos_dev, int n_ctx, const RopeParams & rp, const float * freq_factors, float scale,
+                       cudaStream_t stream, bool pdl) {
+    const size_t smem = sizeof(Attn2Smem) + (size_t) ((n_ctx + 31) & ~31) * sizeof(float);
+    if (D != 128 || (n_head & 1) || n_head_kv <= 0 || n_head % n_head_kv || smem > 200 * 1024) return (int) cudaErrorNotSupported;
+    static FuncAttrCache attr_cache;
+    {
+        cudaError_t e = ensure_dyn_smem(attr_cache, (const void *) k_attn_fused2, smem, false);
+        if (e != cudaSuccess) return (int) e;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(n_head);
+    cfg.blockDim = dim3(A2_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = 2; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 2;
+    return (int) cudaLaunchKernelEx(&cfg, k_attn_fused2, q, k, v, kcache, vcache, out, outq, n_head, n_head_kv, pos_dev, rp, freq_factors, scale, abort_flag());
 }
 
 int launch_soft_max(const float * x, const float * mask, float * y, int ncols, int64_t nrows, int64_t rows_per_mask_cycle, float scale,
