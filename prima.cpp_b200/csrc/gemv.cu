@@ -143,6 +143,16 @@ __device__ __forceinline__ void release_stage(const GemvParams & P, GemvSmemCtl 
     }
 }
 
+// initial stages that were held back until the activation loads had been issued (P.prefill < P.nstage_init)
+__device__ __forceinline__ void fill_rest(const GemvParams & P, GemvSmemCtl * ctl, uint8_t * stages, uint64_t pol) {
+    if (threadIdx.x == 0) {
+        for (int it = P.prefill; it < P.nstage_init; it++) {
+            const int t = blockIdx.x + it * gridDim.x;
+            if (t < P.ntiles) issue_tile(P, ctl, stages, it, t, pol);
+        }
+    }
+}
+
 __device__ __forceinline__ float dot_block(int type, const uint8_t * bp, const ActRegs & r) {
     if (type == T_Q4_K) return dot_q4K(bp, r);
     if (type == T_Q6_K) return dot_q6K(bp, r);
@@ -189,7 +199,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_CTAS_PER_SM) k_gemv_kquant(
     // Weights never depend on the previous kernel: start streaming BEFORE griddepcontrol.wait.  Under PDL this CTA is resident
     // while the tail of the previous GEMV (or a whole small kernel: attention, silu-quant) still runs on other SMs.
     if (threadIdx.x == 0) {
-        for (int it = 0; it < P.nstage_init; it++) {
+        for (int it = 0; it < P.prefill; it++) {
             const int t = blockIdx.x + it * gridDim.x;
             if (t < P.ntiles) issue_tile(P, ctl, stages, it, t, pol);
         }
@@ -225,6 +235,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_CTAS_PER_SM) k_gemv_kquant(
         }
         if ((int) threadIdx.x < nb16) cb = __ldcg(reinterpret_cast<const int4 *>(P.act.bsums) + threadIdx.x);
         if ((int) threadIdx.x < P.nblk) cd = __ldcg(P.act.d + threadIdx.x);
+        fill_rest(P, ctl, stages, pol);   // the small activation loads are out: they do not queue behind the rest of the ring fill
 #pragma unroll
         for (int j = 0; j < NQ_MAX; j++) {
             const int i = threadIdx.x + j * GEMV_THREADS;
@@ -236,6 +247,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_CTAS_PER_SM) k_gemv_kquant(
     } else {
         ProRegs pr;
         prologue_load(P, pr, warp, lane, 0);
+        fill_rest(P, ctl, stages, pol);
         prologue_compute(P, ctl, sa, pr, warp, lane);
     }
     load_act_regs(r, sa, blk, valid);
@@ -639,10 +651,11 @@ bool gemv_fused_prologue_ok(int K) { return K > 0 && K % 256 == 0 && K / 256 <= 
 // ring geometry of one launch: rows per tile of each matrix, stage size, depth — everything that must fit 2 CTAs on an SM
 struct GemvPlan { int wpr, nstage, nstage_init, stage_bytes, smem, rows[GEMV_MAX_MAT]; };
 // tunables (environment, read once): ring geometry experiments without a rebuild
-struct GemvTune { int stage_target, max_stage; };
+struct GemvTune { int stage_target, max_stage, prefill; };
 static const GemvTune tune = [] {
-    GemvTune t{GEMV_STAGE_TARGET, GEMV_MAX_STAGE};
+    GemvTune t{GEMV_STAGE_TARGET, GEMV_MAX_STAGE, GEMV_MAX_STAGE};
     if (const char * e = getenv("PB200_GEMV_STAGE_KB")) t.stage_target = std::max(4, atoi(e)) * 1024;
+    if (const char * e = getenv("PB200_GEMV_PREFILL")) t.prefill = std::max(0, atoi(e));
     if (const char * e = getenv("PB200_GEMV_MAX_STAGE")) t.max_stage = std::min(GEMV_MAX_STAGE, std::max(2, atoi(e)));
     return t;
 }();
@@ -711,6 +724,7 @@ int launch_gemv_kquant_fused(const GemvDesc * d, int nmat, int K, const ActQ & a
     P.nmat = nmat;
     P.nstage = pl.nstage;
     P.nstage_init = pl.nstage_init;
+    P.prefill = std::min(pl.nstage_init, tune.prefill);
     P.stage_bytes = pl.stage_bytes;
     P.act = act;
     P.prologue = pro.kind;

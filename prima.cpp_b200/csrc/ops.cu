@@ -624,20 +624,23 @@ __global__ void __launch_bounds__(256) k_attn_fused(const float * __restrict__ q
 //     (pos -> q -> K rows 4 at a time -> V rows 4 at a time);
 //   * longer contexts stream further 128-row chunks through the same two buffers per tensor.
 constexpr int A2_THREADS = 512, A2_WARPS = 16, A2_CHUNK = 128;
-struct Attn2Smem {   // fixed part; dynamic tail: S[n_ctx padded to 32] floats
+struct __align__(128) Attn2Smem {   // fixed part; dynamic tail: S[n_ctx padded to 32] floats
     uint64_t kbar[2], vbar[2];
     float cand[4];                 // this CTA's arg-max candidate {amax, vmax, idx, -} for the cluster exchange
-    float q_s[128];
-    float o_s[128];
-    float cs[64][2];
-    __half k_s[128], v_s[128];
+    float s_bc[3];
+    volatile int aborted;          // wait watchdog (common.cuh)
     float s_red[A2_WARPS];
     double s_redd[A2_WARPS];
-    float s_bc[2];
-    float red[A2_WARPS][128];
-    __half kbuf[2][A2_CHUNK][128];
-    __half vbuf[2][A2_CHUNK][128];
+    __align__(16) float q_s[128];
+    __align__(16) float o_s[128];
+    __align__(16) float cs[64][2];
+    __align__(16) __half k_s[128];
+    __align__(16) __half v_s[128];
+    __align__(16) float red[A2_WARPS][128];
+    __align__(128) __half kbuf[2][A2_CHUNK][128];
+    __align__(128) __half vbuf[2][A2_CHUNK][128];
 };
+static_assert(offsetof(Attn2Smem, red) % 16 == 0 && offsetof(Attn2Smem, kbuf) % 128 == 0 && sizeof(Attn2Smem) % 128 == 0, "Attn2Smem layout");
 __device__ __forceinline__ void a2_issue_chunk(__half (*dst)[128], const __half * cache, int64_t EK, int hk, int c, int n_cache, uint64_t * bar) {
     const int r0 = c * A2_CHUNK;
     const int nrows = min(A2_CHUNK, n_cache - r0);
@@ -669,7 +672,6 @@ __global__ void __launch_bounds__(A2_THREADS, 1) k_attn_fused2(const float * __r
     extern __shared__ __align__(128) uint8_t a2_raw[];
     Attn2Smem * sm = reinterpret_cast<Attn2Smem *>(a2_raw);
     float * S = reinterpret_cast<float *>(a2_raw + sizeof(Attn2Smem));
-    __shared__ volatile int cta_abort;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int gqa = n_head / n_head_kv;
     const int h = blockIdx.x, hk = h / gqa;
@@ -677,7 +679,7 @@ __global__ void __launch_bounds__(A2_THREADS, 1) k_attn_fused2(const float * __r
     if (threadIdx.x == 0) {
         mbar_init(&sm->kbar[0], A2_THREADS); mbar_init(&sm->kbar[1], A2_THREADS);
         mbar_init(&sm->vbar[0], A2_THREADS); mbar_init(&sm->vbar[1], A2_THREADS);
-        cta_abort = 0;
+        sm->aborted = 0;
         mbar_fence_init();
     }
     __syncthreads();
@@ -754,7 +756,7 @@ __global__ void __launch_bounds__(A2_THREADS, 1) k_attn_fused2(const float * __r
     // ---- scores
     for (int c = 0; c < nchunks; c++) {
         const int b = c & 1;
-        mbar_wait(&sm->kbar[b], (uint32_t) ((c >> 1) & 1), &cta_abort, abort_flag);
+        mbar_wait(&sm->kbar[b], (uint32_t) ((c >> 1) & 1), &sm->aborted, abort_flag);
         const int r0 = c * A2_CHUNK, nrows = min(A2_CHUNK, n_cache - r0);
         for (int r = warp; r < nrows; r += A2_WARPS) {
             const float s = score_row(sm->kbuf[b][r]);
@@ -810,7 +812,7 @@ __global__ void __launch_bounds__(A2_THREADS, 1) k_attn_fused2(const float * __r
     };
     for (int c = 0; c < nchunks; c++) {
         const int b = c & 1;
-        mbar_wait(&sm->vbar[b], (uint32_t) ((c >> 1) & 1), &cta_abort, abort_flag);
+        mbar_wait(&sm->vbar[b], (uint32_t) ((c >> 1) & 1), &sm->aborted, abort_flag);
         const int r0 = c * A2_CHUNK, nrows = min(A2_CHUNK, n_cache - r0);
         for (int r = warp; r < nrows; r += A2_WARPS) pv_row(sm->vbuf[b][r], r0 + r);
         if (c + 2 < nchunks) {
