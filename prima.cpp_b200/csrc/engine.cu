@@ -93,6 +93,7 @@ struct pb200_model {
     float *x_in = nullptr, *x_a = nullptr, *x_b = nullptr, *q = nullptr, *k = nullptr, *v = nullptr, *att = nullptr, *g = nullptr, *u = nullptr,
           *xn = nullptr, *x_out = nullptr, *logits = nullptr;
     ActBuf actE, actQD, actF;
+    unsigned int * gbar = nullptr;     // grid-barrier state of the distributed GEMV prologues (2 words, self-resetting)
     int32_t * tokpos_dev = nullptr;    // [0] token, [1] pos
     int32_t * tokpos_host = nullptr;   // pinned
     float * logits_host = nullptr;     // pinned
@@ -355,7 +356,8 @@ static int enqueue_step(pb200_model * m, uint64_t * nlaunch) {
     cudaStream_t st = m->stream;
     static const bool pdl = getenv("PB200_NO_PDL") == nullptr;   // programmatic dependent launch on every kernel of the step
     static const bool attn_v2 = getenv("PB200_ATTN_V1") == nullptr;   // A/B: round 1's attention kernel + quantize prologue in wo
-    static const bool fuse_norm = getenv("PB200_FUSE_NORM") != nullptr && atoi(getenv("PB200_FUSE_NORM")) != 0;   // A/B: rms-norm in every GEMV CTA's prologue
+    static const bool dist_env = getenv("PB200_NO_DIST") == nullptr;   // A/B: single-CTA rmsnorm / silu kernels in front of the GEMVs instead
+    const bool dist = dist_env && gemv_dist_prologue_ok();
     uint64_t n = 0;
     const int32_t * tok_dev = m->tokpos_dev, * pos_dev = m->tokpos_dev + 1;
     float * x = m->x_in;
@@ -377,14 +379,14 @@ static int enqueue_step(pb200_model * m, uint64_t * nlaunch) {
         // --- attention block ---
         const bool qkv_k = is_kquant(L.wq.type) && is_kquant(L.wk.type) && is_kquant(L.wv.type) && gemv_fused_prologue_ok(E);
         if (qkv_k) {
-            // rms_norm * attn_norm + q8_K quantization run as the GEMV's prologue (no separate kernel)
             GemvDesc d[3] = {{L.wq.data, m->q, L.bq, nullptr, L.wq.type, QD},
                              {L.wk.data, m->k, L.bk, nullptr, L.wk.type, EK},
                              {L.wv.data, m->v, L.bv, nullptr, L.wv.type, EK}};
-            GemvFused pro; pro.kind = 1; pro.in0 = x; pro.in1 = L.attn_norm; pro.eps = hp.rms_eps;
-            if (!fuse_norm) {   // rms_norm * w -> q8_K once, by one CTA; the GEMV (already resident, ring filling) only stages the result
+            GemvFused pro;
+            if (dist) {   // rms_norm * attn_norm -> q8_K inside the GEMV: CTA c produces super-block c, one grid barrier
+                pro.kind = 4; pro.in0 = x; pro.in1 = L.attn_norm; pro.eps = hp.rms_eps; pro.gbar = m->gbar;
+            } else {      // ... or once by a single-CTA kernel in front of it
                 CK(launch_rmsnorm_quant(x, L.attn_norm, E, hp.rms_eps, ACT_Q8_K, m->actE.q, nullptr, st, pdl)); n++;
-                pro = GemvFused{};
             }
             CK(prof_begin(m, tbytes(L.wq) + tbytes(L.wk) + tbytes(L.wv)));
             CK(launch_gemv_kquant_fused(d, 3, E, m->actE.q, pro, st, pdl)); n++; CK(dbg_sync(st, "gemv qkv"));
@@ -412,24 +414,20 @@ static int enqueue_step(pb200_model * m, uint64_t * nlaunch) {
         CK(dbg_sync(st, "attn"));
         {
             GemvDesc d1 = {L.wo.data, x1, nullptr, x, L.wo.type, E};   // ffn_inp = wo.att + inpSA
+            if (!att_quantized) { CK(launch_quantize_act(m->att, QD, act_mode_for(L.wo.type), m->actQD.q, st, pdl)); n++; }
             CK(prof_begin(m, tbytes(L.wo)));
-            if (wo_k) {
-                GemvFused pro; pro.kind = att_quantized ? 0 : 2; pro.in0 = m->att;
-                CK(launch_gemv_kquant_fused(&d1, 1, QD, m->actQD.q, pro, st, pdl)); n++; CK(dbg_sync(st, "gemv wo"));
-            } else {
-                CK(launch_quantize_act(m->att, QD, act_mode_for(L.wo.type), m->actQD.q, st, pdl)); n++;
-                CK(launch_gemv(&d1, 1, QD, m->actQD.q, st, pdl)); n++;
-            }
+            CK(launch_gemv(&d1, 1, QD, m->actQD.q, st, pdl)); n++; CK(dbg_sync(st, "gemv wo"));
             CK(prof_end(m));
         }
         // --- FFN block ---
         const bool gu_k = is_kquant(L.gate.type) && is_kquant(L.up.type) && gemv_fused_prologue_ok(E);
         if (gu_k) {
             GemvDesc d[2] = {{L.gate.data, m->g, nullptr, nullptr, L.gate.type, F}, {L.up.data, m->u, nullptr, nullptr, L.up.type, F}};
-            GemvFused pro; pro.kind = 1; pro.in0 = x1; pro.in1 = L.ffn_norm; pro.eps = hp.rms_eps;
-            if (!fuse_norm) {
+            GemvFused pro;
+            if (dist) {
+                pro.kind = 4; pro.in0 = x1; pro.in1 = L.ffn_norm; pro.eps = hp.rms_eps; pro.gbar = m->gbar;
+            } else {
                 CK(launch_rmsnorm_quant(x1, L.ffn_norm, E, hp.rms_eps, ACT_Q8_K, m->actE.q, nullptr, st, pdl)); n++;
-                pro = GemvFused{};
             }
             CK(prof_begin(m, tbytes(L.gate) + tbytes(L.up)));
             CK(launch_gemv_kquant_fused(d, 2, E, m->actE.q, pro, st, pdl)); n++; CK(dbg_sync(st, "gemv gate|up"));
@@ -447,15 +445,15 @@ static int enqueue_step(pb200_model * m, uint64_t * nlaunch) {
         }
         {
             GemvDesc d1 = {L.down.data, x2, nullptr, x1, L.down.type, E};   // l_out = down.act + ffn_inp
-            CK(prof_begin(m, tbytes(L.down)));
-            // silu(g)*u -> q8_K stays a separate small kernel: under PDL the down GEMV's CTAs are already resident and fill their
-            // rings while it runs (recomputing it in every GEMV CTA cost +17 us per layer, profiles/r1_summary.md)
-            CK(launch_silu_mul_quant(m->g, m->u, F, act_mode_for(L.down.type), m->actF.q, nullptr, st, pdl)); n++; CK(dbg_sync(st, "silu"));
-            if (is_kquant(L.down.type)) {
-                GemvFused pro;   // PRO_NONE
+            const bool down_k = is_kquant(L.down.type) && gemv_fused_prologue_ok(F);
+            if (down_k && dist) {   // silu(g)*u -> q8_K inside the GEMV, distributed over the grid
+                GemvFused pro; pro.kind = 5; pro.in0 = m->g; pro.in1 = m->u; pro.gbar = m->gbar;
+                CK(prof_begin(m, tbytes(L.down)));
                 CK(launch_gemv_kquant_fused(&d1, 1, F, m->actF.q, pro, st, pdl)); n++; CK(dbg_sync(st, "gemv down"));
             } else {
-                CK(launch_gemv(&d1, 1, F, m->actF.q, st, pdl)); n++;
+                CK(launch_silu_mul_quant(m->g, m->u, F, act_mode_for(L.down.type), m->actF.q, nullptr, st, pdl)); n++; CK(dbg_sync(st, "silu"));
+                CK(prof_begin(m, tbytes(L.down)));
+                CK(launch_gemv(&d1, 1, F, m->actF.q, st, pdl)); n++; CK(dbg_sync(st, "gemv down"));
             }
             CK(prof_end(m));
         }
@@ -466,17 +464,12 @@ static int enqueue_step(pb200_model * m, uint64_t * nlaunch) {
     if (m->with_head) {
         GemvDesc d1 = {m->output.data, m->logits, nullptr, nullptr, m->output.type, hp.n_vocab};
         CK(prof_begin(m, tbytes(m->output)));
-        if (is_kquant(m->output.type) && gemv_fused_prologue_ok(E)) {
-            GemvFused pro; pro.kind = 1; pro.in0 = m->x_out; pro.in1 = m->output_norm; pro.eps = hp.rms_eps;
-            bool head_pdl = pdl && m->l1 > m->l0;
-            if (!fuse_norm) {
-                CK(launch_rmsnorm_quant(m->x_out, m->output_norm, E, hp.rms_eps, ACT_Q8_K, m->actE.q, nullptr, st, head_pdl)); n++;
-                pro = GemvFused{};
-                head_pdl = pdl;
-            }
+        const bool head_pdl = pdl && m->l1 > m->l0;   // a stage without layers starts with a copy node: no programmatic edge
+        if (is_kquant(m->output.type) && gemv_fused_prologue_ok(E) && dist) {
+            GemvFused pro; pro.kind = 4; pro.in0 = m->x_out; pro.in1 = m->output_norm; pro.eps = hp.rms_eps; pro.gbar = m->gbar;
             CK(launch_gemv_kquant_fused(&d1, 1, E, m->actE.q, pro, st, head_pdl)); n++;
         } else {
-            CK(launch_rmsnorm_quant(m->x_out, m->output_norm, E, hp.rms_eps, act_mode_for(m->output.type), m->actE.q, nullptr, st, pdl && m->l1 > m->l0)); n++;
+            CK(launch_rmsnorm_quant(m->x_out, m->output_norm, E, hp.rms_eps, act_mode_for(m->output.type), m->actE.q, nullptr, st, head_pdl)); n++;
             CK(launch_gemv(&d1, 1, E, m->actE.q, st, pdl)); n++;
         }
         CK(prof_end(m));
@@ -537,6 +530,8 @@ int pb200_model_finalize(pb200_model * m) {
     CK(mk(m->actE, E));
     CK(mk(m->actQD, QD));
     CK(mk(m->actF, F));
+    CK(m->alloc((void **) &m->gbar, 16));
+    CK(cudaMemset(m->gbar, 0, 16));
     CK(m->alloc((void **) &m->tokpos_dev, 16));
     CK(cudaMemset(m->tokpos_dev, 0, 16));
     CK(cudaMallocHost((void **) &m->tokpos_host, 16));
@@ -678,13 +673,8 @@ static int prefill_ubatch(pb200_model * m, const int32_t * tokens_host, int32_t 
     CK(cudaMemcpyAsync(m->x_out, x + (size_t) (T - 1) * E, (size_t) E * 4, cudaMemcpyDeviceToDevice, st));
     if (m->with_head) {
         GemvDesc d1 = {m->output.data, m->logits, nullptr, nullptr, m->output.type, hp.n_vocab};
-        if (is_kquant(m->output.type) && gemv_fused_prologue_ok(E)) {
-            GemvFused pro; pro.kind = 1; pro.in0 = m->x_out; pro.in1 = m->output_norm; pro.eps = hp.rms_eps;
-            CK(launch_gemv_kquant_fused(&d1, 1, E, m->actE.q, pro, st, false)); n++;
-        } else {
-            CK(launch_rmsnorm_quant(m->x_out, m->output_norm, E, hp.rms_eps, act_mode_for(m->output.type), m->actE.q, nullptr, st, false)); n++;
-            CK(launch_gemv(&d1, 1, E, m->actE.q, st, false)); n++;
-        }
+        CK(launch_rmsnorm_quant(m->x_out, m->output_norm, E, hp.rms_eps, act_mode_for(m->output.type), m->actE.q, nullptr, st, false)); n++;
+        CK(launch_gemv(&d1, 1, E, m->actE.q, st, false)); n++;
     }
     g_launches += n;
     if (m->with_head && logits_host) CK(cudaMemcpyAsync(m->logits_host, m->logits, (size_t) hp.n_vocab * 4, cudaMemcpyDeviceToHost, st));

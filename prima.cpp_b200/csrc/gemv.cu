@@ -36,74 +36,11 @@ __device__ __forceinline__ void stamp(const GemvParams & P, int k) {
     }
 }
 
-// Fused prologue executed by all 8 warps: quantize the activation into shared memory (see PRO_* in gemv.cuh).
-// Warp w owns super-blocks w, w+8, w+16, ... ; lane l owns elements 8l..8l+7 of each.  Blocks are processed four at a
-// time with every global load issued up front, and for PRO_RMSNORM the same registers feed the sum of squares, so the
-// vector is read exactly once (K <= 8192 in one batch; longer vectors loop over batches for the sum, then again to quantize).
 __device__ __forceinline__ void load8(const float * p, float (&v)[8]) {   // .cg: L2 only (data written by the previous grid)
     const float4 a0 = __ldcg(reinterpret_cast<const float4 *>(p)), a1 = __ldcg(reinterpret_cast<const float4 *>(p + 4));
     v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
 }
-constexpr int PRO_B = 4;   // blocks in flight per warp (8 warps x 4 = one batch for K = 8192)
-struct ProRegs { float x[PRO_B][8], w[PRO_B][8]; };
-__device__ __forceinline__ void prologue_load(const GemvParams & P, ProRegs & R, int warp, int lane, int b0) {
-#pragma unroll
-    for (int j = 0; j < PRO_B; j++) {
-        const int b = b0 + warp + j * GEMV_NW;
-        if (b < P.nblk) {
-            load8(P.in0 + b * 256 + lane * 8, R.x[j]);
-            if (P.prologue != PRO_QUANT) load8(P.in1 + b * 256 + lane * 8, R.w[j]);
-        }
-    }
-}
-__device__ __forceinline__ void prologue_compute(const GemvParams & P, GemvSmemCtl * ctl, const ActQ & sa, ProRegs & R, int warp, int lane) {
-    const int tid = warp * 32 + lane;
-    const bool single_batch = P.nblk <= GEMV_NW * PRO_B;
-    float scale = 1.f;
-    if (P.prologue == PRO_RMSNORM) {
-        // sum of squares in double like ggml_compute_forward_rms_norm_f32 (ggml.c:11976-11984); every term is a float product
-        // widened to double, so the partial sums are exact and the grouping (lanes, warps) does not change the result
-        double sum = 0.0;
-        if (single_batch) {
-#pragma unroll
-            for (int j = 0; j < PRO_B; j++) {
-                const int b = warp + j * GEMV_NW;
-                if (b < P.nblk) {
-#pragma unroll
-                    for (int i = 0; i < 8; i++) sum += (double) __fmul_rn(R.x[j][i], R.x[j][i]);
-                }
-            }
-        } else {
-            for (int i = tid; i < P.K; i += GEMV_THREADS) { const float v = __ldcg(P.in0 + i); sum += (double) __fmul_rn(v, v); }
-        }
-        sum = warp_sum_d(sum);
-        if (lane == 0) ctl->red[warp] = sum;
-        __syncthreads();
-        double t = 0.0;
-#pragma unroll
-        for (int i = 0; i < GEMV_NW; i++) t += ctl->red[i];     // every thread: same order, same result
-        const float mean = (float) (t / (double) P.K);
-        scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, P.eps)));
-    }
-    for (int b0 = 0; b0 < P.nblk; b0 += GEMV_NW * PRO_B) {
-        if (b0 > 0) prologue_load(P, R, warp, lane, b0);
-#pragma unroll
-        for (int j = 0; j < PRO_B; j++) {
-            const int b = b0 + warp + j * GEMV_NW;
-            if (b < P.nblk) {
-                if (P.prologue == PRO_RMSNORM) {
-#pragma unroll
-                    for (int i = 0; i < 8; i++) R.x[j][i] = __fmul_rn(__fmul_rn(R.x[j][i], scale), R.w[j][i]);
-                } else if (P.prologue == PRO_SILU_MUL) {
-#pragma unroll
-                    for (int i = 0; i < 8; i++) R.x[j][i] = __fmul_rn(silu_f(R.x[j][i]), R.w[j][i]);
-                }
-                quantize_warp_q8K(R.x[j], lane, b, sa);
-            }
-        }
-    }
-    __syncthreads();
-}
+constexpr int PRO_B = 4;   // super-blocks in flight per warp while summing squares (8 warps x 4 = K 8192 in one batch)
 
 __device__ __forceinline__ void tile_info(const GemvParams & P, int t, int & m, int & r0, int & nrows) {
     m = 0;
@@ -153,10 +90,96 @@ __device__ __forceinline__ void fill_rest(const GemvParams & P, GemvSmemCtl * ct
     }
 }
 
+// TYPE = weight type of every matrix of the launch (one dot routine in the hot loop: the three unrolled routines together are
+// ~126 KB of SASS and the instruction cache became the top stall, profiles/r2_gemv_ncu_v1.md), or 0 = mixed (q|k|v with a Q5_K / Q6_K v)
+template <int TYPE>
 __device__ __forceinline__ float dot_block(int type, const uint8_t * bp, const ActRegs & r) {
+    if (TYPE == T_Q4_K) return dot_q4K(bp, r);
+    if (TYPE == T_Q5_K) return dot_q5K(bp, r);
+    if (TYPE == T_Q6_K) return dot_q6K(bp, r);
     if (type == T_Q4_K) return dot_q4K(bp, r);
     if (type == T_Q6_K) return dot_q6K(bp, r);
     return dot_q5K(bp, r);
+}
+
+// ---- distributed prologue (PRO_*_DIST): CTA c produces super-blocks c, c + grid, ... of the q8_K activation in P.act ----
+__device__ __forceinline__ void dist_prologue(const GemvParams & P, GemvSmemCtl * ctl, int warp, int lane) {
+    const int nblk = P.nblk;
+    if ((int) blockIdx.x >= nblk) return;                       // nothing to produce: straight to the barrier
+    // warp w owns this CTA's w-th block; its operands are requested first so that they travel with the loads of the sum
+    const int myblk = (int) blockIdx.x + warp * (int) gridDim.x;
+    float bx[8], bw[8];
+    if (myblk < nblk) {
+        load8(P.in0 + myblk * 256 + lane * 8, bx);
+        load8(P.in1 + myblk * 256 + lane * 8, bw);
+    }
+    float scale = 1.f;
+    if (P.prologue == PRO_RMSNORM_DIST) {
+        // every producing CTA needs the whole sum of squares (one extra read of the vector per producer: 32 x 32 KB at K = 8192)
+        double sum = 0.0;
+        if (nblk <= GEMV_NW * PRO_B) {
+            float xr[PRO_B][8];
+#pragma unroll
+            for (int j = 0; j < PRO_B; j++) {
+                const int b = warp + j * GEMV_NW;
+                if (b < nblk) load8(P.in0 + b * 256 + lane * 8, xr[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < PRO_B; j++) {
+                if (warp + j * GEMV_NW < nblk) {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) sum += (double) __fmul_rn(xr[j][i], xr[j][i]);
+                }
+            }
+        } else {
+            for (int i = threadIdx.x; i < P.K; i += GEMV_THREADS) { const float v = __ldcg(P.in0 + i); sum += (double) __fmul_rn(v, v); }
+        }
+        sum = warp_sum_d(sum);
+        if (lane == 0) ctl->red[warp] = sum;
+        __syncthreads();
+        double t = 0.0;
+#pragma unroll
+        for (int i = 0; i < GEMV_NW; i++) t += ctl->red[i];
+        const float mean = (float) (t / (double) P.K);
+        scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, P.eps)));
+    }
+    for (int b = myblk; b < nblk; b += GEMV_NW * (int) gridDim.x) {
+        if (b != myblk) { load8(P.in0 + b * 256 + lane * 8, bx); load8(P.in1 + b * 256 + lane * 8, bw); }   // tiny grids only
+        if (P.prologue == PRO_RMSNORM_DIST) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) bx[i] = __fmul_rn(__fmul_rn(bx[i], scale), bw[i]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; i++) bx[i] = __fmul_rn(silu_f(bx[i]), bw[i]);
+        }
+        quantize_warp_q8K(bx, lane, b, P.act);
+    }
+}
+// All CTAs of the launch meet once.  Safe because the persistent grid is co-resident by construction (launcher: grid <= 2 x SMs,
+// gemv_dist_prologue_ok()); bounded like every other wait.  State = {arrivals, departures}; the last CTA to leave re-arms both.
+__device__ __forceinline__ void grid_barrier(const GemvParams & P, GemvSmemCtl * ctl) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(P.gbar, 1u);
+        const unsigned target = gridDim.x;
+        const long long t0 = clock64();
+        unsigned v;
+        int spins = 0;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(P.gbar) : "memory");
+            if (v < target && (++spins & 63) == 0) {
+                if (ctl->aborted) break;
+                if (clock64() - t0 > PB_WAIT_TIMEOUT_CYCLES) { wait_gave_up(&ctl->aborted, P.abort_flag); break; }
+            }
+        } while (v < target);
+        if (atomicAdd(P.gbar + 1, 1u) == target - 1) {   // everybody has seen the full count
+            P.gbar[1] = 0u;
+            __threadfence();
+            P.gbar[0] = 0u;
+        }
+    }
+    __syncthreads();
 }
 
 // split rows (wpr > 1): the leader warp's row whose partials are still being collected
@@ -173,7 +196,7 @@ __device__ __forceinline__ void finish_split_row(const GemvParams & P, GemvSmemC
     }
 }
 
-template <bool TRACE>
+template <int TYPE, bool SPLIT, bool TRACE>
 __global__ void __launch_bounds__(GEMV_THREADS, GEMV_CTAS_PER_SM) k_gemv_kquant(const __grid_constant__ GemvParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
     GemvSmemCtl * ctl = reinterpret_cast<GemvSmemCtl *>(smem);
@@ -208,7 +231,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_CTAS_PER_SM) k_gemv_kquant(
     pdl_wait();      // the activation is produced by the previous kernel in the stream
     stamp<TRACE>(P, 2);
 
-    const int wpr = P.wpr;
+    const int wpr = SPLIT ? P.wpr : 1;
     const int ngroups = GEMV_NW / wpr;
     const int group = warp / wpr, wsub = warp % wpr;
     const int blk = wsub * 32 + lane;
@@ -222,7 +245,12 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_CTAS_PER_SM) k_gemv_kquant(
     sa.s = nullptr;
     sa.qs_stride = ACT_SMEM_QS_STRIDE;
     sa.bs_stride = ACT_SMEM_BS_STRIDE;
-    if (P.prologue == PRO_NONE) {
+    const bool dist = P.prologue == PRO_RMSNORM_DIST || P.prologue == PRO_SILU_DIST;
+    if (dist) {
+        dist_prologue(P, ctl, warp, lane);
+        grid_barrier(P, ctl);
+    }
+    {
         // ONE coalesced copy of the quantized activation per CTA (qs | bsums | d), staged with the padded strides
         constexpr int NQ_MAX = (GEMV_ACT_MAX_NBLK * 16 + GEMV_THREADS - 1) / GEMV_THREADS;   // int4 of qs per thread (7)
         const int nq = P.K / 16, nb16 = P.K / 128;
@@ -244,11 +272,6 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_CTAS_PER_SM) k_gemv_kquant(
         if ((int) threadIdx.x < nb16) *reinterpret_cast<int4 *>(reinterpret_cast<char *>(sa.bsums) + (threadIdx.x >> 1) * (2 * ACT_SMEM_BS_STRIDE) + (threadIdx.x & 1) * 16) = cb;
         if ((int) threadIdx.x < P.nblk) sa.d[threadIdx.x] = cd;
         __syncthreads();
-    } else {
-        ProRegs pr;
-        prologue_load(P, pr, warp, lane, 0);
-        fill_rest(P, ctl, stages, pol);
-        prologue_compute(P, ctl, sa, pr, warp, lane);
     }
     load_act_regs(r, sa, blk, valid);
     finish_act_regs(r);
@@ -274,16 +297,16 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_CTAS_PER_SM) k_gemv_kquant(
         int m, r0, nrows;
         tile_info(P, t, m, r0, nrows);
         const GemvMat & M = P.mat[m];
-        const int type = M.type;
+        const int type = TYPE ? TYPE : M.type;
         const int bpb = type == T_Q4_K ? BYTES_Q4_K : (type == T_Q5_K ? BYTES_Q5_K : BYTES_Q6_K);
         const uint32_t mis = (uint32_t) (((int64_t) r0 * M.row_bytes) & 15);
         const uint8_t * tile = stages + (size_t) s * P.stage_bytes + mis;
         const int first = (group - it * M.rows_per_tile) & (ngroups - 1);                     // this group's first slot in the stage
         // a pending split row pins its stage: never let it get a full ring behind (the refill this wait needs could depend on it)
-        if (pend.active && it - pend.it >= P.nstage - 1) { finish_split_row(P, ctl, stages, pend, group, wpr, lane, pol); pend.active = false; }
+        if (SPLIT && pend.active && it - pend.it >= P.nstage - 1) { finish_split_row(P, ctl, stages, pend, group, wpr, lane, pol); pend.active = false; }
         mbar_wait(&ctl->full[s], ph, &ctl->aborted, P.abort_flag);
         if (TRACE && it == 0) stamp<TRACE>(P, 4);
-        if (wpr == 1) {
+        if (!SPLIT) {
             for (int slot = first; slot < nrows; slot += ngroups) {
                 const int row = r0 + slot;
                 // epilogue operands are requested before the dot so that their L2 latency is off the critical path
@@ -293,7 +316,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_CTAS_PER_SM) k_gemv_kquant(
                     if (M.resid) extra += __ldcg(M.resid + row);
                 }
                 float v = 0.f;
-                if (valid) v = dot_block(type, tile + (size_t) slot * M.row_bytes + (size_t) blk * bpb, r);
+                if (valid) v = dot_block<TYPE>(type, tile + (size_t) slot * M.row_bytes + (size_t) blk * bpb, r);
                 if (slot + ngroups >= nrows) {
                     // last row of this stage for this warp: hand the buffer back before reducing
                     __syncwarp();
@@ -324,7 +347,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_CTAS_PER_SM) k_gemv_kquant(
                 if (M.resid) extra += __ldcg(M.resid + row);
             }
             float v = 0.f;
-            if (valid) v = dot_block(type, tile + (size_t) slot * M.row_bytes + (size_t) blk * bpb, r);
+            if (valid) v = dot_block<TYPE>(type, tile + (size_t) slot * M.row_bytes + (size_t) blk * bpb, r);
             if (!lead) {
                 __syncwarp();
                 if (lane == 0) release_stage(P, ctl, stages, s, it, pol);
@@ -344,7 +367,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_CTAS_PER_SM) k_gemv_kquant(
             }
         }
     }
-    if (pend.active) finish_split_row(P, ctl, stages, pend, group, wpr, lane, pol);
+    if (SPLIT && pend.active) finish_split_row(P, ctl, stages, pend, group, wpr, lane, pol);
     stamp<TRACE>(P, 5);
 }
 
@@ -670,7 +693,10 @@ static bool gemv_plan(const int * types, const int * Ns, int nmat, int K, GemvPl
         if (!is_kquant(types[i]) || Ns[i] < 1) return false;
         const int64_t rb = row_bytes(types[i], K);
         int R = (int) std::max<int64_t>(1, tune.stage_target / rb);
-        if (wpr > 1) R = std::min(R, ngroups);     // split rows: at most one row per warp group and stage
+        if (wpr > 1) {                             // split rows: at most one row per warp group and stage, and a ring of >= 4 stages
+            R = std::min(R, ngroups);
+            while (R > 1 && (GEMV_SMEM_LIMIT - GEMV_CTL_BYTES) / ((R * rb + 16 + 127) / 128 * 128) < 4) R--;
+        }
         R = std::min(R, Ns[i]);
         pl.rows[i] = R;
         biggest = std::max<int64_t>(biggest, R * rb);
@@ -683,9 +709,23 @@ static bool gemv_plan(const int * types, const int * Ns, int nmat, int K, GemvPl
     pl.nstage = std::min(tune.max_stage, (GEMV_SMEM_LIMIT - GEMV_CTL_BYTES) / pl.stage_bytes);
     pl.nstage_init = pl.nstage - act_stages;
     if (pl.nstage_init < 2) return false;
-    if (wpr > 1 && pl.nstage < 4) return false;     // the deferred leader holds one extra stage per group
+    if (wpr > 1 && pl.nstage < 4) return false;     // the deferred leader holds one extra stage per group (callers retry with 1 row per stage)
     pl.smem = GEMV_CTL_BYTES + pl.nstage * pl.stage_bytes;
     return true;
+}
+bool gemv_dist_prologue_ok() {
+    static int cache[PB_MAX_DEV] = {0};   // 0 unknown, 1 yes, 2 no
+    const int dev = cur_device();
+    if (!cache[dev]) {
+        int per_sm = 0;
+        static FuncAttrCache tmp;
+        bool ok = ensure_dyn_smem(tmp, (const void *) k_gemv_kquant<T_Q4_K, false, false>, GEMV_SMEM_LIMIT, true) == cudaSuccess &&
+                  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gemv_kquant<T_Q4_K, false, false>, GEMV_THREADS, GEMV_SMEM_LIMIT) == cudaSuccess &&
+                  per_sm >= GEMV_CTAS_PER_SM;
+        if (!ok) cudaGetLastError();
+        cache[dev] = ok ? 1 : 2;
+    }
+    return cache[dev] == 1;
 }
 int gemv_smem_bytes(int type, int K, int N) {
     GemvPlan pl;
@@ -749,10 +789,23 @@ int launch_gemv_kquant_fused(const GemvDesc * d, int nmat, int K, const ActQ & a
         tiles += (d[i].N + M.rows_per_tile - 1) / M.rows_per_tile;
     }
     P.ntiles = tiles;
-    static FuncAttrCache attr_cache[2];
+    P.gbar = pro.gbar;
+    if ((pro.kind == PRO_RMSNORM_DIST || pro.kind == PRO_SILU_DIST) && (!pro.gbar || !gemv_dist_prologue_ok())) return (int) cudaErrorInvalidValue;
+    // instantiation: weight type (0 = mixed) x split rows x instrumented
+    int ty = types[0];
+    for (int i = 1; i < nmat; i++) if (types[i] != ty) ty = 0;
+    const int ti = ty == T_Q4_K ? 1 : ty == T_Q5_K ? 2 : ty == T_Q6_K ? 3 : 0;
     const bool tr = g_trace_buf != nullptr;
-    const void * fn = tr ? (const void *) k_gemv_kquant<true> : (const void *) k_gemv_kquant<false>;
-    cudaError_t e = ensure_dyn_smem(attr_cache[tr ? 1 : 0], fn, GEMV_SMEM_LIMIT, true);
+    typedef void (*kern_t)(const GemvParams);
+    static const kern_t table[4][2][2] = {
+        {{k_gemv_kquant<0, false, false>, k_gemv_kquant<0, false, true>}, {k_gemv_kquant<0, true, false>, k_gemv_kquant<0, true, true>}},
+        {{k_gemv_kquant<T_Q4_K, false, false>, k_gemv_kquant<T_Q4_K, false, true>}, {k_gemv_kquant<T_Q4_K, true, false>, k_gemv_kquant<T_Q4_K, true, true>}},
+        {{k_gemv_kquant<T_Q5_K, false, false>, k_gemv_kquant<T_Q5_K, false, true>}, {k_gemv_kquant<T_Q5_K, true, false>, k_gemv_kquant<T_Q5_K, true, true>}},
+        {{k_gemv_kquant<T_Q6_K, false, false>, k_gemv_kquant<T_Q6_K, false, true>}, {k_gemv_kquant<T_Q6_K, true, false>, k_gemv_kquant<T_Q6_K, true, true>}}};
+    static FuncAttrCache attr_cache[4][2][2];
+    const int si = pl.wpr > 1 ? 1 : 0;
+    const kern_t fn = table[ti][si][tr ? 1 : 0];
+    cudaError_t e = ensure_dyn_smem(attr_cache[ti][si][tr ? 1 : 0], (const void *) fn, GEMV_SMEM_LIMIT, true);
     if (e != cudaSuccess) return (int) e;
     int grid = sm_count() * GEMV_CTAS_PER_SM;
     if (grid > P.ntiles) grid = P.ntiles;
@@ -766,8 +819,7 @@ int launch_gemv_kquant_fused(const GemvDesc * d, int nmat, int K, const ActQ & a
     attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (tr) return (int) cudaLaunchKernelEx(&cfg, k_gemv_kquant<true>, P);
-    return (int) cudaLaunchKernelEx(&cfg, k_gemv_kquant<false>, P);
+    return (int) cudaLaunchKernelEx(&cfg, fn, P);
 }
 
 static int launch_gemv_blk32(const GemvDesc & d, int K, const ActQ & act, cudaStream_t stream, bool pdl) {

@@ -35,7 +35,7 @@ constexpr int GEMV_THREADS = GEMV_NW * 32;
 constexpr int GEMV_CTAS_PER_SM = 2;
 constexpr int GEMV_MAX_STAGE = 8;
 constexpr int GEMV_SMEM_LIMIT = 113 * 1024;       // 2 x (113 KB + 1 KB reserved per CTA) = the 228 KB of an SM
-constexpr int GEMV_STAGE_TARGET = 20 * 1024;      // bytes per ring stage aimed for (rows per stage = target / row bytes)
+constexpr int GEMV_STAGE_TARGET = 28 * 1024;      // bytes per ring stage aimed for (rows per stage = target / row bytes)
 constexpr int GEMV_ACT_MAX_NBLK = 112;            // K <= 28 672 on the fast path
 constexpr int GEMV_MAX_MAT = 3;
 __host__ __device__ inline int gemv_act_smem_bytes(int nblk) { return nblk * (ACT_SMEM_QS_STRIDE + 2 * ACT_SMEM_BS_STRIDE + 4) + 64; }   // padded qs | padded bsums | d
@@ -53,13 +53,15 @@ struct GemvMat {
     int tile0;             // index of this matrix' first tile in the launch-wide tile list
 };
 
-// Fused prologue: every CTA produces the q8_K activation itself (redundantly, from L2) while its ring is already
-// filling, instead of a separate tiny kernel + launch in front of each GEMV:
-//   PRO_NONE     activation already quantized in HBM (`act`)
-//   PRO_RMSNORM  act = q8_K( rms_norm(in0) * in1 )          llm_build_norm + quantize_row_q8_K   (in1 = norm weight)
-//   PRO_QUANT    act = q8_K( in0 )                          attention output -> wo
-//   PRO_SILU_MUL act = q8_K( silu(in0) * in1 )              llm_build_ffn LLM_FFN_SILU / LLM_FFN_PAR -> ffn_down
-enum : int { PRO_NONE = 0, PRO_RMSNORM = 1, PRO_QUANT = 2, PRO_SILU_MUL = 3 };
+// Prologue: how the launch gets its q8_K activation.
+//   PRO_NONE          already quantized in HBM (`act`): one coalesced copy per CTA into shared memory, then registers
+//   PRO_RMSNORM_DIST  act = q8_K( rms_norm(in0) * in1 )     llm_build_norm + quantize_row_q8_K   (in1 = norm weight)
+//   PRO_SILU_DIST     act = q8_K( silu(in0) * in1 )         llm_build_ffn LLM_FFN_SILU / LLM_FFN_PAR -> ffn_down
+//   Distributed: CTA c quantizes super-block c into `act` (HBM/L2), ONE grid barrier (all CTAs of the persistent grid are
+//   co-resident), then every CTA stages the finished vector like PRO_NONE.  No tiny kernel + launch boundary in front of the GEMV
+//   (measured chain ~9.5 us from "previous GEMV done" to "first tile consumed", profiles/r2_token_trace_v2.txt), and 1/296 of the
+//   work per CTA instead of every CTA recomputing the whole vector from L2 (round 1: ~7 us and 19 MB of L2 reads per launch).
+enum : int { PRO_NONE = 0, PRO_RMSNORM_DIST = 4, PRO_SILU_DIST = 5 };
 
 struct GemvParams {
     GemvMat mat[GEMV_MAX_MAT];
@@ -77,6 +79,7 @@ struct GemvParams {
     const float * in0;
     const float * in1;
     float eps;
+    unsigned int * gbar;           // distributed prologues: {arrivals, departures} of the grid barrier (self-resetting)
     int * abort_flag;              // host-mapped: set by the wait watchdog (never on a healthy run)
     unsigned long long * trace;    // per-CTA %globaltimer stamps (TRACE instantiation only)
 };
