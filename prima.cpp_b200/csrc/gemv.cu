@@ -8,11 +8,12 @@
 
 namespace pb {
 
+constexpr int GEMV_ROWQ = 8;   // rows of one warp group whose partials may be pending (> ring depth: see the split-row loop)
 struct __align__(16) GemvSmemCtl {
     uint64_t full[GEMV_MAX_STAGE];              // "tile of this stage has landed" (expect_tx)
-    uint64_t pbar[GEMV_MAX_STAGE][4];           // wpr > 1: "partials of this stage's row are in shared memory" per warp group
+    uint64_t pbar[GEMV_ROWQ][4];                // split rows: "the partials of the group's row (r mod GEMV_ROWQ) are in shared memory"
     int cnt[GEMV_MAX_STAGE];                    // consumer warps done with the stage; the last one refills it
-    float part[GEMV_MAX_STAGE][GEMV_NW];        // cross-warp partial sums, one slot per stage in flight
+    float part[GEMV_ROWQ][GEMV_NW];             // cross-warp partial sums, one slot per row in flight of each group
     double red[GEMV_NW];                        // rms_norm partial sums of squares
     volatile int aborted;                       // raised by the wait watchdog (common.cuh)
 };
@@ -183,16 +184,14 @@ __device__ __forceinline__ void grid_barrier(const GemvParams & P, GemvSmemCtl *
 }
 
 // split rows (wpr > 1): the leader warp's row whose partials are still being collected
-struct PendingRow { bool active; int s, it; uint64_t tok; float v, extra; float * y; };
-__device__ __forceinline__ void finish_split_row(const GemvParams & P, GemvSmemCtl * ctl, uint8_t * stages, const PendingRow & pr, int group, int wpr,
-                                                 int lane, uint64_t pol) {
+struct PendingRow { bool active; int q; uint64_t tok; float v, extra; float * y; };
+__device__ __forceinline__ void finish_split_row(const GemvParams & P, GemvSmemCtl * ctl, const PendingRow & pr, int group, int wpr, int lane) {
     const uint64_t tok = __shfl_sync(0xffffffffu, pr.tok, 0);
-    mbar_wait_token(&ctl->pbar[pr.s][group], tok, &ctl->aborted, P.abort_flag);
+    mbar_wait_token(&ctl->pbar[pr.q][group], tok, &ctl->aborted, P.abort_flag);
     if (lane == 0) {
         float acc = pr.v;
-        for (int i = 1; i < wpr; i++) acc += ctl->part[pr.s][group * wpr + i];
+        for (int i = 1; i < wpr; i++) acc += ctl->part[pr.q][group * wpr + i];
         *pr.y = acc + pr.extra;
-        release_stage(P, ctl, stages, pr.s, pr.it, pol);   // last: part[s] cannot be overwritten before it was read
     }
 }
 
@@ -211,8 +210,12 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_CTAS_PER_SM) k_gemv_kquant(
         for (int s = 0; s < P.nstage; s++) {
             mbar_init(&ctl->full[s], 1);
             ctl->cnt[s] = 0;
+        }
+        if (SPLIT) {
 #pragma unroll
-            for (int g = 0; g < 4; g++) mbar_init(&ctl->pbar[s][g], P.wpr);
+            for (int q = 0; q < GEMV_ROWQ; q++)
+#pragma unroll
+                for (int g = 0; g < 4; g++) mbar_init(&ctl->pbar[q][g], P.wpr);
         }
         ctl->aborted = 0;
         mbar_fence_init();
@@ -291,6 +294,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_CTAS_PER_SM) k_gemv_kquant(
     // row `slot` of iteration `it` belongs to warp group (it * rows_per_tile + slot) mod ngroups.
     PendingRow pend;
     pend.active = false;
+    int grow = 0;   // rows this warp group has processed (split rows)
     int s = 0;
     uint32_t ph = 0;
     for (int it = 0, t = blockIdx.x; t < P.ntiles; t += gridDim.x, it++, s = (s + 1 == P.nstage ? 0 : s + 1), ph ^= (s == 0 ? 1u : 0u)) {
@@ -302,8 +306,6 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_CTAS_PER_SM) k_gemv_kquant(
         const uint32_t mis = (uint32_t) (((int64_t) r0 * M.row_bytes) & 15);
         const uint8_t * tile = stages + (size_t) s * P.stage_bytes + mis;
         const int first = (group - it * M.rows_per_tile) & (ngroups - 1);                     // this group's first slot in the stage
-        // a pending split row pins its stage: never let it get a full ring behind (the refill this wait needs could depend on it)
-        if (SPLIT && pend.active && it - pend.it >= P.nstage - 1) { finish_split_row(P, ctl, stages, pend, group, wpr, lane, pol); pend.active = false; }
         mbar_wait(&ctl->full[s], ph, &ctl->aborted, P.abort_flag);
         if (TRACE && it == 0) stamp<TRACE>(P, 4);
         if (!SPLIT) {
@@ -330,9 +332,11 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_CTAS_PER_SM) k_gemv_kquant(
                 if (lane == 0) release_stage(P, ctl, stages, s, it, pol);
             }
         } else {
-            // rows split over wpr warps; rows_per_tile <= ngroups, i.e. at most one row per warp group and stage.
-            // Non-leader warps publish their partial and move on; only the group's leader warp waits for them
-            // (mbarrier instead of bar.sync), and it releases the stage last so part[s] cannot be overwritten early.
+            // Rows split over wpr warps; rows_per_tile <= ngroups, i.e. at most one row per warp group and stage.  Every warp hands the
+            // stage back right after its dot (the ring keeps its full depth); the partial sums travel through part[q] / pbar[q] with
+            // q = the group's row count mod GEMV_ROWQ.  Non-leaders publish and move on; the leader finishes row r-1 (which arrived
+            // long ago) just before it releases the stage of row r, so a non-leader that has passed the wait of row r+nstage knows that
+            // row r-1 has been read: slots are reused GEMV_ROWQ = 8 > nstage rows later at the earliest.
             const int slot = first;
             if (slot >= nrows) {   // this group has no row in the stage
                 __syncwarp();
@@ -341,6 +345,8 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_CTAS_PER_SM) k_gemv_kquant(
             }
             const int row = r0 + slot;
             const bool lead = wsub == 0;
+            const int q = grow & (GEMV_ROWQ - 1);
+            grow++;
             float extra = 0.f;
             if (lead && lane == 0) {
                 if (M.bias) extra = M.bias[row];
@@ -353,21 +359,21 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_CTAS_PER_SM) k_gemv_kquant(
                 if (lane == 0) release_stage(P, ctl, stages, s, it, pol);
                 v = warp_sum(v);
                 if (lane == 0) {
-                    ctl->part[s][warp] = v;
-                    mbar_arrive(&ctl->pbar[s][group]);   // release semantics: the partial is visible to the waiter
+                    ctl->part[q][warp] = v;
+                    mbar_arrive(&ctl->pbar[q][group]);   // release semantics: the partial is visible to the waiter
                 }
             } else {
-                // The leader finishes row i only after it has issued its own dot of row i+1 (one row of latency hidden per group:
-                // with a single row in flight the arrive -> wait -> combine chain capped ffn_down at ~4.5 TB/s).
+                if (pend.active) finish_split_row(P, ctl, pend, group, wpr, lane);
+                __syncwarp();
+                if (lane == 0) release_stage(P, ctl, stages, s, it, pol);
                 v = warp_sum(v);
                 uint64_t tok = 0;
-                if (lane == 0) tok = mbar_arrive_token(&ctl->pbar[s][group]);
-                if (pend.active) finish_split_row(P, ctl, stages, pend, group, wpr, lane, pol);
-                pend.active = true; pend.s = s; pend.it = it; pend.tok = tok; pend.v = v; pend.extra = extra; pend.y = M.y + row;
+                if (lane == 0) tok = mbar_arrive_token(&ctl->pbar[q][group]);
+                pend.active = true; pend.q = q; pend.tok = tok; pend.v = v; pend.extra = extra; pend.y = M.y + row;
             }
         }
     }
-    if (SPLIT && pend.active) finish_split_row(P, ctl, stages, pend, group, wpr, lane, pol);
+    if (SPLIT && pend.active) finish_split_row(P, ctl, pend, group, wpr, lane);
     stamp<TRACE>(P, 5);
 }
 
@@ -695,7 +701,7 @@ static bool gemv_plan(const int * types, const int * Ns, int nmat, int K, GemvPl
         int R = (int) std::max<int64_t>(1, tune.stage_target / rb);
         if (wpr > 1) {                             // split rows: at most one row per warp group and stage, and a ring of >= 4 stages
             R = std::min(R, ngroups);
-            while (R > 1 && (GEMV_SMEM_LIMIT - GEMV_CTL_BYTES) / ((R * rb + 16 + 127) / 128 * 128) < 4) R--;
+            while (R > 1 && (GEMV_SMEM_LIMIT - GEMV_CTL_BYTES) / ((R * rb + 16 + 127) / 128 * 128) < 5) R--;
         }
         R = std::min(R, Ns[i]);
         pl.rows[i] = R;
@@ -709,7 +715,7 @@ static bool gemv_plan(const int * types, const int * Ns, int nmat, int K, GemvPl
     pl.nstage = std::min(tune.max_stage, (GEMV_SMEM_LIMIT - GEMV_CTL_BYTES) / pl.stage_bytes);
     pl.nstage_init = pl.nstage - act_stages;
     if (pl.nstage_init < 2) return false;
-    if (wpr > 1 && pl.nstage < 4) return false;     // the deferred leader holds one extra stage per group (callers retry with 1 row per stage)
+    if (pl.nstage >= GEMV_ROWQ) pl.nstage = GEMV_ROWQ - 1;   // split rows reuse their partial-sum slots GEMV_ROWQ rows later (see the kernel)
     pl.smem = GEMV_CTL_BYTES + pl.nstage * pl.stage_bytes;
     return true;
 }
