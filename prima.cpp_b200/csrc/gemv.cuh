@@ -72,6 +72,8 @@ struct GemvParams {
     int wpr;           // warps per row: 1, 2 or 4
     int nstage;        // ring depth of this launch
     int nstage_init;   // stages [nstage_init, nstage) overlay the activation staging area: they join the ring once the activation is in registers
+    int rel_count;     // warps that hand a stage back before it is refilled: all 8, or only its owners (owner_only)
+    int owner_only;    // a stage is always consumed by the same warps: the others skip it entirely (no wait, no release)
     int prefill;       // stages requested before griddepcontrol.wait; the other initial stages follow once the activation loads are out
     int stage_bytes;   // bytes reserved per stage (multiple of 128)
     ActQ act;          // q8_K activation (PRO_NONE)
