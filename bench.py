@@ -11,7 +11,10 @@ layer ranges per rank, hidden state handed off with one NCCL send/recv per stage
 (the sampled token returns to rank 0 before the next step starts) — so per-token latency, not pipelined throughput.
 
 Prints ONE JSON line (rank 0).  `value`: device-resident steps (token id via kernel argument, logits stay in HBM);
-`e2e`: the llama_decode-equivalent host call (token id + position H2D from pinned memory, logits D2H every step).
+`e2e`: measured THROUGH THE DROP-IN BOUNDARY at N=1 — host/llama_graph_host.cpp (the stand-in for libllama's build_llama) builds
+the decode graph with the host's ggml and runs it on the registered "B200_0" ggml backend: token id, position and mask row from host
+memory through ggml_backend_tensor_set, ggml_backend_graph_compute (graph-level fusion inside the plugin), logits back through
+ggml_backend_tensor_get, every step.  `e2e_engine` is the same step through the engine's own C call pb200_decode (what N>1 uses).
 At N=1 the line also carries `prefill`: one --pp (512) token prompt batch through pb200_prefill (tensor-core mat-muls) with its
 own tensor-pipe roofline — extra information next to the headline metric, measured after it, never part of `value`.
 """
@@ -199,6 +202,73 @@ def cpu_reference(model_key, steps, warmup, sample_layers=2):
             "ms_per_step_sample": t_sample * 1e3, "ms_per_token_extrapolated": t_full * 1e3}
 
 
+def cpu_reference_subprocess(model_key, steps, warmup):
+    """The CPU leg runs in a process of its own: it loads the oracle's copy of the reference ggml, which must not share a process
+    with the host ggml that bench.py's boundary leg loads (two ggml cores interpose each other's symbols)."""
+    p = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--model", model_key, "--steps", str(steps), "--warmup", str(warmup)],
+                       capture_output=True, text=True, timeout=1500)
+    for line in reversed(p.stdout.strip().splitlines()):
+        if line.startswith("{"):
+            return json.loads(line)["cpu_baseline"]
+    raise RuntimeError(f"reference arm failed: {p.stderr[-500:]}")
+
+
+def boundary_leg(eng, cfg, hp, args, lib):
+    """e2e through the ggml-backend boundary (N=1): the model lives a second time in the plugin's backend buffers (weights copied
+    device to device from the engine's synthetic ones), the host's ggml builds the decode graph and the plugin computes it."""
+    import numpy as np
+    import torch
+    sys.path.insert(0, str(ROOT / "host"))
+    import host_graph as HG
+    L = hp["n_layer"]
+    names = ["token_embd.weight", "output.weight", "output_norm.weight"]
+    for il in range(L):
+        names += [f"blk.{il}.{w}.weight" for w in ("attn_norm", "ffn_norm") + HG.WEIGHT_ORDER]
+        if hp["rope_mode"] == 2:
+            names += [f"blk.{il}.attn_{x}.bias" for x in "qkv"]
+    info = {n: eng.tensor_device(n) for n in names}
+    types = {n: t for n, (p, b, t) in info.items() if n.endswith(".weight") and t not in (0,)}
+    hm = HG.HostModel(hp, types, "B200_0", has_bias=(hp["rope_mode"] == 2), has_freq_factors=False)
+    cudart = torch.cuda.cudart()
+    for n, (ptr, nbytes, t) in info.items():
+        dst, dbytes = hm.tensor_ptr(n)
+        assert dbytes == nbytes, (n, dbytes, nbytes)
+        rc = cudart.cudaMemcpy(dst, ptr, nbytes, 3)   # cudaMemcpyDeviceToDevice
+        assert int(rc) == 0, (n, rc)
+    torch.cuda.synchronize()
+    nv = hp["n_vocab"]
+    logits = np.zeros(nv, dtype=np.float32)
+    first = PROMPT + args.warmup
+    # same protocol as the engine arm: prompt tokens fill the cache (untimed), warm-up, then K timed steps; host wall clock, since
+    # every step ends with a synchronous logits read
+    for i in range(PROMPT + args.warmup):
+        hm.decode([token_at(i, nv)], i, logits if i >= PROMPT else None)
+    n0 = lib.c.pb200_kernel_launches()
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    sampler.start()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        hm.decode([token_at(first + i, nv)], first + i, logits)
+    dt = time.perf_counter() - t0
+    clocks = sampler.stop()
+    launches = lib.c.pb200_kernel_launches() - n0
+    # parity of the two paths on the same weights / same token / same cache state: one more step through each
+    eng_logits = np.zeros(nv, dtype=np.float32)
+    eng.decode(token_at(first + args.steps, nv), first + args.steps, eng_logits)
+    hm.decode([token_at(first + args.steps, nv)], first + args.steps, logits)
+    n_kv_pad = (first + args.steps + 32) // 32 * 32
+    res = {"value": args.steps / dt, "unit": "tokens/s", "ms_per_step": dt / args.steps * 1e3,
+           "h2d_bytes_per_step": 8 + n_kv_pad * 32 * 4, "d2h_bytes_per_step": nv * 4,
+           "api": "ggml_backend_tensor_set(inp_tokens, inp_pos, KQ_mask) + ggml_backend_graph_compute(B200_0) + ggml_backend_tensor_get(logits) "
+                  "on the graph of host/llama_graph_host.cpp (build_llama restated; the host's ggml = the reference's, unmodified)",
+           "timing": "host wall clock around K synchronous steps", "gpu_launches": int(launches), "launches_per_layer": (launches / args.steps - 3) / L,
+           "graph_nodes": hm.graph_nodes, "graph_builds": int(hm.graph_builds), "clocks": clocks,
+           "max_abs_vs_engine_last_step": float(np.max(np.abs(eng_logits - logits)))}
+    hm.close()
+    return res
+
+
 # ------------------------------------------------------------------------------------------------ main
 def main():
     global PROMPT
@@ -210,6 +280,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n-ctx", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-boundary", action="store_true", help="skip the e2e leg through the ggml-backend plugin (keeps pb200_decode as e2e)")
     ap.add_argument("--prompt", type=int, default=PROMPT, help="untimed prompt tokens decoded before the timed region")
     ap.add_argument("--pp", type=int, default=512, help="prompt-processing batch measured after the decode run (0 = skip; single GPU only)")
     ap.add_argument("--ncu", action="store_true", help="bracket the timed region with cudaProfilerStart/Stop (ncu --profile-from-start off)")
@@ -375,14 +446,15 @@ def main():
     peak, peak_src = peaks()
     ms_step = ms_dev / args.steps
     ms_step_e2e = ms_e2e / args.steps
+    e2e_engine = {"value": 1e3 / ms_step_e2e, "unit": "tokens/s", "h2d_bytes_per_step": 8, "d2h_bytes_per_step": nv * 4,
+                  "ms_per_step": ms_step_e2e, "api": "pb200_decode (token id + position from pinned host memory in, n_vocab f32 logits out)"}
     kv_bytes = 2 * L * (first + args.steps // 2) * hp["n_head_kv"] * 128 * 2
     achieved = gemv_bytes / (gemv_ms * 1e-3) / 1e9
     out = {
         "metric": METRIC, "value": 1e3 / ms_step, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "int8 activations (q8_K) x k-quant weights, int32 dot, f32 accumulate", "data": "synthetic", "config": config,
-        "e2e": {"value": 1e3 / ms_step_e2e, "unit": "tokens/s", "h2d_bytes_per_step": 8, "d2h_bytes_per_step": nv * 4,
-                "ms_per_step": ms_step_e2e, "api": "pb200_decode (token id + position from pinned host memory in, n_vocab f32 logits out)"},
+        "e2e": e2e_engine,
         "gpu_launches": launches,
         "clocks": clocks, "clocks_e2e": clocks_e2e,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
@@ -422,9 +494,15 @@ def main():
         except Exception as ex:   # the extra measurement must never take the headline line down
             out["prefill"] = {"value": None, "unit": "tokens/s", "error": repr(ex)}
 
+    if world == 1 and not args.no_boundary:
+        try:
+            out["e2e_engine"] = e2e_engine
+            out["e2e"] = boundary_leg(eng, cfg, hp, args, lib)
+        except Exception as ex:   # the boundary leg needs host/_ggml (built where the reference tree exists); keep the engine number otherwise
+            out["e2e_boundary_error"] = repr(ex)
     if not args.no_cpu_baseline:
         try:
-            out["cpu_baseline"] = cpu_reference(args.model, 4, 1)
+            out["cpu_baseline"] = cpu_reference_subprocess(args.model, args.steps, args.warmup)
         except Exception as ex:   # the checker must never take the measurement down
             out["cpu_baseline"] = {"value": None, "unit": "tokens/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {ex!r}"}
     print(json.dumps(out))

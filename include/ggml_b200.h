@@ -31,6 +31,8 @@ __attribute__((visibility("default"))) struct ggml_backend_buffer_type * ggml_ba
 __attribute__((visibility("default"))) int ggml_backend_is_b200(struct ggml_backend * backend);
 /* number of graph nodes this backend has executed on the GPU since load (tests: proves the native path ran) */
 __attribute__((visibility("default"))) unsigned long long ggml_backend_b200_nodes_computed(void);
+/* number of fused launches graph_compute has issued (mat-vec groups with folded norm / silu / bias / residual, attention chains) */
+__attribute__((visibility("default"))) unsigned long long ggml_backend_b200_fused_steps(void);
 
 /* Loading the shared object registers the backend automatically (a constructor calls ggml_backend_register,
  * ggml-backend-impl.h:220) unless the environment variable GGML_B200_NO_AUTOREG is set. */

@@ -110,6 +110,35 @@ PB200_API int pb200_attn_decode(const float * q, const void * k_cache_f16, const
 PB200_API int pb200_attn_prefill(const float * q, const void * k_cache_f16, const void * v_cache_f16, float * out, int n_head, int n_head_kv,
                                  int head_dim, const int32_t * pos_dev, int n_tok, int n_kv_max, float scale, void * stream);
 
+/* ---- fused decode launches (what the engine is made of), for graph-level fusion in a host such as the ggml-backend plugin ---- */
+typedef struct pb200_gemv_mat {
+    int32_t type;          /* k-quant type of W (Q4_K / Q5_K / Q6_K) */
+    int32_t _pad;
+    const void * W;        /* [n][k] raw GGUF blocks, 16-byte aligned (padding rule above) */
+    int64_t n;
+    float * y;             /* [n]  y = W . act (+ add[row]) */
+    const float * add;     /* optional [n]: bias or residual added in the epilogue (ggml ADD node folded in) */
+} pb200_gemv_mat;
+/* Up to 3 matrices sharing one activation of length k (k % 256 == 0, k <= 28672), ONE launch.  prologue:
+ *   0  act_ws already holds the q8_K activation (pb200_quantize_act, or pb200_attn_ggml with act_ws_out)
+ *   1  act = q8_K( rms_norm(in0, eps) * in1 )     ggml RMS_NORM + MUL by the norm weight   (llm_build_norm, src/llama.cpp:9772-9802)
+ *   2  act = q8_K( silu(in0) * in1 )              ggml UNARY(SILU) + MUL                    (llm_build_ffn, src/llama.cpp:9858-9907)
+ * computed once, distributed over the launch's CTAs (one in-kernel grid barrier), left in act_ws.  sync_ws: 16 bytes of zero-initialised
+ * device memory owned by the caller (barrier state, self-resetting; one per stream).  pdl != 0: the launch may start while the
+ * previous kernel of the stream drains (programmatic dependent launch); its inputs are read only after that kernel has completed.
+ * Returns PB200_ENOTSUP for types / shapes outside the fast kernel (callers fall back to the single ops). */
+PB200_API int pb200_gemv_fused(int nmat, const pb200_gemv_mat * mats, int64_t k, void * act_ws, int prologue, const float * in0, const float * in1,
+                               float eps, void * sync_ws, int pdl, void * stream);
+/* One token of the reference graph's FA-off attention chain as ONE launch (llm_build_kv_store + llm_build_kqv, src/llama.cpp:9673-9718,
+ * 10032-10165): rope(q), rope(k) -> f16 K row into cell kv_head of k_cache [cell][n_head_kv*128]; v -> f16 into column kv_head of the
+ * TRANSPOSED v cache [n_head_kv*128][vt_stride]; out[h] = softmax(scale * K q_h + mask) . V over n_cells cells (multiple of 32, mask f32
+ * [n_cells], -inf = not visible).  head_dim 128, n_head even.  act_ws_out (optional): also leaves q8_K(out) there for the following
+ * mat-vec.  rope op parameters as in pb200_rope.  Returns PB200_ENOTSUP for shapes it does not handle. */
+PB200_API int pb200_attn_ggml(const float * q, const float * k, const float * v, void * k_cache_f16, void * v_cache_t_f16, int64_t vt_stride, float * out,
+                              void * act_ws_out, int n_head, int n_head_kv, int head_dim, const int32_t * pos_dev, int n_cells, int kv_head,
+                              const float * mask, int n_dims, int mode, float freq_base, float freq_scale, float ext_factor, float attn_factor,
+                              float beta_fast, float beta_slow, int n_ctx_orig, const float * freq_factors, float scale, int pdl, void * stream);
+
 /* ---- decode engine (one model shard per process / GPU) ---- */
 typedef struct pb200_hparams {
     int32_t n_layer, n_embd, n_head, n_head_kv, head_dim, n_ff, n_vocab, n_ctx;
@@ -132,6 +161,9 @@ PB200_API int pb200_model_set_tensor(pb200_model * m, const char * name, int typ
  * llama_tensor_get_type (src/llama.cpp:19271-19556); for benchmarking without a checkpoint */
 PB200_API int pb200_model_synth(pb200_model * m, int ftype, uint64_t seed);
 PB200_API int pb200_model_finalize(pb200_model * m);     /* allocate KV cache + activations, capture the CUDA graph */
+/* device address, size and ggml type of a tensor this shard holds (GGUF names as in pb200_model_set_tensor): lets a host copy
+ * weights device-to-device, e.g. bench.py moving the synthetic model into the ggml-backend buffers of the plugin */
+PB200_API int pb200_model_tensor_device(pb200_model * m, const char * name, const void ** dev_ptr, size_t * nbytes, int * type);
 PB200_API int64_t pb200_model_weight_bytes(const pb200_model * m);    /* algorithmic bytes read per decoded token on this shard */
 /* Prompt processing (prefill): n_tokens tokens at positions pos0 .. pos0+n_tokens-1 through all layers as one batch — the
  * reference's llama_decode with a multi-token ubatch (ne11 > 1: ggml_cuda_op_mul_mat_q, mmq.cu:3-98; attention

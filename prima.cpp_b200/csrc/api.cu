@@ -213,6 +213,56 @@ int pb200_attn_decode(const float * q, const void * k_cache_f16, const void * v_
                               nullptr, (cudaStream_t) stream, false);
 }
 
+int pb200_gemv_fused(int nmat, const pb200_gemv_mat * mats, int64_t k, void * act_ws, int prologue, const float * in0, const float * in1, float eps,
+                     void * sync_ws, int pdl, void * stream) {
+    if (nmat < 1 || nmat > 3 || !mats || !act_ws || k <= 0 || prologue < 0 || prologue > 2) return PB200_EINVAL;
+    if (prologue != 0 && (!in0 || !in1)) return PB200_EINVAL;
+    if (!gemv_fused_prologue_ok((int) k)) return PB200_ENOTSUP;
+    GemvDesc d[3];
+    for (int i = 0; i < nmat; i++) {
+        if (!mats[i].W || !mats[i].y || mats[i].n <= 0) return PB200_EINVAL;
+        if (!is_kquant(mats[i].type) || ((uintptr_t) mats[i].W & 15)) return PB200_ENOTSUP;
+        d[i] = GemvDesc{mats[i].W, mats[i].y, nullptr, mats[i].add, mats[i].type, (int) mats[i].n};
+    }
+    cudaStream_t st = (cudaStream_t) stream;
+    const ActQ act = act_from_ws(act_ws, k);
+    GemvFused pro;
+    bool gemv_pdl = pdl != 0;
+    if (prologue != 0) {
+        if (sync_ws && gemv_dist_prologue_ok()) {
+            pro.kind = prologue == 1 ? 4 : 5; pro.in0 = in0; pro.in1 = in1; pro.eps = eps; pro.gbar = (unsigned int *) sync_ws;
+        } else {   // the grid cannot be made co-resident on this device: produce the activation with a small kernel in front
+            g_launches++;
+            int e = prologue == 1 ? launch_rmsnorm_quant(in0, in1, (int) k, eps, ACT_Q8_K, act, nullptr, st, gemv_pdl)
+                                  : launch_silu_mul_quant(in0, in1, (int) k, ACT_Q8_K, act, nullptr, st, gemv_pdl);
+            if (e) return e;
+            gemv_pdl = true;
+        }
+    }
+    g_launches++;
+    return launch_gemv_kquant_fused(d, nmat, (int) k, act, pro, st, gemv_pdl);
+}
+
+int pb200_attn_ggml(const float * q, const float * k, const float * v, void * k_cache_f16, void * v_cache_t_f16, int64_t vt_stride, float * out,
+                    void * act_ws_out, int n_head, int n_head_kv, int head_dim, const int32_t * pos_dev, int n_cells, int kv_head, const float * mask,
+                    int n_dims, int mode, float freq_base, float freq_scale, float ext_factor, float attn_factor, float beta_fast, float beta_slow,
+                    int n_ctx_orig, const float * freq_factors, float scale, int pdl, void * stream) {
+    if (!q || !k || !v || !k_cache_f16 || !v_cache_t_f16 || !out || !pos_dev || !mask || n_head <= 0 || n_head_kv <= 0) return PB200_EINVAL;
+    if (head_dim != 128 || n_dims > head_dim || (n_dims & 1) || (mode != 0 && mode != 2)) return PB200_ENOTSUP;
+    RopeParams rp;
+    rope_params_init(rp, n_dims, mode, n_ctx_orig, freq_base, freq_scale, ext_factor, attn_factor, beta_fast, beta_slow);
+    ActQ outq{};
+    if (act_ws_out) {
+        if (((int64_t) n_head * head_dim) % 256 != 0) return PB200_ENOTSUP;
+        outq = act_from_ws(act_ws_out, (int64_t) n_head * head_dim);
+    }
+    const int rc = launch_attn_ggml(q, k, v, (__half *) k_cache_f16, (__half *) v_cache_t_f16, vt_stride, out, outq, n_head, n_head_kv, head_dim, pos_dev,
+                                    n_cells, kv_head, mask, rp, freq_factors, scale, (cudaStream_t) stream, pdl != 0);
+    if (rc == (int) cudaErrorNotSupported) return PB200_ENOTSUP;
+    if (rc == 0) g_launches++;
+    return rc;
+}
+
 int pb200_attn_prefill(const float * q, const void * k_cache_f16, const void * v_cache_f16, float * out, int n_head, int n_head_kv, int head_dim,
                        const int32_t * pos_dev, int n_tok, int n_kv_max, float scale, void * stream) {
     if (!q || !k_cache_f16 || !v_cache_f16 || !out || !pos_dev || head_dim != 128 || n_head_kv <= 0 || n_head % n_head_kv || n_tok <= 0 || n_kv_max <= 0)

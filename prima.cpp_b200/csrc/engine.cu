@@ -561,6 +561,24 @@ int pb200_model_finalize(pb200_model * m) {
 
 int64_t pb200_model_weight_bytes(const pb200_model * m) { return m ? m->weight_bytes : 0; }
 
+int pb200_model_tensor_device(pb200_model * m, const char * name, const void ** dev_ptr, size_t * nbytes, int * type) {
+    if (!m || !name || !dev_ptr || !nbytes) return PB200_EINVAL;
+    bool is_f32 = false;
+    float ** slot = nullptr;
+    int64_t n_f32 = 0;
+    Tensor * t = find_tensor(m, name, is_f32, &slot, n_f32);
+    if (is_f32) {
+        if (!slot || !*slot) return PB200_ESTATE;
+        *dev_ptr = *slot; *nbytes = (size_t) n_f32 * 4;
+        if (type) *type = T_F32;
+        return 0;
+    }
+    if (!t || !t->data) return PB200_ESTATE;
+    *dev_ptr = t->data; *nbytes = t->bytes;
+    if (type) *type = t->type;
+    return 0;
+}
+
 }  // extern "C"
 
 // ---------------------------------------------------------------------------------------------------------------

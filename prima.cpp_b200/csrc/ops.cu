@@ -641,9 +641,10 @@ struct __align__(128) Attn2Smem {   // fixed part; dynamic tail: S[n_ctx padded 
     __align__(128) __half vbuf[2][A2_CHUNK][128];
 };
 static_assert(offsetof(Attn2Smem, red) % 16 == 0 && offsetof(Attn2Smem, kbuf) % 128 == 0 && sizeof(Attn2Smem) % 128 == 0, "Attn2Smem layout");
-__device__ __forceinline__ void a2_issue_chunk(__half (*dst)[128], const __half * cache, int64_t EK, int hk, int c, int n_cache, uint64_t * bar) {
+// K (both layouts) and the engine's row-major V: 128 cells x 256 B, one 16-byte piece per cp.async
+__device__ __forceinline__ void a2_issue_chunk(__half (*dst)[128], const __half * cache, int64_t EK, int hk, int c, int ncell, uint64_t * bar) {
     const int r0 = c * A2_CHUNK;
-    const int nrows = min(A2_CHUNK, n_cache - r0);
+    const int nrows = min(A2_CHUNK, ncell - r0);
     const int pieces = nrows * 16;                      // 16-byte pieces: 16 per 256-byte row
     for (int i = threadIdx.x; i < pieces; i += A2_THREADS) {
         const int r = i >> 4, cpart = i & 15;
@@ -651,6 +652,20 @@ __device__ __forceinline__ void a2_issue_chunk(__half (*dst)[128], const __half 
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(&dst[r][cpart * 8])), "l"(src) : "memory");
     }
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");   // fires when this thread's copies have landed
+}
+// ggml's FA-off V cache is TRANSPOSED (llm_build_kv_store, src/llama.cpp:9698-9716): channel-major [n_embd_v_gqa][n_ctx].
+// The chunk is staged as dst[channel][cell in chunk]; ncell and the chunk start are multiples of 8 cells (16-byte pieces).
+__device__ __forceinline__ void a2_issue_chunk_vt(__half (*dst)[128], const __half * cache, int64_t vt_stride, int hk, int c, int ncell, uint64_t * bar) {
+    const int r0 = c * A2_CHUNK;
+    const int ncol = min(A2_CHUNK, ncell - r0);
+    const int ppc = ncol >> 3;                           // pieces per channel
+    const int pieces = 128 * ppc;
+    for (int i = threadIdx.x; i < pieces; i += A2_THREADS) {
+        const int d = i / ppc, part = i - d * ppc;
+        const __half * src = cache + (int64_t) (hk * 128 + d) * vt_stride + r0 + part * 8;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(&dst[d][part * 8])), "l"(src) : "memory");
+    }
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -664,18 +679,40 @@ __device__ __forceinline__ float ld_dsmem_f32(const float * local_addr, uint32_t
     return v;
 }
 
-__global__ void __launch_bounds__(A2_THREADS, 1) k_attn_fused2(const float * __restrict__ q, const float * __restrict__ k, const float * __restrict__ v,
-                                                               __half * __restrict__ kc, __half * __restrict__ vc, float * __restrict__ out, ActQ outq,
-                                                               int n_head, int n_head_kv, const int32_t * __restrict__ pos_dev, RopeParams rp,
-                                                               const float * __restrict__ freq_factors, float scale, int * abort_flag) {
+struct Attn2Params {
+    const float * q; const float * k; const float * v;   // this token's projections (f32, pre-RoPE)
+    __half * kc;                  // K cache [cell][n_head_kv * 128]
+    __half * vc;                  // V cache: engine [cell][n_head_kv * 128]; GGML: transposed [n_head_kv * 128][vt_stride]
+    float * out;                  // [n_head * 128]
+    ActQ outq;                    // optional q8_K of out (qs == nullptr: skip)
+    int n_head, n_head_kv;
+    const int32_t * pos_dev;      // the token's position (RoPE); engine layout: also the cell it is stored in
+    RopeParams rp;
+    const float * freq_factors;
+    float scale;
+    int * abort_flag;
+    // GGML layout only (the FA-off chain of llm_build_kqv, src/llama.cpp:10032-10165)
+    int n_cells;                  // cells attended: the graph's n_kv (multiple of 32)
+    int kv_head;                  // cell this token's K / V are stored in (offset of the cache views of llm_build_kv_store)
+    int64_t vt_stride;            // elements between two channels of the transposed V cache (n_ctx)
+    const float * mask;           // [n_cells] additive f32 mask row of this token (0 / -inf), soft_max_ext src1
+};
+
+// GGML = false: the engine's cache (V row-major, cell == position, causal window [0, pos]).
+// GGML = true: the tensors of the reference's graph: K cache row-major, V cache transposed, explicit mask row, explicit cell.
+template <bool GGML>
+__global__ void __launch_bounds__(A2_THREADS, 1) k_attn2(const __grid_constant__ Attn2Params P) {
     constexpr int D = 128;
     extern __shared__ __align__(128) uint8_t a2_raw[];
     Attn2Smem * sm = reinterpret_cast<Attn2Smem *>(a2_raw);
     float * S = reinterpret_cast<float *>(a2_raw + sizeof(Attn2Smem));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_head = P.n_head, n_head_kv = P.n_head_kv;
     const int gqa = n_head / n_head_kv;
     const int h = blockIdx.x, hk = h / gqa;
     const int64_t EK = (int64_t) n_head_kv * D;
+    __half * const kc = P.kc;
+    __half * const vc = P.vc;
     if (threadIdx.x == 0) {
         mbar_init(&sm->kbar[0], A2_THREADS); mbar_init(&sm->kbar[1], A2_THREADS);
         mbar_init(&sm->vbar[0], A2_THREADS); mbar_init(&sm->vbar[1], A2_THREADS);
@@ -684,19 +721,26 @@ __global__ void __launch_bounds__(A2_THREADS, 1) k_attn_fused2(const float * __r
     }
     __syncthreads();
     pdl_trigger();
-    // ---- independent of the producing GEMV: position (written before this token's first kernel), cache rows of earlier tokens
-    const int pos = *pos_dev;
-    const int n_kv = pos + 1, n_cache = pos;                   // row `pos` itself comes from shared memory (k_s / v_s)
-    const int nchunks = (n_cache + A2_CHUNK - 1) / A2_CHUNK;
-    if (nchunks > 0) a2_issue_chunk(sm->kbuf[0], kc, EK, hk, 0, n_cache, &sm->kbar[0]);
-    if (nchunks > 1) a2_issue_chunk(sm->kbuf[1], kc, EK, hk, 1, n_cache, &sm->kbar[1]);
-    if (nchunks > 0) a2_issue_chunk(sm->vbuf[0], vc, EK, hk, 0, n_cache, &sm->vbar[0]);
-    if (nchunks > 1) a2_issue_chunk(sm->vbuf[1], vc, EK, hk, 1, n_cache, &sm->vbar[1]);
+    // ---- independent of the producing GEMV: position (written before this token's first kernel), cache cells of earlier tokens
+    const int pos = *P.pos_dev;
+    const int ncell = GGML ? P.n_cells : pos + 1;              // cells attended
+    const int fresh = GGML ? P.kv_head : pos;                  // this token's cell: its K / V come from shared memory, not from the cache
+    const int nchunks = (ncell + A2_CHUNK - 1) / A2_CHUNK;
+    a2_issue_chunk(sm->kbuf[0], kc, EK, hk, 0, ncell, &sm->kbar[0]);
+    if (nchunks > 1) a2_issue_chunk(sm->kbuf[1], kc, EK, hk, 1, ncell, &sm->kbar[1]);
+    if (GGML) {
+        a2_issue_chunk_vt(sm->vbuf[0], vc, P.vt_stride, hk, 0, ncell, &sm->vbar[0]);
+        if (nchunks > 1) a2_issue_chunk_vt(sm->vbuf[1], vc, P.vt_stride, hk, 1, ncell, &sm->vbar[1]);
+    } else {
+        a2_issue_chunk(sm->vbuf[0], vc, EK, hk, 0, ncell, &sm->vbar[0]);
+        if (nchunks > 1) a2_issue_chunk(sm->vbuf[1], vc, EK, hk, 1, ncell, &sm->vbar[1]);
+    }
+    const RopeParams & rp = P.rp;
     const int half_dims = rp.n_dims / 2;
     const bool neox = rp.mode & 2;
     if (threadIdx.x < 64 && (int) threadIdx.x < half_dims) {
         float c, s;
-        rope_cos_sin(rp, pos, threadIdx.x, freq_factors, c, s);
+        rope_cos_sin(rp, pos, threadIdx.x, P.freq_factors, c, s);
         sm->cs[threadIdx.x][0] = c; sm->cs[threadIdx.x][1] = s;
     }
     pdl_wait();
@@ -706,13 +750,13 @@ __global__ void __launch_bounds__(A2_THREADS, 1) k_attn_fused2(const float * __r
         const int t = threadIdx.x;
         if (t < 128) {
             const int pair = t & 63;
-            const float * src = t < 64 ? q + (int64_t) h * D : k + (int64_t) hk * D;
+            const float * src = t < 64 ? P.q + (int64_t) h * D : P.k + (int64_t) hk * D;
             if (pair < half_dims) {
                 const int i0 = neox ? pair : 2 * pair, i1 = neox ? pair + half_dims : 2 * pair + 1;
                 x0 = __ldcg(src + i0); x1 = __ldcg(src + i1);
             }
         } else if (t < 256) {
-            vv = __ldcg(v + (int64_t) hk * D + (t - 128));
+            vv = __ldcg(P.v + (int64_t) hk * D + (t - 128));
         }
     }
     __syncthreads();   // cs[] visible
@@ -721,7 +765,7 @@ __global__ void __launch_bounds__(A2_THREADS, 1) k_attn_fused2(const float * __r
         if (t < 128) {
             const int pair = t & 63;
             const bool is_q = t < 64;
-            const float * src = is_q ? q + (int64_t) h * D : k + (int64_t) hk * D;
+            const float * src = is_q ? P.q + (int64_t) h * D : P.k + (int64_t) hk * D;
             if (pair < half_dims) {
                 const int i0 = neox ? pair : 2 * pair, i1 = neox ? pair + half_dims : 2 * pair + 1;
                 float y0, y1;
@@ -738,9 +782,13 @@ __global__ void __launch_bounds__(A2_THREADS, 1) k_attn_fused2(const float * __r
         }
     }
     __syncthreads();
-    if (h % gqa == 0 && threadIdx.x < 32) {   // one CTA per kv head publishes the fresh row (8 B per lane, coalesced)
-        *reinterpret_cast<uint2 *>(kc + (int64_t) pos * EK + (int64_t) hk * D + 4 * lane) = *reinterpret_cast<const uint2 *>(sm->k_s + 4 * lane);
-        *reinterpret_cast<uint2 *>(vc + (int64_t) pos * EK + (int64_t) hk * D + 4 * lane) = *reinterpret_cast<const uint2 *>(sm->v_s + 4 * lane);
+    if (h % gqa == 0) {   // one CTA per kv head publishes the fresh K / V
+        if (threadIdx.x < 32) *reinterpret_cast<uint2 *>(kc + (int64_t) fresh * EK + (int64_t) hk * D + 4 * lane) = *reinterpret_cast<const uint2 *>(sm->k_s + 4 * lane);
+        if (GGML) {
+            if (threadIdx.x >= 128 && threadIdx.x < 256) vc[(int64_t) (hk * D + (threadIdx.x - 128)) * P.vt_stride + fresh] = sm->v_s[threadIdx.x - 128];
+        } else {
+            if (threadIdx.x < 32) *reinterpret_cast<uint2 *>(vc + (int64_t) fresh * EK + (int64_t) hk * D + 4 * lane) = *reinterpret_cast<const uint2 *>(sm->v_s + 4 * lane);
+        }
     }
     const float q0 = sm->q_s[4 * lane], q1 = sm->q_s[4 * lane + 1], q2 = sm->q_s[4 * lane + 2], q3 = sm->q_s[4 * lane + 3];
     auto score_row = [&](const __half * krow) -> float {
@@ -753,28 +801,29 @@ __global__ void __launch_bounds__(A2_THREADS, 1) k_attn_fused2(const float * __r
         s = fmaf(k23.y, q3, s);
         return warp_sum(s);
     };
-    // ---- scores
+    // ---- scores  (soft_max_ext: s * scale, then + mask; ggml.c ggml_compute_forward_soft_max_f32)
     for (int c = 0; c < nchunks; c++) {
         const int b = c & 1;
-        mbar_wait(&sm->kbar[b], (uint32_t) ((c >> 1) & 1), &sm->aborted, abort_flag);
-        const int r0 = c * A2_CHUNK, nrows = min(A2_CHUNK, n_cache - r0);
+        mbar_wait(&sm->kbar[b], (uint32_t) ((c >> 1) & 1), &sm->aborted, P.abort_flag);
+        const int r0 = c * A2_CHUNK, nrows = min(A2_CHUNK, ncell - r0);
         for (int r = warp; r < nrows; r += A2_WARPS) {
-            const float s = score_row(sm->kbuf[b][r]);
-            if (lane == 0) S[r0 + r] = __fmul_rn(s, scale);
+            const int p = r0 + r;
+            const float s = score_row(p == fresh ? sm->k_s : sm->kbuf[b][r]);
+            if (lane == 0) {
+                float t = __fmul_rn(s, P.scale);
+                if (GGML) t = __fadd_rn(t, P.mask[p]);
+                S[p] = t;
+            }
         }
         if (c + 2 < nchunks) {
             __syncthreads();   // every warp is done with this buffer
-            a2_issue_chunk(sm->kbuf[b], kc, EK, hk, c + 2, n_cache, &sm->kbar[b]);
+            a2_issue_chunk(sm->kbuf[b], kc, EK, hk, c + 2, ncell, &sm->kbar[b]);
         }
     }
-    if (warp == 0) {
-        const float s = score_row(sm->k_s);
-        if (lane == 0) S[pos] = __fmul_rn(s, scale);
-    }
     __syncthreads();
-    // ---- softmax (ggml.c:13783: max, expf, double sum, p = e * float(1/sum))
+    // ---- softmax (max, expf, double sum, p = e * float(1/sum))
     float m = -INFINITY;
-    for (int p = threadIdx.x; p < n_kv; p += A2_THREADS) m = fmaxf(m, S[p]);
+    for (int p = threadIdx.x; p < ncell; p += A2_THREADS) m = fmaxf(m, S[p]);
     m = warp_max(m);
     if (lane == 0) sm->s_red[warp] = m;
     __syncthreads();
@@ -786,8 +835,9 @@ __global__ void __launch_bounds__(A2_THREADS, 1) k_attn_fused2(const float * __r
     __syncthreads();
     const float mx = sm->s_bc[0];
     double dsum = 0.0;
-    for (int p = threadIdx.x; p < n_kv; p += A2_THREADS) {
-        const float e = expf(__fsub_rn(S[p], mx));
+    for (int p = threadIdx.x; p < ncell; p += A2_THREADS) {
+        const float sv = S[p];
+        const float e = (GGML && sv == -INFINITY) ? 0.f : expf(__fsub_rn(sv, mx));
         S[p] = e;
         dsum += (double) e;
     }
@@ -801,36 +851,79 @@ __global__ void __launch_bounds__(A2_THREADS, 1) k_attn_fused2(const float * __r
     }
     __syncthreads();
     const float inv = sm->s_bc[1];
-    // ---- P.V with f16-rounded probabilities
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    auto pv_row = [&](const __half * vrow, int p) {
-        const float w = __half2float(__float2half_rn(__fmul_rn(S[p], inv)));
-        const uint2 vraw = *reinterpret_cast<const uint2 *>(vrow + 4 * lane);
-        const float2 v01 = __half22float2(*reinterpret_cast<const __half2 *>(&vraw.x));
-        const float2 v23 = __half22float2(*reinterpret_cast<const __half2 *>(&vraw.y));
-        a0 = fmaf(v01.x, w, a0); a1 = fmaf(v01.y, w, a1); a2 = fmaf(v23.x, w, a2); a3 = fmaf(v23.y, w, a3);
-    };
-    for (int c = 0; c < nchunks; c++) {
-        const int b = c & 1;
-        mbar_wait(&sm->vbar[b], (uint32_t) ((c >> 1) & 1), &sm->aborted, abort_flag);
-        const int r0 = c * A2_CHUNK, nrows = min(A2_CHUNK, n_cache - r0);
-        for (int r = warp; r < nrows; r += A2_WARPS) pv_row(sm->vbuf[b][r], r0 + r);
-        if (c + 2 < nchunks) {
-            __syncthreads();
-            a2_issue_chunk(sm->vbuf[b], vc, EK, hk, c + 2, n_cache, &sm->vbar[b]);
+    if (GGML) {
+        // ---- P.V over the transposed cache: warp w owns channels w, w+16, ...; lane l owns cells 2l, 2l+1, 64+2l, 64+2l+1 of a chunk
+        for (int p = threadIdx.x; p < ncell; p += A2_THREADS) S[p] = __half2float(__float2half_rn(__fmul_rn(S[p], inv)));   // f16-rounded probabilities
+        __syncthreads();
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc[i] = 0.f;
+        for (int c = 0; c < nchunks; c++) {
+            const int b = c & 1;
+            mbar_wait(&sm->vbar[b], (uint32_t) ((c >> 1) & 1), &sm->aborted, P.abort_flag);
+            const int r0 = c * A2_CHUNK, ncol = min(A2_CHUNK, ncell - r0);
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const int cl = 2 * lane + 64 * j;
+                if (cl < ncol) {
+                    const float w0 = S[r0 + cl], w1 = S[r0 + cl + 1];
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const int d = warp + A2_WARPS * i;
+                        float2 vf = __half22float2(*reinterpret_cast<const __half2 *>(&sm->vbuf[b][d][cl]));
+                        if (r0 + cl == fresh) vf.x = __half2float(sm->v_s[d]);
+                        if (r0 + cl + 1 == fresh) vf.y = __half2float(sm->v_s[d]);
+                        acc[i] = fmaf(vf.x, w0, acc[i]);
+                        acc[i] = fmaf(vf.y, w1, acc[i]);
+                    }
+                }
+            }
+            if (c + 2 < nchunks) {
+                __syncthreads();
+                a2_issue_chunk_vt(sm->vbuf[b], vc, P.vt_stride, hk, c + 2, ncell, &sm->vbar[b]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const float t = warp_sum(acc[i]);
+            if (lane == 0) {
+                const int d = warp + A2_WARPS * i;
+                P.out[(int64_t) h * D + d] = t;
+                sm->o_s[d] = t;
+            }
+        }
+    } else {
+        // ---- P.V with f16-rounded probabilities, row-major V: lane owns 4 channels, warps split the cells
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        auto pv_row = [&](const __half * vrow, int p) {
+            const float w = __half2float(__float2half_rn(__fmul_rn(S[p], inv)));
+            const uint2 vraw = *reinterpret_cast<const uint2 *>(vrow + 4 * lane);
+            const float2 v01 = __half22float2(*reinterpret_cast<const __half2 *>(&vraw.x));
+            const float2 v23 = __half22float2(*reinterpret_cast<const __half2 *>(&vraw.y));
+            a0 = fmaf(v01.x, w, a0); a1 = fmaf(v01.y, w, a1); a2 = fmaf(v23.x, w, a2); a3 = fmaf(v23.y, w, a3);
+        };
+        for (int c = 0; c < nchunks; c++) {
+            const int b = c & 1;
+            mbar_wait(&sm->vbar[b], (uint32_t) ((c >> 1) & 1), &sm->aborted, P.abort_flag);
+            const int r0 = c * A2_CHUNK, nrows = min(A2_CHUNK, ncell - r0);
+            for (int r = warp; r < nrows; r += A2_WARPS) pv_row(r0 + r == fresh ? sm->v_s : sm->vbuf[b][r], r0 + r);
+            if (c + 2 < nchunks) {
+                __syncthreads();
+                a2_issue_chunk(sm->vbuf[b], vc, EK, hk, c + 2, ncell, &sm->vbar[b]);
+            }
+        }
+        *reinterpret_cast<float4 *>(&sm->red[warp][4 * lane]) = make_float4(a0, a1, a2, a3);
+        __syncthreads();
+        if (threadIdx.x < 128) {
+            float t = 0.f;
+#pragma unroll
+            for (int i = 0; i < A2_WARPS; i++) t += sm->red[i][threadIdx.x];
+            P.out[(int64_t) h * D + threadIdx.x] = t;
+            sm->o_s[threadIdx.x] = t;
         }
     }
-    if (warp == (pos % A2_WARPS)) pv_row(sm->v_s, pos);
-    *reinterpret_cast<float4 *>(&sm->red[warp][4 * lane]) = make_float4(a0, a1, a2, a3);
-    __syncthreads();
-    if (threadIdx.x < 128) {
-        float t = 0.f;
-#pragma unroll
-        for (int i = 0; i < A2_WARPS; i++) t += sm->red[i][threadIdx.x];
-        out[(int64_t) h * D + threadIdx.x] = t;
-        sm->o_s[threadIdx.x] = t;
-    }
     // ---- q8_K of the output: heads (2j, 2j+1) = cluster ranks (0, 1) = super-block j  (quantize_row_q8_K_ref, ggml-quants.c:3785-3822)
+    const ActQ & outq = P.outq;
     if (outq.qs) {
         __syncthreads();
         const uint32_t rank = h & 1u;
@@ -1189,19 +1282,19 @@ int launch_attn_fused(const float * q, const float * k, const float * v, __half 
     return (int) cudaLaunchKernelEx(&cfg, k_attn_fused, q, k, v, kcache, vcache, out, n_head, n_head_kv, pos_dev, rp, freq_factors, scale);
 }
 
-// v2: returns cudaErrorNotSupported when the shape is outside what the clustered kernel handles (caller uses launch_attn_fused + a quantize prologue)
-int launch_attn_fused2(const float * q, const float * k, const float * v, __half * kcache, __half * vcache, float * out, const ActQ & outq, int n_head,
-                       int n_head_kv, int D, const int32_t * pos_dev, int n_ctx, const RopeParams & rp, const float * freq_factors, float scale,
-                       cudaStream_t stream, bool pdl) {
-    const size_t smem = sizeof(Attn2Smem) + (size_t) ((n_ctx + 31) & ~31) * sizeof(float);
-    if (D != 128 || (n_head & 1) || n_head_kv <= 0 || n_head % n_head_kv || smem > 200 * 1024) return (int) cudaErrorNotSupported;
+// v2: returns cudaErrorNotSupported when the shape is outside what the clustered kernel handles (caller uses launch_attn_fused + a quantize kernel)
+template <bool GGML>
+static int launch_attn2(Attn2Params & P, int n_score_slots, cudaStream_t stream, bool pdl) {
+    const size_t smem = sizeof(Attn2Smem) + (size_t) ((n_score_slots + 31) & ~31) * sizeof(float);
+    if ((P.n_head & 1) || P.n_head_kv <= 0 || P.n_head % P.n_head_kv || smem > 200 * 1024) return (int) cudaErrorNotSupported;
     static FuncAttrCache attr_cache;
     {
-        cudaError_t e = ensure_dyn_smem(attr_cache, (const void *) k_attn_fused2, smem, false);
+        cudaError_t e = ensure_dyn_smem(attr_cache, (const void *) k_attn2<GGML>, smem, false);
         if (e != cudaSuccess) return (int) e;
     }
+    P.abort_flag = abort_flag();
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(n_head);
+    cfg.gridDim = dim3(P.n_head);
     cfg.blockDim = dim3(A2_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
@@ -1212,7 +1305,28 @@ int launch_attn_fused2(const float * q, const float * k, const float * v, __half
     attr[1].val.clusterDim.x = 2; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 2;
-    return (int) cudaLaunchKernelEx(&cfg, k_attn_fused2, q, k, v, kcache, vcache, out, outq, n_head, n_head_kv, pos_dev, rp, freq_factors, scale, abort_flag());
+    return (int) cudaLaunchKernelEx(&cfg, k_attn2<GGML>, P);
+}
+int launch_attn_fused2(const float * q, const float * k, const float * v, __half * kcache, __half * vcache, float * out, const ActQ & outq, int n_head,
+                       int n_head_kv, int D, const int32_t * pos_dev, int n_ctx, const RopeParams & rp, const float * freq_factors, float scale,
+                       cudaStream_t stream, bool pdl) {
+    if (D != 128) return (int) cudaErrorNotSupported;
+    Attn2Params P{};
+    P.q = q; P.k = k; P.v = v; P.kc = kcache; P.vc = vcache; P.out = out; P.outq = outq; P.n_head = n_head; P.n_head_kv = n_head_kv;
+    P.pos_dev = pos_dev; P.rp = rp; P.freq_factors = freq_factors; P.scale = scale;
+    return launch_attn2<false>(P, n_ctx, stream, pdl);
+}
+// the reference graph's tensors (FA off): K cache rows, transposed V cache, explicit mask row and destination cell
+int launch_attn_ggml(const float * q, const float * k, const float * v, __half * kcache, __half * vcache_t, int64_t vt_stride, float * out, const ActQ & outq,
+                     int n_head, int n_head_kv, int D, const int32_t * pos_dev, int n_cells, int kv_head, const float * mask, const RopeParams & rp,
+                     const float * freq_factors, float scale, cudaStream_t stream, bool pdl) {
+    if (D != 128 || n_cells <= 0 || (n_cells & 7) || kv_head < 0 || kv_head >= n_cells || (vt_stride & 7) || ((uintptr_t) vcache_t & 15) || ((uintptr_t) kcache & 15) || !mask)
+        return (int) cudaErrorNotSupported;
+    Attn2Params P{};
+    P.q = q; P.k = k; P.v = v; P.kc = kcache; P.vc = vcache_t; P.out = out; P.outq = outq; P.n_head = n_head; P.n_head_kv = n_head_kv;
+    P.pos_dev = pos_dev; P.rp = rp; P.freq_factors = freq_factors; P.scale = scale;
+    P.n_cells = n_cells; P.kv_head = kv_head; P.vt_stride = vt_stride; P.mask = mask;
+    return launch_attn2<true>(P, n_cells, stream, pdl);
 }
 
 int launch_soft_max(const float * x, const float * mask, float * y, int ncols, int64_t nrows, int64_t rows_per_mask_cycle, float scale,

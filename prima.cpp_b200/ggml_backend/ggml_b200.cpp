@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -25,6 +26,7 @@
 #define B200_MAX_DEVICES 16
 
 static std::atomic<unsigned long long> g_nodes{0};
+static std::atomic<unsigned long long> g_fused_steps{0};
 
 #define CUDA_OK(expr)                                                                                   \
     do {                                                                                                \
@@ -40,11 +42,39 @@ struct b200_device_ctx {
     int device;
     std::string name, description;
 };
+// ---- execution plan of the fused decode path (see graph_compute) ----
+struct b200_step {
+    int kind;                 // 0 = single node, 1 = fused GEMV group, 2 = fused attention
+    int node;                 // kind 0: node index
+    // kind 1
+    int nmat, mm[3], out[3], add_vec[3];   // MUL_MAT node, node whose buffer receives y, node/leaf supplying the added vector (-1 none; see add_src)
+    int add_src[3];                        // which src of the ADD node is the vector
+    int prologue;                          // 0 quantize src1 with a separate kernel, 1 rms-norm, 2 silu, 3 activation left quantized by the attention step
+    int p0, p1;                            // prologue 1: RMS_NORM node, MUL node; prologue 2: UNARY node, MUL node
+    int ws;                                // workspace role
+    // kind 2
+    int rope_q, rope_k, cpy_k, cpy_v, kq, soft, kqv, cont, quant_out;
+};
+struct b200_plan {
+    uint64_t key;
+    int n_nodes;
+    std::vector<b200_step> steps;
+};
+
 struct b200_backend_ctx {
     int device;
     cudaStream_t stream = nullptr;
     void * act_ws = nullptr;       // quantized-activation workspace (grown on demand)
     size_t act_ws_bytes = 0;
+    // fused decode path (graph_compute): one activation workspace per role so that a producer never overwrites what the
+    // previous launch may still be reading under programmatic dependent launch; barrier state of pb200_gemv_fused; plan cache
+    void * fact_ws[3] = {nullptr, nullptr, nullptr};   // 0: norm prologue (K = n_embd), 1: attention output, 2: silu prologue (K = n_ff)
+    size_t fact_bytes[3] = {0, 0, 0};
+    void * sync_ws = nullptr;
+    float * attn_tmp = nullptr;
+    size_t attn_tmp_floats = 0;
+    cudaEvent_t copy_event = nullptr;
+    std::vector<b200_plan *> plans;
     void * mmq_ws = nullptr;       // fp16 activation tiles for the tensor-core path (grown on demand)
     size_t mmq_ws_bytes = 0;
     std::string name;
@@ -306,7 +336,7 @@ static bool b200_compute_node(b200_backend_ctx * ctx, ggml_tensor * dst) {
         case GGML_OP_CONT: {
             // enumerate in the SOURCE's logical order when shapes agree, else both sides must be contiguous-compatible
             const ggml_tensor * d = dst->op == GGML_OP_CPY ? dst->src[1] : dst;
-            void * out = dst->op == GGML_OP_CPY ? dst->src[1]->data : dst->data;
+            void * out = dst->data;   // a CPY node is a view of its destination (ggml_cpy_impl): same address, and what the CPU backend writes to
             int64_t ne[4], sb[4], db[4];
             if (ggml_are_same_shape(a, d)) {
                 for (int i = 0; i < 4; i++) { ne[i] = a->ne[i]; sb[i] = a->nb[i]; db[i] = d->nb[i]; }
@@ -343,6 +373,11 @@ static void b200_backend_free(ggml_backend_t backend) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->act_ws) cudaFree(ctx->act_ws);
     if (ctx->mmq_ws) cudaFree(ctx->mmq_ws);
+    for (void * p : ctx->fact_ws) if (p) cudaFree(p);
+    if (ctx->sync_ws) cudaFree(ctx->sync_ws);
+    if (ctx->attn_tmp) cudaFree(ctx->attn_tmp);
+    if (ctx->copy_event) cudaEventDestroy(ctx->copy_event);
+    for (b200_plan * p : ctx->plans) delete p;
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     delete backend;
@@ -365,12 +400,362 @@ static void b200_backend_synchronize(ggml_backend_t backend) {
     cudaSetDevice(ctx->device);
     CUDA_OK(cudaStreamSynchronize(ctx->stream));
 }
-static enum ggml_status b200_backend_graph_compute(ggml_backend_t backend, ggml_cgraph * cgraph) {
-    b200_backend_ctx * ctx = (b200_backend_ctx *) backend->context;
-    cudaSetDevice(ctx->device);
-    const int n = ggml_graph_n_nodes(cgraph);
+// ====================================================================================================================
+// graph_compute.  The reference dispatches node by node and hides the launch overhead behind a CUDA graph
+// (ggml_backend_cuda_graph_compute, ggml-cuda.cu:2508-2778).  Here the decode graph (one token) of build_llama / build_qwen2
+// (src/llama.cpp:11000-11216, 12736-12916, FA off) is pattern-matched into the fused launches of the engine:
+//     RMS_NORM -> MUL(norm weight) -> {MUL_MAT k-quant}x1..3 [-> ADD bias]            => ONE pb200_gemv_fused (rms-norm prologue)
+//     ROPE q, ROPE k, CPY k -> cache, CPY v^T -> cache, MUL_MAT(K,q), SOFT_MAX, MUL_MAT(V,p), CONT  => ONE pb200_attn_ggml
+//     MUL_MAT(wo) -> ADD residual                                                     => ONE pb200_gemv_fused (activation quantized by the attention launch)
+//     UNARY(SILU) -> MUL -> MUL_MAT(down) -> ADD residual                             => ONE pb200_gemv_fused (silu prologue)
+// i.e. 5 launches per layer instead of ~25, every launch chained with programmatic dependent launch so that the next kernel's
+// weight stream starts while the previous one drains.  Anything that does not match runs 1:1 as before.  The plan is derived once
+// per graph topology (llama.cpp rebuilds the same topology every token; n_kv changes it every 32 tokens) and re-bound to the
+// tensors' current addresses / view offsets on every call — the reference patches its captured graph for the same reason
+// (ggml-cuda.cu:2602-2617, 2741-2752).  No CUDA graph is needed on top: the host enqueues ~5 launches per layer (~1 ms per 70B token)
+// while the device needs ~9 ms, so the stream never runs dry.
+static uint64_t fnv(uint64_t h, uint64_t v) { h ^= v; return h * 0x100000001b3ull; }
+static int node_index_of(const ggml_cgraph * g, const ggml_tensor * t, int hint_end) {
+    for (int i = hint_end - 1; i >= 0; i--) if (ggml_graph_node((ggml_cgraph *) g, i) == t) return i;
+    return -1;
+}
+static uint64_t graph_key(ggml_cgraph * g) {
+    const int n = ggml_graph_n_nodes(g);
+    uint64_t h = 0xcbf29ce484222325ull;
+    h = fnv(h, (uint64_t) n);
     for (int i = 0; i < n; i++) {
-        ggml_tensor * node = ggml_graph_node(cgraph, i);
+        const ggml_tensor * t = ggml_graph_node(g, i);
+        h = fnv(h, (uint64_t) t->op);
+        h = fnv(h, (uint64_t) t->type);
+        for (int d = 0; d < 4; d++) { h = fnv(h, (uint64_t) t->ne[d]); h = fnv(h, (uint64_t) t->nb[d]); }
+        for (int k = 0; k < 4; k++) {
+            const ggml_tensor * sN = t->src[k];
+            h = fnv(h, sN ? (uint64_t) sN->op * 131 + (uint64_t) sN->type * 7 + (uint64_t) sN->ne[0] : 0x9e37ull);
+        }
+    }
+    return h;
+}
+static bool is_kq(enum ggml_type t) { return t == GGML_TYPE_Q4_K || t == GGML_TYPE_Q5_K || t == GGML_TYPE_Q6_K; }
+static bool is_vec_f32(const ggml_tensor * t, int64_t n) {
+    return t && t->type == GGML_TYPE_F32 && t->ne[0] == n && t->ne[1] == 1 && t->ne[2] == 1 && t->ne[3] == 1 && t->nb[0] == sizeof(float);
+}
+static const ggml_tensor * strip_views(const ggml_tensor * t) {   // RESHAPE / PERMUTE / TRANSPOSE / VIEW of a COMPUTED tensor
+    while (t && (t->op == GGML_OP_RESHAPE || t->op == GGML_OP_PERMUTE || t->op == GGML_OP_TRANSPOSE || t->op == GGML_OP_VIEW) && t->src[0]) t = t->src[0];
+    return t;
+}
+
+struct graph_info {
+    ggml_cgraph * g;
+    int n;
+    std::vector<std::vector<int>> cons;   // consumers of node i (direct src references, views included as nodes)
+    int idx(const ggml_tensor * t) const { for (int i = 0; i < n; i++) if (ggml_graph_node(g, i) == t) return i; return -1; }
+};
+// consumers of a node "through" no-op views: the real ops that eventually read it
+static void real_consumers(const graph_info & G, int i, std::vector<int> & out) {
+    for (int c : G.cons[i]) {
+        const ggml_tensor * t = ggml_graph_node(G.g, c);
+        if (is_noop(t->op)) real_consumers(G, c, out); else out.push_back(c);
+    }
+}
+
+static bool plan_attention(const graph_info & G, int soft, std::vector<char> & taken, b200_step & st) {
+    ggml_cgraph * g = G.g;
+    const ggml_tensor * sm = ggml_graph_node(g, soft);
+    const ggml_tensor * kq = sm->src[0], * mask = sm->src[1];
+    if (!kq || kq->op != GGML_OP_MUL_MAT || !mask || mask->type != GGML_TYPE_F32) return false;
+    float scale, max_bias;
+    memcpy(&scale, sm->op_params, 4); memcpy(&max_bias, (const float *) sm->op_params + 1, 4);
+    if (max_bias != 0.0f) return false;
+    const ggml_tensor * kview = kq->src[0], * qp = kq->src[1];
+    if (!kview || kview->type != GGML_TYPE_F16 || kview->op != GGML_OP_VIEW || !kview->view_src) return false;
+    const ggml_tensor * ropeq = strip_views(qp);
+    if (!ropeq || ropeq->op != GGML_OP_ROPE || qp->ne[0] != 128 || qp->ne[1] != 1 || qp->ne[3] != 1) return false;   // [D, n_tokens = 1, H]
+    const int64_t D = 128, H = qp->ne[2], n_kv = kview->ne[1], HK = kview->ne[2];
+    if (kview->ne[0] != D || HK <= 0 || H % HK || (H & 1) || (n_kv & 31)) return false;
+    if (kview->nb[1] != (size_t) (HK * D * 2) || kview->nb[2] != (size_t) (D * 2) || kview->view_offs != 0) return false;
+    if (mask->ne[0] != n_kv || !ggml_is_contiguous(mask)) return false;
+    // the single consumer chain soft_max -> mul_mat(v, p) -> permute -> cont
+    std::vector<int> c1; real_consumers(G, soft, c1);
+    if (c1.size() != 1) return false;
+    const int kqv_i = c1[0];
+    const ggml_tensor * kqv = ggml_graph_node(g, kqv_i);
+    if (kqv->op != GGML_OP_MUL_MAT || kqv->src[1] != sm) return false;
+    const ggml_tensor * vview = kqv->src[0];
+    if (!vview || vview->type != GGML_TYPE_F16 || vview->op != GGML_OP_VIEW || !vview->view_src || vview->view_offs != 0) return false;
+    if (vview->ne[0] != n_kv || vview->ne[1] != D || vview->ne[2] != HK || vview->nb[0] != 2 || vview->nb[2] != vview->nb[1] * (size_t) D) return false;
+    std::vector<int> c2; real_consumers(G, kqv_i, c2);
+    if (c2.size() != 1) return false;
+    const int cont_i = c2[0];
+    const ggml_tensor * cont = ggml_graph_node(g, cont_i);
+    if (cont->op != GGML_OP_CONT || cont->type != GGML_TYPE_F32 || ggml_nelements(cont) != D * H || !ggml_is_contiguous(cont)) return false;
+    // q side: rope(reshape(Qcur)) consumed only by kq
+    const int ropeq_i = G.idx(ropeq), kq_i = G.idx(kq);
+    if (ropeq_i < 0 || kq_i < 0) return false;
+    { std::vector<int> c; real_consumers(G, ropeq_i, c); if (c.size() != 1 || c[0] != kq_i) return false; }
+    { std::vector<int> c; real_consumers(G, kq_i, c); if (c.size() != 1 || c[0] != soft) return false; }
+    // k side: a ROPE node with the same parameters whose only consumer is a CPY into a view of the same K cache tensor
+    int ropek_i = -1, cpyk_i = -1;
+    for (int i = 0; i < G.n; i++) {
+        const ggml_tensor * t = ggml_graph_node(g, i);
+        if (t->op != GGML_OP_CPY || !t->src[1] || t->src[1]->view_src != kview->view_src || taken[i]) continue;
+        const ggml_tensor * rk = strip_views(t->src[0]);
+        if (!rk || rk->op != GGML_OP_ROPE) continue;
+        ropek_i = G.idx(rk); cpyk_i = i;
+    }
+    if (ropek_i < 0) return false;
+    const ggml_tensor * ropek = ggml_graph_node(g, ropek_i), * cpyk = ggml_graph_node(g, cpyk_i);
+    { std::vector<int> c; real_consumers(G, ropek_i, c); if (c.size() != 1 || c[0] != cpyk_i) return false; }
+    if (memcmp(ropeq->op_params, ropek->op_params, sizeof(int32_t) * 11) != 0 || ropeq->src[1] != ropek->src[1] || ropeq->src[2] != ropek->src[2]) return false;
+    const int32_t * rp = (const int32_t *) ropeq->op_params;
+    if ((rp[2] != 0 && rp[2] != 2) || rp[1] > D || (rp[1] & 1)) return false;
+    if (ropeq->src[1]->type != GGML_TYPE_I32 || (ropeq->src[2] && ropeq->src[2]->type != GGML_TYPE_F32)) return false;
+    if (!ropeq->src[0] || !ropek->src[0] || ggml_nelements(ropek->src[0]) != HK * D || ropek->src[0]->type != GGML_TYPE_F32) return false;
+    if (cpyk->src[1]->type != GGML_TYPE_F16 || ggml_nelements(cpyk->src[1]) != HK * D) return false;
+    // v side: CPY(transpose(Vcur)) into a [1, HK*D] strided view of the same V cache tensor
+    int cpyv_i = -1;
+    for (int i = 0; i < G.n; i++) {
+        const ggml_tensor * t = ggml_graph_node(g, i);
+        if (t->op == GGML_OP_CPY && t->src[1] && t->src[1]->view_src == vview->view_src && !taken[i]) cpyv_i = i;
+    }
+    if (cpyv_i < 0) return false;
+    const ggml_tensor * cpyv = ggml_graph_node(g, cpyv_i);
+    const ggml_tensor * vdst = cpyv->src[1], * vsrc = strip_views(cpyv->src[0]);
+    if (vdst->type != GGML_TYPE_F16 || vdst->ne[0] != 1 || vdst->ne[1] != HK * D || vdst->nb[1] != vview->nb[1]) return false;
+    if (!vsrc || vsrc->type != GGML_TYPE_F32 || ggml_nelements(vsrc) != HK * D || !ggml_is_contiguous(vsrc)) return false;
+    if (!ggml_is_contiguous(ropeq->src[0]) || !ggml_is_contiguous(ropek->src[0])) return false;
+    const int nodes[8] = {ropeq_i, ropek_i, cpyk_i, cpyv_i, kq_i, soft, kqv_i, cont_i};
+    for (int i : nodes) if (taken[i]) return false;
+    // everything the launch reads must be computed before the CONT position (where the step runs), its output after
+    if (G.idx(vsrc) > cont_i) return false;
+    for (int i : nodes) taken[i] = 1;
+    st = b200_step{};
+    st.kind = 2; st.rope_q = ropeq_i; st.rope_k = ropek_i; st.cpy_k = cpyk_i; st.cpy_v = cpyv_i; st.kq = kq_i; st.soft = soft; st.kqv = kqv_i; st.cont = cont_i;
+    st.node = cont_i; st.quant_out = 0;
+    return true;
+}
+
+// vector added to a mul_mat result by the single consumer ADD (bias or residual): returns the ADD node index or -1
+static int find_add(const graph_info & G, int mm_i, int & vec_src) {
+    std::vector<int> c; real_consumers(G, mm_i, c);
+    if (c.size() != 1) return -1;
+    const ggml_tensor * a = ggml_graph_node(G.g, c[0]), * mm = ggml_graph_node(G.g, mm_i);
+    if (a->op != GGML_OP_ADD || a->type != GGML_TYPE_F32 || !ggml_is_contiguous(a)) return -1;
+    for (int k = 0; k < 2; k++) {
+        if (a->src[k] == mm && is_vec_f32(a->src[1 - k], mm->ne[0]) && ggml_is_contiguous(a->src[1 - k])) { vec_src = 1 - k; return c[0]; }
+    }
+    return -1;
+}
+
+static b200_plan * build_plan(ggml_cgraph * g, uint64_t key) {
+    graph_info G;
+    G.g = g; G.n = ggml_graph_n_nodes(g);
+    G.cons.assign(G.n, {});
+    for (int i = 0; i < G.n; i++) {
+        const ggml_tensor * t = ggml_graph_node(g, i);
+        for (int k = 0; k < GGML_MAX_SRC; k++) {
+            if (!t->src[k]) continue;
+            const int j = node_index_of(g, t->src[k], i);
+            if (j >= 0) G.cons[j].push_back(i);
+        }
+    }
+    std::vector<char> taken(G.n, 0);
+    std::vector<b200_step> at(G.n);          // fused step anchored at node i (kind != 0)
+    std::vector<char> has(G.n, 0);
+    static const bool no_fuse = getenv("GGML_B200_NO_FUSE") != nullptr;
+    if (!no_fuse) {
+        // 1) attention chains (anchor: SOFT_MAX)
+        for (int i = 0; i < G.n; i++) {
+            const ggml_tensor * t = ggml_graph_node(g, i);
+            if (t->op != GGML_OP_SOFT_MAX || taken[i]) continue;
+            b200_step st;
+            if (plan_attention(G, i, taken, st)) { at[st.node] = st; has[st.node] = 1; }
+        }
+        // 2) mat-vec groups (anchor: the activation shared by k-quant MUL_MATs with one column)
+        for (int i = 0; i < G.n; i++) {
+            const ggml_tensor * t = ggml_graph_node(g, i);
+            if (t->op != GGML_OP_MUL_MAT || taken[i]) continue;
+            const ggml_tensor * W = t->src[0], * X = t->src[1];
+            if (!is_kq(W->type) || !ggml_is_contiguous(W) || W->ne[2] != 1 || W->ne[3] != 1) continue;
+            const int64_t K = W->ne[0];
+            if (!is_vec_f32(X, K) || K % 256 != 0 || K > 28672 || t->type != GGML_TYPE_F32 || !ggml_is_contiguous(t)) continue;
+            b200_step st{};
+            st.kind = 1; st.prologue = 0; st.p0 = st.p1 = -1; st.ws = 0;
+            const int xi = node_index_of(g, X, i);
+            std::vector<int> group;
+            if (xi >= 0 && X->op == GGML_OP_MUL) {
+                // prologue candidates: MUL(RMS_NORM(x), w) or MUL(SILU(g), u), intermediate results read by nobody else
+                for (int k = 0; k < 2; k++) {
+                    const ggml_tensor * a = X->src[k], * b = X->src[1 - k];
+                    const int ai = node_index_of(g, a, xi);
+                    if (ai < 0 || taken[ai] || taken[xi]) continue;
+                    std::vector<int> ca; real_consumers(G, ai, ca);
+                    if (ca.size() != 1 || ca[0] != xi) continue;
+                    if (a->op == GGML_OP_RMS_NORM && is_vec_f32(b, K) && ggml_is_contiguous(b) && is_vec_f32(a->src[0], K) && ggml_is_contiguous(a->src[0])) {
+                        st.prologue = 1; st.p0 = ai; st.p1 = xi; st.ws = 0; break;
+                    }
+                    if (a->op == GGML_OP_UNARY && ggml_get_unary_op(a) == GGML_UNARY_OP_SILU && is_vec_f32(b, K) && ggml_is_contiguous(b) &&
+                        is_vec_f32(a->src[0], K) && ggml_is_contiguous(a->src[0])) {
+                        st.prologue = 2; st.p0 = ai; st.p1 = xi; st.ws = 2; break;
+                    }
+                }
+            } else if (xi >= 0 && has[xi] && at[xi].kind == 2 && K % 256 == 0) {
+                st.prologue = 3; st.ws = 1;                                   // X is the CONT of a fused attention step
+            }
+            // all k-quant mat-vecs fed by X
+            std::vector<int> cx;
+            if (xi >= 0) real_consumers(G, xi, cx); else cx.push_back(i);
+            bool all_mm = true;
+            for (int c : cx) {
+                const ggml_tensor * m = ggml_graph_node(g, c);
+                if (m->op != GGML_OP_MUL_MAT || m->src[1] != X || !is_kq(m->src[0]->type) || m->src[0]->ne[0] != K || !ggml_is_contiguous(m->src[0]) ||
+                    m->src[0]->ne[2] != 1 || m->src[0]->ne[3] != 1 || !ggml_is_contiguous(m) || taken[c]) { all_mm = false; break; }
+            }
+            if (!all_mm) {
+                if (st.prologue == 1 || st.prologue == 2) { st.prologue = 0; st.p0 = st.p1 = -1; }   // somebody else reads the activation: keep it materialised
+                if (st.prologue == 3) st.prologue = 0;
+                group.push_back(i);
+            } else {
+                group = cx;
+            }
+            if ((int) group.size() > 3) { group.resize(3); if (st.prologue == 1 || st.prologue == 2) { st.prologue = 0; st.p0 = st.p1 = -1; } }
+            int last = 0;
+            st.nmat = (int) group.size();
+            for (int j = 0; j < st.nmat; j++) {
+                st.mm[j] = group[j]; st.out[j] = group[j]; st.add_vec[j] = -1; st.add_src[j] = 0;
+                int vs = 0;
+                const int ad = find_add(G, group[j], vs);
+                // with several matrices the step runs later than some of its ADDs: only fold vectors that cannot have been recycled
+                // by the graph allocator in between (leafs: biases)
+                if (ad >= 0 && !taken[ad] && (st.nmat == 1 || ggml_graph_node(g, ad)->src[vs]->op == GGML_OP_NONE)) { st.out[j] = ad; st.add_vec[j] = ad; st.add_src[j] = vs; }
+                last = std::max(last, st.out[j]);
+            }
+            // the step runs at the position of its last node: nobody may read an output before that
+            bool ok = true;
+            for (int j = 0; j < st.nmat && ok; j++) {
+                std::vector<int> co; real_consumers(G, st.out[j], co);
+                for (int c : co) if (c <= last) ok = false;
+            }
+            if (!ok) {   // degrade to a single mat-vec without folded ADD
+                st.nmat = 1; st.mm[0] = i; st.out[0] = i; st.add_vec[0] = -1; last = i;
+                if (st.prologue != 0 && !(all_mm && group.size() == 1)) { st.prologue = 0; st.p0 = st.p1 = -1; }
+            }
+            if (st.prologue == 3) at[xi].quant_out = 1;
+            for (int j = 0; j < st.nmat; j++) { taken[st.mm[j]] = 1; taken[st.out[j]] = 1; }
+            if (st.p0 >= 0) { taken[st.p0] = 1; taken[st.p1] = 1; }
+            st.node = last;
+            at[last] = st; has[last] = 1;
+        }
+    }
+    b200_plan * plan = new b200_plan();
+    plan->key = key; plan->n_nodes = G.n;
+    for (int i = 0; i < G.n; i++) {
+        if (has[i]) { plan->steps.push_back(at[i]); continue; }
+        if (taken[i]) continue;
+        const ggml_tensor * t = ggml_graph_node(g, i);
+        if (ggml_is_empty(t) || is_noop(t->op)) continue;
+        b200_step st{};
+        st.kind = 0; st.node = i;
+        plan->steps.push_back(st);
+    }
+    return plan;
+}
+
+static void * grow_ws(b200_backend_ctx * ctx, int role, size_t need) {
+    if (need > ctx->fact_bytes[role]) {
+        if (ctx->fact_ws[role]) { CUDA_OK(cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->fact_ws[role]); }
+        CUDA_OK(cudaMalloc(&ctx->fact_ws[role], need + 256));
+        ctx->fact_bytes[role] = need;
+    }
+    return ctx->fact_ws[role];
+}
+static bool overlaps(const void * a, size_t na, const void * b, size_t nb) {
+    const char * pa = (const char *) a, * pb = (const char *) b;
+    return pa < pb + nb && pb < pa + na;
+}
+
+static bool run_gemv_step(b200_backend_ctx * ctx, ggml_cgraph * g, const b200_step & st) {
+    const ggml_tensor * m0 = ggml_graph_node(g, st.mm[0]);
+    const int64_t K = m0->src[0]->ne[0];
+    pb200_gemv_mat mats[3];
+    for (int j = 0; j < st.nmat; j++) {
+        const ggml_tensor * mm = ggml_graph_node(g, st.mm[j]);
+        const ggml_tensor * out = ggml_graph_node(g, st.out[j]);
+        mats[j].type = (int32_t) mm->src[0]->type; mats[j]._pad = 0;
+        mats[j].W = mm->src[0]->data; mats[j].n = mm->src[0]->ne[1];
+        mats[j].y = (float *) out->data;
+        mats[j].add = st.add_vec[j] >= 0 ? (const float *) out->src[st.add_src[j]]->data : nullptr;
+    }
+    void * ws = grow_ws(ctx, st.ws, pb200_act_workspace_bytes(K));
+    if (!ctx->sync_ws) { CUDA_OK(cudaMalloc(&ctx->sync_ws, 256)); CUDA_OK(cudaMemsetAsync(ctx->sync_ws, 0, 256, ctx->stream)); }
+    int rc;
+    if (st.prologue == 1) {
+        const ggml_tensor * nrm = ggml_graph_node(g, st.p0), * mul = ggml_graph_node(g, st.p1);
+        float eps; memcpy(&eps, nrm->op_params, 4);
+        const ggml_tensor * w = mul->src[0] == nrm ? mul->src[1] : mul->src[0];
+        rc = pb200_gemv_fused(st.nmat, mats, K, ws, 1, (const float *) nrm->src[0]->data, (const float *) w->data, eps, ctx->sync_ws, 1, ctx->stream);
+    } else if (st.prologue == 2) {
+        const ggml_tensor * un = ggml_graph_node(g, st.p0), * mul = ggml_graph_node(g, st.p1);
+        const ggml_tensor * u = mul->src[0] == un ? mul->src[1] : mul->src[0];
+        rc = pb200_gemv_fused(st.nmat, mats, K, ws, 2, (const float *) un->src[0]->data, (const float *) u->data, 0.f, ctx->sync_ws, 1, ctx->stream);
+    } else {
+        if (st.prologue == 0) {
+            PB_OK(pb200_quantize_act((int) m0->src[0]->type, (const float *) m0->src[1]->data, K, ws, ctx->stream));
+        }
+        rc = pb200_gemv_fused(st.nmat, mats, K, ws, 0, nullptr, nullptr, 0.f, ctx->sync_ws, 1, ctx->stream);
+    }
+    if (rc == PB200_ENOTSUP) return false;
+    PB_OK(rc);
+    return true;
+}
+
+static bool run_attn_step(b200_backend_ctx * ctx, ggml_cgraph * g, const b200_step & st) {
+    const ggml_tensor * ropeq = ggml_graph_node(g, st.rope_q), * ropek = ggml_graph_node(g, st.rope_k);
+    const ggml_tensor * cpyk = ggml_graph_node(g, st.cpy_k), * cpyv = ggml_graph_node(g, st.cpy_v);
+    const ggml_tensor * kq = ggml_graph_node(g, st.kq), * sm = ggml_graph_node(g, st.soft), * kqv = ggml_graph_node(g, st.kqv);
+    ggml_tensor * cont = ggml_graph_node(g, st.cont);
+    const ggml_tensor * kview = kq->src[0], * vview = kqv->src[0], * mask = sm->src[1];
+    const int64_t D = 128, H = kq->src[1]->ne[2], HK = kview->ne[2], n_kv = kview->ne[1];
+    const int64_t vt_stride = (int64_t) (vview->nb[1] / 2);
+    const int64_t k_off = (const char *) cpyk->data - (const char *) kview->data;   // the CPY nodes are views of their destinations
+    const int64_t v_off = (const char *) cpyv->data - (const char *) vview->data;
+    if (k_off < 0 || k_off % (HK * D * 2) != 0 || v_off != (k_off / (HK * D * 2)) * 2) return false;
+    const int kv_head = (int) (k_off / (HK * D * 2));
+    if (kv_head >= n_kv) return false;
+    const int32_t * p = (const int32_t *) ropeq->op_params;
+    float fb, fs, ef, af, bf, bsl, scale;
+    memcpy(&fb, p + 5, 4); memcpy(&fs, p + 6, 4); memcpy(&ef, p + 7, 4); memcpy(&af, p + 8, 4); memcpy(&bf, p + 9, 4); memcpy(&bsl, p + 10, 4);
+    memcpy(&scale, sm->op_params, 4);
+    const float * q = (const float *) ropeq->src[0]->data, * k = (const float *) ropek->src[0]->data;
+    const float * v = (const float *) strip_views(cpyv->src[0])->data;
+    float * out = (float *) cont->data;
+    const size_t out_bytes = (size_t) (H * D) * 4;
+    // the graph allocator may have placed the CONT result on top of q / k / v (their last readers are folded into this launch):
+    // heads finish at different times, so only the exact q <-> out aliasing (head h reads and writes its own slice) is safe
+    bool via_tmp = overlaps(out, out_bytes, k, (size_t) (HK * D) * 4) || overlaps(out, out_bytes, v, (size_t) (HK * D) * 4) ||
+                   (overlaps(out, out_bytes, q, out_bytes) && (const void *) out != (const void *) q) ||
+                   overlaps(out, out_bytes, mask->data, (size_t) n_kv * 4);
+    if (via_tmp) {
+        if (ctx->attn_tmp_floats < (size_t) (H * D)) {
+            if (ctx->attn_tmp) { CUDA_OK(cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->attn_tmp); }
+            CUDA_OK(cudaMalloc((void **) &ctx->attn_tmp, out_bytes + 256));
+            ctx->attn_tmp_floats = (size_t) (H * D);
+        }
+        out = ctx->attn_tmp;
+    }
+    void * ws = st.quant_out ? grow_ws(ctx, 1, pb200_act_workspace_bytes(H * D)) : nullptr;
+    const int rc = pb200_attn_ggml(q, k, v, (void *) kview->data, (void *) vview->data, vt_stride, out, ws, (int) H, (int) HK, (int) D,
+                                   (const int32_t *) ropeq->src[1]->data, (int) n_kv, kv_head, (const float *) mask->data, p[1], p[2], fb, fs, ef, af, bf, bsl, p[4],
+                                   ropeq->src[2] ? (const float *) ropeq->src[2]->data : nullptr, scale, 1, ctx->stream);
+    if (rc == PB200_ENOTSUP) return false;
+    PB_OK(rc);
+    if (via_tmp) CUDA_OK(cudaMemcpyAsync(cont->data, out, out_bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    return true;
+}
+
+static void run_nodes_unfused(b200_backend_ctx * ctx, ggml_cgraph * g, const int * idx, int n) {
+    for (int k = 0; k < n; k++) {
+        if (idx[k] < 0) continue;
+        ggml_tensor * node = ggml_graph_node(g, idx[k]);
         if (ggml_is_empty(node) || is_noop(node->op)) continue;
         if (!b200_compute_node(ctx, node)) {
             fprintf(stderr, "ggml-b200: op %s not supported inside graph_compute (supports_op must be consulted)\n", ggml_op_name(node->op));
@@ -378,15 +763,89 @@ static enum ggml_status b200_backend_graph_compute(ggml_backend_t backend, ggml_
         }
         g_nodes++;
     }
+}
+
+static enum ggml_status b200_backend_graph_compute(ggml_backend_t backend, ggml_cgraph * cgraph) {
+    b200_backend_ctx * ctx = (b200_backend_ctx *) backend->context;
+    cudaSetDevice(ctx->device);
+    const uint64_t key = graph_key(cgraph);
+    b200_plan * plan = nullptr;
+    for (b200_plan * p : ctx->plans) if (p->key == key && p->n_nodes == ggml_graph_n_nodes(cgraph)) { plan = p; break; }
+    if (!plan) {
+        plan = build_plan(cgraph, key);
+        if (ctx->plans.size() >= 16) { delete ctx->plans.front(); ctx->plans.erase(ctx->plans.begin()); }
+        ctx->plans.push_back(plan);
+    }
+    for (const b200_step & st : plan->steps) {
+        if (st.kind == 0) {
+            run_nodes_unfused(ctx, cgraph, &st.node, 1);
+        } else if (st.kind == 1) {
+            if (run_gemv_step(ctx, cgraph, st)) { g_nodes += st.nmat; g_fused_steps++; continue; }
+            // shape outside the fused kernel: the nodes of the group, in graph order
+            std::vector<int> nodes;
+            if (st.p0 >= 0) { nodes.push_back(st.p0); nodes.push_back(st.p1); }
+            for (int j = 0; j < st.nmat; j++) { nodes.push_back(st.mm[j]); if (st.out[j] != st.mm[j]) nodes.push_back(st.out[j]); }
+            std::sort(nodes.begin(), nodes.end());
+            run_nodes_unfused(ctx, cgraph, nodes.data(), (int) nodes.size());
+        } else {
+            if (run_attn_step(ctx, cgraph, st)) {
+                g_nodes += 8; g_fused_steps++;
+                if (st.quant_out) continue;
+                continue;
+            }
+            int nodes[8] = {st.rope_q, st.rope_k, st.cpy_k, st.cpy_v, st.kq, st.soft, st.kqv, st.cont};
+            std::sort(nodes, nodes + 8);
+            run_nodes_unfused(ctx, cgraph, nodes, 8);
+        }
+    }
     return GGML_STATUS_SUCCESS;   // asynchronous: work is enqueued on the backend stream
 }
+
+// ---- the entries the scheduler uses to move tensors between backends and to order their streams (ggml-cuda.cu:2392-2445, 2780-2823) ----
+static bool b200_backend_cpy_tensor_async(ggml_backend_t backend_src, ggml_backend_t backend_dst, const ggml_tensor * src, ggml_tensor * dst) {
+    if (!ggml_backend_is_b200(backend_src) || !ggml_backend_is_b200(backend_dst)) return false;
+    ggml_backend_buffer_t bs = src->view_src ? src->view_src->buffer : src->buffer, bd = dst->view_src ? dst->view_src->buffer : dst->buffer;
+    if (!bs || !bd || bs->iface.get_name != b200_buffer_get_name || bd->iface.get_name != b200_buffer_get_name) return false;
+    if (!ggml_is_contiguous(src) || !ggml_is_contiguous(dst) || ggml_nbytes(src) != ggml_nbytes(dst)) return false;
+    b200_backend_ctx * cs = (b200_backend_ctx *) backend_src->context, * cd = (b200_backend_ctx *) backend_dst->context;
+    const int dev_s = ((b200_buffer_ctx *) bs->context)->device, dev_d = ((b200_buffer_ctx *) bd->context)->device;
+    if (cs->device != dev_s || cd->device != dev_d) return false;
+    cudaSetDevice(cs->device);
+    if (backend_src == backend_dst) {
+        CUDA_OK(cudaMemcpyAsync(dst->data, src->data, ggml_nbytes(dst), cudaMemcpyDeviceToDevice, cs->stream));
+        return true;
+    }
+    // copy on the source stream (peer copy over NVLink between devices), then make the destination stream wait for it
+    if (dev_s == dev_d) CUDA_OK(cudaMemcpyAsync(dst->data, src->data, ggml_nbytes(dst), cudaMemcpyDeviceToDevice, cs->stream));
+    else CUDA_OK(cudaMemcpyPeerAsync(dst->data, dev_d, src->data, dev_s, ggml_nbytes(dst), cs->stream));
+    if (!cs->copy_event) CUDA_OK(cudaEventCreateWithFlags(&cs->copy_event, cudaEventDisableTiming));
+    CUDA_OK(cudaEventRecord(cs->copy_event, cs->stream));
+    cudaSetDevice(cd->device);
+    CUDA_OK(cudaStreamWaitEvent(cd->stream, cs->copy_event, 0));
+    return true;
+}
+static void b200_backend_event_record(ggml_backend_t backend, ggml_backend_event_t event) {
+    b200_backend_ctx * ctx = (b200_backend_ctx *) backend->context;
+    cudaSetDevice(ctx->device);
+    CUDA_OK(cudaEventRecord((cudaEvent_t) event->context, ctx->stream));
+}
+static void b200_backend_event_wait(ggml_backend_t backend, ggml_backend_event_t event) {
+    if (ggml_backend_is_b200(backend)) {
+        b200_backend_ctx * ctx = (b200_backend_ctx *) backend->context;
+        cudaSetDevice(ctx->device);
+        CUDA_OK(cudaStreamWaitEvent(ctx->stream, (cudaEvent_t) event->context, 0));
+    } else {
+        CUDA_OK(cudaEventSynchronize((cudaEvent_t) event->context));   // a foreign backend: block the host instead
+    }
+}
+
 static const ggml_backend_i b200_backend_iface = {
     /* .get_name                = */ b200_backend_get_name,
     /* .free                    = */ b200_backend_free,
     /* .get_default_buffer_type = */ b200_backend_get_default_buft,
     /* .set_tensor_async        = */ b200_backend_set_tensor_async,
     /* .get_tensor_async        = */ b200_backend_get_tensor_async,
-    /* .cpy_tensor_async        = */ nullptr,
+    /* .cpy_tensor_async        = */ b200_backend_cpy_tensor_async,
     /* .synchronize             = */ b200_backend_synchronize,
     /* .graph_plan_create       = */ nullptr,
     /* .graph_plan_free         = */ nullptr,
@@ -396,8 +855,8 @@ static const ggml_backend_i b200_backend_iface = {
     /* .supports_op             = */ nullptr,
     /* .supports_buft           = */ nullptr,
     /* .offload_op              = */ nullptr,
-    /* .event_record            = */ nullptr,
-    /* .event_wait              = */ nullptr,
+    /* .event_record            = */ b200_backend_event_record,
+    /* .event_wait              = */ b200_backend_event_wait,
 };
 
 // ---------------------------------------------------------------------------------------------------- device + reg
@@ -413,7 +872,7 @@ static void b200_dev_get_props(ggml_backend_dev_t dev, ggml_backend_dev_props * 
     props->description = b200_dev_get_description(dev);
     props->type = b200_dev_get_type(dev);
     b200_dev_get_memory(dev, &props->memory_free, &props->memory_total);
-    props->caps = { /* async */ true, /* host_buffer */ false, /* buffer_from_host_ptr */ false, /* events */ false };
+    props->caps = { /* async */ true, /* host_buffer */ true, /* buffer_from_host_ptr */ false, /* events */ true };
 }
 static ggml_backend_t b200_dev_init_backend(ggml_backend_dev_t dev, const char *) { return ggml_backend_b200_init(((b200_device_ctx *) dev->context)->device); }
 static ggml_backend_buffer_type_t b200_dev_get_buft(ggml_backend_dev_t dev) { return ggml_backend_b200_buffer_type(((b200_device_ctx *) dev->context)->device); }
@@ -421,6 +880,53 @@ static bool b200_dev_supports_buft(ggml_backend_dev_t dev, ggml_backend_buffer_t
     return buft->iface.get_name == b200_buft_get_name && buft->device == dev;
 }
 static bool b200_dev_offload_op(ggml_backend_dev_t, const ggml_tensor *) { return false; }   // never pull CPU-resident weights over PCIe (App. B)
+
+// ---- events (ggml-cuda.cu:3210-3256) and the pinned host buffer type (ggml-cuda.cu:1008-1080): what ggml_backend_sched uses to
+// overlap the copies of a split's inputs with the previous split's compute ----
+static ggml_backend_event_t b200_dev_event_new(ggml_backend_dev_t dev) {
+    cudaSetDevice(((b200_device_ctx *) dev->context)->device);
+    cudaEvent_t ev = nullptr;
+    if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return new ggml_backend_event{dev, ev};
+}
+static void b200_dev_event_free(ggml_backend_dev_t dev, ggml_backend_event_t event) {
+    cudaSetDevice(((b200_device_ctx *) dev->context)->device);
+    cudaEventDestroy((cudaEvent_t) event->context);
+    delete event;
+}
+static void b200_dev_event_synchronize(ggml_backend_dev_t dev, ggml_backend_event_t event) {
+    cudaSetDevice(((b200_device_ctx *) dev->context)->device);
+    CUDA_OK(cudaEventSynchronize((cudaEvent_t) event->context));
+}
+static const char * b200_host_buft_name(ggml_backend_buffer_type_t) { return "B200_Host"; }
+static const char * b200_host_buffer_name(ggml_backend_buffer_t) { return "B200_Host"; }
+static void b200_host_buffer_free(ggml_backend_buffer_t buffer) { cudaFreeHost(buffer->context); }
+static ggml_backend_buffer_t b200_host_buft_alloc(ggml_backend_buffer_type_t buft, size_t size) {
+    void * ptr = nullptr;
+    if (cudaMallocHost(&ptr, size > 0 ? size : 1) != cudaSuccess) {   // no pinned memory left: plain host memory still works, only slower
+        cudaGetLastError();
+        return ggml_backend_buft_alloc_buffer(ggml_backend_cpu_buffer_type(), size);
+    }
+    // a CPU buffer over pinned pages: the CPU backend computes in it, H2D / D2H copies from it are asynchronous DMA
+    ggml_backend_buffer_t buffer = ggml_backend_cpu_buffer_from_ptr(ptr, size);
+    buffer->buft = buft;
+    buffer->iface.get_name = b200_host_buffer_name;
+    buffer->iface.free_buffer = b200_host_buffer_free;
+    return buffer;
+}
+static ggml_backend_buffer_type_t b200_dev_get_host_buft(ggml_backend_dev_t dev) {
+    static ggml_backend_buffer_type host_buft;
+    static std::once_flag once;
+    std::call_once(once, [dev] {
+        ggml_backend_buffer_type_t cpu = ggml_backend_cpu_buffer_type();
+        host_buft.iface = cpu->iface;            // alignment / alloc size / is_host as for any CPU buffer
+        host_buft.iface.get_name = b200_host_buft_name;
+        host_buft.iface.alloc_buffer = b200_host_buft_alloc;
+        host_buft.device = dev->reg->iface.get_device(dev->reg, 0);
+        host_buft.context = nullptr;
+    });
+    return &host_buft;
+}
 
 static const ggml_backend_device_i b200_device_iface = {
     /* .get_name             = */ b200_dev_get_name,
@@ -430,14 +936,14 @@ static const ggml_backend_device_i b200_device_iface = {
     /* .get_props            = */ b200_dev_get_props,
     /* .init_backend         = */ b200_dev_init_backend,
     /* .get_buffer_type      = */ b200_dev_get_buft,
-    /* .get_host_buffer_type = */ nullptr,
+    /* .get_host_buffer_type = */ b200_dev_get_host_buft,
     /* .buffer_from_host_ptr = */ nullptr,
     /* .supports_op          = */ b200_supports_op,
     /* .supports_buft        = */ b200_dev_supports_buft,
     /* .offload_op           = */ b200_dev_offload_op,
-    /* .event_new            = */ nullptr,
-    /* .event_free           = */ nullptr,
-    /* .event_synchronize    = */ nullptr,
+    /* .event_new            = */ b200_dev_event_new,
+    /* .event_free           = */ b200_dev_event_free,
+    /* .event_synchronize    = */ b200_dev_event_synchronize,
 };
 
 struct b200_reg_ctx {
@@ -451,7 +957,18 @@ static ggml_backend_dev_t b200_reg_get_device(ggml_backend_reg_t reg, size_t i) 
     GGML_ASSERT(i < ctx->devices.size());
     return &ctx->devices[i];
 }
-static void * b200_reg_get_proc_address(ggml_backend_reg_t, const char *) { return nullptr; }   // no split buffers / host registration on this path
+// names llama.cpp looks up (src/llama.cpp:3772, 21261; ggml-cuda.cu:3280-3292).  Row-split buffers are not provided (prima disables
+// tensor split, src/llama.cpp:21106-21107); host-memory registration maps to cudaHostRegister like the reference's.
+static bool b200_register_host_buffer(void * buffer, size_t size) {
+    if (cudaHostRegister(buffer, size, cudaHostRegisterPortable | cudaHostRegisterReadOnly) != cudaSuccess) { cudaGetLastError(); return false; }
+    return true;
+}
+static void b200_unregister_host_buffer(void * buffer) { if (cudaHostUnregister(buffer) != cudaSuccess) cudaGetLastError(); }
+static void * b200_reg_get_proc_address(ggml_backend_reg_t, const char * name) {
+    if (strcmp(name, "ggml_backend_register_host_buffer") == 0) return (void *) b200_register_host_buffer;
+    if (strcmp(name, "ggml_backend_unregister_host_buffer") == 0) return (void *) b200_unregister_host_buffer;
+    return nullptr;   // "ggml_backend_split_buffer_type", "ggml_backend_set_n_threads": not applicable
+}
 static const ggml_backend_reg_i b200_reg_iface = {
     /* .get_name         = */ b200_reg_get_name,
     /* .get_device_count = */ b200_reg_device_count,
@@ -506,6 +1023,7 @@ ggml_backend_t ggml_backend_b200_init(int device) {
 
 int ggml_backend_is_b200(ggml_backend_t backend) { return backend != nullptr && ggml_guid_matches(backend->guid, b200_guid()); }
 unsigned long long ggml_backend_b200_nodes_computed(void) { return g_nodes.load(); }
+unsigned long long ggml_backend_b200_fused_steps(void) { return g_fused_steps.load(); }
 
 }  // extern "C"
 

@@ -89,6 +89,8 @@ class Lib:
         c.pb200_debug_read.argtypes = [vp, C.c_char_p, vp, i64]
         c.pb200_profile_step.argtypes = [vp, i32, i32, C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(i32), C.POINTER(C.c_double)]
         c.pb200_set_use_graph.argtypes = [vp, C.c_int]
+        c.pb200_model_tensor_device.argtypes = [vp, C.c_char_p, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(C.c_int)]
+        c.pb200_aborted.restype = C.c_int
 
     @classmethod
     def get(cls) -> "Lib":
@@ -171,6 +173,12 @@ class Model:
         import numpy as np
         a = np.ascontiguousarray(h, dtype=np.float32)
         self.lib.check(self.lib.c.pb200_set_hidden(self.h, a.ctypes.data_as(C.c_void_p)), "set_hidden")
+
+    def tensor_device(self, name: str) -> tuple[int, int, int]:
+        """(device address, bytes, ggml type) of a tensor held by this shard."""
+        p, n, t = C.c_void_p(), C.c_size_t(), C.c_int()
+        self.lib.check(self.lib.c.pb200_model_tensor_device(self.h, name.encode(), C.byref(p), C.byref(n), C.byref(t)), f"tensor_device {name}")
+        return p.value, n.value, t.value
 
     def set_use_graph(self, on: bool) -> None:
         self.lib.c.pb200_set_use_graph(self.h, int(on))
