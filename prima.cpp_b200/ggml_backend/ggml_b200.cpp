@@ -52,14 +52,24 @@ struct b200_step {
     int prologue;                          // 0 quantize src1 with a separate kernel, 1 rms-norm, 2 silu, 3 activation left quantized by the attention step
     int p0, p1;                            // prologue 1: RMS_NORM node, MUL node; prologue 2: UNARY node, MUL node
     int ws;                                // workspace role
+    int out_scratch[3];                    // >= 0: the result never leaves the fused steps (q, k, v, gate, up): it goes to this private buffer
+    int in_scratch[2];                     // prologue 2: gate / up come from these private buffers
     // kind 2
     int rope_q, rope_k, cpy_k, cpy_v, kq, soft, kqv, cont, quant_out;
+    int q_scratch, k_scratch, v_scratch;   // private buffers holding this token's q / k / v (see out_scratch)
+    int out_private;                       // the f32 attention output is read by nobody (wo takes the quantized copy): keep it private
 };
 struct b200_plan {
     uint64_t key;
     int n_nodes;
     std::vector<b200_step> steps;
 };
+// Why private buffers: the graph allocator (ggml_gallocr) recycles a tensor's memory right after its last consumer IN GRAPH ORDER.
+// A fused step reads q / k / v (or gate / up) later than the nodes it replaces would have, by which time the allocator may have handed
+// their memory to another tensor of the same size (measured: Vcur lands exactly on Kcur).  Results that are consumed only inside
+// fused steps therefore never touch the graph's buffers; results that escape (ffn_inp, l_out, logits) are written at their own
+// node's position like the unfused path would.
+enum { SCR_Q = 0, SCR_K = 1, SCR_V = 2, SCR_G = 3, SCR_U = 4, SCR_ATT = 5, SCR_COUNT = 6 };
 
 struct b200_backend_ctx {
     int device;
@@ -73,6 +83,8 @@ struct b200_backend_ctx {
     void * sync_ws = nullptr;
     float * attn_tmp = nullptr;
     size_t attn_tmp_floats = 0;
+    float * scratch[SCR_COUNT] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t scratch_floats[SCR_COUNT] = {0, 0, 0, 0, 0, 0};
     cudaEvent_t copy_event = nullptr;
     std::vector<b200_plan *> plans;
     void * mmq_ws = nullptr;       // fp16 activation tiles for the tensor-core path (grown on demand)
@@ -376,6 +388,7 @@ static void b200_backend_free(ggml_backend_t backend) {
     for (void * p : ctx->fact_ws) if (p) cudaFree(p);
     if (ctx->sync_ws) cudaFree(ctx->sync_ws);
     if (ctx->attn_tmp) cudaFree(ctx->attn_tmp);
+    for (float * p : ctx->scratch) if (p) cudaFree(p);
     if (ctx->copy_event) cudaEventDestroy(ctx->copy_event);
     for (b200_plan * p : ctx->plans) delete p;
     cudaStreamDestroy(ctx->stream);
@@ -562,13 +575,18 @@ static b200_plan * build_plan(ggml_cgraph * g, uint64_t key) {
     std::vector<b200_step> at(G.n);          // fused step anchored at node i (kind != 0)
     std::vector<char> has(G.n, 0);
     static const bool no_fuse = getenv("GGML_B200_NO_FUSE") != nullptr;
-    if (!no_fuse) {
-        // 1) attention chains (anchor: SOFT_MAX)
+    bool fused_ok = !no_fuse;
+    std::vector<int> attn_anchor;
+    if (fused_ok) {
+        // 1) attention chains (anchor: SOFT_MAX; the step runs at its CONT node)
         for (int i = 0; i < G.n; i++) {
             const ggml_tensor * t = ggml_graph_node(g, i);
             if (t->op != GGML_OP_SOFT_MAX || taken[i]) continue;
             b200_step st;
-            if (plan_attention(G, i, taken, st)) { at[st.node] = st; has[st.node] = 1; }
+            if (plan_attention(G, i, taken, st)) {
+                st.q_scratch = st.k_scratch = st.v_scratch = -1; st.out_private = 0;
+                at[st.node] = st; has[st.node] = 1; attn_anchor.push_back(st.node);
+            }
         }
         // 2) mat-vec groups (anchor: the activation shared by k-quant MUL_MATs with one column)
         for (int i = 0; i < G.n; i++) {
@@ -580,14 +598,15 @@ static b200_plan * build_plan(ggml_cgraph * g, uint64_t key) {
             if (!is_vec_f32(X, K) || K % 256 != 0 || K > 28672 || t->type != GGML_TYPE_F32 || !ggml_is_contiguous(t)) continue;
             b200_step st{};
             st.kind = 1; st.prologue = 0; st.p0 = st.p1 = -1; st.ws = 0;
+            for (int j = 0; j < 3; j++) st.out_scratch[j] = -1;
+            st.in_scratch[0] = st.in_scratch[1] = -1;
             const int xi = node_index_of(g, X, i);
-            std::vector<int> group;
-            if (xi >= 0 && X->op == GGML_OP_MUL) {
+            if (xi >= 0 && X->op == GGML_OP_MUL && !taken[xi]) {
                 // prologue candidates: MUL(RMS_NORM(x), w) or MUL(SILU(g), u), intermediate results read by nobody else
                 for (int k = 0; k < 2; k++) {
                     const ggml_tensor * a = X->src[k], * b = X->src[1 - k];
                     const int ai = node_index_of(g, a, xi);
-                    if (ai < 0 || taken[ai] || taken[xi]) continue;
+                    if (ai < 0 || taken[ai]) continue;
                     std::vector<int> ca; real_consumers(G, ai, ca);
                     if (ca.size() != 1 || ca[0] != xi) continue;
                     if (a->op == GGML_OP_RMS_NORM && is_vec_f32(b, K) && ggml_is_contiguous(b) && is_vec_f32(a->src[0], K) && ggml_is_contiguous(a->src[0])) {
@@ -595,14 +614,25 @@ static b200_plan * build_plan(ggml_cgraph * g, uint64_t key) {
                     }
                     if (a->op == GGML_OP_UNARY && ggml_get_unary_op(a) == GGML_UNARY_OP_SILU && is_vec_f32(b, K) && ggml_is_contiguous(b) &&
                         is_vec_f32(a->src[0], K) && ggml_is_contiguous(a->src[0])) {
-                        st.prologue = 2; st.p0 = ai; st.p1 = xi; st.ws = 2; break;
+                        // gate and up must have been redirected to private buffers by the group that produced them (liveness, see above)
+                        const int gi = node_index_of(g, a->src[0], ai), ui = node_index_of(g, b, xi);
+                        int sg = -1, su = -1;
+                        for (int q = 0; q < G.n; q++) {
+                            if (!has[q] || at[q].kind != 1) continue;
+                            for (int j = 0; j < at[q].nmat; j++) {
+                                if (at[q].out[j] == gi) sg = at[q].out_scratch[j];
+                                if (at[q].out[j] == ui) su = at[q].out_scratch[j];
+                            }
+                        }
+                        if (sg >= 0 && su >= 0) { st.prologue = 2; st.p0 = ai; st.p1 = xi; st.ws = 2; st.in_scratch[0] = sg; st.in_scratch[1] = su; }
+                        break;
                     }
                 }
-            } else if (xi >= 0 && has[xi] && at[xi].kind == 2 && K % 256 == 0) {
+            } else if (xi >= 0 && has[xi] && at[xi].kind == 2) {
                 st.prologue = 3; st.ws = 1;                                   // X is the CONT of a fused attention step
             }
             // all k-quant mat-vecs fed by X
-            std::vector<int> cx;
+            std::vector<int> cx, group;
             if (xi >= 0) real_consumers(G, xi, cx); else cx.push_back(i);
             bool all_mm = true;
             for (int c : cx) {
@@ -610,16 +640,18 @@ static b200_plan * build_plan(ggml_cgraph * g, uint64_t key) {
                 if (m->op != GGML_OP_MUL_MAT || m->src[1] != X || !is_kq(m->src[0]->type) || m->src[0]->ne[0] != K || !ggml_is_contiguous(m->src[0]) ||
                     m->src[0]->ne[2] != 1 || m->src[0]->ne[3] != 1 || !ggml_is_contiguous(m) || taken[c]) { all_mm = false; break; }
             }
-            if (!all_mm) {
-                if (st.prologue == 1 || st.prologue == 2) { st.prologue = 0; st.p0 = st.p1 = -1; }   // somebody else reads the activation: keep it materialised
-                if (st.prologue == 3) st.prologue = 0;
+            if (!all_mm || cx.size() > 3) {
+                // somebody else reads the activation (or too many matrices): keep it materialised, one launch per matrix
+                if (st.prologue == 1 || st.prologue == 2) { st.prologue = 0; st.p0 = st.p1 = -1; st.in_scratch[0] = st.in_scratch[1] = -1; }
+                if (st.prologue == 3 && cx.size() != 1) st.prologue = 0;
                 group.push_back(i);
             } else {
                 group = cx;
+                std::sort(group.begin(), group.end());
             }
-            if ((int) group.size() > 3) { group.resize(3); if (st.prologue == 1 || st.prologue == 2) { st.prologue = 0; st.p0 = st.p1 = -1; } }
-            int last = 0;
             st.nmat = (int) group.size();
+            int last = 0;
+            bool need_graph_buffers = false;
             for (int j = 0; j < st.nmat; j++) {
                 st.mm[j] = group[j]; st.out[j] = group[j]; st.add_vec[j] = -1; st.add_src[j] = 0;
                 int vs = 0;
@@ -629,15 +661,38 @@ static b200_plan * build_plan(ggml_cgraph * g, uint64_t key) {
                 if (ad >= 0 && !taken[ad] && (st.nmat == 1 || ggml_graph_node(g, ad)->src[vs]->op == GGML_OP_NONE)) { st.out[j] = ad; st.add_vec[j] = ad; st.add_src[j] = vs; }
                 last = std::max(last, st.out[j]);
             }
-            // the step runs at the position of its last node: nobody may read an output before that
-            bool ok = true;
-            for (int j = 0; j < st.nmat && ok; j++) {
-                std::vector<int> co; real_consumers(G, st.out[j], co);
-                for (int c : co) if (c <= last) ok = false;
-            }
-            if (!ok) {   // degrade to a single mat-vec without folded ADD
-                st.nmat = 1; st.mm[0] = i; st.out[0] = i; st.add_vec[0] = -1; last = i;
-                if (st.prologue != 0 && !(all_mm && group.size() == 1)) { st.prologue = 0; st.p0 = st.p1 = -1; }
+            if (st.nmat > 1) {
+                // results of a multi-matrix group are produced at ONE point in time: each must be consumed only inside fused steps
+                // (attention: q / k / v; silu prologue: gate / up) so that it can live in a private buffer
+                for (int j = 0; j < st.nmat; j++) {
+                    std::vector<int> co; real_consumers(G, st.out[j], co);
+                    int slot = -1;
+                    for (int anchor : attn_anchor) {
+                        const b200_step & A = at[anchor];
+                        const ggml_tensor * o = ggml_graph_node(g, st.out[j]);
+                        if (co.size() == 1 && co[0] == A.rope_q && strip_views(ggml_graph_node(g, A.rope_q)->src[0]) == o) slot = SCR_Q;
+                        if (co.size() == 1 && co[0] == A.rope_k && strip_views(ggml_graph_node(g, A.rope_k)->src[0]) == o) slot = SCR_K;
+                        if (co.size() == 1 && co[0] == A.cpy_v && strip_views(ggml_graph_node(g, A.cpy_v)->src[0]) == o) slot = SCR_V;
+                    }
+                    if (slot < 0 && co.size() == 1) {
+                        const ggml_tensor * c0 = ggml_graph_node(g, co[0]);
+                        if (c0->op == GGML_OP_UNARY && ggml_get_unary_op(c0) == GGML_UNARY_OP_SILU) slot = SCR_G;
+                        else if (c0->op == GGML_OP_MUL) {
+                            const ggml_tensor * other = c0->src[0] == ggml_graph_node(g, st.out[j]) ? c0->src[1] : c0->src[0];
+                            if (other && other->op == GGML_OP_UNARY && ggml_get_unary_op(other) == GGML_UNARY_OP_SILU) slot = SCR_U;
+                        }
+                    }
+                    st.out_scratch[j] = slot;
+                    if (slot < 0) need_graph_buffers = true;
+                }
+                if (need_graph_buffers) {   // not the llama / qwen2 motif: one launch per matrix at its own position, activation materialised
+                    if (st.prologue == 1 || st.prologue == 2) { st.prologue = 0; st.p0 = st.p1 = -1; }
+                    st.nmat = 1; st.mm[0] = i; st.out[0] = i; st.add_vec[0] = -1; st.out_scratch[0] = -1;
+                    int vs = 0;
+                    const int ad = find_add(G, i, vs);
+                    if (ad >= 0 && !taken[ad]) { st.out[0] = ad; st.add_vec[0] = ad; st.add_src[0] = vs; }
+                    last = st.out[0];
+                }
             }
             if (st.prologue == 3) at[xi].quant_out = 1;
             for (int j = 0; j < st.nmat; j++) { taken[st.mm[j]] = 1; taken[st.out[j]] = 1; }
@@ -645,12 +700,31 @@ static b200_plan * build_plan(ggml_cgraph * g, uint64_t key) {
             st.node = last;
             at[last] = st; has[last] = 1;
         }
+        // 3) every fused attention must take q / k / v from private buffers filled by a fused group, and its f32 result is private when
+        //    wo consumes the quantized copy; a SILU prologue needs its producer likewise.  Anything else: no fusion for this graph.
+        for (int anchor : attn_anchor) {
+            b200_step & A = at[anchor];
+            const ggml_tensor * qs = strip_views(ggml_graph_node(g, A.rope_q)->src[0]), * ks = strip_views(ggml_graph_node(g, A.rope_k)->src[0]);
+            const ggml_tensor * vs = strip_views(ggml_graph_node(g, A.cpy_v)->src[0]);
+            for (int q = 0; q < G.n; q++) {
+                if (!has[q] || at[q].kind != 1) continue;
+                for (int j = 0; j < at[q].nmat; j++) {
+                    const ggml_tensor * o = ggml_graph_node(g, at[q].out[j]);
+                    if (o == qs && at[q].out_scratch[j] == SCR_Q) A.q_scratch = SCR_Q;
+                    if (o == ks && at[q].out_scratch[j] == SCR_K) A.k_scratch = SCR_K;
+                    if (o == vs && at[q].out_scratch[j] == SCR_V) A.v_scratch = SCR_V;
+                }
+            }
+            if (A.q_scratch < 0 || A.k_scratch < 0 || A.v_scratch < 0) fused_ok = false;
+            std::vector<int> co; real_consumers(G, A.cont, co);
+            A.out_private = (A.quant_out && co.size() == 1) ? 1 : 0;
+        }
     }
     b200_plan * plan = new b200_plan();
     plan->key = key; plan->n_nodes = G.n;
     for (int i = 0; i < G.n; i++) {
-        if (has[i]) { plan->steps.push_back(at[i]); continue; }
-        if (taken[i]) continue;
+        if (fused_ok && has[i]) { plan->steps.push_back(at[i]); continue; }
+        if (fused_ok && taken[i]) continue;
         const ggml_tensor * t = ggml_graph_node(g, i);
         if (ggml_is_empty(t) || is_noop(t->op)) continue;
         b200_step st{};
@@ -660,6 +734,14 @@ static b200_plan * build_plan(ggml_cgraph * g, uint64_t key) {
     return plan;
 }
 
+static float * grow_scratch(b200_backend_ctx * ctx, int slot, size_t floats) {
+    if (floats > ctx->scratch_floats[slot]) {
+        if (ctx->scratch[slot]) { CUDA_OK(cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->scratch[slot]); }
+        CUDA_OK(cudaMalloc((void **) &ctx->scratch[slot], floats * 4 + 256));
+        ctx->scratch_floats[slot] = floats;
+    }
+    return ctx->scratch[slot];
+}
 static void * grow_ws(b200_backend_ctx * ctx, int role, size_t need) {
     if (need > ctx->fact_bytes[role]) {
         if (ctx->fact_ws[role]) { CUDA_OK(cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->fact_ws[role]); }
@@ -682,7 +764,7 @@ static bool run_gemv_step(b200_backend_ctx * ctx, ggml_cgraph * g, const b200_st
         const ggml_tensor * out = ggml_graph_node(g, st.out[j]);
         mats[j].type = (int32_t) mm->src[0]->type; mats[j]._pad = 0;
         mats[j].W = mm->src[0]->data; mats[j].n = mm->src[0]->ne[1];
-        mats[j].y = (float *) out->data;
+        mats[j].y = st.out_scratch[j] >= 0 ? grow_scratch(ctx, st.out_scratch[j], (size_t) mm->src[0]->ne[1]) : (float *) out->data;
         mats[j].add = st.add_vec[j] >= 0 ? (const float *) out->src[st.add_src[j]]->data : nullptr;
     }
     void * ws = grow_ws(ctx, st.ws, pb200_act_workspace_bytes(K));
@@ -696,7 +778,8 @@ static bool run_gemv_step(b200_backend_ctx * ctx, ggml_cgraph * g, const b200_st
     } else if (st.prologue == 2) {
         const ggml_tensor * un = ggml_graph_node(g, st.p0), * mul = ggml_graph_node(g, st.p1);
         const ggml_tensor * u = mul->src[0] == un ? mul->src[1] : mul->src[0];
-        rc = pb200_gemv_fused(st.nmat, mats, K, ws, 2, (const float *) un->src[0]->data, (const float *) u->data, 0.f, ctx->sync_ws, 1, ctx->stream);
+        (void) un; (void) mul; (void) u;
+        rc = pb200_gemv_fused(st.nmat, mats, K, ws, 2, ctx->scratch[st.in_scratch[0]], ctx->scratch[st.in_scratch[1]], 0.f, ctx->sync_ws, 1, ctx->stream);
     } else {
         if (st.prologue == 0) {
             PB_OK(pb200_quantize_act((int) m0->src[0]->type, (const float *) m0->src[1]->data, K, ws, ctx->stream));
@@ -725,15 +808,13 @@ static bool run_attn_step(b200_backend_ctx * ctx, ggml_cgraph * g, const b200_st
     float fb, fs, ef, af, bf, bsl, scale;
     memcpy(&fb, p + 5, 4); memcpy(&fs, p + 6, 4); memcpy(&ef, p + 7, 4); memcpy(&af, p + 8, 4); memcpy(&bf, p + 9, 4); memcpy(&bsl, p + 10, 4);
     memcpy(&scale, sm->op_params, 4);
-    const float * q = (const float *) ropeq->src[0]->data, * k = (const float *) ropek->src[0]->data;
-    const float * v = (const float *) strip_views(cpyv->src[0])->data;
-    float * out = (float *) cont->data;
+    const float * q = ctx->scratch[st.q_scratch], * k = ctx->scratch[st.k_scratch], * v = ctx->scratch[st.v_scratch];   // filled by the fused q|k|v group
+    float * out = st.out_private ? grow_scratch(ctx, SCR_ATT, (size_t) (H * D)) : (float *) cont->data;
     const size_t out_bytes = (size_t) (H * D) * 4;
     // the graph allocator may have placed the CONT result on top of q / k / v (their last readers are folded into this launch):
     // heads finish at different times, so only the exact q <-> out aliasing (head h reads and writes its own slice) is safe
-    bool via_tmp = overlaps(out, out_bytes, k, (size_t) (HK * D) * 4) || overlaps(out, out_bytes, v, (size_t) (HK * D) * 4) ||
-                   (overlaps(out, out_bytes, q, out_bytes) && (const void *) out != (const void *) q) ||
-                   overlaps(out, out_bytes, mask->data, (size_t) n_kv * 4);
+    // q / k / v are private; the only graph tensor read while heads finish at different times is the mask row
+    bool via_tmp = !st.out_private && overlaps(out, out_bytes, mask->data, (size_t) n_kv * 4);
     if (via_tmp) {
         if (ctx->attn_tmp_floats < (size_t) (H * D)) {
             if (ctx->attn_tmp) { CUDA_OK(cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->attn_tmp); }
