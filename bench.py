@@ -256,10 +256,12 @@ def boundary_leg(eng, cfg, hp, args, lib):
     dt = time.perf_counter() - t0
     clocks = sampler.stop()
     launches = lib.c.pb200_kernel_launches() - n0
-    # parity of the two paths on the same weights / same token / same cache state: one more step through each
+    # the two paths on the same weights: a token at position 0 of an empty cache through each (later steps sit on different histories
+    # of a random-init, unit-gain 80-layer net and are not comparable; the whole-graph parity test lives in tests/test_gpu_ggml_graph.py)
     eng_logits = np.zeros(nv, dtype=np.float32)
-    eng.decode(token_at(first + args.steps, nv), first + args.steps, eng_logits)
-    hm.decode([token_at(first + args.steps, nv)], first + args.steps, logits)
+    eng.kv_clear(); hm.kv_clear()
+    eng.decode(token_at(1, nv), 0, eng_logits)
+    hm.decode([token_at(1, nv)], 0, logits)
     n_kv_pad = (first + args.steps + 32) // 32 * 32
     res = {"value": args.steps / dt, "unit": "tokens/s", "ms_per_step": dt / args.steps * 1e3,
            "h2d_bytes_per_step": 8 + n_kv_pad * 32 * 4, "d2h_bytes_per_step": nv * 4,
@@ -267,7 +269,7 @@ def boundary_leg(eng, cfg, hp, args, lib):
                   "on the graph of host/llama_graph_host.cpp (build_llama restated; the host's ggml = the reference's, unmodified)",
            "timing": "host wall clock around K synchronous steps", "gpu_launches": int(launches), "launches_per_layer": (launches / args.steps - 3) / L,
            "graph_nodes": hm.graph_nodes, "graph_builds": int(hm.graph_builds), "clocks": clocks,
-           "max_abs_vs_engine_last_step": float(np.max(np.abs(eng_logits - logits)))}
+           "max_abs_vs_engine_first_token": float(np.max(np.abs(eng_logits - logits)))}
     hm.close()
     return res
 

@@ -18,6 +18,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/ggml_b200.h"
@@ -461,7 +462,8 @@ struct graph_info {
     ggml_cgraph * g;
     int n;
     std::vector<std::vector<int>> cons;   // consumers of node i (direct src references, views included as nodes)
-    int idx(const ggml_tensor * t) const { for (int i = 0; i < n; i++) if (ggml_graph_node(g, i) == t) return i; return -1; }
+    std::unordered_map<const ggml_tensor *, int> index;
+    int idx(const ggml_tensor * t) const { auto it = index.find(t); return it == index.end() ? -1 : it->second; }
 };
 // consumers of a node "through" no-op views: the real ops that eventually read it
 static void real_consumers(const graph_info & G, int i, std::vector<int> & out) {
@@ -508,7 +510,8 @@ static bool plan_attention(const graph_info & G, int soft, std::vector<char> & t
     { std::vector<int> c; real_consumers(G, kq_i, c); if (c.size() != 1 || c[0] != soft) return false; }
     // k side: a ROPE node with the same parameters whose only consumer is a CPY into a view of the same K cache tensor
     int ropek_i = -1, cpyk_i = -1;
-    for (int i = 0; i < G.n; i++) {
+    const int w0 = std::max(0, soft - 96), w1 = std::min(G.n, soft + 16);   // the chain of one layer sits within a few dozen nodes
+    for (int i = w0; i < w1; i++) {
         const ggml_tensor * t = ggml_graph_node(g, i);
         if (t->op != GGML_OP_CPY || !t->src[1] || t->src[1]->view_src != kview->view_src || taken[i]) continue;
         const ggml_tensor * rk = strip_views(t->src[0]);
@@ -526,7 +529,7 @@ static bool plan_attention(const graph_info & G, int soft, std::vector<char> & t
     if (cpyk->src[1]->type != GGML_TYPE_F16 || ggml_nelements(cpyk->src[1]) != HK * D) return false;
     // v side: CPY(transpose(Vcur)) into a [1, HK*D] strided view of the same V cache tensor
     int cpyv_i = -1;
-    for (int i = 0; i < G.n; i++) {
+    for (int i = w0; i < w1; i++) {
         const ggml_tensor * t = ggml_graph_node(g, i);
         if (t->op == GGML_OP_CPY && t->src[1] && t->src[1]->view_src == vview->view_src && !taken[i]) cpyv_i = i;
     }
@@ -563,12 +566,14 @@ static b200_plan * build_plan(ggml_cgraph * g, uint64_t key) {
     graph_info G;
     G.g = g; G.n = ggml_graph_n_nodes(g);
     G.cons.assign(G.n, {});
+    G.index.reserve((size_t) G.n * 2);
+    for (int i = 0; i < G.n; i++) G.index[ggml_graph_node(g, i)] = i;
     for (int i = 0; i < G.n; i++) {
         const ggml_tensor * t = ggml_graph_node(g, i);
         for (int k = 0; k < GGML_MAX_SRC; k++) {
             if (!t->src[k]) continue;
-            const int j = node_index_of(g, t->src[k], i);
-            if (j >= 0) G.cons[j].push_back(i);
+            const int j = G.idx(t->src[k]);
+            if (j >= 0 && j < i) G.cons[j].push_back(i);
         }
     }
     std::vector<char> taken(G.n, 0);
@@ -600,12 +605,12 @@ static b200_plan * build_plan(ggml_cgraph * g, uint64_t key) {
             st.kind = 1; st.prologue = 0; st.p0 = st.p1 = -1; st.ws = 0;
             for (int j = 0; j < 3; j++) st.out_scratch[j] = -1;
             st.in_scratch[0] = st.in_scratch[1] = -1;
-            const int xi = node_index_of(g, X, i);
+            const int xi = G.idx(X);
             if (xi >= 0 && X->op == GGML_OP_MUL && !taken[xi]) {
                 // prologue candidates: MUL(RMS_NORM(x), w) or MUL(SILU(g), u), intermediate results read by nobody else
                 for (int k = 0; k < 2; k++) {
                     const ggml_tensor * a = X->src[k], * b = X->src[1 - k];
-                    const int ai = node_index_of(g, a, xi);
+                    const int ai = G.idx(a);
                     if (ai < 0 || taken[ai]) continue;
                     std::vector<int> ca; real_consumers(G, ai, ca);
                     if (ca.size() != 1 || ca[0] != xi) continue;
@@ -615,9 +620,9 @@ static b200_plan * build_plan(ggml_cgraph * g, uint64_t key) {
                     if (a->op == GGML_OP_UNARY && ggml_get_unary_op(a) == GGML_UNARY_OP_SILU && is_vec_f32(b, K) && ggml_is_contiguous(b) &&
                         is_vec_f32(a->src[0], K) && ggml_is_contiguous(a->src[0])) {
                         // gate and up must have been redirected to private buffers by the group that produced them (liveness, see above)
-                        const int gi = node_index_of(g, a->src[0], ai), ui = node_index_of(g, b, xi);
+                        const int gi = G.idx(a->src[0]), ui = G.idx(b);
                         int sg = -1, su = -1;
-                        for (int q = 0; q < G.n; q++) {
+                        for (int q = std::max(0, i - 64); q < i; q++) {
                             if (!has[q] || at[q].kind != 1) continue;
                             for (int j = 0; j < at[q].nmat; j++) {
                                 if (at[q].out[j] == gi) sg = at[q].out_scratch[j];
@@ -668,6 +673,7 @@ static b200_plan * build_plan(ggml_cgraph * g, uint64_t key) {
                     std::vector<int> co; real_consumers(G, st.out[j], co);
                     int slot = -1;
                     for (int anchor : attn_anchor) {
+                        if (anchor < i || anchor > i + 96) continue;
                         const b200_step & A = at[anchor];
                         const ggml_tensor * o = ggml_graph_node(g, st.out[j]);
                         if (co.size() == 1 && co[0] == A.rope_q && strip_views(ggml_graph_node(g, A.rope_q)->src[0]) == o) slot = SCR_Q;
@@ -706,7 +712,7 @@ static b200_plan * build_plan(ggml_cgraph * g, uint64_t key) {
             b200_step & A = at[anchor];
             const ggml_tensor * qs = strip_views(ggml_graph_node(g, A.rope_q)->src[0]), * ks = strip_views(ggml_graph_node(g, A.rope_k)->src[0]);
             const ggml_tensor * vs = strip_views(ggml_graph_node(g, A.cpy_v)->src[0]);
-            for (int q = 0; q < G.n; q++) {
+            for (int q = std::max(0, anchor - 96); q < anchor; q++) {
                 if (!has[q] || at[q].kind != 1) continue;
                 for (int j = 0; j < at[q].nmat; j++) {
                     const ggml_tensor * o = ggml_graph_node(g, at[q].out[j]);
