@@ -250,10 +250,12 @@ def boundary_leg(eng, cfg, hp, args, lib):
     sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
     sampler.start()
     torch.cuda.synchronize()
+    hm.phase_seconds()
     t0 = time.perf_counter()
     for i in range(args.steps):
         hm.decode([token_at(first + i, nv)], first + i, logits)
     dt = time.perf_counter() - t0
+    phases = {k: v / args.steps * 1e3 for k, v in hm.phase_seconds().items()}
     clocks = sampler.stop()
     launches = lib.c.pb200_kernel_launches() - n0
     # the two paths on the same weights: a token at position 0 of an empty cache through each (later steps sit on different histories
@@ -268,7 +270,7 @@ def boundary_leg(eng, cfg, hp, args, lib):
            "api": "ggml_backend_tensor_set(inp_tokens, inp_pos, KQ_mask) + ggml_backend_graph_compute(B200_0) + ggml_backend_tensor_get(logits) "
                   "on the graph of host/llama_graph_host.cpp (build_llama restated; the host's ggml = the reference's, unmodified)",
            "timing": "host wall clock around K synchronous steps", "gpu_launches": int(launches), "launches_per_layer": (launches / args.steps - 3) / L,
-           "graph_nodes": hm.graph_nodes, "graph_builds": int(hm.graph_builds), "clocks": clocks,
+           "graph_nodes": hm.graph_nodes, "graph_builds": int(hm.graph_builds), "host_ms_per_step": phases, "clocks": clocks,
            "max_abs_vs_engine_first_token": float(np.max(np.abs(eng_logits - logits)))}
     hm.close()
     return res

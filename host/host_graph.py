@@ -62,6 +62,7 @@ def load(with_plugin: bool = True):
     g.lgh_graph_nodes.argtypes = [vp]
     g.lgh_decode.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_int]
     g.lgh_get_hidden.argtypes = [vp, vp]
+    g.lgh_phase_seconds.argtypes = [vp, C.POINTER(C.c_double)]
     _libs = (g, plug)
     return _libs
 
@@ -125,6 +126,12 @@ class HostModel:
 
     def kv_clear(self) -> None:
         self.g.lgh_kv_clear(self.h)
+
+    def phase_seconds(self) -> dict:
+        """Host seconds since the last call in: graph (re)build + allocation, input upload, graph_compute (enqueue), wait + logits read."""
+        a = (C.c_double * 4)()
+        self.g.lgh_phase_seconds(self.h, a)
+        return {"graph_build": a[0], "set_inputs": a[1], "graph_compute_call": a[2], "wait_and_get": a[3]}
 
     @property
     def graph_builds(self) -> int:

@@ -15,6 +15,7 @@
 #include "ggml-alloc.h"
 #include "ggml-backend.h"
 
+#include <chrono>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -55,7 +56,9 @@ struct lgh_ctx {
     std::vector<ggml_tensor *> k_views, v_views;
     std::vector<float> mask_host;
     uint64_t n_graph_builds = 0;
+    double t_build = 0, t_set = 0, t_enqueue = 0, t_get = 0;   // host seconds spent per phase (diagnostics for bench.py)
 };
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 static ggml_tensor * new_w(lgh_ctx * c, const char * name, int type, int64_t ne0, int64_t ne1) {
     ggml_tensor * t = ne1 > 0 ? ggml_new_tensor_2d(c->wctx, (ggml_type) type, ne0, ne1) : ggml_new_tensor_1d(c->wctx, (ggml_type) type, ne0);
@@ -260,7 +263,9 @@ int lgh_decode(void * p, const int32_t * tokens, int n_tokens, int pos0, float *
     int64_t n_kv = ((pos0 + n_tokens + 31) / 32) * 32;
     if (n_kv < 32) n_kv = 32;
     if (n_kv > hp.n_ctx) n_kv = hp.n_ctx;
+    double t0 = now_s();
     if (!g->gf || g->g_tokens != n_tokens || g->g_nkv != n_kv) build_graph(g, n_tokens, n_kv);
+    g->t_build += now_s() - t0; t0 = now_s();
     // re-point the cache store views at kv_head (what a rebuilt graph would carry in view_offs)
     for (size_t iv = 0; iv < g->k_views.size(); iv++) {
         ggml_tensor * kv = g->k_views[iv], * vv = g->v_views[iv];
@@ -278,15 +283,24 @@ int lgh_decode(void * p, const int32_t * tokens, int n_tokens, int pos0, float *
     ggml_backend_tensor_set(g->inp_tokens, tokens, 0, sizeof(int32_t) * (size_t) n_tokens);
     ggml_backend_tensor_set(g->inp_pos, posv.data(), 0, sizeof(int32_t) * (size_t) n_tokens);
     ggml_backend_tensor_set(g->kq_mask, g->mask_host.data(), 0, sizeof(float) * g->mask_host.size());
+    g->t_set += now_s() - t0; t0 = now_s();
     const ggml_status st = ggml_backend_graph_compute(g->backend, g->gf);
     if (st != GGML_STATUS_SUCCESS) return -2;
+    g->t_enqueue += now_s() - t0; t0 = now_s();
     if (logits) {
         if (all_logits) ggml_backend_tensor_get(g->logits, logits, 0, sizeof(float) * (size_t) hp.n_vocab * (size_t) n_tokens);
         else ggml_backend_tensor_get(g->logits, logits, sizeof(float) * (size_t) hp.n_vocab * (size_t) (n_tokens - 1), sizeof(float) * (size_t) hp.n_vocab);
     } else {
         ggml_backend_synchronize(g->backend);
     }
+    g->t_get += now_s() - t0;
     return 0;
+}
+// host seconds spent so far in {graph (re)build + allocation, input upload, graph_compute call, wait + logits read}; resets the counters
+void lgh_phase_seconds(void * p, double * out4) {
+    lgh_ctx * g = (lgh_ctx *) p;
+    out4[0] = g->t_build; out4[1] = g->t_set; out4[2] = g->t_enqueue; out4[3] = g->t_get;
+    g->t_build = g->t_set = g->t_enqueue = g->t_get = 0;
 }
 
 // last-layer output of the previous lgh_decode ([n_tokens][n_embd])

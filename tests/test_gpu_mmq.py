@@ -35,7 +35,7 @@ def run_mmq(lib, t, W, N, K, X, bias=None, ldx=None, resid=None):
     lib.check(lib.c.pb200_mul_mat_q(t, ptr(Wd), N, K, ptr(xd), ldx, T, ptr(y), ptr(bd) if bd is not None else None,
                                     ptr(rd) if rd is not None else None, ptr(ws), None), "mul_mat_q")
     sync()
-    assert lib.c.pb200_mul_mat_q_aborted() == 0, "tcgen05 pipeline gave up (watchdog)"
+    assert lib.c.pb200_aborted() == 0, "tcgen05 pipeline gave up (watchdog)"
     return y.cpu().numpy()
 
 
