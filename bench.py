@@ -333,6 +333,8 @@ def main():
     t0 = time.perf_counter()
     eng = pkg.Model(H, local, (l0, l1), with_embd=(rank == 0), with_head=(rank == world - 1))
     eng.synth(cfg["ftype"], 1234 + rank)
+    if world > 1:
+        eng.set_n_seq(world)          # one sequence slot per stage: the ring keeps every GPU busy (RingRunner)
     eng.finalize()
     t_load = time.perf_counter() - t0
     nv, E = hp["n_vocab"], hp["n_embd"]
@@ -346,7 +348,13 @@ def main():
     if world > 1:
         hid_in = torch.as_tensor(DevBuf(eng.hidden_in_ptr, E), device=torch.device("cuda", local))
         hid_out = torch.as_tensor(DevBuf(eng.hidden_out_ptr, E), device=torch.device("cuda", local))
-    tok_t = torch.zeros(1, dtype=torch.int64, device=torch.device("cuda", local))
+    class DevI32:
+        def __init__(self, ptr, n):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (ptr, False), "version": 2}
+
+    cuda_dev = torch.device("cuda", local)
+    # latency mode (one sequence, slot 0): the last stage's device argmax lands in sample slot 0, stage 0 receives it into a scratch word
+    tok_t = torch.as_tensor(DevI32(eng.sample_ptr(0), 1), device=cuda_dev) if rank == world - 1 else torch.zeros(1, dtype=torch.int32, device=cuda_dev)
     logits_t = torch.as_tensor(DevBuf(eng.logits_ptr, nv), device=torch.device("cuda", local)) if rank == world - 1 else None
     logits_host = np.zeros(nv, dtype=np.float32)
 
@@ -366,13 +374,17 @@ def main():
     stage = EngineStage()
     runner = pkg.PipelineRunner(stage, rank, world, dist, tok_t)
 
+    def sample_dev(_logits):
+        eng.argmax_seq(0, False)      # device argmax (pb200_argmax_seq): no torch kernel, no host sync on the step path
+        return tok_t
+
     def step(i, pos, host_io):
         """One token through the pipeline.  Synthetic token ids (llama-bench tg uses random ids, llama-bench.cpp:1452-1470);
         in pipeline mode the last stage still returns a sampled token (argmax) to rank 0 so that steps stay strictly
         sequential like real decoding."""
         stage.host_io = host_io
         with torch.cuda.stream(ext):
-            runner.step(token_at(i, nv), pos, sample=lambda lg: torch.argmax(lg))
+            runner.step(token_at(i, nv), pos, sample=sample_dev)
 
     def barrier():
         torch.cuda.synchronize()
@@ -435,6 +447,51 @@ def main():
         t = torch.tensor([e0.elapsed_time(e1) / args.steps], device=torch.device("cuda", local), dtype=torch.float64)
         dist.all_reduce(t)
         stage_ms = float(t.item())
+    # ring mode (N > 1): one independent sequence per stage in flight, every GPU busy in every slot; aggregate tokens/s
+    ring = None
+    if world > 1:
+        class RingStage:
+            hidden_in, hidden_out = hid_in, hid_out
+            _tin = [torch.as_tensor(DevI32(eng.token_ptr(s), 1), device=cuda_dev) for s in range(world)]
+            _tout = [torch.as_tensor(DevI32(eng.sample_ptr(s), 1), device=cuda_dev) for s in range(world)]
+
+            def token_in(self, s):
+                return self._tin[s]
+
+            def token_out(self, s):
+                return self._tout[s]
+
+            def begin(self, s, token, pos):
+                eng.set_tokpos_seq(s, token, pos)
+
+            def run(self, s):
+                eng.step_seq_dev(s, True)
+                if rank == world - 1:
+                    eng.argmax_seq(s, False)
+
+        rr = pkg.RingRunner(RingStage(), rank, world, dist)
+        seeds = [(token_at(1000 + s, nv), PROMPT) for s in range(world)]
+        barrier()
+        with torch.cuda.stream(ext):
+            rr.slots(world * (1 + args.warmup), first_tokens=seeds)          # fill the pipeline + warm-up rounds
+        sampler = ClockSampler(local)
+        sampler.start()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = lib.c.pb200_kernel_launches()
+        with torch.cuda.stream(ext):
+            e0.record()
+            rr.slots(world * args.steps)                                      # K rounds: every sequence advances K tokens
+            e1.record()
+        barrier()
+        ring_ms = e0.elapsed_time(e1)
+        ring_launches = lib.c.pb200_kernel_launches() - n0
+        ring_clocks = sampler.stop()
+        t = torch.tensor([ring_ms], device=cuda_dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        lt = torch.tensor([ring_launches], device=cuda_dev)
+        dist.all_reduce(lt)
+        ring = {"ms": float(t.item()), "launches": int(lt.item()), "clocks": ring_clocks, "tokens": world * args.steps}
     # live roofline of the dominant kernel (k_gemv_kquant): CUDA events around every GEMV launch of profiled steps
     prof = [eng.profile_step(token_at(first + i, nv), first + i) for i in range(4)]
     gemv_ms = sum(p["gemv_ms"] for p in prof) / len(prof)
@@ -473,6 +530,23 @@ def main():
                                     "frac_of_8TBs_north_star": (wb + kv_bytes) / (ms_step * 1e-3) / 8e12}},
         "model_load_s": t_load,
     }
+    if ring is not None:
+        # headline at N > 1: aggregate decode throughput of the ring with N sequences (each b = 1) in flight; the single-sequence
+        # latency run above stays in `latency_b1` (serial across stages by nature: N GPUs cannot cut one token's latency)
+        out["latency_b1"] = {"value": out["value"], "unit": "tokens/s", "ms_per_token": ms_step, "e2e": out["e2e"], "gpu_launches": launches}
+        out["value"] = ring["tokens"] / (ring["ms"] * 1e-3)
+        out["ms_per_step"] = ring["ms"] / args.steps
+        out["scaling"] = "weak"
+        out["gpu_launches"] = ring["launches"]
+        out["clocks"] = ring["clocks"]
+        out["config"]["parallelism"] = (f"layer pipeline pp{world}, {world} independent b=1 sequences in flight (one per stage, prima's piped ring); "
+                                        f"a step = one round = {world} tokens; hand-off = grouped NCCL send/recv, tokens / positions / greedy argmax stay on the device")
+        out["roofline"]["whole_step"] = {"algorithmic_bytes_per_token": wb + kv_bytes, "achieved": (wb + kv_bytes) * ring["tokens"] / (ring["ms"] * 1e-3) / 1e9 / world,
+                                         "frac": (wb + kv_bytes) * ring["tokens"] / (ring["ms"] * 1e-3) / 1e9 / world / peak,
+                                         "note": "per GPU: every token reads the whole model once, spread over the stages"}
+        out["e2e"] = {"value": out["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                      "note": "ring mode keeps tokens on the device (device argmax feeds the next step): there is no per-step host transfer to time; "
+                              "the host-in / host-out call is measured in latency_b1.e2e"}
     if stage_ms is not None:
         out["pipeline"] = {"stages": world, "hand_offs_per_token": world, "sum_of_stage_ms": stage_ms, "pipelined_ms_per_token": ms_step,
                            "exposed_handoff_ms": max(0.0, ms_step - stage_ms), "exposed_frac": max(0.0, ms_step - stage_ms) / ms_step,

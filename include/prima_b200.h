@@ -179,6 +179,19 @@ PB200_API int pb200_decode(pb200_model * m, int32_t token, int32_t pos, float * 
 /* device-resident variant: enqueue one step on the model stream, no host copies, no synchronisation */
 PB200_API int pb200_decode_async(pb200_model * m, int32_t token, int32_t pos);
 PB200_API int pb200_synchronize(pb200_model * m);
+/* Several independent sequences per shard (each with its own KV cache, token and position slot): what keeps every stage of the layer
+ * pipeline busy — prima's piped ring with one token per stage in flight (src/llama.cpp:17825-18029, 18299-18387).  Set before finalize. */
+PB200_API int pb200_model_set_n_seq(pb200_model * m, int n_seq);
+PB200_API int pb200_decode_seq_async(pb200_model * m, int seq, int32_t token, int32_t pos);   /* pb200_decode_async on slot seq */
+/* one step of slot seq with token id and position taken from device memory (written by a hand-off, pb200_set_tokpos_seq or
+ * pb200_argmax_seq); nothing crosses the host.  advance_pos != 0: the slot's position is incremented afterwards. */
+PB200_API int pb200_step_seq_dev(pb200_model * m, int seq, int advance_pos);
+PB200_API int pb200_set_tokpos_seq(pb200_model * m, int seq, int32_t token, int32_t pos);
+/* greedy sampling on the device (ggml-cuda/argmax.cu:7): argmax of the slot's logits -> pb200_sample_device(m, seq); feed_back != 0 on a
+ * shard that also holds the embedding writes it into the slot's token as well (single-GPU generation without a host round trip) */
+PB200_API int pb200_argmax_seq(pb200_model * m, int seq, int feed_back);
+PB200_API int32_t * pb200_token_device(pb200_model * m, int seq);    /* int32[2]: {token, position} of the slot */
+PB200_API int32_t * pb200_sample_device(pb200_model * m, int seq);   /* int32: greedy token of the slot's last step */
 PB200_API float * pb200_logits_device(pb200_model * m);      /* [n_vocab] f32 */
 PB200_API float * pb200_hidden_in_device(pb200_model * m);   /* [n_embd] f32: input of layer_begin (written by the previous stage) */
 PB200_API float * pb200_hidden_out_device(pb200_model * m);  /* [n_embd] f32: output of layer_end-1 */

@@ -98,7 +98,9 @@ struct pb200_model {
     int32_t * tokpos_host = nullptr;   // pinned
     float * logits_host = nullptr;     // pinned
     RopeParams rp{};
-    cudaGraphExec_t graph_exec = nullptr;
+    int n_seq = 1;                      // independent sequences with their own KV cache / token / position (the pipeline keeps one per stage in flight)
+    std::vector<cudaGraphExec_t> graph_exec;   // one captured step per sequence slot
+    int32_t * sample_dev = nullptr;     // [n_seq] greedy token of the last step (pb200_argmax_seq)
     uint64_t launches_per_step = 0;
     int64_t weight_bytes = 0;
     std::vector<void *> allocs;
@@ -240,7 +242,7 @@ void pb200_model_free(pb200_model * m) {
     if (!m) return;
     cudaSetDevice(m->device);
     cudaStreamSynchronize(m->stream);
-    if (m->graph_exec) cudaGraphExecDestroy(m->graph_exec);
+    for (cudaGraphExec_t ge : m->graph_exec) if (ge) cudaGraphExecDestroy(ge);
     for (void * p : m->allocs) cudaFree(p);
     for (void * p : m->pf.allocs) cudaFree(p);
     if (m->tokpos_host) cudaFreeHost(m->tokpos_host);
@@ -349,7 +351,7 @@ static int prof_end(pb200_model * m) {
 static int64_t tbytes(const Tensor & t) { return (int64_t) t.bytes; }
 
 // one decode step enqueued on m->stream (captured into the CUDA graph by finalize)
-static int enqueue_step(pb200_model * m, uint64_t * nlaunch) {
+static int enqueue_step(pb200_model * m, int seq, uint64_t * nlaunch) {
     const pb200_hparams & hp = m->hp;
     const int E = hp.n_embd, H = hp.n_head, HK = hp.n_head_kv, D = hp.head_dim, F = hp.n_ff;
     const int QD = H * D, EK = HK * D;
@@ -359,7 +361,8 @@ static int enqueue_step(pb200_model * m, uint64_t * nlaunch) {
     static const bool dist_env = getenv("PB200_NO_DIST") == nullptr;   // A/B: single-CTA rmsnorm / silu kernels in front of the GEMVs instead
     const bool dist = dist_env && gemv_dist_prologue_ok();
     uint64_t n = 0;
-    const int32_t * tok_dev = m->tokpos_dev, * pos_dev = m->tokpos_dev + 1;
+    const int32_t * tok_dev = m->tokpos_dev + 4 * seq, * pos_dev = m->tokpos_dev + 4 * seq + 1;
+    const size_t nl_ = m->layers.size();
     float * x = m->x_in;
     if (m->with_embd) {
         CK(launch_get_rows(m->tok_embd.data, m->tok_embd.type, E, tok_dev, 1, m->x_a, st, pdl)); n++; CK(dbg_sync(st, "get_rows"));
@@ -370,8 +373,8 @@ static int enqueue_step(pb200_model * m, uint64_t * nlaunch) {
     float * bufs[3] = {m->x_a, m->x_b, m->xn};
     for (int il = m->l0; il < m->l1; il++) {
         Layer & L = m->layers[il - m->l0];
-        __half * kc = m->kcache + (size_t) (il - m->l0) * hp.n_ctx * EK;
-        __half * vc = m->vcache + (size_t) (il - m->l0) * hp.n_ctx * EK;
+        __half * kc = m->kcache + ((size_t) seq * nl_ + (size_t) (il - m->l0)) * hp.n_ctx * EK;
+        __half * vc = m->vcache + ((size_t) seq * nl_ + (size_t) (il - m->l0)) * hp.n_ctx * EK;
         float * x1 = nullptr, * x2 = nullptr;
         for (int i = 0; i < 3 && (!x1 || !x2); i++)
             if (bufs[i] != x) { if (!x1) x1 = bufs[i]; else x2 = bufs[i]; }
@@ -500,7 +503,7 @@ int pb200_model_finalize(pb200_model * m) {
     }
     m->weight_bytes = wb;
     const size_t nl = m->layers.size();
-    const size_t kvb = nl * (size_t) hp.n_ctx * EK * sizeof(__half);
+    const size_t kvb = (size_t) m->n_seq * nl * (size_t) hp.n_ctx * EK * sizeof(__half);
     if (nl) {
         CK(m->alloc((void **) &m->kcache, kvb));
         CK(m->alloc((void **) &m->vcache, kvb));
@@ -532,25 +535,29 @@ int pb200_model_finalize(pb200_model * m) {
     CK(mk(m->actF, F));
     CK(m->alloc((void **) &m->gbar, 16));
     CK(cudaMemset(m->gbar, 0, 16));
-    CK(m->alloc((void **) &m->tokpos_dev, 16));
-    CK(cudaMemset(m->tokpos_dev, 0, 16));
+    CK(m->alloc((void **) &m->tokpos_dev, 16 * (size_t) m->n_seq));
+    CK(cudaMemset(m->tokpos_dev, 0, 16 * (size_t) m->n_seq));
+    CK(m->alloc((void **) &m->sample_dev, 4 * (size_t) m->n_seq));
+    CK(cudaMemset(m->sample_dev, 0, 4 * (size_t) m->n_seq));
     CK(cudaMallocHost((void **) &m->tokpos_host, 16));
     if (m->with_head) CK(cudaMallocHost((void **) &m->logits_host, (size_t) hp.n_vocab * 4));
     rope_params_init(m->rp, hp.head_dim, hp.rope_mode, hp.n_ctx_orig, hp.rope_freq_base, hp.rope_freq_scale, 0.0f, 1.0f, 32.0f, 1.0f);
     CK(cudaDeviceSynchronize());
 
-    // warm-up (sets kernel attributes outside of capture), then capture the whole token as one graph
-    CK(enqueue_step(m, &m->launches_per_step));
+    // warm-up (sets kernel attributes outside of capture), then capture the whole token as one graph per sequence slot
+    CK(enqueue_step(m, 0, &m->launches_per_step));
     CK(cudaStreamSynchronize(m->stream));
     if (nl) { CK(cudaMemset(m->kcache, 0, kvb)); CK(cudaMemset(m->vcache, 0, kvb)); }
-    cudaGraph_t graph = nullptr;
-    cudaError_t e = cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal);
-    if (e == cudaSuccess) {
-        int rc = enqueue_step(m, nullptr);
+    m->graph_exec.assign((size_t) m->n_seq, nullptr);
+    for (int sq = 0; sq < m->n_seq; sq++) {
+        cudaGraph_t graph = nullptr;
+        cudaError_t e = cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal);
+        if (e != cudaSuccess) break;
+        int rc = enqueue_step(m, sq, nullptr);
         e = cudaStreamEndCapture(m->stream, &graph);
         if (rc == 0 && e == cudaSuccess && graph) {
-            e = cudaGraphInstantiate(&m->graph_exec, graph, 0);
-            if (e != cudaSuccess) m->graph_exec = nullptr;
+            e = cudaGraphInstantiate(&m->graph_exec[sq], graph, 0);
+            if (e != cudaSuccess) m->graph_exec[sq] = nullptr;
         }
         if (graph) cudaGraphDestroy(graph);
     }
@@ -706,21 +713,55 @@ extern "C" {
 int pb200_kv_clear(pb200_model * m) {
     if (!m || !m->finalized) return PB200_ESTATE;
     cudaSetDevice(m->device);
-    const size_t kvb = m->layers.size() * (size_t) m->hp.n_ctx * m->hp.n_head_kv * m->hp.head_dim * sizeof(__half);
+    const size_t kvb = (size_t) m->n_seq * m->layers.size() * (size_t) m->hp.n_ctx * m->hp.n_head_kv * m->hp.head_dim * sizeof(__half);
     if (kvb) { CK(cudaMemsetAsync(m->kcache, 0, kvb, m->stream)); CK(cudaMemsetAsync(m->vcache, 0, kvb, m->stream)); }
     return (int) cudaStreamSynchronize(m->stream);
 }
 
-static int step(pb200_model * m) {
-    if (m->use_graph && m->graph_exec) {
+static int step(pb200_model * m, int seq = 0) {
+    if (m->use_graph && (size_t) seq < m->graph_exec.size() && m->graph_exec[seq]) {
         g_launches += m->launches_per_step;
-        return (int) cudaGraphLaunch(m->graph_exec, m->stream);
+        return (int) cudaGraphLaunch(m->graph_exec[seq], m->stream);
     }
     uint64_t n = 0;
-    int rc = enqueue_step(m, &n);
+    int rc = enqueue_step(m, seq, &n);
     g_launches += n;
     return rc;
 }
+
+// greedy sampling on the device (ggml_cuda_argmax, ggml-cuda/argmax.cu:7; first index of the maximum like ggml_compute_forward_argmax)
+__global__ void __launch_bounds__(1024) k_argmax(const float * __restrict__ x, int n, int32_t * __restrict__ out, int32_t * __restrict__ out2) {
+    __shared__ float sv[32];
+    __shared__ int si[32];
+    pdl_trigger();
+    pdl_wait();
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = threadIdx.x; i < n; i += 1024) {
+        const float v = x[i];
+        if (v > best) { best = v; bi = i; }       // ascending i per thread: strict '>' keeps the first occurrence
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (lane == 0) { sv[warp] = best; si[warp] = bi; }
+    __syncthreads();
+    if (warp == 0) {
+        best = sv[lane]; bi = si[lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        if (lane == 0) { *out = bi; if (out2) *out2 = bi; }
+    }
+}
+__global__ void k_advance_pos(int32_t * tp) { pdl_trigger(); pdl_wait(); tp[1] += 1; }
 
 int pb200_decode_async(pb200_model * m, int32_t token, int32_t pos) {
     if (!m || !m->finalized) return PB200_ESTATE;
@@ -750,6 +791,60 @@ int pb200_decode(pb200_model * m, int32_t token, int32_t pos, float * logits_hos
     return check_clear_abort() ? PB200_EABORTED : 0;
 }
 
+// ---- several sequences in flight (prima's ring keeps every stage busy with a different token, src/llama.cpp:17825-18029, 18299-18387) ----
+int pb200_model_set_n_seq(pb200_model * m, int n_seq) {
+    if (!m || n_seq < 1 || n_seq > 64) return PB200_EINVAL;
+    if (m->finalized) return PB200_ESTATE;
+    m->n_seq = n_seq;
+    return 0;
+}
+int pb200_decode_seq_async(pb200_model * m, int seq, int32_t token, int32_t pos) {
+    if (!m || !m->finalized) return PB200_ESTATE;
+    if (seq < 0 || seq >= m->n_seq || pos < 0 || pos >= m->hp.n_ctx || token < 0 || token >= m->hp.n_vocab) return PB200_EINVAL;
+    cudaSetDevice(m->device);
+    k_set_tokpos<<<1, 1, 0, m->stream>>>(m->tokpos_dev + 4 * seq, token, pos);
+    CK(cudaGetLastError());
+    return step(m, seq);
+}
+// token and position of the slot are ALREADY in device memory (pb200_token_device: written by the previous stage's hand-off or by
+// pb200_argmax_seq); nothing crosses the host.  advance_pos: bump the slot's position afterwards for its next step.
+int pb200_step_seq_dev(pb200_model * m, int seq, int advance_pos) {
+    if (!m || !m->finalized) return PB200_ESTATE;
+    if (seq < 0 || seq >= m->n_seq) return PB200_EINVAL;
+    cudaSetDevice(m->device);
+    CK(step(m, seq));
+    if (advance_pos) {
+        k_advance_pos<<<1, 1, 0, m->stream>>>(m->tokpos_dev + 4 * seq);
+        g_launches++;
+        CK(cudaGetLastError());
+    }
+    return 0;
+}
+int pb200_set_tokpos_seq(pb200_model * m, int seq, int32_t token, int32_t pos) {
+    if (!m || !m->finalized) return PB200_ESTATE;
+    if (seq < 0 || seq >= m->n_seq) return PB200_EINVAL;
+    cudaSetDevice(m->device);
+    k_set_tokpos<<<1, 1, 0, m->stream>>>(m->tokpos_dev + 4 * seq, token, pos);
+    return (int) cudaGetLastError();
+}
+// greedy token of the slot's logits -> sample_dev[seq] (and, when this shard also holds the embedding, straight into the slot's token)
+int pb200_argmax_seq(pb200_model * m, int seq, int feed_back) {
+    if (!m || !m->finalized || !m->with_head) return PB200_ESTATE;
+    if (seq < 0 || seq >= m->n_seq) return PB200_EINVAL;
+    cudaSetDevice(m->device);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(1); cfg.blockDim = dim3(1024); cfg.stream = m->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    g_launches++;
+    return (int) cudaLaunchKernelEx(&cfg, k_argmax, (const float *) m->logits, (int) m->hp.n_vocab, m->sample_dev + seq,
+                                    (int32_t *) (feed_back && m->with_embd ? m->tokpos_dev + 4 * seq : nullptr));
+}
+int32_t * pb200_token_device(pb200_model * m, int seq) { return (m && seq >= 0 && seq < m->n_seq) ? m->tokpos_dev + 4 * seq : nullptr; }
+int32_t * pb200_sample_device(pb200_model * m, int seq) { return (m && seq >= 0 && seq < m->n_seq) ? m->sample_dev + seq : nullptr; }
+
 int pb200_synchronize(pb200_model * m) {
     if (!m) return PB200_EINVAL;
     cudaSetDevice(m->device);
@@ -777,7 +872,7 @@ int pb200_profile_step(pb200_model * m, int32_t token, int32_t pos, double * gem
     m->prof_n = 0;
     CK(cudaEventRecord(e0, m->stream));
     uint64_t n = 0;
-    int rc = enqueue_step(m, &n);
+    int rc = enqueue_step(m, 0, &n);
     m->profiling = false;
     if (rc) return rc;
     g_launches += n;

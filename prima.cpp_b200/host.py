@@ -91,6 +91,14 @@ class Lib:
         c.pb200_set_use_graph.argtypes = [vp, C.c_int]
         c.pb200_model_tensor_device.argtypes = [vp, C.c_char_p, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(C.c_int)]
         c.pb200_aborted.restype = C.c_int
+        c.pb200_model_set_n_seq.argtypes = [vp, C.c_int]
+        c.pb200_decode_seq_async.argtypes = [vp, C.c_int, i32, i32]
+        c.pb200_step_seq_dev.argtypes = [vp, C.c_int, C.c_int]
+        c.pb200_set_tokpos_seq.argtypes = [vp, C.c_int, i32, i32]
+        c.pb200_argmax_seq.argtypes = [vp, C.c_int, C.c_int]
+        for n in ("pb200_token_device", "pb200_sample_device"):
+            getattr(c, n).restype = vp
+            getattr(c, n).argtypes = [vp, C.c_int]
 
     @classmethod
     def get(cls) -> "Lib":
@@ -179,6 +187,27 @@ class Model:
         p, n, t = C.c_void_p(), C.c_size_t(), C.c_int()
         self.lib.check(self.lib.c.pb200_model_tensor_device(self.h, name.encode(), C.byref(p), C.byref(n), C.byref(t)), f"tensor_device {name}")
         return p.value, n.value, t.value
+
+    def set_n_seq(self, n: int) -> None:
+        self.lib.check(self.lib.c.pb200_model_set_n_seq(self.h, n), "set_n_seq")
+
+    def decode_seq_async(self, seq: int, token: int, pos: int) -> None:
+        self.lib.check(self.lib.c.pb200_decode_seq_async(self.h, seq, token, pos), "decode_seq_async")
+
+    def step_seq_dev(self, seq: int, advance_pos: bool = True) -> None:
+        self.lib.check(self.lib.c.pb200_step_seq_dev(self.h, seq, int(advance_pos)), "step_seq_dev")
+
+    def set_tokpos_seq(self, seq: int, token: int, pos: int) -> None:
+        self.lib.check(self.lib.c.pb200_set_tokpos_seq(self.h, seq, token, pos), "set_tokpos_seq")
+
+    def argmax_seq(self, seq: int, feed_back: bool = False) -> None:
+        self.lib.check(self.lib.c.pb200_argmax_seq(self.h, seq, int(feed_back)), "argmax_seq")
+
+    def token_ptr(self, seq: int) -> int:
+        return self.lib.c.pb200_token_device(self.h, seq)
+
+    def sample_ptr(self, seq: int) -> int:
+        return self.lib.c.pb200_sample_device(self.h, seq)
 
     def set_use_graph(self, on: bool) -> None:
         self.lib.c.pb200_set_use_graph(self.h, int(on))

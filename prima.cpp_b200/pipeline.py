@@ -47,9 +47,64 @@ class PipelineRunner:
         if not self.last:
             d.send(st.hidden_out, dst=self.rank + 1)
         if self.last:
-            self.tok.copy_(sample(st.logits).reshape(1))
+            # sample(logits) returns a 1-element device tensor (the engine's device argmax leaves it in place: no copy, no host sync)
+            t = sample(st.logits).reshape(1)
+            if t.data_ptr() != self.tok.data_ptr():
+                self.tok.copy_(t)
             d.send(self.tok, dst=0)
         if self.first:
+            # the returned token lands in device memory; the next step is ordered after it on the stream (no host round trip)
             d.recv(self.tok, src=self.world - 1)
-            return int(self.tok.cpu().item())   # the master must see the token before the next step can start
+            if not self.tok.is_cuda:
+                return int(self.tok.item())     # CPU tensors (gloo tests): the value is already here
         return None
+
+
+class RingRunner:
+    """Several tokens in flight: prima's piped ring proper (src/llama.cpp:17825-18029, 18299-18387) with one independent sequence
+    per stage, so that every GPU works in every time slot instead of one GPU at a time.
+
+    world = N stages, S = N sequence slots.  In time slot t stage r runs its layers on sequence (t - r) mod N.  At the START of every
+    slot each stage does ONE grouped exchange (ncclGroupStart/End through torch.distributed.batch_isend_irecv): it forwards the
+    result of its previous slot (hidden state to stage r+1; the last stage returns the sampled token id to stage 0) and receives the
+    input of this slot.  The exchange is a ring, grouped per stage, so it cannot deadlock, and nothing crosses the host: token ids
+    and positions stay in device memory (pb200_step_seq_dev), the greedy sample is a device kernel (pb200_argmax_seq).
+
+    The stage object provides: hidden_in / hidden_out (tensors aliasing the engine's buffers), token_in(seq) / token_out(seq)
+    (int32[1] tensors: where a returned token lands on stage 0 / where the last stage leaves its sample), begin(seq, token, pos)
+    (stage 0: first token of a sequence; other stages: position only) and run(seq) (one step of the slot, sampling included on the
+    last stage).  The same class drives CPU tensors over gloo in tests/test_pipeline_gloo.py."""
+
+    def __init__(self, stage, rank: int, world: int, dist):
+        if world < 2 or dist is None:
+            raise ValueError("RingRunner needs world >= 2 and torch.distributed")
+        self.stage, self.rank, self.world, self.dist = stage, rank, world, dist
+        self.t = 0
+
+    def slots(self, n: int, first_tokens=None) -> None:
+        """Runs time slots self.t .. self.t + n - 1 (the same n on every rank).  first_tokens[s] = (token, pos) seeds sequence s."""
+        st, d, r, N = self.stage, self.dist, self.rank, self.world
+        nxt, prv = (r + 1) % N, (r - 1) % N
+        for _ in range(n):
+            t = self.t
+            a = t - r                      # this stage's slot index in its own sequence of work; < 0 while the pipeline fills
+            ops = []
+            if a - 1 >= 0:                 # forward the result of the previous slot
+                sp = (a - 1) % N
+                ops.append(d.P2POp(d.isend, st.token_out(sp) if r == N - 1 else st.hidden_out, nxt))
+            if a >= 0:
+                sq = a % N
+                if r == 0:
+                    if a >= N:
+                        ops.append(d.P2POp(d.irecv, st.token_in(sq), prv))       # the token stage N-1 sampled for this sequence
+                else:
+                    ops.append(d.P2POp(d.irecv, st.hidden_in, prv))
+            if ops:
+                for w in d.batch_isend_irecv(ops):
+                    w.wait()               # NCCL: orders the current stream after the exchange, does not block the host
+            if a >= 0:
+                sq = a % N
+                if a < N and first_tokens is not None:
+                    st.begin(sq, *first_tokens[sq])
+                st.run(sq)
+            self.t += 1

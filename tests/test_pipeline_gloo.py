@@ -89,3 +89,74 @@ def test_layer_windows(pkg):
     assert b[0] == 0 and b[-1] == 32 and all(b[i] < b[i + 1] for i in range(3))
     with pytest.raises(ValueError):
         pkg.layer_windows(2, 3)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# RingRunner: one sequence per stage in flight (the mode bench.py reports at N > 1)
+class ToyRingStage(ToyStage):
+    def __init__(self, l0, l1, first, last, n_seq):
+        super().__init__(l0, l1, first, last)
+        self.tok = [torch.zeros(1, dtype=torch.int32) for _ in range(n_seq)]      # stage 0: token of the slot
+        self.pos = [0] * n_seq
+        self.smp = [torch.zeros(1, dtype=torch.int32) for _ in range(n_seq)]      # last stage: greedy sample of the slot
+        self.history = [[] for _ in range(n_seq)]
+
+    def token_in(self, s):
+        return self.tok[s]
+
+    def token_out(self, s):
+        return self.smp[s]
+
+    def begin(self, s, token, pos):
+        self.tok[s][0] = token
+        self.pos[s] = pos
+
+    def run(self, s):
+        self.decode_async(int(self.tok[s][0]), self.pos[s])
+        self.pos[s] += 1
+        if self.last:
+            self.smp[s][0] = int(torch.argmax(self.logits))
+            self.history[s].append(int(self.smp[s][0]))
+
+
+def _ring_worker(rank, world, port, q, rounds):
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+    import pkgload
+    import torch.distributed as dist
+    pkg = pkgload.load()
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    b = pkg.layer_windows(ToyStage.L, world)
+    st = ToyRingStage(b[rank], b[rank + 1], rank == 0, rank == world - 1, world)
+    rr = pkg.RingRunner(st, rank, world, dist)
+    seeds = [(3 + s, 2 * s) for s in range(world)]
+    rr.slots(world * rounds + world - 1, first_tokens=seeds)     # + world - 1: let the last stage finish the last round
+    if rank == world - 1:
+        q.put(st.history)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_ring_of_sequences_matches_sequential_decoding(world):
+    rounds = 4
+    want = []
+    for s in range(world):
+        single = ToyStage(0, ToyStage.L, True, True)
+        tok, pos, hist = 3 + s, 2 * s, []
+        for _ in range(rounds):
+            single.decode_async(tok, pos)
+            tok = int(torch.argmax(single.logits)); pos += 1
+            hist.append(tok)
+        want.append(hist)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ring_worker, args=(r, world, port, q, rounds)) for r in range(world)]
+    [p.start() for p in procs]
+    got = q.get(timeout=120)
+    [p.join(60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    assert [h[:rounds] for h in got] == want
