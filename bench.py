@@ -270,7 +270,8 @@ def boundary_leg(eng, cfg, hp, args, lib):
            "api": "ggml_backend_tensor_set(inp_tokens, inp_pos, KQ_mask) + ggml_backend_graph_compute(B200_0) + ggml_backend_tensor_get(logits) "
                   "on the graph of host/llama_graph_host.cpp (build_llama restated; the host's ggml = the reference's, unmodified)",
            "timing": "host wall clock around K synchronous steps", "gpu_launches": int(launches), "launches_per_layer": (launches / args.steps - 3) / L,
-           "graph_nodes": hm.graph_nodes, "graph_builds": int(hm.graph_builds), "host_ms_per_step": phases, "clocks": clocks,
+           "graph_nodes": hm.graph_nodes, "graph_builds": int(hm.graph_builds), "cuda_graph_replays": int(hm.plug.ggml_backend_b200_graph_replays()),
+           "host_ms_per_step": phases, "clocks": clocks,
            "max_abs_vs_engine_first_token": float(np.max(np.abs(eng_logits - logits)))}
     hm.close()
     return res

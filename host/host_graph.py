@@ -47,6 +47,7 @@ def load(with_plugin: bool = True):
         plug = C.CDLL(str(PLUGIN), mode=C.RTLD_GLOBAL)
         plug.ggml_backend_b200_nodes_computed.restype = C.c_ulonglong
         plug.ggml_backend_b200_fused_steps.restype = C.c_ulonglong
+        plug.ggml_backend_b200_graph_replays.restype = C.c_ulonglong
     g = C.CDLL(str(drv), mode=C.RTLD_GLOBAL)
     vp = C.c_void_p
     g.lgh_create.restype = vp

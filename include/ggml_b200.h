@@ -33,6 +33,8 @@ __attribute__((visibility("default"))) int ggml_backend_is_b200(struct ggml_back
 __attribute__((visibility("default"))) unsigned long long ggml_backend_b200_nodes_computed(void);
 /* number of fused launches graph_compute has issued (mat-vec groups with folded norm / silu / bias / residual, attention chains) */
 __attribute__((visibility("default"))) unsigned long long ggml_backend_b200_fused_steps(void);
+/* graph_compute calls served by replaying a captured CUDA graph (same topology and tensor addresses as an earlier call) */
+__attribute__((visibility("default"))) unsigned long long ggml_backend_b200_graph_replays(void);
 
 /* Loading the shared object registers the backend automatically (a constructor calls ggml_backend_register,
  * ggml-backend-impl.h:220) unless the environment variable GGML_B200_NO_AUTOREG is set. */

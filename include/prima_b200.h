@@ -49,6 +49,7 @@ PB200_API int          pb200_device_count(void);
 PB200_API int          pb200_sm_count(void);              /* of the current device */
 PB200_API int64_t      pb200_row_bytes(int type, int64_t k);   /* ggml_row_size */
 PB200_API uint64_t     pb200_kernel_launches(void);       /* kernels launched by this library since load (bench `gpu_launches`) */
+PB200_API void         pb200_kernel_launches_add(uint64_t n);   /* a host that replays a CUDA graph of this library's launches accounts for them here */
 
 /* ---- single ops, device buffers ---- */
 /* workspace for the quantized activation of length k (any mode): bytes to allocate */
@@ -133,10 +134,11 @@ PB200_API int pb200_gemv_fused(int nmat, const pb200_gemv_mat * mats, int64_t k,
  * 10032-10165): rope(q), rope(k) -> f16 K row into cell kv_head of k_cache [cell][n_head_kv*128]; v -> f16 into column kv_head of the
  * TRANSPOSED v cache [n_head_kv*128][vt_stride]; out[h] = softmax(scale * K q_h + mask) . V over n_cells cells (multiple of 32, mask f32
  * [n_cells], -inf = not visible).  head_dim 128, n_head even.  act_ws_out (optional): also leaves q8_K(out) there for the following
- * mat-vec.  rope op parameters as in pb200_rope.  Returns PB200_ENOTSUP for shapes it does not handle. */
+ * mat-vec.  kv_head_dev (optional): the cell is read from this device word instead of kv_head, so a CUDA graph that captured the launch can
+ * be replayed for the next token.  rope op parameters as in pb200_rope.  Returns PB200_ENOTSUP for shapes it does not handle. */
 PB200_API int pb200_attn_ggml(const float * q, const float * k, const float * v, void * k_cache_f16, void * v_cache_t_f16, int64_t vt_stride, float * out,
                               void * act_ws_out, int n_head, int n_head_kv, int head_dim, const int32_t * pos_dev, int n_cells, int kv_head,
-                              const float * mask, int n_dims, int mode, float freq_base, float freq_scale, float ext_factor, float attn_factor,
+                              const int32_t * kv_head_dev, const float * mask, int n_dims, int mode, float freq_base, float freq_scale, float ext_factor, float attn_factor,
                               float beta_fast, float beta_slow, int n_ctx_orig, const float * freq_factors, float scale, int pdl, void * stream);
 
 /* ---- decode engine (one model shard per process / GPU) ---- */

@@ -52,6 +52,7 @@ int pb200_device_count(void) {
 int pb200_sm_count(void) { return sm_count(); }
 int64_t pb200_row_bytes(int type, int64_t k) { return row_bytes(type, k); }
 uint64_t pb200_kernel_launches(void) { return g_launches.load(); }
+void pb200_kernel_launches_add(uint64_t n) { g_launches += n; }
 
 size_t pb200_act_workspace_bytes(int64_t k) {
     const int64_t kp = (k + 255) / 256 * 256;
@@ -244,8 +245,8 @@ int pb200_gemv_fused(int nmat, const pb200_gemv_mat * mats, int64_t k, void * ac
 }
 
 int pb200_attn_ggml(const float * q, const float * k, const float * v, void * k_cache_f16, void * v_cache_t_f16, int64_t vt_stride, float * out,
-                    void * act_ws_out, int n_head, int n_head_kv, int head_dim, const int32_t * pos_dev, int n_cells, int kv_head, const float * mask,
-                    int n_dims, int mode, float freq_base, float freq_scale, float ext_factor, float attn_factor, float beta_fast, float beta_slow,
+                    void * act_ws_out, int n_head, int n_head_kv, int head_dim, const int32_t * pos_dev, int n_cells, int kv_head,
+                    const int32_t * kv_head_dev, const float * mask, int n_dims, int mode, float freq_base, float freq_scale, float ext_factor, float attn_factor, float beta_fast, float beta_slow,
                     int n_ctx_orig, const float * freq_factors, float scale, int pdl, void * stream) {
     if (!q || !k || !v || !k_cache_f16 || !v_cache_t_f16 || !out || !pos_dev || !mask || n_head <= 0 || n_head_kv <= 0) return PB200_EINVAL;
     if (head_dim != 128 || n_dims > head_dim || (n_dims & 1) || (mode != 0 && mode != 2)) return PB200_ENOTSUP;
@@ -257,7 +258,7 @@ int pb200_attn_ggml(const float * q, const float * k, const float * v, void * k_
         outq = act_from_ws(act_ws_out, (int64_t) n_head * head_dim);
     }
     const int rc = launch_attn_ggml(q, k, v, (__half *) k_cache_f16, (__half *) v_cache_t_f16, vt_stride, out, outq, n_head, n_head_kv, head_dim, pos_dev,
-                                    n_cells, kv_head, mask, rp, freq_factors, scale, (cudaStream_t) stream, pdl != 0);
+                                    n_cells, kv_head, kv_head_dev, mask, rp, freq_factors, scale, (cudaStream_t) stream, pdl != 0);
     if (rc == (int) cudaErrorNotSupported) return PB200_ENOTSUP;
     if (rc == 0) g_launches++;
     return rc;

@@ -99,8 +99,8 @@ int launch_attn_fused2(const float * q, const float * k, const float * v, __half
 // the same kernel on the reference graph's tensors (FA off, one token): K cache [cell][n_head_kv*128] f16, V cache TRANSPOSED
 // [n_head_kv*128][vt_stride] f16, additive f32 mask row over n_cells (multiple of 32) cells, this token stored in cell kv_head
 int launch_attn_ggml(const float * q, const float * k, const float * v, __half * kcache, __half * vcache_t, int64_t vt_stride, float * out, const ActQ & outq,
-                     int n_head, int n_head_kv, int D, const int32_t * pos_dev, int n_cells, int kv_head, const float * mask, const RopeParams & rp,
-                     const float * freq_factors, float scale, cudaStream_t stream, bool pdl);
+                     int n_head, int n_head_kv, int D, const int32_t * pos_dev, int n_cells, int kv_head, const int32_t * kv_head_dev, const float * mask,
+                     const RopeParams & rp, const float * freq_factors, float scale, cudaStream_t stream, bool pdl);
 
 // soft_max_ext for the plugin: y[r][:] = softmax(x[r][:]*scale + mask[r % mask_rows][:])  (softmax.cu:14-116)
 int launch_soft_max(const float * x, const float * mask, float * y, int ncols, int64_t nrows, int64_t rows_per_mask_cycle, float scale,

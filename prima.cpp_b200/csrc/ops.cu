@@ -694,6 +694,7 @@ struct Attn2Params {
     // GGML layout only (the FA-off chain of llm_build_kqv, src/llama.cpp:10032-10165)
     int n_cells;                  // cells attended: the graph's n_kv (multiple of 32)
     int kv_head;                  // cell this token's K / V are stored in (offset of the cache views of llm_build_kv_store)
+    const int32_t * kv_head_dev;  // if set: the cell is read from device memory instead (a captured CUDA graph is replayed with a new cell)
     int64_t vt_stride;            // elements between two channels of the transposed V cache (n_ctx)
     const float * mask;           // [n_cells] additive f32 mask row of this token (0 / -inf), soft_max_ext src1
 };
@@ -724,7 +725,7 @@ __global__ void __launch_bounds__(A2_THREADS, 1) k_attn2(const __grid_constant__
     // ---- independent of the producing GEMV: position (written before this token's first kernel), cache cells of earlier tokens
     const int pos = *P.pos_dev;
     const int ncell = GGML ? P.n_cells : pos + 1;              // cells attended
-    const int fresh = GGML ? P.kv_head : pos;                  // this token's cell: its K / V come from shared memory, not from the cache
+    const int fresh = GGML ? (P.kv_head_dev ? *P.kv_head_dev : P.kv_head) : pos;                  // this token's cell: its K / V come from shared memory, not from the cache
     const int nchunks = (ncell + A2_CHUNK - 1) / A2_CHUNK;
     a2_issue_chunk(sm->kbuf[0], kc, EK, hk, 0, ncell, &sm->kbar[0]);
     if (nchunks > 1) a2_issue_chunk(sm->kbuf[1], kc, EK, hk, 1, ncell, &sm->kbar[1]);
@@ -1318,14 +1319,14 @@ int launch_attn_fused2(const float * q, const float * k, const float * v, __half
 }
 // the reference graph's tensors (FA off): K cache rows, transposed V cache, explicit mask row and destination cell
 int launch_attn_ggml(const float * q, const float * k, const float * v, __half * kcache, __half * vcache_t, int64_t vt_stride, float * out, const ActQ & outq,
-                     int n_head, int n_head_kv, int D, const int32_t * pos_dev, int n_cells, int kv_head, const float * mask, const RopeParams & rp,
-                     const float * freq_factors, float scale, cudaStream_t stream, bool pdl) {
+                     int n_head, int n_head_kv, int D, const int32_t * pos_dev, int n_cells, int kv_head, const int32_t * kv_head_dev, const float * mask,
+                     const RopeParams & rp, const float * freq_factors, float scale, cudaStream_t stream, bool pdl) {
     if (D != 128 || n_cells <= 0 || (n_cells & 7) || kv_head < 0 || kv_head >= n_cells || (vt_stride & 7) || ((uintptr_t) vcache_t & 15) || ((uintptr_t) kcache & 15) || !mask)
         return (int) cudaErrorNotSupported;
     Attn2Params P{};
     P.q = q; P.k = k; P.v = v; P.kc = kcache; P.vc = vcache_t; P.out = out; P.outq = outq; P.n_head = n_head; P.n_head_kv = n_head_kv;
     P.pos_dev = pos_dev; P.rp = rp; P.freq_factors = freq_factors; P.scale = scale;
-    P.n_cells = n_cells; P.kv_head = kv_head; P.vt_stride = vt_stride; P.mask = mask;
+    P.n_cells = n_cells; P.kv_head = kv_head; P.kv_head_dev = kv_head_dev; P.vt_stride = vt_stride; P.mask = mask;
     return launch_attn2<true>(P, n_cells, stream, pdl);
 }
 

@@ -28,6 +28,7 @@
 
 static std::atomic<unsigned long long> g_nodes{0};
 static std::atomic<unsigned long long> g_fused_steps{0};
+static std::atomic<unsigned long long> g_graph_replays{0};
 
 #define CUDA_OK(expr)                                                                                   \
     do {                                                                                                \
@@ -64,6 +65,14 @@ struct b200_plan {
     uint64_t key;
     int n_nodes;
     std::vector<b200_step> steps;
+    // CUDA graph of the whole step sequence, valid while every tensor keeps its address (`bind`); the destination cell of the
+    // attention launches is read from device memory so that the same graph serves token after token
+    // (the reference captures node by node and patches the cpy nodes: ggml-cuda.cu:2602-2617, 2640, 2741-2771)
+    cudaGraphExec_t exec = nullptr;
+    uint64_t bind = 0;
+    int seen = 0;
+    uint64_t launches = 0, nodes = 0, fused = 0;
+    ~b200_plan() { if (exec) cudaGraphExecDestroy(exec); }
 };
 // Why private buffers: the graph allocator (ggml_gallocr) recycles a tensor's memory right after its last consumer IN GRAPH ORDER.
 // A fused step reads q / k / v (or gate / up) later than the nodes it replaces would have, by which time the allocator may have handed
@@ -87,6 +96,10 @@ struct b200_backend_ctx {
     float * scratch[SCR_COUNT] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t scratch_floats[SCR_COUNT] = {0, 0, 0, 0, 0, 0};
     cudaEvent_t copy_event = nullptr;
+    int32_t * kvh_dev = nullptr;       // destination cell of the current token (device word read by the captured attention launches)
+    int32_t * kvh_host = nullptr;      // pinned staging words for it
+    unsigned kvh_idx = 0;
+    bool capturing = false, capture_failed = false;
     std::vector<b200_plan *> plans;
     void * mmq_ws = nullptr;       // fp16 activation tiles for the tensor-core path (grown on demand)
     size_t mmq_ws_bytes = 0;
@@ -391,6 +404,8 @@ static void b200_backend_free(ggml_backend_t backend) {
     if (ctx->attn_tmp) cudaFree(ctx->attn_tmp);
     for (float * p : ctx->scratch) if (p) cudaFree(p);
     if (ctx->copy_event) cudaEventDestroy(ctx->copy_event);
+    if (ctx->kvh_dev) cudaFree(ctx->kvh_dev);
+    if (ctx->kvh_host) cudaFreeHost(ctx->kvh_host);
     for (b200_plan * p : ctx->plans) delete p;
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -442,6 +457,7 @@ static uint64_t graph_key(ggml_cgraph * g) {
         h = fnv(h, (uint64_t) t->op);
         h = fnv(h, (uint64_t) t->type);
         for (int d = 0; d < 4; d++) { h = fnv(h, (uint64_t) t->ne[d]); h = fnv(h, (uint64_t) t->nb[d]); }
+        for (int d = 0; d < 12; d++) h = fnv(h, (uint64_t) (uint32_t) t->op_params[d]);
         for (int k = 0; k < 4; k++) {
             const ggml_tensor * sN = t->src[k];
             h = fnv(h, sN ? (uint64_t) sN->op * 131 + (uint64_t) sN->type * 7 + (uint64_t) sN->ne[0] : 0x9e37ull);
@@ -741,6 +757,7 @@ static b200_plan * build_plan(ggml_cgraph * g, uint64_t key) {
 }
 
 static float * grow_scratch(b200_backend_ctx * ctx, int slot, size_t floats) {
+    if (floats > ctx->scratch_floats[slot] && ctx->capturing) { ctx->capture_failed = true; return ctx->scratch[slot]; }
     if (floats > ctx->scratch_floats[slot]) {
         if (ctx->scratch[slot]) { CUDA_OK(cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->scratch[slot]); }
         CUDA_OK(cudaMalloc((void **) &ctx->scratch[slot], floats * 4 + 256));
@@ -749,6 +766,7 @@ static float * grow_scratch(b200_backend_ctx * ctx, int slot, size_t floats) {
     return ctx->scratch[slot];
 }
 static void * grow_ws(b200_backend_ctx * ctx, int role, size_t need) {
+    if (need > ctx->fact_bytes[role] && ctx->capturing) { ctx->capture_failed = true; return ctx->fact_ws[role]; }   // no allocation inside a capture
     if (need > ctx->fact_bytes[role]) {
         if (ctx->fact_ws[role]) { CUDA_OK(cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->fact_ws[role]); }
         CUDA_OK(cudaMalloc(&ctx->fact_ws[role], need + 256));
@@ -822,6 +840,7 @@ static bool run_attn_step(b200_backend_ctx * ctx, ggml_cgraph * g, const b200_st
     // q / k / v are private; the only graph tensor read while heads finish at different times is the mask row
     bool via_tmp = !st.out_private && overlaps(out, out_bytes, mask->data, (size_t) n_kv * 4);
     if (via_tmp) {
+        if (ctx->attn_tmp_floats < (size_t) (H * D) && ctx->capturing) { ctx->capture_failed = true; return false; }
         if (ctx->attn_tmp_floats < (size_t) (H * D)) {
             if (ctx->attn_tmp) { CUDA_OK(cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->attn_tmp); }
             CUDA_OK(cudaMalloc((void **) &ctx->attn_tmp, out_bytes + 256));
@@ -831,7 +850,8 @@ static bool run_attn_step(b200_backend_ctx * ctx, ggml_cgraph * g, const b200_st
     }
     void * ws = st.quant_out ? grow_ws(ctx, 1, pb200_act_workspace_bytes(H * D)) : nullptr;
     const int rc = pb200_attn_ggml(q, k, v, (void *) kview->data, (void *) vview->data, vt_stride, out, ws, (int) H, (int) HK, (int) D,
-                                   (const int32_t *) ropeq->src[1]->data, (int) n_kv, kv_head, (const float *) mask->data, p[1], p[2], fb, fs, ef, af, bf, bsl, p[4],
+                                   (const int32_t *) ropeq->src[1]->data, (int) n_kv, kv_head, ctx->capturing ? ctx->kvh_dev : nullptr, (const float *) mask->data, p[1], p[2],
+                                   fb, fs, ef, af, bf, bsl, p[4],
                                    ropeq->src[2] ? (const float *) ropeq->src[2]->data : nullptr, scale, 1, ctx->stream);
     if (rc == PB200_ENOTSUP) return false;
     PB_OK(rc);
@@ -852,17 +872,7 @@ static void run_nodes_unfused(b200_backend_ctx * ctx, ggml_cgraph * g, const int
     }
 }
 
-static enum ggml_status b200_backend_graph_compute(ggml_backend_t backend, ggml_cgraph * cgraph) {
-    b200_backend_ctx * ctx = (b200_backend_ctx *) backend->context;
-    cudaSetDevice(ctx->device);
-    const uint64_t key = graph_key(cgraph);
-    b200_plan * plan = nullptr;
-    for (b200_plan * p : ctx->plans) if (p->key == key && p->n_nodes == ggml_graph_n_nodes(cgraph)) { plan = p; break; }
-    if (!plan) {
-        plan = build_plan(cgraph, key);
-        if (ctx->plans.size() >= 16) { delete ctx->plans.front(); ctx->plans.erase(ctx->plans.begin()); }
-        ctx->plans.push_back(plan);
-    }
+static void run_plan(b200_backend_ctx * ctx, ggml_cgraph * cgraph, b200_plan * plan) {
     for (const b200_step & st : plan->steps) {
         if (st.kind == 0) {
             run_nodes_unfused(ctx, cgraph, &st.node, 1);
@@ -875,16 +885,101 @@ static enum ggml_status b200_backend_graph_compute(ggml_backend_t backend, ggml_
             std::sort(nodes.begin(), nodes.end());
             run_nodes_unfused(ctx, cgraph, nodes.data(), (int) nodes.size());
         } else {
-            if (run_attn_step(ctx, cgraph, st)) {
-                g_nodes += 8; g_fused_steps++;
-                if (st.quant_out) continue;
-                continue;
-            }
+            if (run_attn_step(ctx, cgraph, st)) { g_nodes += 8; g_fused_steps++; continue; }
             int nodes[8] = {st.rope_q, st.rope_k, st.cpy_k, st.cpy_v, st.kq, st.soft, st.kqv, st.cont};
             std::sort(nodes, nodes + 8);
             run_nodes_unfused(ctx, cgraph, nodes, 8);
         }
     }
+}
+
+// destination cell of this call (-1: the plan has no fused attention, -2: the layers disagree)
+static int plan_kv_head(ggml_cgraph * g, const b200_plan * plan) {
+    int kvh = -1;
+    for (const b200_step & st : plan->steps) {
+        if (st.kind != 2) continue;
+        const ggml_tensor * cpyk = ggml_graph_node(g, st.cpy_k), * kq = ggml_graph_node(g, st.kq);
+        const ggml_tensor * kview = kq->src[0];
+        const int64_t row = kview->ne[2] * 128 * 2;
+        const int64_t off = (const char *) cpyk->data - (const char *) kview->data;
+        const int v = (off >= 0 && off % row == 0) ? (int) (off / row) : -2;
+        if (kvh == -1) kvh = v; else if (kvh != v) return -2;
+        if (v < 0 || v >= kview->ne[1]) return -2;
+    }
+    return kvh;
+}
+
+static enum ggml_status b200_backend_graph_compute(ggml_backend_t backend, ggml_cgraph * cgraph) {
+    b200_backend_ctx * ctx = (b200_backend_ctx *) backend->context;
+    cudaSetDevice(ctx->device);
+    const uint64_t key = graph_key(cgraph);
+    b200_plan * plan = nullptr;
+    for (b200_plan * p : ctx->plans) if (p->key == key && p->n_nodes == ggml_graph_n_nodes(cgraph)) { plan = p; break; }
+    if (!plan) {
+        plan = build_plan(cgraph, key);
+        if (ctx->plans.size() >= 16) { CUDA_OK(cudaStreamSynchronize(ctx->stream)); delete ctx->plans.front(); ctx->plans.erase(ctx->plans.begin()); }
+        ctx->plans.push_back(plan);
+    }
+    static const bool use_graphs = getenv("GGML_B200_NO_GRAPHS") == nullptr;
+    // which addresses this call binds: every node's data except the cache-store nodes (their address IS the destination cell)
+    std::vector<char> is_store((size_t) plan->n_nodes, 0);
+    bool has_attn = false;
+    for (const b200_step & st : plan->steps) if (st.kind == 2) { is_store[st.cpy_k] = is_store[st.cpy_v] = 1; has_attn = true; }
+    uint64_t bind = 0xcbf29ce484222325ull;
+    for (int i = 0; i < plan->n_nodes; i++) {
+        const ggml_tensor * t = ggml_graph_node(cgraph, i);
+        if (is_store[i]) continue;
+        bind = fnv(bind, (uint64_t) (uintptr_t) t->data);
+        for (int k = 0; k < 3; k++) if (t->src[k] && !is_store[i]) bind = fnv(bind, (uint64_t) (uintptr_t) t->src[k]->data);
+    }
+    const int kvh = has_attn ? plan_kv_head(cgraph, plan) : -1;
+    const bool graphable = use_graphs && kvh != -2 && plan->steps.size() >= 8;
+    if (graphable && !ctx->kvh_dev) {
+        CUDA_OK(cudaMalloc((void **) &ctx->kvh_dev, 256));
+        CUDA_OK(cudaMallocHost((void **) &ctx->kvh_host, 64 * sizeof(int32_t)));
+    }
+    auto push_cell = [&]() {
+        if (kvh >= 0) {   // a ring of pinned words: the host may run several calls ahead of the copies
+            int32_t * w = ctx->kvh_host + (ctx->kvh_idx++ & 63);
+            *w = kvh;
+            CUDA_OK(cudaMemcpyAsync(ctx->kvh_dev, w, 4, cudaMemcpyHostToDevice, ctx->stream));
+        }
+    };
+    if (graphable && plan->exec && plan->bind == bind) {
+        // replay: same topology, same addresses; only the destination cell (and the input tensors' contents) changed
+        push_cell();
+        CUDA_OK(cudaGraphLaunch(plan->exec, ctx->stream));
+        g_nodes += plan->nodes; g_fused_steps += plan->fused; g_graph_replays++;
+        pb200_kernel_launches_add(plan->launches);
+        return GGML_STATUS_SUCCESS;
+    }
+    if (plan->exec) { CUDA_OK(cudaStreamSynchronize(ctx->stream)); cudaGraphExecDestroy(plan->exec); plan->exec = nullptr; }
+    if (graphable && plan->bind == bind && plan->seen >= 1) {
+        // second call with these addresses: every workspace has its final size, capture the whole step sequence once
+        const unsigned long long n0 = g_nodes.load(), f0 = g_fused_steps.load();
+        const uint64_t l0 = pb200_kernel_launches();
+        ctx->capturing = true; ctx->capture_failed = false;
+        cudaGraph_t graph = nullptr;
+        push_cell();
+        if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            run_plan(ctx, cgraph, plan);
+            cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+            ctx->capturing = false;
+            if (e == cudaSuccess && graph && !ctx->capture_failed && cudaGraphInstantiate(&plan->exec, graph, 0) == cudaSuccess) {
+                plan->nodes = g_nodes.load() - n0; plan->fused = g_fused_steps.load() - f0; plan->launches = pb200_kernel_launches() - l0;
+                cudaGraphDestroy(graph);
+                CUDA_OK(cudaGraphLaunch(plan->exec, ctx->stream));
+                return GGML_STATUS_SUCCESS;
+            }
+            if (graph) cudaGraphDestroy(graph);
+            plan->exec = nullptr;
+            cudaGetLastError();
+        }
+        ctx->capturing = false;
+        plan->seen = -1000000;          // this plan cannot be captured: direct launches from now on
+    }
+    run_plan(ctx, cgraph, plan);
+    if (plan->bind == bind) plan->seen++; else { plan->bind = bind; plan->seen = 1; }
     return GGML_STATUS_SUCCESS;   // asynchronous: work is enqueued on the backend stream
 }
 
@@ -1111,6 +1206,7 @@ ggml_backend_t ggml_backend_b200_init(int device) {
 int ggml_backend_is_b200(ggml_backend_t backend) { return backend != nullptr && ggml_guid_matches(backend->guid, b200_guid()); }
 unsigned long long ggml_backend_b200_nodes_computed(void) { return g_nodes.load(); }
 unsigned long long ggml_backend_b200_fused_steps(void) { return g_fused_steps.load(); }
+unsigned long long ggml_backend_b200_graph_replays(void) { return g_graph_replays.load(); }
 
 }  // extern "C"
 

@@ -59,5 +59,6 @@ res = {"arch": arch, "n_tokens": n_tok, "max_abs_per_token": [float(x) for x in 
        "hidden_max_abs": float(np.max(np.abs(hid["CPU"] - hid["B200_0"]))), "kv_max_abs": kv_err,
        "argmax_agree": float(np.mean(out["CPU"].argmax(1) == out["B200_0"].argmax(1))),
        "launches_per_token": launches, "n_layer": n_layer, "graph_nodes": models["B200_0"].graph_nodes,
-       "fused_steps": int(plug.ggml_backend_b200_fused_steps() - fused0), "graph_builds": int(models["B200_0"].graph_builds)}
+       "fused_steps": int(plug.ggml_backend_b200_fused_steps() - fused0), "graph_builds": int(models["B200_0"].graph_builds),
+       "graph_replays": int(plug.ggml_backend_b200_graph_replays())}
 print(json.dumps(res))

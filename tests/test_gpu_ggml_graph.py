@@ -35,6 +35,16 @@ def test_whole_graph_matches_cpu_backend_and_is_fused(cuda, arch):
     assert max(per_layer) <= 6.0, (r["launches_per_token"], r["graph_nodes"])
     assert r["fused_steps"] >= 40 * (5 * r["n_layer"]), r["fused_steps"]
     assert r["graph_builds"] <= 3          # one topology per 32-cell bucket of n_kv: the plan is reused token after token
+    assert r["graph_replays"] >= 40 - 2 * 3, r["graph_replays"]   # per bucket: one direct call, one capture, then CUDA-graph replays
+
+
+def test_graph_replay_equals_direct_launches(cuda):
+    """GGML_B200_NO_GRAPHS=1 issues the same fused launches directly every token; replaying the captured CUDA graph (with the
+    destination cell read from device memory) must give bit-identical logits, i.e. the same errors against the CPU backend."""
+    a = run("qwen2", 20)
+    b = run("qwen2", 20, env={"GGML_B200_NO_GRAPHS": "1"})
+    assert a["graph_replays"] > 0 and b["graph_replays"] == 0
+    assert a["max_abs_per_token"] == b["max_abs_per_token"] and a["kv_max_abs"] == b["kv_max_abs"]
 
 
 def test_fused_equals_unfused_node_by_node(cuda):
