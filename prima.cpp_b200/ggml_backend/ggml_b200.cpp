@@ -922,15 +922,25 @@ static enum ggml_status b200_backend_graph_compute(ggml_backend_t backend, ggml_
     }
     static const bool use_graphs = getenv("GGML_B200_NO_GRAPHS") == nullptr;
     // which addresses this call binds: every node's data except the cache-store nodes (their address IS the destination cell)
-    std::vector<char> is_store((size_t) plan->n_nodes, 0);
     bool has_attn = false;
-    for (const b200_step & st : plan->steps) if (st.kind == 2) { is_store[st.cpy_k] = is_store[st.cpy_v] = 1; has_attn = true; }
+    std::vector<const ggml_tensor *> store;       // the cache-store nodes and their destination views
+    for (const b200_step & st : plan->steps) {
+        if (st.kind != 2) continue;
+        has_attn = true;
+        for (int i : {st.cpy_k, st.cpy_v}) {
+            const ggml_tensor * c = ggml_graph_node(cgraph, i);
+            store.push_back(c);
+            if (c->src[1]) store.push_back(c->src[1]);
+        }
+    }
+    std::sort(store.begin(), store.end());
+    auto is_store = [&](const ggml_tensor * t) { return std::binary_search(store.begin(), store.end(), t); };
     uint64_t bind = 0xcbf29ce484222325ull;
     for (int i = 0; i < plan->n_nodes; i++) {
         const ggml_tensor * t = ggml_graph_node(cgraph, i);
-        if (is_store[i]) continue;
+        if (is_store(t)) continue;
         bind = fnv(bind, (uint64_t) (uintptr_t) t->data);
-        for (int k = 0; k < 3; k++) if (t->src[k] && !is_store[i]) bind = fnv(bind, (uint64_t) (uintptr_t) t->src[k]->data);
+        for (int k = 0; k < 3; k++) if (t->src[k] && !is_store(t->src[k])) bind = fnv(bind, (uint64_t) (uintptr_t) t->src[k]->data);
     }
     const int kvh = has_attn ? plan_kv_head(cgraph, plan) : -1;
     const bool graphable = use_graphs && kvh != -2 && plan->steps.size() >= 8;
