@@ -69,6 +69,8 @@ struct b200_plan {
     // attention launches is read from device memory so that the same graph serves token after token
     // (the reference captures node by node and patches the cpy nodes: ggml-cuda.cu:2602-2617, 2640, 2741-2771)
     cudaGraphExec_t exec = nullptr;
+    std::vector<int> store_nodes;      // cache-store nodes and their destination views: their address IS the destination cell
+    bool has_attn = false;
     uint64_t bind = 0;
     int seen = 0;
     uint64_t launches = 0, nodes = 0, fused = 0;
@@ -100,6 +102,7 @@ struct b200_backend_ctx {
     int32_t * kvh_host = nullptr;      // pinned staging words for it
     unsigned kvh_idx = 0;
     bool capturing = false, capture_failed = false;
+    std::vector<char> skip;
     std::vector<b200_plan *> plans;
     void * mmq_ws = nullptr;       // fp16 activation tiles for the tensor-core path (grown on demand)
     size_t mmq_ws_bytes = 0;
@@ -448,20 +451,22 @@ static int node_index_of(const ggml_cgraph * g, const ggml_tensor * t, int hint_
     for (int i = hint_end - 1; i >= 0; i--) if (ggml_graph_node((ggml_cgraph *) g, i) == t) return i;
     return -1;
 }
+// topology signature of a graph: ops, types, shapes, strides that matter, op parameters, what each node reads.  Computed on every
+// graph_compute call (the host may rebuild a different graph in the same memory), so it is kept to three multiplies per node.
 static uint64_t graph_key(ggml_cgraph * g) {
     const int n = ggml_graph_n_nodes(g);
-    uint64_t h = 0xcbf29ce484222325ull;
-    h = fnv(h, (uint64_t) n);
+    uint64_t h = fnv(0xcbf29ce484222325ull, (uint64_t) n);
     for (int i = 0; i < n; i++) {
         const ggml_tensor * t = ggml_graph_node(g, i);
-        h = fnv(h, (uint64_t) t->op);
-        h = fnv(h, (uint64_t) t->type);
-        for (int d = 0; d < 4; d++) { h = fnv(h, (uint64_t) t->ne[d]); h = fnv(h, (uint64_t) t->nb[d]); }
-        for (int d = 0; d < 12; d++) h = fnv(h, (uint64_t) (uint32_t) t->op_params[d]);
-        for (int k = 0; k < 4; k++) {
+        const uint64_t w0 = (uint64_t) t->op | ((uint64_t) t->type << 8) | ((uint64_t) t->ne[0] << 16) ^ ((uint64_t) t->ne[1] << 40);
+        const uint64_t w1 = (uint64_t) t->ne[2] ^ ((uint64_t) t->nb[1] << 12) ^ ((uint64_t) t->nb[2] << 36) ^ (uint64_t) (uint32_t) t->op_params[0] ^
+                            ((uint64_t) (uint32_t) t->op_params[1] << 32) ^ ((uint64_t) (uint32_t) t->op_params[2] << 17) ^ ((uint64_t) (uint32_t) t->op_params[5] << 7);
+        uint64_t w2 = 0;
+        for (int k = 0; k < 3; k++) {
             const ggml_tensor * sN = t->src[k];
-            h = fnv(h, sN ? (uint64_t) sN->op * 131 + (uint64_t) sN->type * 7 + (uint64_t) sN->ne[0] : 0x9e37ull);
+            w2 = w2 * 1315423911ull + (sN ? (uint64_t) sN->op * 131 + (uint64_t) sN->type * 7 + (uint64_t) sN->ne[0] * 3 + (uint64_t) sN->ne[1] : 0x9e37ull);
         }
+        h = fnv(fnv(fnv(h, w0), w1), w2);
     }
     return h;
 }
@@ -744,6 +749,16 @@ static b200_plan * build_plan(ggml_cgraph * g, uint64_t key) {
     }
     b200_plan * plan = new b200_plan();
     plan->key = key; plan->n_nodes = G.n;
+    if (fused_ok) {
+        for (int anchor : attn_anchor) {
+            plan->has_attn = true;
+            for (int i : {at[anchor].cpy_k, at[anchor].cpy_v}) {
+                plan->store_nodes.push_back(i);
+                const int v = G.idx(ggml_graph_node(g, i)->src[1]);
+                if (v >= 0) plan->store_nodes.push_back(v);
+            }
+        }
+    }
     for (int i = 0; i < G.n; i++) {
         if (fused_ok && has[i]) { plan->steps.push_back(at[i]); continue; }
         if (fused_ok && taken[i]) continue;
@@ -922,25 +937,16 @@ static enum ggml_status b200_backend_graph_compute(ggml_backend_t backend, ggml_
     }
     static const bool use_graphs = getenv("GGML_B200_NO_GRAPHS") == nullptr;
     // which addresses this call binds: every node's data except the cache-store nodes (their address IS the destination cell)
-    bool has_attn = false;
-    std::vector<const ggml_tensor *> store;       // the cache-store nodes and their destination views
-    for (const b200_step & st : plan->steps) {
-        if (st.kind != 2) continue;
-        has_attn = true;
-        for (int i : {st.cpy_k, st.cpy_v}) {
-            const ggml_tensor * c = ggml_graph_node(cgraph, i);
-            store.push_back(c);
-            if (c->src[1]) store.push_back(c->src[1]);
-        }
-    }
-    std::sort(store.begin(), store.end());
-    auto is_store = [&](const ggml_tensor * t) { return std::binary_search(store.begin(), store.end(), t); };
+    const bool has_attn = plan->has_attn;
+    ctx->skip.assign((size_t) plan->n_nodes, 0);
+    for (int i : plan->store_nodes) ctx->skip[(size_t) i] = 1;
     uint64_t bind = 0xcbf29ce484222325ull;
     for (int i = 0; i < plan->n_nodes; i++) {
+        if (ctx->skip[(size_t) i]) continue;
         const ggml_tensor * t = ggml_graph_node(cgraph, i);
-        if (is_store(t)) continue;
-        bind = fnv(bind, (uint64_t) (uintptr_t) t->data);
-        for (int k = 0; k < 3; k++) if (t->src[k] && !is_store(t->src[k])) bind = fnv(bind, (uint64_t) (uintptr_t) t->src[k]->data);
+        uint64_t w = (uint64_t) (uintptr_t) t->data;
+        for (int k = 0; k < 3; k++) if (t->src[k]) w = w * 1315423911ull + (uint64_t) (uintptr_t) t->src[k]->data;   // leafs (weights, inputs) included
+        bind = fnv(bind, w);
     }
     const int kvh = has_attn ? plan_kv_head(cgraph, plan) : -1;
     const bool graphable = use_graphs && kvh != -2 && plan->steps.size() >= 8;
