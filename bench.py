@@ -52,6 +52,15 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic(model_key):
+    """DRAM bytes (read + write) the GEMV launches of one token move, from the committed `ncu --set full` capture of the shipped kernel
+    (profiles/r2_gemv_traffic.json: per-launch dram__bytes_read.sum + dram__bytes_write.sum at every launch shape of the model)."""
+    p = ROOT / "profiles" / "r2_gemv_traffic.json"
+    if model_key != "llama3-70b" or not p.exists():
+        return None
+    return float(json.loads(p.read_text())["llama3-70b_q4_K_M_per_token_MB"]) * 1e6
+
+
 def tensor_peak():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -198,7 +207,8 @@ def cpu_reference(model_key, steps, warmup, sample_layers=2):
     return {"value": 1.0 / t_full, "unit": "tokens/s", "cores": threads, "kind": kind,
             "sample": f"{steps} decode steps of {sample_layers} full-size layers + lm_head of {cfg['name']} (synthetic blocks) on the reference CPU "
                       f"ggml backend ({O.ref_variant() if kind == 'reference' else 'C port'}, OpenMP, GGML_USE_LLAMAFILE off), "
-                      f"extrapolated to {L} layers: t_layer={t_layer * 1e3:.2f} ms, t_head={t_head * 1e3:.2f} ms",
+                      + (f"extrapolated to {L} layers: " if sample_layers != L else "the whole model, nothing extrapolated: ")
+                      + f"t_layer={t_layer * 1e3:.2f} ms, t_head={t_head * 1e3:.2f} ms",
             "ms_per_step_sample": t_sample * 1e3, "ms_per_token_extrapolated": t_full * 1e3}
 
 
@@ -306,8 +316,9 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        steps, warm = min(args.steps, 6), min(args.warmup, 1)
-        cb = cpu_reference(args.model, steps, warm)
+        steps, warm = min(args.steps, 256), min(args.warmup, 64)   # the same K / W as the B200 arm (each step = the bounded sample below)
+        # Llama-3-8B (config C1) fits the bounded budget whole: every layer is timed, nothing is extrapolated
+        cb = cpu_reference(args.model, steps, warm, sample_layers=(MODELS[args.model]["hp"]["n_layer"] if args.model == "llama3-8b" else 2))
         print(json.dumps({"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "tokens/s", "n_gpus": args.gpus, "steps": steps,
                           "warmup": warm, "ms_per_step": cb["ms_per_token_extrapolated"], "higher_is_better": True, "scaling": "strong",
                           "vs_baseline": None, "dtype": "int8 x k-quant dot, f32 accumulate", "data": "synthetic", "config": config,
@@ -522,7 +533,8 @@ def main():
         "e2e": e2e_engine,
         "gpu_launches": launches,
         "clocks": clocks, "clocks_e2e": clocks_e2e,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(args.model),
+                     "traffic_note": "ncu dram__bytes_read.sum + dram__bytes_write.sum summed over the same launches (profiles/r2_gemv_traffic.json); algorithmic bytes are `how`",
                      "kernel": "k_gemv_kquant (TMA-staged k-quant GEMV)", "peak_source": peak_src,
                      "how": f"algorithmic bytes of the {gemv_launches} GEMV launches of one token ({gemv_bytes} B = sum of ggml_nbytes of the weight "
                             f"matrices read) / their summed CUDA-event durations ({gemv_ms:.3f} ms, events on the launching stream, mean of 4 profiled steps)",

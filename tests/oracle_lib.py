@@ -41,6 +41,9 @@ def _cpu_flags() -> set:
 
 
 def ref_variant() -> str:
+    forced = os.environ.get("PB200_REF_VARIANT")          # tests/test_reference_self_divergence.py runs both builds
+    if forced in ("v3", "v4") and (ORACLE / "_ref" / forced / "libggml_ref.so").exists():
+        return forced
     need_v4 = {"avx512f", "avx512bw", "avx512cd", "avx512dq", "avx512vl"}
     return "v4" if need_v4 <= _cpu_flags() and (ORACLE / "_ref" / "v4" / "libggml_ref.so").exists() else "v3"
 
