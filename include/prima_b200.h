@@ -111,6 +111,14 @@ PB200_API int pb200_attn_decode(const float * q, const void * k_cache_f16, const
 PB200_API int pb200_attn_prefill(const float * q, const void * k_cache_f16, const void * v_cache_f16, float * out, int n_head, int n_head_kv,
                                  int head_dim, const int32_t * pos_dev, int n_tok, int n_kv_max, float scale, void * stream);
 
+/* GGML_OP_FLASH_ATTN_EXT (ggml_cuda_flash_attn_ext, ggml-cuda/fattn.cu:298-345; CPU ggml.c:15538-15748) with f16 K / V:
+ * dst[D][n_head][n_tokens] = softmax(scale * K q + slope * mask) . V per (token, head); online softmax split over the KV range and
+ * merged (flash_attn_combine_results, fattn-common.cuh:519-561).  Byte strides: q_nb = {nb1 (token), nb2 (head)}, k_nb / v_nb =
+ * {nb1 (cell), nb2 (kv head)}; mask f16 [n_kv] rows of mask_nb1 bytes or NULL; max_bias = ALiBi, logit_softcap = Gemma-2 style cap. */
+PB200_API int pb200_flash_attn_ext(const float * q, const void * k_f16, const void * v_f16, const void * mask_f16, float * dst, int head_dim, int n_tokens,
+                                   int n_head, int n_head_kv, int n_kv, const int64_t * q_nb, const int64_t * k_nb, const int64_t * v_nb, int64_t mask_nb1,
+                                   float scale, float max_bias, float logit_softcap, void * stream);
+
 /* ---- fused decode launches (what the engine is made of), for graph-level fusion in a host such as the ggml-backend plugin ---- */
 typedef struct pb200_gemv_mat {
     int32_t type;          /* k-quant type of W (Q4_K / Q5_K / Q6_K) */

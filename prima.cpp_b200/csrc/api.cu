@@ -264,6 +264,16 @@ int pb200_attn_ggml(const float * q, const float * k, const float * v, void * k_
     return rc;
 }
 
+int pb200_flash_attn_ext(const float * q, const void * k_f16, const void * v_f16, const void * mask_f16, float * dst, int head_dim, int n_tokens, int n_head,
+                         int n_head_kv, int n_kv, const int64_t * q_nb, const int64_t * k_nb, const int64_t * v_nb, int64_t mask_nb1, float scale,
+                         float max_bias, float logit_softcap, void * stream) {
+    if (!q || !k_f16 || !v_f16 || !dst || !q_nb || !k_nb || !v_nb || n_kv <= 0) return PB200_EINVAL;
+    if (head_dim > 256) return PB200_ENOTSUP;
+    g_launches++;
+    return launch_flash_attn_ext(q, k_f16, v_f16, mask_f16, dst, head_dim, n_tokens, n_head, n_head_kv, n_kv, q_nb, k_nb, v_nb, mask_nb1, scale, max_bias,
+                                 logit_softcap, (cudaStream_t) stream);
+}
+
 int pb200_attn_prefill(const float * q, const void * k_cache_f16, const void * v_cache_f16, float * out, int n_head, int n_head_kv, int head_dim,
                        const int32_t * pos_dev, int n_tok, int n_kv_max, float scale, void * stream) {
     if (!q || !k_cache_f16 || !v_cache_f16 || !out || !pos_dev || head_dim != 128 || n_head_kv <= 0 || n_head % n_head_kv || n_tok <= 0 || n_kv_max <= 0)

@@ -1143,6 +1143,80 @@ __global__ void __launch_bounds__(256) k_mul_mat_f16(const char * __restrict__ A
     if (lane == 0) *reinterpret_cast<float *>(D + i0 * m.d[0] + i1 * m.d[1] + i2 * m.d[2] + i3 * m.d[3]) = acc;
 }
 
+// ------------------------------------------------------------------------------------------------
+// GGML_OP_FLASH_ATTN_EXT (ggml_cuda_flash_attn_ext, ggml-cuda/fattn.cu:298-345; CPU: ggml_compute_forward_flash_attn_ext_f16,
+// ggml.c:15538-15748): out[h][t] = softmax(scale * K q + slope * mask) . V with f16 K / V, one CTA per (token, head).
+// The 8 warps split the KV range and each runs the online softmax (running max M, sum S, f32 accumulator: one lane owns the
+// dimensions lane, lane + 32, ...), then the partial results are merged like the reference's split-KV combine
+// (flash_attn_combine_results, fattn-common.cuh:519-561).  Cells whose mask is -inf are skipped as on the CPU; ALiBi slope and
+// logit soft-cap follow ggml.c:15601-15605, 15652-15656.  Any head size up to 256 (64 / 80 / 128 / 256 in the reference's tests).
+constexpr int FA_WARPS = 8, FA_MAXD = 256;
+struct FlashParams {
+    const float * q; const __half * k; const __half * v; const __half * mask; float * dst;
+    int D, n_tok, n_head, n_head_kv, n_kv;
+    int64_t q_nb1, q_nb2, k_nb1, k_nb2, v_nb1, v_nb2, mask_nb1;    // bytes
+    float scale, max_bias, softcap, m0, m1;
+    int n_head_log2;
+};
+__global__ void __launch_bounds__(FA_WARPS * 32) k_flash_attn_ext(const __grid_constant__ FlashParams P) {
+    __shared__ float s_q[FA_MAXD];
+    __shared__ float s_acc[FA_WARPS][FA_MAXD];
+    __shared__ float s_M[FA_WARPS], s_S[FA_WARPS];
+    const int t = blockIdx.x, h = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int D = P.D;
+    const int hk = h / (P.n_head / P.n_head_kv);
+    const float * q = reinterpret_cast<const float *>(reinterpret_cast<const char *>(P.q) + t * P.q_nb1 + h * P.q_nb2);
+    // the CPU converts q to f16 before the dot (q_to_vec_dot, ggml.c:15630): same rounding here
+    for (int d = threadIdx.x; d < D; d += FA_WARPS * 32) s_q[d] = __half2float(__float2half_rn(q[d]));
+    __syncthreads();
+    const float slope = P.max_bias > 0.0f ? (h < P.n_head_log2 ? powf(P.m0, (float) (h + 1)) : powf(P.m1, (float) (2 * (h - P.n_head_log2) + 1))) : 1.0f;
+    const __half * mp = P.mask ? reinterpret_cast<const __half *>(reinterpret_cast<const char *>(P.mask) + t * P.mask_nb1) : nullptr;
+    constexpr int NPL = FA_MAXD / 32;
+    float qr[NPL], acc[NPL];
+#pragma unroll
+    for (int i = 0; i < NPL; i++) { const int d = lane + 32 * i; qr[i] = d < D ? s_q[d] : 0.f; acc[i] = 0.f; }
+    float M = -INFINITY, S = 0.f;
+    float scale = P.scale;
+    if (P.softcap != 0.0f) scale /= P.softcap;
+    for (int c = warp; c < P.n_kv; c += FA_WARPS) {
+        const float mv = mp ? slope * __half2float(mp[c]) : 0.0f;
+        if (mv == -INFINITY) continue;
+        const __half * kr = reinterpret_cast<const __half *>(reinterpret_cast<const char *>(P.k) + c * P.k_nb1 + hk * P.k_nb2);
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < NPL; i++) { const int d = lane + 32 * i; if (d < D) s = fmaf(__half2float(kr[d]), qr[i], s); }
+        s = warp_sum(s);
+        s *= scale;
+        if (P.softcap != 0.0f) s = P.softcap * tanhf(s);
+        s += mv;
+        float ms = 1.0f, vs = 1.0f;
+        if (s > M) { ms = expf(M - s); M = s; } else { vs = expf(s - M); }
+        const __half * vr = reinterpret_cast<const __half *>(reinterpret_cast<const char *>(P.v) + c * P.v_nb1 + hk * P.v_nb2);
+#pragma unroll
+        for (int i = 0; i < NPL; i++) { const int d = lane + 32 * i; if (d < D) acc[i] = fmaf(__half2float(vr[d]), vs, acc[i] * ms); }
+        S = S * ms + vs;
+    }
+    if (lane == 0) { s_M[warp] = M; s_S[warp] = S; }
+#pragma unroll
+    for (int i = 0; i < NPL; i++) { const int d = lane + 32 * i; if (d < D) s_acc[warp][d] = acc[i]; }
+    __syncthreads();
+    float Mg = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < FA_WARPS; w++) Mg = fmaxf(Mg, s_M[w]);
+    float Sg = 0.f;
+#pragma unroll
+    for (int w = 0; w < FA_WARPS; w++) Sg += s_M[w] == -INFINITY ? 0.f : s_S[w] * expf(s_M[w] - Mg);
+    const float inv = 1.0f / Sg;
+    float * out = P.dst + ((int64_t) t * P.n_head + h) * D;      // dst is [D, n_head, n_tok] (the op writes the permuted result)
+    for (int d = threadIdx.x; d < D; d += FA_WARPS * 32) {
+        float a = 0.f;
+#pragma unroll
+        for (int w = 0; w < FA_WARPS; w++) a += s_M[w] == -INFINITY ? 0.f : s_acc[w][d] * expf(s_M[w] - Mg);
+        out[d] = a * inv;
+    }
+}
+
 // ================================================================================================ launchers
 int launch_copy_strided(const void * src, void * dst, int dst_is_f16, const int64_t ne[4], const int64_t sb[4], const int64_t db[4], cudaStream_t stream) {
     Copy4 c;
@@ -1328,6 +1402,24 @@ int launch_attn_ggml(const float * q, const float * k, const float * v, __half *
     P.pos_dev = pos_dev; P.rp = rp; P.freq_factors = freq_factors; P.scale = scale;
     P.n_cells = n_cells; P.kv_head = kv_head; P.kv_head_dev = kv_head_dev; P.vt_stride = vt_stride; P.mask = mask;
     return launch_attn2<true>(P, n_cells, stream, pdl);
+}
+
+int launch_flash_attn_ext(const float * q, const void * k, const void * v, const void * mask, float * dst, int D, int n_tok, int n_head, int n_head_kv,
+                          int n_kv, const int64_t * q_nb, const int64_t * k_nb, const int64_t * v_nb, int64_t mask_nb1, float scale, float max_bias,
+                          float softcap, cudaStream_t stream) {
+    if (D <= 0 || D > FA_MAXD || n_tok <= 0 || n_head <= 0 || n_head_kv <= 0 || n_head % n_head_kv || n_tok > 2147483647 || n_head > 65535)
+        return (int) cudaErrorInvalidValue;
+    FlashParams P{};
+    P.q = q; P.k = (const __half *) k; P.v = (const __half *) v; P.mask = (const __half *) mask; P.dst = dst;
+    P.D = D; P.n_tok = n_tok; P.n_head = n_head; P.n_head_kv = n_head_kv; P.n_kv = n_kv;
+    P.q_nb1 = q_nb[0]; P.q_nb2 = q_nb[1]; P.k_nb1 = k_nb[0]; P.k_nb2 = k_nb[1]; P.v_nb1 = v_nb[0]; P.v_nb2 = v_nb[1]; P.mask_nb1 = mask_nb1;
+    P.scale = scale; P.max_bias = max_bias; P.softcap = softcap;
+    P.n_head_log2 = 1;
+    while (P.n_head_log2 * 2 <= n_head) P.n_head_log2 *= 2;
+    P.m0 = powf(2.0f, -max_bias / P.n_head_log2);
+    P.m1 = powf(2.0f, -(max_bias / 2.0f) / P.n_head_log2);
+    k_flash_attn_ext<<<dim3(n_tok, n_head), FA_WARPS * 32, 0, stream>>>(P);
+    return (int) cudaGetLastError();
 }
 
 int launch_soft_max(const float * x, const float * mask, float * y, int ncols, int64_t nrows, int64_t rows_per_mask_cycle, float scale,

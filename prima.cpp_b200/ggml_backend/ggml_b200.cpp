@@ -264,6 +264,13 @@ static bool b200_supports_op(ggml_backend_dev_t, const ggml_tensor * op) {
         case GGML_OP_DUP:
         case GGML_OP_CONT:
             return a->type == GGML_TYPE_F32 && (op->type == GGML_TYPE_F32 || op->type == GGML_TYPE_F16) && ggml_nelements(a) == ggml_nelements(op);
+        case GGML_OP_FLASH_ATTN_EXT: {   // f16 K / V (the KV cache types this backend runs with), any head size up to 256, one batch
+            const ggml_tensor * k = op->src[1], * v = op->src[2], * m = op->src[3];
+            return a->type == GGML_TYPE_F32 && k->type == GGML_TYPE_F16 && v->type == GGML_TYPE_F16 && op->type == GGML_TYPE_F32 && a->ne[0] <= 256 &&
+                   a->ne[0] == k->ne[0] && a->ne[0] == v->ne[0] && a->ne[3] == 1 && k->ne[3] == 1 && v->ne[3] == 1 && k->ne[2] == v->ne[2] && k->ne[1] == v->ne[1] &&
+                   k->ne[2] > 0 && a->ne[2] % k->ne[2] == 0 && a->nb[0] == sizeof(float) && k->nb[0] == 2 && v->nb[0] == 2 && ggml_is_contiguous(op) &&
+                   (m == nullptr || (m->type == GGML_TYPE_F16 && m->ne[0] == k->ne[1] && m->ne[1] >= a->ne[1] && m->nb[0] == 2));
+        }
         case GGML_OP_GET_ROWS:
             return (a->type == GGML_TYPE_F32 || a->type == GGML_TYPE_F16 || type_is_quant(a->type)) && b->type == GGML_TYPE_I32 && op->type == GGML_TYPE_F32 &&
                    ggml_is_contiguous(a) && ggml_is_contiguous(b) && ggml_is_contiguous(op) && a->ne[2] == 1 && a->ne[3] == 1 && b->ne[2] == 1 && b->ne[3] == 1;
@@ -380,6 +387,15 @@ static bool b200_compute_node(b200_backend_ctx * ctx, ggml_tensor * dst) {
                 return false;
             }
             PB_OK(pb200_copy_strided(a->data, out, d->type == GGML_TYPE_F16, ne, sb, db, st));
+            return true;
+        }
+        case GGML_OP_FLASH_ATTN_EXT: {
+            const ggml_tensor * k = dst->src[1], * v = dst->src[2], * m = dst->src[3];
+            float scale, max_bias, softcap;
+            memcpy(&scale, (const float *) dst->op_params + 0, 4); memcpy(&max_bias, (const float *) dst->op_params + 1, 4); memcpy(&softcap, (const float *) dst->op_params + 2, 4);
+            const int64_t qnb[2] = {(int64_t) a->nb[1], (int64_t) a->nb[2]}, knb[2] = {(int64_t) k->nb[1], (int64_t) k->nb[2]}, vnb[2] = {(int64_t) v->nb[1], (int64_t) v->nb[2]};
+            PB_OK(pb200_flash_attn_ext((const float *) a->data, k->data, v->data, m ? m->data : nullptr, (float *) dst->data, (int) a->ne[0], (int) a->ne[1], (int) a->ne[2],
+                                       (int) k->ne[2], (int) k->ne[1], qnb, knb, vnb, m ? (int64_t) m->nb[1] : 0, scale, max_bias, softcap, st));
             return true;
         }
         case GGML_OP_GET_ROWS:

@@ -14,7 +14,7 @@ import oracle_lib as O
 pytestmark = pytest.mark.gpu
 ROOT = Path(__file__).resolve().parent.parent
 PLUGIN = ROOT / "prima.cpp_b200" / "libggml-b200.so"
-OPS = ["MUL_MAT", "RMS_NORM", "ROPE", "SOFT_MAX", "ADD", "MUL", "CPY", "CONT", "DUP", "GET_ROWS", "SILU"]
+OPS = ["MUL_MAT", "RMS_NORM", "ROPE", "SOFT_MAX", "ADD", "MUL", "CPY", "CONT", "DUP", "GET_ROWS", "SILU", "FLASH_ATTN_EXT"]
 
 
 def run_tbo(args, timeout=900):
