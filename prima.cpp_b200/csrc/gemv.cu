@@ -237,7 +237,10 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_CTAS_PER_SM) k_gemv_kquant(
     const int wpr = SPLIT ? P.wpr : 1;
     const int ngroups = GEMV_NW / wpr;
     const int group = warp / wpr, wsub = warp % wpr;
-    const int blk = wsub * 32 + lane;
+    // short rows (nblk <= 16, e.g. K = 4096 of Llama-3-8B): a warp holds 32 / nblk_p2 rows side by side, lane = (row in the slot, super-block)
+    const int nbp = SPLIT ? 32 : P.nblk_p2, rpw = 32 / nbp;
+    const int sub = SPLIT ? 0 : lane / nbp;
+    const int blk = SPLIT ? wsub * 32 + lane : (lane & (nbp - 1));
     const bool valid = blk < P.nblk;
 
     ActRegs r;
@@ -305,30 +308,37 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_CTAS_PER_SM) k_gemv_kquant(
         const int bpb = type == T_Q4_K ? BYTES_Q4_K : (type == T_Q5_K ? BYTES_Q5_K : BYTES_Q6_K);
         const uint32_t mis = (uint32_t) (((int64_t) r0 * M.row_bytes) & 15);
         const uint8_t * tile = stages + (size_t) s * P.stage_bytes + mis;
-        const int first = (group - it * M.rows_per_tile) & (ngroups - 1);                     // this group's first slot in the stage
-        if (P.owner_only && first >= M.rows_per_tile) continue;   // not an owner of this stage (stable per stage: see gemv_plan)
+        const int spt = M.rows_per_tile / rpw;                                                // row slots per tile (a slot = rpw rows, one per sub-warp)
+        const int first = (group - it * spt) & (ngroups - 1);                                 // this group's first slot in the stage
+        if (P.owner_only && first >= spt) continue;   // not an owner of this stage (stable per stage: see gemv_plan)
         mbar_wait(&ctl->full[s], ph, &ctl->aborted, P.abort_flag);
         if (TRACE && it == 0) stamp<TRACE>(P, 4);
         if (!SPLIT) {
-            for (int slot = first; slot < nrows; slot += ngroups) {
-                const int row = r0 + slot;
+            const int nslots = (nrows + rpw - 1) / rpw;
+            for (int slot = first; slot < nslots; slot += ngroups) {
+                const int rit = slot * rpw + sub;                 // row inside the tile
+                const int row = r0 + rit;
+                const bool has_row = rit < nrows;
+                const bool writer = (lane & (nbp - 1)) == 0 && has_row;
                 // epilogue operands are requested before the dot so that their L2 latency is off the critical path
                 float extra = 0.f;
-                if (lane == 0) {
+                if (writer) {
                     if (M.bias) extra = M.bias[row];
                     if (M.resid) extra += __ldcg(M.resid + row);
                 }
                 float v = 0.f;
-                if (valid) v = dot_block<TYPE>(type, tile + (size_t) slot * M.row_bytes + (size_t) blk * bpb, r);
-                if (slot + ngroups >= nrows) {
+                if (valid && has_row) v = dot_block<TYPE>(type, tile + (size_t) rit * M.row_bytes + (size_t) blk * bpb, r);
+                if (slot + ngroups >= nslots) {
                     // last row of this stage for this warp: hand the buffer back before reducing
                     __syncwarp();
                     if (lane == 0) release_stage(P, ctl, stages, s, it, pol);
                 }
-                v = warp_sum(v);
-                if (lane == 0) M.y[row] = v + extra;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+                    if (o < nbp) v += __shfl_xor_sync(0xffffffffu, v, o);      // reduce inside the sub-warp of the row
+                if (writer) M.y[row] = v + extra;
             }
-            if (first >= nrows) {   // no row for this warp in the stage: still release it
+            if (first >= nslots) {   // no row for this warp in the stage: still release it
                 __syncwarp();
                 if (lane == 0) release_stage(P, ctl, stages, s, it, pol);
             }
@@ -679,7 +689,7 @@ int gemv_set_trace(unsigned long long * dev_buf, int slots) {
 bool gemv_fused_prologue_ok(int K) { return K > 0 && K % 256 == 0 && K / 256 <= GEMV_ACT_MAX_NBLK; }
 
 // ring geometry of one launch: rows per tile of each matrix, stage size, depth — everything that must fit 2 CTAs on an SM
-struct GemvPlan { int wpr, nstage, nstage_init, stage_bytes, smem, owner_only, rel_count, rows[GEMV_MAX_MAT]; };
+struct GemvPlan { int wpr, nblk_p2, nstage, nstage_init, stage_bytes, smem, owner_only, rel_count, rows[GEMV_MAX_MAT]; };
 // tunables (environment, read once): ring geometry experiments without a rebuild
 struct GemvTune { int stage_target, max_stage, prefill; };
 static const GemvTune tune = [] {
@@ -695,16 +705,21 @@ static bool gemv_plan(const int * types, const int * Ns, int nmat, int K, GemvPl
     int wpr = 1;
     while (wpr * 32 < nblk) wpr *= 2;
     const int ngroups = GEMV_NW / wpr;
+    int nbp = 1;
+    while (nbp < nblk && nbp < 32) nbp *= 2;
+    const int rpw = wpr > 1 ? 1 : 32 / nbp;          // rows a warp holds side by side (short rows)
+    pl.nblk_p2 = nbp;
     int64_t biggest = 0;
     for (int i = 0; i < nmat; i++) {
         if (!is_kquant(types[i]) || Ns[i] < 1) return false;
         const int64_t rb = row_bytes(types[i], K);
         int R = (int) std::max<int64_t>(1, tune.stage_target / rb);
+        R = std::max(rpw, R / rpw * rpw);              // whole slots
         if (wpr > 1) {                             // split rows: at most one row per warp group and stage, and a ring of >= 4 stages
             R = std::min(R, ngroups);
             while (R > 1 && (GEMV_SMEM_LIMIT - GEMV_CTL_BYTES) / ((R * rb + 16 + 127) / 128 * 128) < 5) R--;
         }
-        R = std::min(R, Ns[i]);
+        if (R > Ns[i]) R = (Ns[i] + rpw - 1) / rpw * rpw;   // (ragged rows of the last slot are masked in the kernel)
         pl.rows[i] = R;
         biggest = std::max<int64_t>(biggest, R * rb);
     }
@@ -723,7 +738,7 @@ static bool gemv_plan(const int * types, const int * Ns, int nmat, int K, GemvPl
     {
         bool same = true;
         for (int i = 1; i < nmat; i++) same = same && pl.rows[i] == pl.rows[0];
-        const int R = pl.rows[0];
+        const int R = pl.rows[0] / rpw;          // row slots per tile
         if (same && R < ngroups && !getenv("PB200_GEMV_VISIT_ALL")) {
             int g = R, b = ngroups;
             while (b) { const int t = g % b; g = b; b = t; }
@@ -787,6 +802,7 @@ int launch_gemv_kquant_fused(const GemvDesc * d, int nmat, int K, const ActQ & a
     }
     GemvParams P{};
     P.wpr = pl.wpr;
+    P.nblk_p2 = pl.nblk_p2;
     P.nblk = K / 256;
     P.K = K;
     P.nmat = nmat;

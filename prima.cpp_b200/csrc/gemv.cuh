@@ -70,6 +70,7 @@ struct GemvParams {
     int K;
     int nblk;          // K / 256
     int wpr;           // warps per row: 1, 2 or 4
+    int nblk_p2;       // lanes per row: nblk rounded up to a power of two, at most 32.  Short rows (K <= 4096) put 32 / nblk_p2 rows in one warp
     int nstage;        // ring depth of this launch
     int nstage_init;   // stages [nstage_init, nstage) overlay the activation staging area: they join the ring once the activation is in registers
     int rel_count;     // warps that hand a stage back before it is refilled: all 8, or only its owners (owner_only)
