@@ -231,7 +231,8 @@ int pb200_gemv_fused(int nmat, const pb200_gemv_mat * mats, int64_t k, void * ac
     bool gemv_pdl = pdl != 0;
     if (prologue != 0) {
         if (sync_ws && gemv_dist_prologue_ok()) {
-            pro.kind = prologue == 1 ? 4 : 5; pro.in0 = in0; pro.in1 = in1; pro.eps = eps; pro.gbar = (unsigned int *) sync_ws;
+            static const int kind_add = getenv("PB200_NO_CLUSTER") ? 0 : 2;
+            pro.kind = (prologue == 1 ? 4 : 5) + kind_add; pro.in0 = in0; pro.in1 = in1; pro.eps = eps; pro.gbar = (unsigned int *) sync_ws;
         } else {   // the grid cannot be made co-resident on this device: produce the activation with a small kernel in front
             g_launches++;
             int e = prologue == 1 ? launch_rmsnorm_quant(in0, in1, (int) k, eps, ACT_Q8_K, act, nullptr, st, gemv_pdl)

@@ -61,7 +61,11 @@ struct GemvMat {
 //   co-resident), then every CTA stages the finished vector like PRO_NONE.  No tiny kernel + launch boundary in front of the GEMV
 //   (measured chain ~9.5 us from "previous GEMV done" to "first tile consumed", profiles/r2_token_trace_v2.txt), and 1/296 of the
 //   work per CTA instead of every CTA recomputing the whole vector from L2 (round 1: ~7 us and 19 MB of L2 reads per launch).
-enum : int { PRO_NONE = 0, PRO_RMSNORM_DIST = 4, PRO_SILU_DIST = 5 };
+//   Cluster variants (PRO_RMSNORM_CLUSTER, PRO_SILU_CLUSTER): the launch runs as thread-block clusters of GEMV_CLUSTER CTAs; each CTA
+//   quantizes 1/GEMV_CLUSTER of the super-blocks into ITS OWN shared memory, the cluster exchanges them through distributed shared
+//   memory (two cluster barriers + one DSMEM copy, ~1 us) — no grid barrier, no round trip through L2 for the finished vector.
+enum : int { PRO_NONE = 0, PRO_RMSNORM_DIST = 4, PRO_SILU_DIST = 5, PRO_RMSNORM_CLUSTER = 6, PRO_SILU_CLUSTER = 7 };
+constexpr int GEMV_CLUSTER = 4;
 
 struct GemvParams {
     GemvMat mat[GEMV_MAX_MAT];

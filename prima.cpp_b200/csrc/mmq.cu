@@ -88,7 +88,8 @@ __device__ __forceinline__ bool mmq_wait_(MmqCtl * ctl, uint64_t * bar, uint32_t
         if ((++spins & 255) == 0) {
             if (ctl->abort) return false;
             if (clock64() - t0 > PB_WAIT_TIMEOUT_CYCLES) {
-                wait_gave_up(&ctl->abort, abort_flag);
+                ctl->abort = 1;                                          // inline on purpose: a call in this kernel costs 7-12 registers
+                if (abort_flag) *(volatile int *) abort_flag = 1;        // host-mapped; visible at the latest when the launch ends
                 return false;
             }
         }
