@@ -287,6 +287,105 @@ def boundary_leg(eng, cfg, hp, args, lib):
     return res
 
 
+# ------------------------------------------------------------------------------------------------ same-box GPU comparator
+def ggml_cuda_arm(args, cfg, hp, config):
+    """--impl ggml-cuda: the reference's OWN ggml-cuda backend (unmodified, built for sm_100 by oracle/Makefile.cudaref — BASELINE.md §3
+    "the existing kernel to beat") on the same box, same synthetic weights, same host graph (host/llama_graph_host.cpp), same protocol
+    as the B200 arm's e2e leg: host token / position / mask in, logits out, every step.  Measurement infrastructure: none of the
+    product's kernels run inside the timed region (the engine is used before it, to synthesise the weights, and is then freed)."""
+    import numpy as np
+    import torch
+    import pkgload
+    sys.path.insert(0, str(ROOT / "host"))
+    import host_graph as HG
+    pkg = pkgload.load()
+    lib = pkg.Lib.get()
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    L, nv, E = hp["n_layer"], hp["n_vocab"], hp["n_embd"]
+    eng = pkg.Model(pkg.HParams(**hp), 0, (0, L), with_embd=True, with_head=True)
+    eng.synth(cfg["ftype"], 1234)
+    eng.finalize()
+    names = ["token_embd.weight", "output.weight", "output_norm.weight"]
+    for il in range(L):
+        names += [f"blk.{il}.{w}.weight" for w in ("attn_norm", "ffn_norm") + HG.WEIGHT_ORDER]
+        if hp["rope_mode"] == 2:
+            names += [f"blk.{il}.attn_{x}.bias" for x in "qkv"]
+    info = {n: eng.tensor_device(n) for n in names}
+    types = {n: t for n, (p_, b_, t) in info.items() if n.endswith(".weight") and t not in (0,)}
+    # ggml-cuda has no k-quant GET_ROWS (ggml-cuda.cu:3033-3047; llama.cpp gathers the embedding row on the CPU): the table is handed
+    # over dequantized to f32 — same values, and the gather is not part of what is compared
+    emb_ptr, emb_bytes, emb_type = info["token_embd.weight"]
+    types["token_embd.weight"] = 0
+    hm = HG.HostModel(hp, types, "CUDA0", has_bias=(hp["rope_mode"] == 2), has_freq_factors=False)
+
+    class U8:
+        def __init__(self, ptr, n):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+    for n, (ptr, nbytes, t) in info.items():
+        dst, dbytes = hm.tensor_ptr(n)
+        if n == "token_embd.weight":
+            assert dbytes == nv * E * 4
+            ids = torch.arange(nv, dtype=torch.int32, device=dev)
+            step_rows = 8192
+            for r0 in range(0, nv, step_rows):
+                nr = min(step_rows, nv - r0)
+                lib.check(lib.c.pb200_get_rows(emb_type, C.c_void_p(emb_ptr), C.c_int64(E), C.c_void_p(ids.data_ptr() + 4 * r0), C.c_int64(nr),
+                                               C.c_void_p(dst + r0 * E * 4), None), "get_rows")
+            torch.cuda.synchronize()
+            continue
+        assert dbytes == nbytes, (n, dbytes, nbytes)
+        torch.as_tensor(U8(dst, nbytes), device=dev).copy_(torch.as_tensor(U8(ptr, nbytes), device=dev))
+    torch.cuda.synchronize()
+    eng_logits = np.zeros(nv, dtype=np.float32)
+    eng.kv_clear()
+    eng.decode(token_at(1, nv), 0, eng_logits)
+    wbytes = eng.weight_bytes()
+    eng.close()
+    del eng
+    torch.cuda.empty_cache()
+    logits = np.zeros(nv, dtype=np.float32)
+    hm.decode([token_at(1, nv)], 0, logits)
+    nmse = float(np.sum((logits - eng_logits) ** 2) / max(np.sum(eng_logits ** 2), 1e-30))
+    hm.kv_clear()
+    first = PROMPT + args.warmup
+    for i in range(first):
+        hm.decode([token_at(i, nv)], i, logits if i >= PROMPT else None)
+    sampler = ClockSampler(0)
+    sampler.start()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        hm.decode([token_at(first + i, nv)], first + i, logits)
+    dt = time.perf_counter() - t0
+    clocks = sampler.stop()
+    hbm, src = peaks()
+    n_kv_pad = (first + args.steps + 32) // 32 * 32
+    v = args.steps / dt
+    line = {"impl": "ggml-cuda", "metric": METRIC, "value": v, "unit": "tokens/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "q8_1 activations x k-quant weights (mul_mat_vec_q), f32 accumulate", "data": "synthetic", "config": config,
+            "what": "the reference's unmodified ggml-cuda backend compiled -arch=sm_100 (oracle/Makefile.cudaref), CUDA graphs on, same box, same weights, "
+                    "same host graph and host I/O as the B200 arm's e2e leg",
+            "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 8 + n_kv_pad * 32 * 4, "d2h_bytes_per_step": nv * 4},
+            "roofline": {"bound": "hbm", "achieved": wbytes * v / 1e9, "peak": hbm, "unit": "GB/s", "frac": wbytes * v / 1e9 / hbm, "peak_source": src,
+                         "how": "whole step: algorithmic weight bytes per token x tokens/s"},
+            "logits_nmse_vs_b200_engine_first_token": nmse, "clocks": clocks, "graph_nodes": hm.graph_nodes}
+    hm.close()
+    print(json.dumps(line))
+
+
+def ggml_cuda_subprocess(model_key, steps, warmup, n_ctx):
+    p = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "ggml-cuda", "--model", model_key, "--steps", str(steps), "--warmup", str(warmup),
+                        "--n-ctx", str(n_ctx)], capture_output=True, text=True, timeout=900)
+    for line in reversed(p.stdout.strip().splitlines()):
+        if line.startswith("{"):
+            d = json.loads(line)
+            return {k: d[k] for k in ("value", "unit", "ms_per_step", "what", "roofline", "logits_nmse_vs_b200_engine_first_token", "clocks")}
+    return {"unavailable": (p.stderr or p.stdout)[-300:]}
+
+
 # ------------------------------------------------------------------------------------------------ main
 def main():
     global PROMPT
@@ -295,7 +394,8 @@ def main():
     ap.add_argument("--steps", type=int, default=128)
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--model", default="llama3-70b", choices=sorted(MODELS))
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "ggml-cuda"])
+    ap.add_argument("--no-gpu-comparator", action="store_true", help="skip the same-box ggml-cuda comparator leg (N=1 only)")
     ap.add_argument("--n-ctx", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-boundary", action="store_true", help="skip the e2e leg through the ggml-backend plugin (keeps pb200_decode as e2e)")
@@ -323,6 +423,11 @@ def main():
                           "warmup": warm, "ms_per_step": cb["ms_per_token_extrapolated"], "higher_is_better": True, "scaling": "strong",
                           "vs_baseline": None, "dtype": "int8 x k-quant dot, f32 accumulate", "data": "synthetic", "config": config,
                           "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    if args.impl == "ggml-cuda":
+        if rank == 0:
+            ggml_cuda_arm(args, cfg, hp, config)
         return
 
     import numpy as np
@@ -594,6 +699,16 @@ def main():
             out["e2e"] = boundary_leg(eng, cfg, hp, args, lib)
         except Exception as ex:   # the boundary leg needs host/_ggml (built where the reference tree exists); keep the engine number otherwise
             out["e2e_boundary_error"] = repr(ex)
+    if world == 1 and not args.no_gpu_comparator:
+        # same-box GPU comparator: the reference's own ggml-cuda (sm_100 build) in a process of its own, after this one released the GPU memory
+        try:
+            eng.close()
+            torch.cuda.empty_cache()
+            out["gpu_comparator"] = ggml_cuda_subprocess(args.model, min(args.steps, 64), min(args.warmup, 8), args.n_ctx)
+            if out["gpu_comparator"].get("value"):
+                out["gpu_comparator"]["b200_e2e_over_ggml_cuda"] = out["e2e"]["value"] / out["gpu_comparator"]["value"]
+        except Exception as ex:
+            out["gpu_comparator"] = {"unavailable": repr(ex)}
     if not args.no_cpu_baseline:
         try:
             out["cpu_baseline"] = cpu_reference_subprocess(args.model, args.steps, args.warmup)

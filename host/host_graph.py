@@ -12,6 +12,8 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 HOST = ROOT / "host"
 PLUGIN = ROOT / "prima.cpp_b200" / "libggml-b200.so"
+# same-box GPU comparator (measurement infrastructure, oracle/Makefile.cudaref): the reference's own ggml-cuda backend built for sm_100
+CUDAREF = ROOT / "oracle" / "_ref" / "cuda" / "libggml-cuda-ref.so"
 
 
 class HParams(C.Structure):
@@ -28,11 +30,13 @@ def build() -> None:
 _libs = None
 
 
-def load(with_plugin: bool = True):
+def load(with_plugin: bool = True, with_cudaref: bool = False):
     """Returns (graph_lib, plugin_lib or None)."""
     global _libs
     if _libs is not None:
         return _libs
+    if with_cudaref and not CUDAREF.exists():
+        raise RuntimeError(f"{CUDAREF} is missing: make -C oracle -f Makefile.cudaref (needs /root/reference)")
     core = HOST / "_ggml" / "libggml_host.so"
     drv = HOST / "_ggml" / "libllama_graph_host.so"
     if not core.exists() or not drv.exists():
@@ -48,6 +52,8 @@ def load(with_plugin: bool = True):
         plug.ggml_backend_b200_nodes_computed.restype = C.c_ulonglong
         plug.ggml_backend_b200_fused_steps.restype = C.c_ulonglong
         plug.ggml_backend_b200_graph_replays.restype = C.c_ulonglong
+    if with_cudaref:
+        C.CDLL(str(CUDAREF), mode=C.RTLD_GLOBAL)   # its constructor registers the "CUDA" backend (oracle/cudaref_register.cpp)
     g = C.CDLL(str(drv), mode=C.RTLD_GLOBAL)
     vp = C.c_void_p
     g.lgh_create.restype = vp
@@ -76,7 +82,7 @@ class HostModel:
 
     def __init__(self, hp: dict, types: dict, backend: str, n_threads: int = 8, has_bias: bool = False, has_freq_factors: bool = False):
         """types: tensor name -> ggml_type for "token_embd.weight", "output.weight" and "blk.N.<WEIGHT_ORDER>.weight"."""
-        self.g, self.plug = load(with_plugin=backend.startswith("B200"))
+        self.g, self.plug = load(with_plugin=backend.startswith("B200"), with_cudaref=backend.startswith("CUDA"))
         self.hp = hp
         H = HParams(**{k: hp[k] for k in ("n_layer", "n_embd", "n_head", "n_head_kv", "head_dim", "n_ff", "n_vocab", "n_ctx", "rope_mode", "n_ctx_orig",
                                           "rope_freq_base", "rope_freq_scale", "rms_eps")}, has_bias=int(has_bias), has_freq_factors=int(has_freq_factors))

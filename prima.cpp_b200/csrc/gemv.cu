@@ -69,6 +69,35 @@ __device__ __forceinline__ void issue_tile(const GemvParams & P, GemvSmemCtl * c
     mbar_arrive_expect_tx(&ctl->full[s], bytes);
     bulk_g2s(stages + (size_t) s * P.stage_bytes, M.W + a0, bytes, &ctl->full[s], pol);
 }
+// L2 look-ahead of tile t of THIS launch (same byte range issue_tile will move later)
+__device__ __forceinline__ void prefetch_tile(const GemvParams & P, int t) {
+    int m, r0, nrows;
+    tile_info(P, t, m, r0, nrows);
+    const GemvMat & M = P.mat[m];
+    const int64_t g0 = (int64_t) r0 * M.row_bytes;
+    const int64_t g1 = g0 + (int64_t) nrows * M.row_bytes;
+    const int64_t a0 = g0 & ~(int64_t) 15;
+    int64_t a1 = (g1 + 15) & ~(int64_t) 15;
+    const int64_t lim = (M.total_bytes + 15) & ~(int64_t) 15;
+    if (a1 > lim) a1 = lim;
+    bulk_prefetch_l2(M.W + a0, (uint32_t) (a1 - a0));
+}
+// chunk c of the NEXT launch's weights (its matrices back to back) -> L2
+__device__ __forceinline__ void prefetch_next(const GemvParams & P, int c) {
+    int64_t off = (int64_t) c * P.next_chunk;
+#pragma unroll
+    for (int i = 0; i < GEMV_MAX_MAT; i++) {
+        if (i < P.next_n) {
+            if (off < P.next_bytes[i]) {
+                const int64_t n = min((int64_t) P.next_chunk, P.next_bytes[i] - off);
+                bulk_prefetch_l2(P.next_W[i] + off, (uint32_t) n);
+                return;
+            }
+            off -= P.next_bytes[i];
+            off = (off + P.next_chunk - 1) / P.next_chunk * P.next_chunk;   // chunks never straddle two matrices
+        }
+    }
+}
 // called by lane 0 of a consumer warp when the warp no longer needs stage s (iteration it): the last of the 8 warps refills it
 __device__ __forceinline__ void release_stage(const GemvParams & P, GemvSmemCtl * ctl, uint8_t * stages, int s, int it, uint64_t pol) {
     __threadfence_block();
@@ -78,6 +107,8 @@ __device__ __forceinline__ void release_stage(const GemvParams & P, GemvSmemCtl 
         if (t < P.ntiles) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy reads of the stage before the async-proxy refill
             issue_tile(P, ctl, stages, s, t, pol);
+        } else if (P.next_n) {
+            prefetch_next(P, t - P.ntiles);
         }
     }
 }
@@ -326,6 +357,19 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_CTAS_PER_SM) k_gemv_kquant(
             const int t = blockIdx.x + it * gridDim.x;
             if (t < P.ntiles) issue_tile(P, ctl, stages, it, t, pol);
         }
+    } else if (threadIdx.x == 32) {
+        // L2 look-ahead (gemv.cuh): the tiles this CTA will want right after its prologue; ring slots of a short launch that never
+        // get a tile fetch the next launch's first chunks
+        for (int it = P.nstage_init; it < P.nstage + P.l2pf; it++) {
+            const int t = blockIdx.x + it * gridDim.x;
+            if (t < P.ntiles) prefetch_tile(P, t);
+            else if (P.next_n && it < P.nstage) prefetch_next(P, t - P.ntiles);
+        }
+        if (P.next_n)
+            for (int it = 0; it < P.nstage_init; it++) {
+                const int t = blockIdx.x + it * gridDim.x;
+                if (t >= P.ntiles) prefetch_next(P, t - P.ntiles);
+            }
     }
     stamp<TRACE>(P, 1);
     pdl_wait();      // the activation is produced by the previous kernel in the stream
@@ -793,9 +837,11 @@ bool gemv_fused_prologue_ok(int K) { return K > 0 && K % 256 == 0 && K / 256 <= 
 // ring geometry of one launch: rows per tile of each matrix, stage size, depth — everything that must fit 2 CTAs on an SM
 struct GemvPlan { int wpr, nblk_p2, nstage, nstage_init, stage_bytes, smem, owner_only, rel_count, rows[GEMV_MAX_MAT]; };
 // tunables (environment, read once): ring geometry experiments without a rebuild
-struct GemvTune { int stage_target, max_stage, prefill; };
+struct GemvTune { int stage_target, max_stage, prefill, l2pf, next_chunk; };
 static const GemvTune tune = [] {
-    GemvTune t{GEMV_STAGE_TARGET, GEMV_MAX_STAGE, GEMV_MAX_STAGE};
+    GemvTune t{GEMV_STAGE_TARGET, GEMV_MAX_STAGE, GEMV_MAX_STAGE, GEMV_L2PF_STAGES, GEMV_NEXT_CHUNK};
+    if (const char * e = getenv("PB200_GEMV_L2PF")) t.l2pf = std::max(0, atoi(e));
+    if (const char * e = getenv("PB200_GEMV_NEXT_KB")) t.next_chunk = std::max(0, atoi(e)) * 1024;
     if (const char * e = getenv("PB200_GEMV_STAGE_KB")) t.stage_target = std::max(4, atoi(e)) * 1024;
     if (const char * e = getenv("PB200_GEMV_PREFILL")) t.prefill = std::max(0, atoi(e));
     if (const char * e = getenv("PB200_GEMV_MAX_STAGE")) t.max_stage = std::min(GEMV_MAX_STAGE, std::max(2, atoi(e)));
@@ -960,6 +1006,16 @@ int launch_gemv_kquant_fused(const GemvDesc * d, int nmat, int K, const ActQ & a
     }
     P.ntiles = tiles;
     P.gbar = pro.gbar;
+    P.l2pf = tune.l2pf;
+    P.next_chunk = tune.next_chunk;
+    P.next_n = 0;
+    if (tune.next_chunk > 0)
+        for (int i = 0; i < pro.next_n && i < GEMV_MAX_MAT; i++) {
+            if (!pro.next_W[i] || pro.next_bytes[i] < 16 || ((uintptr_t) pro.next_W[i] & 15)) break;
+            P.next_W[P.next_n] = (const uint8_t *) pro.next_W[i];
+            P.next_bytes[P.next_n] = pro.next_bytes[i] & ~(int64_t) 15;
+            P.next_n++;
+        }
     // the cluster prologue needs every cluster of the launch resident at once; otherwise the grid-distributed one (same arithmetic)
     if ((P.prologue == PRO_RMSNORM_CLUSTER || P.prologue == PRO_SILU_CLUSTER) && !gemv_cluster_prologue_ok(P.ntiles)) P.prologue -= 2;
     if ((P.prologue == PRO_RMSNORM_DIST || P.prologue == PRO_SILU_DIST) && (!pro.gbar || !gemv_dist_prologue_ok())) return (int) cudaErrorInvalidValue;

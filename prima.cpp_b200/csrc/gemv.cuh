@@ -38,6 +38,8 @@ constexpr int GEMV_SMEM_LIMIT = 113 * 1024;       // 2 x (113 KB + 1 KB reserved
 constexpr int GEMV_STAGE_TARGET = 28 * 1024;      // bytes per ring stage aimed for (rows per stage = target / row bytes)
 constexpr int GEMV_ACT_MAX_NBLK = 112;            // K <= 28 672 on the fast path
 constexpr int GEMV_MAX_MAT = 3;
+constexpr int GEMV_L2PF_STAGES = 4;               // L2 look-ahead of a launch's own tiles beyond its ring (stages per CTA)
+constexpr int GEMV_NEXT_CHUNK = 24 * 1024;        // L2 look-ahead into the next launch's weights: bytes per spare ring slot
 __host__ __device__ inline int gemv_act_smem_bytes(int nblk) { return nblk * (ACT_SMEM_QS_STRIDE + 2 * ACT_SMEM_BS_STRIDE + 4) + 64; }   // padded qs | padded bsums | d
 
 struct GemvMat {
@@ -87,6 +89,15 @@ struct GemvParams {
     const float * in1;
     float eps;
     unsigned int * gbar;           // distributed prologues: {arrivals, departures} of the grid barrier (self-resetting)
+    // L2 look-ahead (keeps HBM busy across the dependency chain at every launch boundary, where nothing else can stream):
+    //   self:  before griddepcontrol.wait every CTA asks for its tiles [nstage_init, nstage + l2pf) — the ones its ring cannot hold yet;
+    //   next:  a ring slot that has no tile left to fetch (the CTA's last nstage refills) fetches a chunk of the NEXT launch's
+    //          weights into L2 instead: the stream of weight bytes continues through this launch's tail and the next one's prologue.
+    int l2pf;
+    int next_n;                    // matrices of the next launch (0: no hint)
+    int next_chunk;                // bytes per look-ahead chunk (multiple of 16)
+    const uint8_t * next_W[GEMV_MAX_MAT];
+    int64_t next_bytes[GEMV_MAX_MAT];   // multiples of 16
     int * abort_flag;              // host-mapped: set by the wait watchdog (never on a healthy run)
     unsigned long long * trace;    // per-CTA %globaltimer stamps (TRACE instantiation only)
 };

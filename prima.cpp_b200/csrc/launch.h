@@ -23,6 +23,11 @@ struct GemvFused {       // fused activation prologue of the k-quant GEMV (PRO_*
     const float * in1 = nullptr;
     float eps = 0.f;
     unsigned int * gbar = nullptr;   // kinds 4, 5: two zero-initialised words of device memory owned by the caller (grid barrier state)
+    // optional hint: the weight matrices the NEXT GEMV launch of the stream will read (16-B aligned).  The tail of this launch pulls
+    // their first bytes into L2 so that HBM keeps streaming through the launch boundary (gemv.cuh: L2 look-ahead)
+    int next_n = 0;
+    const void * next_W[3] = {nullptr, nullptr, nullptr};
+    int64_t next_bytes[3] = {0, 0, 0};
 };
 
 // ---- per-device host state (gemv.cu): cudaFuncSetAttribute / SM count are per device, one process may drive several ----
