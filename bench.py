@@ -341,7 +341,7 @@ def ggml_cuda_arm(args, cfg, hp, config):
     eng_logits = np.zeros(nv, dtype=np.float32)
     eng.kv_clear()
     eng.decode(token_at(1, nv), 0, eng_logits)
-    wbytes = eng.weight_bytes()
+    wbytes = eng.weight_bytes
     eng.close()
     del eng
     torch.cuda.empty_cache()

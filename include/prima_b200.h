@@ -138,12 +138,6 @@ typedef struct pb200_gemv_mat {
  * Returns PB200_ENOTSUP for types / shapes outside the fast kernel (callers fall back to the single ops). */
 PB200_API int pb200_gemv_fused(int nmat, const pb200_gemv_mat * mats, int64_t k, void * act_ws, int prologue, const float * in0, const float * in1,
                                float eps, void * sync_ws, int pdl, void * stream);
-/* Optional L2 look-ahead hint for the NEXT pb200_gemv_fused call of this thread (consumed by it, then forgotten): the n <= 3 weight
- * matrices (16-byte aligned, `bytes` each) that the mat-vec launch AFTER that one will stream.  The hinted launch uses its spare ring
- * slots to pull their first bytes into L2, so HBM keeps streaming through the launch boundary instead of idling during the next
- * launch's dependency wait + prologue (replaces nothing in the reference: ggml-cuda launches every mat-vec cold).  Purely a
- * performance hint: results never depend on it.  n = 0 clears a pending hint. */
-PB200_API int pb200_gemv_next_hint(int n, const void * const * W, const int64_t * bytes);
 /* One token of the reference graph's FA-off attention chain as ONE launch (llm_build_kv_store + llm_build_kqv, src/llama.cpp:9673-9718,
  * 10032-10165): rope(q), rope(k) -> f16 K row into cell kv_head of k_cache [cell][n_head_kv*128]; v -> f16 into column kv_head of the
  * TRANSPOSED v cache [n_head_kv*128][vt_stride]; out[h] = softmax(scale * K q_h + mask) . V over n_cells cells (multiple of 32, mask f32

@@ -214,18 +214,6 @@ int pb200_attn_decode(const float * q, const void * k_cache_f16, const void * v_
                               nullptr, (cudaStream_t) stream, false);
 }
 
-static thread_local GemvFused g_next_hint;   // only the next_* fields are used
-int pb200_gemv_next_hint(int n, const void * const * W, const int64_t * bytes) {
-    g_next_hint.next_n = 0;
-    if (n < 0 || n > 3 || (n > 0 && (!W || !bytes))) return PB200_EINVAL;
-    for (int i = 0; i < n; i++) {
-        if (!W[i] || bytes[i] < 0) { g_next_hint.next_n = 0; return PB200_EINVAL; }
-        g_next_hint.next_W[i] = W[i]; g_next_hint.next_bytes[i] = bytes[i];
-    }
-    g_next_hint.next_n = n;
-    return 0;
-}
-
 int pb200_gemv_fused(int nmat, const pb200_gemv_mat * mats, int64_t k, void * act_ws, int prologue, const float * in0, const float * in1, float eps,
                      void * sync_ws, int pdl, void * stream) {
     if (nmat < 1 || nmat > 3 || !mats || !act_ws || k <= 0 || prologue < 0 || prologue > 2) return PB200_EINVAL;
@@ -240,14 +228,10 @@ int pb200_gemv_fused(int nmat, const pb200_gemv_mat * mats, int64_t k, void * ac
     cudaStream_t st = (cudaStream_t) stream;
     const ActQ act = act_from_ws(act_ws, k);
     GemvFused pro;
-    pro.next_n = g_next_hint.next_n;
-    for (int i = 0; i < pro.next_n; i++) { pro.next_W[i] = g_next_hint.next_W[i]; pro.next_bytes[i] = g_next_hint.next_bytes[i]; }
-    g_next_hint.next_n = 0;
     bool gemv_pdl = pdl != 0;
     if (prologue != 0) {
         if (sync_ws && gemv_dist_prologue_ok()) {
-            static const int kind_add = getenv("PB200_NO_CLUSTER") ? 0 : 2;
-            pro.kind = (prologue == 1 ? 4 : 5) + kind_add; pro.in0 = in0; pro.in1 = in1; pro.eps = eps; pro.gbar = (unsigned int *) sync_ws;
+            pro.kind = prologue == 1 ? 4 : 5; pro.in0 = in0; pro.in1 = in1; pro.eps = eps; pro.gbar = (unsigned int *) sync_ws;
         } else {   // the grid cannot be made co-resident on this device: produce the activation with a small kernel in front
             g_launches++;
             int e = prologue == 1 ? launch_rmsnorm_quant(in0, in1, (int) k, eps, ACT_Q8_K, act, nullptr, st, gemv_pdl)

@@ -146,7 +146,7 @@ __device__ __forceinline__ bool mbar_try_token(uint64_t * bar, uint64_t token) {
         : "memory");
     return ok != 0;
 }
-static __device__ __forceinline__ void wait_gave_up(volatile int * cta_abort, int * abort_flag) {
+static __device__ __noinline__ void wait_gave_up(volatile int * cta_abort, int * abort_flag) {
     *cta_abort = 1;
     if (abort_flag) { *(volatile int *) abort_flag = 1; __threadfence_system(); }
 }

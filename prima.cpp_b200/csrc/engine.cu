@@ -360,7 +360,6 @@ static int enqueue_step(pb200_model * m, int seq, uint64_t * nlaunch) {
     static const bool attn_v2 = getenv("PB200_ATTN_V1") == nullptr;   // A/B: round 1's attention kernel + quantize prologue in wo
     static const bool dist_env = getenv("PB200_NO_DIST") == nullptr;   // A/B: single-CTA rmsnorm / silu kernels in front of the GEMVs instead
     const bool dist = dist_env && gemv_dist_prologue_ok();
-    static const int kind_add = getenv("PB200_NO_CLUSTER") ? 0 : 2;   // 6 / 7: cluster prologue (falls back to 4 / 5 inside the launcher when clusters cannot fill the device)
     uint64_t n = 0;
     const int32_t * tok_dev = m->tokpos_dev + 4 * seq, * pos_dev = m->tokpos_dev + 4 * seq + 1;
     const size_t nl_ = m->layers.size();
@@ -372,18 +371,8 @@ static int enqueue_step(pb200_model * m, int seq, uint64_t * nlaunch) {
     const float kq_scale = 1.0f / sqrtf((float) D);
     // three rotating hidden-state buffers so that a residual source is never overwritten by its consumer
     float * bufs[3] = {m->x_a, m->x_b, m->xn};
-    // L2 look-ahead hints (gemv.cuh): every GEMV launch is told which weights the next one will stream
-    auto hint = [](GemvFused & pro, std::initializer_list<const Tensor *> ts) {
-        pro.next_n = 0;
-        for (const Tensor * t : ts) {
-            if (!t || !t->data || pro.next_n >= 3) break;
-            pro.next_W[pro.next_n] = t->data; pro.next_bytes[pro.next_n] = (int64_t) t->bytes; pro.next_n++;
-        }
-    };
     for (int il = m->l0; il < m->l1; il++) {
         Layer & L = m->layers[il - m->l0];
-        // what follows this layer's ffn_down: the next layer's q|k|v, the head, or (next token) this stage's first layer
-        const Layer * Ln = il + 1 < m->l1 ? &m->layers[il + 1 - m->l0] : (m->with_head ? nullptr : &m->layers[0]);
         __half * kc = m->kcache + ((size_t) seq * nl_ + (size_t) (il - m->l0)) * hp.n_ctx * EK;
         __half * vc = m->vcache + ((size_t) seq * nl_ + (size_t) (il - m->l0)) * hp.n_ctx * EK;
         float * x1 = nullptr, * x2 = nullptr;
@@ -398,11 +387,10 @@ static int enqueue_step(pb200_model * m, int seq, uint64_t * nlaunch) {
                              {L.wv.data, m->v, L.bv, nullptr, L.wv.type, EK}};
             GemvFused pro;
             if (dist) {   // rms_norm * attn_norm -> q8_K inside the GEMV: CTA c produces super-block c, one grid barrier
-                pro.kind = 4 + kind_add; pro.in0 = x; pro.in1 = L.attn_norm; pro.eps = hp.rms_eps; pro.gbar = m->gbar;
+                pro.kind = 4; pro.in0 = x; pro.in1 = L.attn_norm; pro.eps = hp.rms_eps; pro.gbar = m->gbar;
             } else {      // ... or once by a single-CTA kernel in front of it
                 CK(launch_rmsnorm_quant(x, L.attn_norm, E, hp.rms_eps, ACT_Q8_K, m->actE.q, nullptr, st, pdl)); n++;
             }
-            hint(pro, {&L.wo});
             CK(prof_begin(m, tbytes(L.wq) + tbytes(L.wk) + tbytes(L.wv)));
             CK(launch_gemv_kquant_fused(d, 3, E, m->actE.q, pro, st, pdl)); n++; CK(dbg_sync(st, "gemv qkv"));
             CK(prof_end(m));
@@ -431,14 +419,7 @@ static int enqueue_step(pb200_model * m, int seq, uint64_t * nlaunch) {
             GemvDesc d1 = {L.wo.data, x1, nullptr, x, L.wo.type, E};   // ffn_inp = wo.att + inpSA
             if (!att_quantized) { CK(launch_quantize_act(m->att, QD, act_mode_for(L.wo.type), m->actQD.q, st, pdl)); n++; }
             CK(prof_begin(m, tbytes(L.wo)));
-            if (wo_k) {
-                GemvFused pro;
-                hint(pro, {&L.gate, &L.up});
-                CK(launch_gemv_kquant_fused(&d1, 1, QD, m->actQD.q, pro, st, pdl));
-            } else {
-                CK(launch_gemv(&d1, 1, QD, m->actQD.q, st, pdl));
-            }
-            n++; CK(dbg_sync(st, "gemv wo"));
+            CK(launch_gemv(&d1, 1, QD, m->actQD.q, st, pdl)); n++; CK(dbg_sync(st, "gemv wo"));
             CK(prof_end(m));
         }
         // --- FFN block ---
@@ -447,11 +428,10 @@ static int enqueue_step(pb200_model * m, int seq, uint64_t * nlaunch) {
             GemvDesc d[2] = {{L.gate.data, m->g, nullptr, nullptr, L.gate.type, F}, {L.up.data, m->u, nullptr, nullptr, L.up.type, F}};
             GemvFused pro;
             if (dist) {
-                pro.kind = 4 + kind_add; pro.in0 = x1; pro.in1 = L.ffn_norm; pro.eps = hp.rms_eps; pro.gbar = m->gbar;
+                pro.kind = 4; pro.in0 = x1; pro.in1 = L.ffn_norm; pro.eps = hp.rms_eps; pro.gbar = m->gbar;
             } else {
                 CK(launch_rmsnorm_quant(x1, L.ffn_norm, E, hp.rms_eps, ACT_Q8_K, m->actE.q, nullptr, st, pdl)); n++;
             }
-            hint(pro, {&L.down});
             CK(prof_begin(m, tbytes(L.gate) + tbytes(L.up)));
             CK(launch_gemv_kquant_fused(d, 2, E, m->actE.q, pro, st, pdl)); n++; CK(dbg_sync(st, "gemv gate|up"));
             CK(prof_end(m));
@@ -470,8 +450,7 @@ static int enqueue_step(pb200_model * m, int seq, uint64_t * nlaunch) {
             GemvDesc d1 = {L.down.data, x2, nullptr, x1, L.down.type, E};   // l_out = down.act + ffn_inp
             const bool down_k = is_kquant(L.down.type) && gemv_fused_prologue_ok(F);
             if (down_k && dist) {   // silu(g)*u -> q8_K inside the GEMV, distributed over the grid
-                GemvFused pro; pro.kind = 5 + kind_add; pro.in0 = m->g; pro.in1 = m->u; pro.gbar = m->gbar;
-                if (Ln) hint(pro, {&Ln->wq, &Ln->wk, &Ln->wv}); else hint(pro, {&m->output});
+                GemvFused pro; pro.kind = 5; pro.in0 = m->g; pro.in1 = m->u; pro.gbar = m->gbar;
                 CK(prof_begin(m, tbytes(L.down)));
                 CK(launch_gemv_kquant_fused(&d1, 1, F, m->actF.q, pro, st, pdl)); n++; CK(dbg_sync(st, "gemv down"));
             } else {
@@ -490,8 +469,7 @@ static int enqueue_step(pb200_model * m, int seq, uint64_t * nlaunch) {
         CK(prof_begin(m, tbytes(m->output)));
         const bool head_pdl = pdl && m->l1 > m->l0;   // a stage without layers starts with a copy node: no programmatic edge
         if (is_kquant(m->output.type) && gemv_fused_prologue_ok(E) && dist) {
-            GemvFused pro; pro.kind = 4 + kind_add; pro.in0 = m->x_out; pro.in1 = m->output_norm; pro.eps = hp.rms_eps; pro.gbar = m->gbar;
-            if (m->l1 > m->l0) hint(pro, {&m->layers[0].wq, &m->layers[0].wk, &m->layers[0].wv});   // the next token starts there
+            GemvFused pro; pro.kind = 4; pro.in0 = m->x_out; pro.in1 = m->output_norm; pro.eps = hp.rms_eps; pro.gbar = m->gbar;
             CK(launch_gemv_kquant_fused(&d1, 1, E, m->actE.q, pro, st, head_pdl)); n++;
         } else {
             CK(launch_rmsnorm_quant(m->x_out, m->output_norm, E, hp.rms_eps, act_mode_for(m->output.type), m->actE.q, nullptr, st, head_pdl)); n++;

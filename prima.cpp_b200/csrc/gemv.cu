@@ -15,7 +15,6 @@ struct __align__(16) GemvSmemCtl {
     int cnt[GEMV_MAX_STAGE];                    // consumer warps done with the stage; the last one refills it
     float part[GEMV_ROWQ][GEMV_NW];             // cross-warp partial sums, one slot per row in flight of each group
     double red[GEMV_NW];                        // rms_norm partial sums of squares
-    double csum;                                // this CTA's share of the sum of squares (read by its cluster peers)
     volatile int aborted;                       // raised by the wait watchdog (common.cuh)
 };
 constexpr int GEMV_CTL_BYTES = 768;
@@ -69,35 +68,6 @@ __device__ __forceinline__ void issue_tile(const GemvParams & P, GemvSmemCtl * c
     mbar_arrive_expect_tx(&ctl->full[s], bytes);
     bulk_g2s(stages + (size_t) s * P.stage_bytes, M.W + a0, bytes, &ctl->full[s], pol);
 }
-// L2 look-ahead of tile t of THIS launch (same byte range issue_tile will move later)
-__device__ __forceinline__ void prefetch_tile(const GemvParams & P, int t) {
-    int m, r0, nrows;
-    tile_info(P, t, m, r0, nrows);
-    const GemvMat & M = P.mat[m];
-    const int64_t g0 = (int64_t) r0 * M.row_bytes;
-    const int64_t g1 = g0 + (int64_t) nrows * M.row_bytes;
-    const int64_t a0 = g0 & ~(int64_t) 15;
-    int64_t a1 = (g1 + 15) & ~(int64_t) 15;
-    const int64_t lim = (M.total_bytes + 15) & ~(int64_t) 15;
-    if (a1 > lim) a1 = lim;
-    bulk_prefetch_l2(M.W + a0, (uint32_t) (a1 - a0));
-}
-// chunk c of the NEXT launch's weights (its matrices back to back) -> L2
-__device__ __forceinline__ void prefetch_next(const GemvParams & P, int c) {
-    int64_t off = (int64_t) c * P.next_chunk;
-#pragma unroll
-    for (int i = 0; i < GEMV_MAX_MAT; i++) {
-        if (i < P.next_n) {
-            if (off < P.next_bytes[i]) {
-                const int64_t n = min((int64_t) P.next_chunk, P.next_bytes[i] - off);
-                bulk_prefetch_l2(P.next_W[i] + off, (uint32_t) n);
-                return;
-            }
-            off -= P.next_bytes[i];
-            off = (off + P.next_chunk - 1) / P.next_chunk * P.next_chunk;   // chunks never straddle two matrices
-        }
-    }
-}
 // called by lane 0 of a consumer warp when the warp no longer needs stage s (iteration it): the last of the 8 warps refills it
 __device__ __forceinline__ void release_stage(const GemvParams & P, GemvSmemCtl * ctl, uint8_t * stages, int s, int it, uint64_t pol) {
     __threadfence_block();
@@ -107,8 +77,6 @@ __device__ __forceinline__ void release_stage(const GemvParams & P, GemvSmemCtl 
         if (t < P.ntiles) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy reads of the stage before the async-proxy refill
             issue_tile(P, ctl, stages, s, t, pol);
-        } else if (P.next_n) {
-            prefetch_next(P, t - P.ntiles);
         }
     }
 }
@@ -188,102 +156,6 @@ __device__ __forceinline__ void dist_prologue(const GemvParams & P, GemvSmemCtl 
         quantize_warp_q8K(bx, lane, b, P.act);
     }
 }
-// ---- cluster prologue (PRO_*_CLUSTER) ----
-__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
-__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
-__device__ __forceinline__ uint32_t dsmem_addr(const void * local, uint32_t rank) {
-    uint32_t remote;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local)), "r"(rank));
-    return remote;
-}
-__device__ __forceinline__ int4 ld_dsmem_int4(uint32_t addr) {
-    int4 v;
-    asm volatile("ld.shared::cluster.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
-    return v;
-}
-__device__ __forceinline__ float ld_dsmem_f32(uint32_t addr) { float v; asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory"); return v; }
-__device__ __forceinline__ double ld_dsmem_f64(uint32_t addr) { double v; asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory"); return v; }
-
-// CTA `rank` of the cluster owns super-blocks rank, rank + C, rank + 2C, ...; warp w the (w, w + 8, ...)-th of those.  Leaves the whole
-// activation in this CTA's `sa` (padded shared-memory layout).  Ends with cluster_arrive(): the caller must cluster_wait() before it
-// recycles the staging area (the peers may still be copying from it) — and before it exits.
-constexpr int CL_B = 4;   // owned blocks per warp held in registers (8 warps x 4 x GEMV_CLUSTER = 128 >= GEMV_ACT_MAX_NBLK)
-__device__ __forceinline__ void cluster_prologue(const GemvParams & P, GemvSmemCtl * ctl, const ActQ & sa, int warp, int lane) {
-    constexpr int C = GEMV_CLUSTER;
-    const uint32_t rank = cluster_ctarank();
-    const int nblk = P.nblk;
-    float bx[CL_B][8], bw[CL_B][8];
-#pragma unroll
-    for (int j = 0; j < CL_B; j++) {
-        const int b = (int) rank + C * (warp + GEMV_NW * j);
-        if (b < nblk) {
-            load8(P.in0 + b * 256 + lane * 8, bx[j]);
-            load8(P.in1 + b * 256 + lane * 8, bw[j]);
-        }
-    }
-    float scale = 1.f;
-    if (P.prologue == PRO_RMSNORM_CLUSTER) {
-        double sum = 0.0;
-#pragma unroll
-        for (int j = 0; j < CL_B; j++) {
-            if ((int) rank + C * (warp + GEMV_NW * j) < nblk) {
-#pragma unroll
-                for (int i = 0; i < 8; i++) sum += (double) __fmul_rn(bx[j][i], bx[j][i]);
-            }
-        }
-        sum = warp_sum_d(sum);
-        if (lane == 0) ctl->red[warp] = sum;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double t = 0.0;
-#pragma unroll
-            for (int i = 0; i < GEMV_NW; i++) t += ctl->red[i];
-            ctl->csum = t;
-        }
-        cluster_arrive();
-        cluster_wait();                                  // every CTA's share is published
-        double t = 0.0;
-#pragma unroll
-        for (int q = 0; q < C; q++) t += ld_dsmem_f64(dsmem_addr(&ctl->csum, (uint32_t) q));   // same order in every CTA: same total
-        const float mean = (float) (t / (double) P.K);
-        scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, P.eps)));
-    }
-#pragma unroll
-    for (int j = 0; j < CL_B; j++) {
-        const int b = (int) rank + C * (warp + GEMV_NW * j);
-        if (b < nblk) {
-            if (P.prologue == PRO_RMSNORM_CLUSTER) {
-#pragma unroll
-                for (int i = 0; i < 8; i++) bx[j][i] = __fmul_rn(__fmul_rn(bx[j][i], scale), bw[j][i]);
-            } else {
-#pragma unroll
-                for (int i = 0; i < 8; i++) bx[j][i] = __fmul_rn(silu_f(bx[j][i]), bw[j][i]);
-            }
-            quantize_warp_q8K(bx[j], lane, b, sa);       // into THIS CTA's shared memory
-        }
-    }
-    cluster_arrive();
-    cluster_wait();                                      // every CTA's blocks are in its shared memory
-    // gather the peers' blocks: per block 16 x 16 B of qs, 2 x 16 B of bsums, 1 scale
-    for (int i = threadIdx.x; i < nblk * 19; i += GEMV_THREADS) {
-        const int b = i / 19, part = i - b * 19;
-        const uint32_t owner = (uint32_t) (b % C);
-        if (owner == rank) continue;
-        if (part < 16) {
-            int8_t * p = sa.qs + b * ACT_SMEM_QS_STRIDE + part * 16;
-            *reinterpret_cast<int4 *>(p) = ld_dsmem_int4(dsmem_addr(p, owner));
-        } else if (part < 18) {
-            char * p = reinterpret_cast<char *>(sa.bsums) + b * (2 * ACT_SMEM_BS_STRIDE) + (part - 16) * 16;
-            *reinterpret_cast<int4 *>(p) = ld_dsmem_int4(dsmem_addr(p, owner));
-        } else {
-            sa.d[b] = ld_dsmem_f32(dsmem_addr(sa.d + b, owner));
-        }
-    }
-    cluster_arrive();                                    // done reading the peers (matched by the caller's cluster_wait)
-    __syncthreads();
-}
-
 // All CTAs of the launch meet once.  Safe because the persistent grid is co-resident by construction (launcher: grid <= 2 x SMs,
 // gemv_dist_prologue_ok()); bounded like every other wait.  State = {arrivals, departures}; the last CTA to leave re-arms both.
 __device__ __forceinline__ void grid_barrier(const GemvParams & P, GemvSmemCtl * ctl) {
@@ -357,19 +229,6 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_CTAS_PER_SM) k_gemv_kquant(
             const int t = blockIdx.x + it * gridDim.x;
             if (t < P.ntiles) issue_tile(P, ctl, stages, it, t, pol);
         }
-    } else if (threadIdx.x == 32) {
-        // L2 look-ahead (gemv.cuh): the tiles this CTA will want right after its prologue; ring slots of a short launch that never
-        // get a tile fetch the next launch's first chunks
-        for (int it = P.nstage_init; it < P.nstage + P.l2pf; it++) {
-            const int t = blockIdx.x + it * gridDim.x;
-            if (t < P.ntiles) prefetch_tile(P, t);
-            else if (P.next_n && it < P.nstage) prefetch_next(P, t - P.ntiles);
-        }
-        if (P.next_n)
-            for (int it = 0; it < P.nstage_init; it++) {
-                const int t = blockIdx.x + it * gridDim.x;
-                if (t >= P.ntiles) prefetch_next(P, t - P.ntiles);
-            }
     }
     stamp<TRACE>(P, 1);
     pdl_wait();      // the activation is produced by the previous kernel in the stream
@@ -393,15 +252,11 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_CTAS_PER_SM) k_gemv_kquant(
     sa.qs_stride = ACT_SMEM_QS_STRIDE;
     sa.bs_stride = ACT_SMEM_BS_STRIDE;
     const bool dist = P.prologue == PRO_RMSNORM_DIST || P.prologue == PRO_SILU_DIST;
-    const bool clus = P.prologue == PRO_RMSNORM_CLUSTER || P.prologue == PRO_SILU_CLUSTER;
     if (dist) {
         dist_prologue(P, ctl, warp, lane);
         grid_barrier(P, ctl);
     }
-    if (clus) {
-        fill_rest(P, ctl, stages, pol);
-        cluster_prologue(P, ctl, sa, warp, lane);
-    } else {
+    {
         // ONE coalesced copy of the quantized activation per CTA (qs | bsums | d), staged with the padded strides
         constexpr int NQ_MAX = (GEMV_ACT_MAX_NBLK * 16 + GEMV_THREADS - 1) / GEMV_THREADS;   // int4 of qs per thread (7)
         const int nq = P.K / 16, nb16 = P.K / 128;
@@ -426,7 +281,6 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_CTAS_PER_SM) k_gemv_kquant(
     }
     load_act_regs(r, sa, blk, valid);
     finish_act_regs(r);
-    if (clus) cluster_wait();   // the peers have finished copying out of this CTA's staging area (and it may exit / recycle it)
     if (P.nstage_init < P.nstage) {
         __syncthreads();   // every warp has its registers: hand the staging area to the ring
         if (threadIdx.x == 0) {
@@ -837,11 +691,9 @@ bool gemv_fused_prologue_ok(int K) { return K > 0 && K % 256 == 0 && K / 256 <= 
 // ring geometry of one launch: rows per tile of each matrix, stage size, depth — everything that must fit 2 CTAs on an SM
 struct GemvPlan { int wpr, nblk_p2, nstage, nstage_init, stage_bytes, smem, owner_only, rel_count, rows[GEMV_MAX_MAT]; };
 // tunables (environment, read once): ring geometry experiments without a rebuild
-struct GemvTune { int stage_target, max_stage, prefill, l2pf, next_chunk; };
+struct GemvTune { int stage_target, max_stage, prefill; };
 static const GemvTune tune = [] {
-    GemvTune t{GEMV_STAGE_TARGET, GEMV_MAX_STAGE, GEMV_MAX_STAGE, GEMV_L2PF_STAGES, GEMV_NEXT_CHUNK};
-    if (const char * e = getenv("PB200_GEMV_L2PF")) t.l2pf = std::max(0, atoi(e));
-    if (const char * e = getenv("PB200_GEMV_NEXT_KB")) t.next_chunk = std::max(0, atoi(e)) * 1024;
+    GemvTune t{GEMV_STAGE_TARGET, GEMV_MAX_STAGE, GEMV_MAX_STAGE};
     if (const char * e = getenv("PB200_GEMV_STAGE_KB")) t.stage_target = std::max(4, atoi(e)) * 1024;
     if (const char * e = getenv("PB200_GEMV_PREFILL")) t.prefill = std::max(0, atoi(e));
     if (const char * e = getenv("PB200_GEMV_MAX_STAGE")) t.max_stage = std::min(GEMV_MAX_STAGE, std::max(2, atoi(e)));
@@ -918,28 +770,6 @@ bool gemv_dist_prologue_ok() {
     }
     return cache[dev] == 1;
 }
-// clusters of GEMV_CLUSTER CTAs with the kernel's footprint can fill the device (otherwise the cluster prologue would run in waves)
-bool gemv_cluster_prologue_ok(int ntiles) {
-    static int cache[PB_MAX_DEV] = {0};   // max active clusters + 1
-    const int dev = cur_device();
-    if (!cache[dev]) {
-        int n = 0;
-        static FuncAttrCache tmp;
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(sm_count() * GEMV_CTAS_PER_SM / GEMV_CLUSTER * GEMV_CLUSTER);
-        cfg.blockDim = dim3(GEMV_THREADS);
-        cfg.dynamicSmemBytes = GEMV_SMEM_LIMIT;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = GEMV_CLUSTER; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr; cfg.numAttrs = 1;
-        if (ensure_dyn_smem(tmp, (const void *) k_gemv_kquant<T_Q4_K, false, false>, GEMV_SMEM_LIMIT, true) != cudaSuccess ||
-            cudaOccupancyMaxActiveClusters(&n, (const void *) k_gemv_kquant<T_Q4_K, false, false>, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
-        cache[dev] = n + 1;
-    }
-    const int want = std::min(sm_count() * GEMV_CTAS_PER_SM, ntiles) / GEMV_CLUSTER;
-    return want >= 1 && cache[dev] - 1 >= want;
-}
 int gemv_smem_bytes(int type, int K, int N) {
     GemvPlan pl;
     return gemv_plan(&type, &N, 1, K, pl) ? pl.smem : 0;
@@ -1006,19 +836,7 @@ int launch_gemv_kquant_fused(const GemvDesc * d, int nmat, int K, const ActQ & a
     }
     P.ntiles = tiles;
     P.gbar = pro.gbar;
-    P.l2pf = tune.l2pf;
-    P.next_chunk = tune.next_chunk;
-    P.next_n = 0;
-    if (tune.next_chunk > 0)
-        for (int i = 0; i < pro.next_n && i < GEMV_MAX_MAT; i++) {
-            if (!pro.next_W[i] || pro.next_bytes[i] < 16 || ((uintptr_t) pro.next_W[i] & 15)) break;
-            P.next_W[P.next_n] = (const uint8_t *) pro.next_W[i];
-            P.next_bytes[P.next_n] = pro.next_bytes[i] & ~(int64_t) 15;
-            P.next_n++;
-        }
-    // the cluster prologue needs every cluster of the launch resident at once; otherwise the grid-distributed one (same arithmetic)
-    if ((P.prologue == PRO_RMSNORM_CLUSTER || P.prologue == PRO_SILU_CLUSTER) && !gemv_cluster_prologue_ok(P.ntiles)) P.prologue -= 2;
-    if ((P.prologue == PRO_RMSNORM_DIST || P.prologue == PRO_SILU_DIST) && (!pro.gbar || !gemv_dist_prologue_ok())) return (int) cudaErrorInvalidValue;
+    if ((pro.kind == PRO_RMSNORM_DIST || pro.kind == PRO_SILU_DIST) && (!pro.gbar || !gemv_dist_prologue_ok())) return (int) cudaErrorInvalidValue;
     // instantiation: weight type (0 = mixed) x split rows x instrumented
     int ty = types[0];
     for (int i = 1; i < nmat; i++) if (types[i] != ty) ty = 0;
@@ -1037,26 +855,16 @@ int launch_gemv_kquant_fused(const GemvDesc * d, int nmat, int K, const ActQ & a
     if (e != cudaSuccess) return (int) e;
     int grid = sm_count() * GEMV_CTAS_PER_SM;
     if (grid > P.ntiles) grid = P.ntiles;
-    const bool clus = P.prologue == PRO_RMSNORM_CLUSTER || P.prologue == PRO_SILU_CLUSTER;
-    if (clus) {
-        grid = grid / GEMV_CLUSTER * GEMV_CLUSTER;
-        if (grid < GEMV_CLUSTER || P.nblk > GEMV_NW * CL_B * GEMV_CLUSTER) return (int) cudaErrorInvalidValue;   // callers check gemv_cluster_prologue_ok()
-    }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(GEMV_THREADS);
     cfg.dynamicSmemBytes = pl.smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[2];
+    cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (clus) {
-        attr[1].id = cudaLaunchAttributeClusterDimension;
-        attr[1].val.clusterDim.x = GEMV_CLUSTER; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
-        cfg.numAttrs = 2;
-    }
     return (int) cudaLaunchKernelEx(&cfg, fn, P);
 }
 

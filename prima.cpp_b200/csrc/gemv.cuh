@@ -38,8 +38,6 @@ constexpr int GEMV_SMEM_LIMIT = 113 * 1024;       // 2 x (113 KB + 1 KB reserved
 constexpr int GEMV_STAGE_TARGET = 28 * 1024;      // bytes per ring stage aimed for (rows per stage = target / row bytes)
 constexpr int GEMV_ACT_MAX_NBLK = 112;            // K <= 28 672 on the fast path
 constexpr int GEMV_MAX_MAT = 3;
-constexpr int GEMV_L2PF_STAGES = 4;               // L2 look-ahead of a launch's own tiles beyond its ring (stages per CTA)
-constexpr int GEMV_NEXT_CHUNK = 24 * 1024;        // L2 look-ahead into the next launch's weights: bytes per spare ring slot
 __host__ __device__ inline int gemv_act_smem_bytes(int nblk) { return nblk * (ACT_SMEM_QS_STRIDE + 2 * ACT_SMEM_BS_STRIDE + 4) + 64; }   // padded qs | padded bsums | d
 
 struct GemvMat {
@@ -63,11 +61,14 @@ struct GemvMat {
 //   co-resident), then every CTA stages the finished vector like PRO_NONE.  No tiny kernel + launch boundary in front of the GEMV
 //   (measured chain ~9.5 us from "previous GEMV done" to "first tile consumed", profiles/r2_token_trace_v2.txt), and 1/296 of the
 //   work per CTA instead of every CTA recomputing the whole vector from L2 (round 1: ~7 us and 19 MB of L2 reads per launch).
-//   Cluster variants (PRO_RMSNORM_CLUSTER, PRO_SILU_CLUSTER): the launch runs as thread-block clusters of GEMV_CLUSTER CTAs; each CTA
-//   quantizes 1/GEMV_CLUSTER of the super-blocks into ITS OWN shared memory, the cluster exchanges them through distributed shared
-//   memory (two cluster barriers + one DSMEM copy, ~1 us) — no grid barrier, no round trip through L2 for the finished vector.
-enum : int { PRO_NONE = 0, PRO_RMSNORM_DIST = 4, PRO_SILU_DIST = 5, PRO_RMSNORM_CLUSTER = 6, PRO_SILU_CLUSTER = 7 };
-constexpr int GEMV_CLUSTER = 4;
+//   Built, measured on the B200 and REMOVED in round 2 (profiles/r2_ab_sweeps.txt, ab14-ab16):
+//   * L2 look-ahead — prefetching a launch's tiles beyond its ring, and the next launch's first weights from ring slots that have no tile
+//     left, to keep HBM busy during the dependency chain at a launch boundary: DRAM bytes unchanged (ncu), the launch that is fed from L2
+//     gains (ffn_down -4.6 us) but the prefetching launch loses more (gate|up +7 us), and the small latency-critical loads of the prologue
+//     queue behind the prefetches: 107 -> 98-105 tok/s in every setting tried (cp.async.bulk.prefetch.L2 and per-line prefetch.global.L2);
+//   * a cluster variant of the distributed prologue (4 CTAs exchange their quarter of the activation through distributed shared memory
+//     instead of the grid barrier + L2 round trip): same tokens/s, and its code cost the hot loop 4 % (109.9 -> 105.4).
+enum : int { PRO_NONE = 0, PRO_RMSNORM_DIST = 4, PRO_SILU_DIST = 5 };
 
 struct GemvParams {
     GemvMat mat[GEMV_MAX_MAT];
@@ -89,15 +90,6 @@ struct GemvParams {
     const float * in1;
     float eps;
     unsigned int * gbar;           // distributed prologues: {arrivals, departures} of the grid barrier (self-resetting)
-    // L2 look-ahead (keeps HBM busy across the dependency chain at every launch boundary, where nothing else can stream):
-    //   self:  before griddepcontrol.wait every CTA asks for its tiles [nstage_init, nstage + l2pf) — the ones its ring cannot hold yet;
-    //   next:  a ring slot that has no tile left to fetch (the CTA's last nstage refills) fetches a chunk of the NEXT launch's
-    //          weights into L2 instead: the stream of weight bytes continues through this launch's tail and the next one's prologue.
-    int l2pf;
-    int next_n;                    // matrices of the next launch (0: no hint)
-    int next_chunk;                // bytes per look-ahead chunk (multiple of 16)
-    const uint8_t * next_W[GEMV_MAX_MAT];
-    int64_t next_bytes[GEMV_MAX_MAT];   // multiples of 16
     int * abort_flag;              // host-mapped: set by the wait watchdog (never on a healthy run)
     unsigned long long * trace;    // per-CTA %globaltimer stamps (TRACE instantiation only)
 };

@@ -18,16 +18,11 @@ struct GemvDesc {
 };
 
 struct GemvFused {       // fused activation prologue of the k-quant GEMV (PRO_* in gemv.cuh)
-    int kind = 0;        // 0 none (activation already quantized); rms_norm(in0)*in1 / silu(in0)*in1: 4 / 5 distributed over the grid, 6 / 7 over clusters (PRO_* in gemv.cuh)
+    int kind = 0;        // 0 none (activation already quantized), 4 rms_norm(in0)*in1, 5 silu(in0)*in1 — distributed over the grid (PRO_* in gemv.cuh)
     const float * in0 = nullptr;
     const float * in1 = nullptr;
     float eps = 0.f;
     unsigned int * gbar = nullptr;   // kinds 4, 5: two zero-initialised words of device memory owned by the caller (grid barrier state)
-    // optional hint: the weight matrices the NEXT GEMV launch of the stream will read (16-B aligned).  The tail of this launch pulls
-    // their first bytes into L2 so that HBM keeps streaming through the launch boundary (gemv.cuh: L2 look-ahead)
-    int next_n = 0;
-    const void * next_W[3] = {nullptr, nullptr, nullptr};
-    int64_t next_bytes[3] = {0, 0, 0};
 };
 
 // ---- per-device host state (gemv.cu): cudaFuncSetAttribute / SM count are per device, one process may drive several ----
@@ -49,7 +44,6 @@ int gemv_smem_bytes(int type, int K, int N);        // dynamic shared memory of 
 int launch_gemv_kquant(const GemvDesc * d, int nmat, int K, const ActQ & act, cudaStream_t stream, bool pdl);
 int launch_gemv_kquant_fused(const GemvDesc * d, int nmat, int K, const ActQ & act, const GemvFused & pro, cudaStream_t stream, bool pdl);
 bool gemv_fused_prologue_ok(int K);
-bool gemv_cluster_prologue_ok(int ntiles);   // clusters of 4 CTAs of the kernel can all be resident for a launch with this many tiles (kinds 6, 7)
 bool gemv_dist_prologue_ok();   // the full persistent grid is co-resident on the current device (needed by the in-kernel grid barrier)
 // any supported type / any K, one warp per row, direct global loads
 int launch_gemv_generic(const GemvDesc & d, int K, const ActQ & act, cudaStream_t stream, bool pdl);

@@ -810,18 +810,8 @@ static bool overlaps(const void * a, size_t na, const void * b, size_t nb) {
     return pa < pb + nb && pb < pa + na;
 }
 
-static bool run_gemv_step(b200_backend_ctx * ctx, ggml_cgraph * g, const b200_step & st, const b200_step * next) {
+static bool run_gemv_step(b200_backend_ctx * ctx, ggml_cgraph * g, const b200_step & st) {
     const ggml_tensor * m0 = ggml_graph_node(g, st.mm[0]);
-    {   // L2 look-ahead hint: the weights of the next fused mat-vec of the plan (pb200_gemv_next_hint)
-        const void * nw[3]; int64_t nb[3]; int nn = 0;
-        if (next)
-            for (int j = 0; j < next->nmat && j < 3; j++) {
-                const ggml_tensor * w = ggml_graph_node(g, next->mm[j])->src[0];
-                if (!w->data || ((uintptr_t) w->data & 15)) break;
-                nw[nn] = w->data; nb[nn] = (int64_t) ggml_nbytes(w); nn++;
-            }
-        pb200_gemv_next_hint(nn, nw, nb);
-    }
     const int64_t K = m0->src[0]->ne[0];
     pb200_gemv_mat mats[3];
     for (int j = 0; j < st.nmat; j++) {
@@ -914,18 +904,11 @@ static void run_nodes_unfused(b200_backend_ctx * ctx, ggml_cgraph * g, const int
 }
 
 static void run_plan(b200_backend_ctx * ctx, ggml_cgraph * cgraph, b200_plan * plan) {
-    const size_t ns = plan->steps.size();
-    // the fused mat-vec that follows each one (the last one wraps to the first: the next token's graph has the same weights)
-    const b200_step * first_gemv = nullptr;
-    for (const b200_step & st : plan->steps) if (st.kind == 1) { first_gemv = &st; break; }
-    for (size_t si = 0; si < ns; si++) {
-        const b200_step & st = plan->steps[si];
+    for (const b200_step & st : plan->steps) {
         if (st.kind == 0) {
             run_nodes_unfused(ctx, cgraph, &st.node, 1);
         } else if (st.kind == 1) {
-            const b200_step * next = first_gemv;
-            for (size_t sj = si + 1; sj < ns; sj++) if (plan->steps[sj].kind == 1) { next = &plan->steps[sj]; break; }
-            if (run_gemv_step(ctx, cgraph, st, next == &st ? nullptr : next)) { g_nodes += st.nmat; g_fused_steps++; continue; }
+            if (run_gemv_step(ctx, cgraph, st)) { g_nodes += st.nmat; g_fused_steps++; continue; }
             // shape outside the fused kernel: the nodes of the group, in graph order
             std::vector<int> nodes;
             if (st.p0 >= 0) { nodes.push_back(st.p0); nodes.push_back(st.p1); }

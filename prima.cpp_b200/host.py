@@ -12,7 +12,9 @@ TYPES = {"f32": 0, "f16": 1, "q5_1": 7, "q8_0": 8, "q4_K": 12, "q5_K": 13, "q6_K
 
 
 def lib_path() -> Path:
-    return PKG / "libprima_b200.so"
+    import os
+    alt = os.environ.get("PB200_LIB")   # development only: A/B of two builds of the library on one box (tools/runs/*.sh)
+    return Path(alt) if alt else PKG / "libprima_b200.so"
 
 
 def build(force: bool = False) -> Path:
