@@ -617,12 +617,18 @@ static int pf_reserve(pb200_model * m, int T) {
 }
 
 // y[t][:] = W . x[t][:] (+ bias): tensor-core path when the type / K allow it, otherwise the decode GEMV row by row
-static int pf_matmul(pb200_model * m, const Tensor & W, const float * x, int T, float * y, const float * bias, const float * resid, uint64_t & n) {
+// same_x_as: the matrix of the previous pf_matmul call when it read the same x (q -> k -> v, gate -> up): its tiled fp16 activation image
+// in the workspace is reused if both went down the tensor-core path with the same activation format
+static bool pf_tc(const Tensor & W, int T) { return mmq_supported(W.type, W.K) && T >= 8; }
+static int pf_matmul(pb200_model * m, const Tensor & W, const float * x, int T, float * y, const float * bias, const float * resid, uint64_t & n,
+                     const Tensor * same_x_as = nullptr, const MmqPre * pre = nullptr) {
     cudaStream_t st = m->stream;
-    if (mmq_supported(W.type, W.K) && T >= 8) {
-        n += 2;
-        return (int) launch_mmq(W.type, W.data, W.N, W.K, x, W.K, T, y, bias, resid, m->pf.ws, st);
+    if (pf_tc(W, T)) {
+        const bool reuse = same_x_as && pf_tc(*same_x_as, T) && same_x_as->K == W.K && is_kquant(same_x_as->type) == is_kquant(W.type);
+        n += reuse ? 1 : 2;
+        return (int) launch_mmq(W.type, W.data, W.N, W.K, x, W.K, T, y, bias, resid, m->pf.ws, st, reuse, reuse ? nullptr : pre);
     }
+    if (pre) return (int) cudaErrorInvalidValue;   // callers fuse a producer only when pf_tc(W, T) && is_kquant(W.type)
     ActQ act = act_from_ws(m->actF.base, W.K);
     for (int t = 0; t < T; t++) {
         CK(launch_quantize_act(x + (size_t) t * W.K, (int) W.K, act_mode_for(W.type), act, st, false));
@@ -677,10 +683,19 @@ static int prefill_ubatch(pb200_model * m, const int32_t * tokens_host, int32_t 
         __half * kc = m->kcache + (size_t) (il - m->l0) * hp.n_ctx * EK;
         __half * vc = m->vcache + (size_t) (il - m->l0) * hp.n_ctx * EK;
         // --- attention block ---
-        CK(launch_rms_norm(x, P.xn, E, T, hp.rms_eps, st, L.attn_norm)); n++;
-        CK(pf_matmul(m, L.wq, P.xn, T, P.q, L.bq, nullptr, n));
-        CK(pf_matmul(m, L.wk, P.xn, T, P.k, L.bk, nullptr, n));
-        CK(pf_matmul(m, L.wv, P.xn, T, P.v, L.bv, nullptr, n));
+        // rms_norm * attn_norm rides in the activation pass of q (k and v reuse its image) when all three take the tensor-core path
+        const bool qkv_fused = pf_tc(L.wq, T) && pf_tc(L.wk, T) && pf_tc(L.wv, T) && is_kquant(L.wq.type) && is_kquant(L.wk.type) && is_kquant(L.wv.type);
+        if (qkv_fused) {
+            MmqPre pre; pre.kind = 2; pre.aux = L.attn_norm; pre.eps = hp.rms_eps;
+            CK(pf_matmul(m, L.wq, x, T, P.q, L.bq, nullptr, n, nullptr, &pre));
+            CK(pf_matmul(m, L.wk, x, T, P.k, L.bk, nullptr, n, &L.wq));
+            CK(pf_matmul(m, L.wv, x, T, P.v, L.bv, nullptr, n, &L.wk));
+        } else {
+            CK(launch_rms_norm(x, P.xn, E, T, hp.rms_eps, st, L.attn_norm)); n++;
+            CK(pf_matmul(m, L.wq, P.xn, T, P.q, L.bq, nullptr, n));
+            CK(pf_matmul(m, L.wk, P.xn, T, P.k, L.bk, nullptr, n, &L.wq));
+            CK(pf_matmul(m, L.wv, P.xn, T, P.v, L.bv, nullptr, n, &L.wk));
+        }
         CK(launch_rope(P.q, P.q, T, H, D, QD, D, P.pos, m->rp, m->rope_ff, st)); n++;
         CK(launch_rope(P.k, P.k, T, HK, D, EK, D, P.pos, m->rp, m->rope_ff, st)); n++;
         CK(launch_cpy_f32_f16(P.k, kc + (size_t) pos0 * EK, (int64_t) T * EK, st)); n++;
@@ -688,11 +703,22 @@ static int prefill_ubatch(pb200_model * m, const int32_t * tokens_host, int32_t 
         CK(launch_attn_batch(P.q, kc, vc, P.att, H, HK, D, P.pos, T, pos0 + T, kq_scale, st)); n++;
         CK(pf_matmul(m, L.wo, P.att, T, y, nullptr, x, n));                  // ffn_inp = wo.att + inpSA (residual in the epilogue)
         // --- FFN block ---
-        CK(launch_rms_norm(y, P.xn, E, T, hp.rms_eps, st, L.ffn_norm)); n++;
-        CK(pf_matmul(m, L.gate, P.xn, T, P.g, nullptr, nullptr, n));
-        CK(pf_matmul(m, L.up, P.xn, T, P.u, nullptr, nullptr, n));
-        CK(launch_silu_mul(P.g, P.u, P.g, (int64_t) T * F, st)); n++;
-        CK(pf_matmul(m, L.down, P.g, T, x, nullptr, y, n));                  // l_out = down.act + ffn_inp   (x is free: y holds ffn_inp)
+        if (pf_tc(L.gate, T) && pf_tc(L.up, T) && is_kquant(L.gate.type) && is_kquant(L.up.type)) {
+            MmqPre pre; pre.kind = 2; pre.aux = L.ffn_norm; pre.eps = hp.rms_eps;
+            CK(pf_matmul(m, L.gate, y, T, P.g, nullptr, nullptr, n, nullptr, &pre));
+            CK(pf_matmul(m, L.up, y, T, P.u, nullptr, nullptr, n, &L.gate));
+        } else {
+            CK(launch_rms_norm(y, P.xn, E, T, hp.rms_eps, st, L.ffn_norm)); n++;
+            CK(pf_matmul(m, L.gate, P.xn, T, P.g, nullptr, nullptr, n));
+            CK(pf_matmul(m, L.up, P.xn, T, P.u, nullptr, nullptr, n, &L.gate));
+        }
+        if (pf_tc(L.down, T) && is_kquant(L.down.type)) {                     // silu(g) * u inside ffn_down's activation pass
+            MmqPre pre; pre.kind = 1; pre.aux = P.u; pre.ld_aux = F;
+            CK(pf_matmul(m, L.down, P.g, T, x, nullptr, y, n, nullptr, &pre));   // l_out = down.act + ffn_inp   (x is free: y holds ffn_inp)
+        } else {
+            CK(launch_silu_mul(P.g, P.u, P.g, (int64_t) T * F, st)); n++;
+            CK(pf_matmul(m, L.down, P.g, T, x, nullptr, y, n));
+        }
     }
     // hidden state of the last token -> the decode path's output head
     CK(cudaMemcpyAsync(m->x_out, x + (size_t) (T - 1) * E, (size_t) E * 4, cudaMemcpyDeviceToDevice, st));

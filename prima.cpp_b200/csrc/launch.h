@@ -115,8 +115,16 @@ int launch_soft_max(const float * x, const float * mask, float * y, int ncols, i
 // batched k-quant mat-mul on tcgen05 (mmq.cu): dst[T][N] = X[T][K] . W[N][K]^T (+ bias[N]); ws from mmq_workspace_bytes
 size_t mmq_workspace_bytes(int64_t K, int64_t T);
 bool mmq_supported(int type, int64_t K);
+struct MmqPre {            // producer fused into the activation pass: 1: x <- silu(x) * aux[t][k] (ld_aux floats per row), 2: x <- rms_norm(x, eps) * aux[k]
+    int kind = 0;
+    const float * aux = nullptr;
+    int64_t ld_aux = 0;
+    float eps = 0.f;
+};
 cudaError_t launch_mmq(int type, const void * W, int64_t N, int64_t K, const float * x, int64_t ldx, int64_t T, float * dst, const float * bias,
-                       const float * resid, void * ws, cudaStream_t st);   // resid: [T][N] added in the epilogue (must not alias dst)
+                       const float * resid, void * ws, cudaStream_t st, bool reuse_prep = false, const MmqPre * pre = nullptr);
+// resid: [T][N] added in the epilogue (must not alias dst).  reuse_prep: ws already holds this x (same K, T) from the previous launch_mmq
+// on the stream (q|k|v and gate|up share one activation: the q8_K -> fp16 tiling pass runs once)
 int launch_get_rows(const void * table, int type, int K, const int32_t * ids, int n_ids, float * y, cudaStream_t stream, bool pdl);
 
 // element-wise helpers for the plugin

@@ -12,8 +12,14 @@
 // Also the 32-element block types Q8_0 / Q5_1 (K % 64 == 0; activations quantized per 32 values like their CPU dot): Qwen2.5-72B's
 // ffn_down, whose K = 29 568 rules the k-quants out (src/llama.cpp:19516-19551).
 //
-// One CTA owns 128 weight rows x (1 or 2) token tiles of BN <= 256 columns — two accumulators (all 512 TMEM columns) share
-// every expanded weight stage when T is large enough — and walks K in 64-element steps:
+// Work decomposition (round 2: stream-K, persistent).  A work UNIT = one 256-element K group of one output tile (128 weight rows x 1 or 2
+// token tiles of BN <= 256 columns: two accumulators = all 512 TMEM columns share every expanded weight stage when T is large enough).
+// The units of a launch, ordered tile by tile, are cut into one contiguous range per CTA (at most one CTA per SM), so every SM gets the same
+// number of 64-element MMA steps whatever N, K and T are: round 1's one-tile-per-CTA grid left 84 of 148 SMs idle on an 8192-row matrix
+// at 512 tokens and 2/3 of the last wave idle on ffn_gate/up.  A CTA walks its range segment by segment (segment = its part of one
+// tile); a segment that covers the tile's whole K stores its result, a partial one adds it into the pre-zeroed dst with fp32 atomics
+// (two or three addends per element: the order of fp32 adds is the only non-determinism, below the kernel's own fp16 rounding).
+// Inside a CTA the pipeline never drains between segments (raw-block ring, A and B stages and their barriers run on CTA-wide counters):
 //   warp 0      owns TMEM; one lane issues 4 x tcgen05.mma (M=128, N=BN, K=16, kind::f16) per step and accumulator, one commit per step
 //   warp 1      activation producer: one cp.async.bulk per step of the pre-tiled fp16 chunk (BN x 128 B, already in the
 //               UMMA swizzle-128B image), 4-deep ring
@@ -23,6 +29,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -49,8 +56,9 @@ struct MmqParams {
     const float * resid;   // [T][N] or null: residual added in the epilogue
     int64_t row_bytes, total_bytes;
     int nraw, b_nst;       // ring depths chosen at launch from the shared-memory budget
-    int nacc, ttiles;      // accumulators (token tiles) per CTA, number of token tiles
-    int ksplit;            // 1, or 2: blockIdx.z takes half of K and the halves meet in dst by atomic add (dst pre-zeroed)
+    int nacc, ttiles;      // accumulators (token tiles) per output tile, number of token tiles
+    int ngrp, rtiles;      // 256-K groups per row (the last one may be short: 32-element block types), row tiles
+    int upc, total_units;  // work units per CTA (CTA c owns units [c * upc, min((c + 1) * upc, total_units)) ), units of the launch
     int N, K, T, BN, bpb, slot;   // slot: bytes reserved per row in a raw stage (16-B aligned window around one block)
     uint32_t tmem_cols, idesc;
 };
@@ -59,7 +67,7 @@ struct MmqCtl {
     uint64_t raw_full[3], raw_empty[3];
     uint64_t a_ready[MMQ_A_NST], b_full[MMQ_B_NST];
     uint64_t step_done[MMQ_B_NST];   // one tcgen05.commit per step: step u arrives on step_done[u % 4]; frees A stage u % 2 and B stage u % b_nst
-    uint64_t acc_ready;
+    uint64_t acc_ready, acc_free;    // per segment: accumulators complete (tcgen05.commit) / read out by the 4 epilogue warps
     uint32_t tmem_base;
     volatile int abort;
 };
@@ -264,19 +272,15 @@ __global__ void __launch_bounds__(MMQ_THREADS, 1) k_mmq_tc(const __grid_constant
     MmqCtl * ctl = reinterpret_cast<MmqCtl *>(raw + P.nraw * MMQ_BM * P.slot);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row0 = blockIdx.x * MMQ_BM;
-    const int tt0 = blockIdx.y * P.nacc;                         // first token tile of this CTA
-    const int nacc = min(P.nacc, P.ttiles - tt0);                // the last CTA of an odd count has one
-    const int nstep_all = P.K / MMQ_BK;                          // 64-element steps; a 256-K group (4 steps) is one raw fetch
-    const int nsb = ((nstep_all + 3) / 4) / P.ksplit;            // groups this CTA walks (ksplit > 1 only when they divide evenly) ...
-    const int sb0 = blockIdx.z * nsb;                            // ... starting here
-    const int nchunk = min(nsb * 4, nstep_all - sb0 * 4);        // the last group of a K % 256 != 0 row (32-element block types) is short
+    const int nstep_all = P.K / MMQ_BK;                          // 64-element steps of a whole row; group sb holds steps [4 sb, min(4 sb + 4, nstep_all))
+    const int w0 = blockIdx.x * P.upc, w1 = min(w0 + P.upc, P.total_units);   // this CTA's units
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 3; i++) { mbar_init(&ctl->raw_full[i], MMQ_DQ_WARPS * 32); mbar_init(&ctl->raw_empty[i], MMQ_DQ_WARPS); }
         for (int i = 0; i < MMQ_A_NST; i++) mbar_init(&ctl->a_ready[i], MMQ_DQ_WARPS);
         for (int i = 0; i < MMQ_B_NST; i++) { mbar_init(&ctl->b_full[i], 1); mbar_init(&ctl->step_done[i], 1); }
         mbar_init(&ctl->acc_ready, 1);
+        mbar_init(&ctl->acc_free, 4);
         ctl->abort = 0;
         mbar_fence_init();
     }
@@ -289,42 +293,62 @@ __global__ void __launch_bounds__(MMQ_THREADS, 1) k_mmq_tc(const __grid_constant
     tc_fence_after();
     const uint32_t tmem = *(volatile uint32_t *) &ctl->tmem_base;
 
+    // Every role walks the same segments: unit w -> tile w / ngrp (token-tile group tile / rtiles, row tile tile % rtiles), K group w % ngrp.
     if (warp == 0) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            for (int u = 0; u < nchunk; u++) {
-                const int sa = u % MMQ_A_NST, ra = u / MMQ_A_NST, sb = u % P.b_nst, rb = u / P.b_nst;
-                if (!mmq_wait(ctl, &ctl->b_full[sb], rb & 1)) break;
-                if (!mmq_wait(ctl, &ctl->a_ready[sa], ra & 1)) break;
+            int g = 0, seg = 0;                                  // CTA-wide step and segment counters (barrier phases follow them)
+            bool ok = true;
+            for (int w = w0; w < w1 && ok; seg++) {
+                const int tile = w / P.ngrp, sbb = w - tile * P.ngrp, sbe = min(P.ngrp, sbb + (w1 - w));
+                const int nacc = min(P.nacc, P.ttiles - (tile / P.rtiles) * P.nacc);
+                const int nsteps = min(4 * sbe, nstep_all) - 4 * sbb;
+                if (seg > 0 && !mmq_wait(ctl, &ctl->acc_free, (seg - 1) & 1)) break;   // the previous segment's accumulators have been read out
                 tc_fence_after();
-                const uint64_t da = umma_desc_sw128(smem_u32(a_st + (size_t) sa * MMQ_A_BYTES));
-                const uint64_t db = umma_desc_sw128(smem_u32(b_st + (size_t) sb * b_bytes));
-                const uint64_t db2 = umma_desc_sw128(smem_u32(b_st + (size_t) sb * b_bytes + b1));
+                for (int u = 0; u < nsteps; u++, g++) {
+                    const int sa = g % MMQ_A_NST, sb = g % P.b_nst;
+                    if (!mmq_wait(ctl, &ctl->b_full[sb], (g / P.b_nst) & 1)) { ok = false; break; }
+                    if (!mmq_wait(ctl, &ctl->a_ready[sa], (g / MMQ_A_NST) & 1)) { ok = false; break; }
+                    tc_fence_after();
+                    const uint64_t da = umma_desc_sw128(smem_u32(a_st + (size_t) sa * MMQ_A_BYTES));
+                    const uint64_t db = umma_desc_sw128(smem_u32(b_st + (size_t) sb * b_bytes));
+                    const uint64_t db2 = umma_desc_sw128(smem_u32(b_st + (size_t) sb * b_bytes + b1));
 #pragma unroll
-                for (int k = 0; k < MMQ_BK / 16; k++) {
-                    umma_f16(tmem, da + 2 * k, db + 2 * k, P.idesc, (u | k) != 0);
-                    if (nacc == 2) umma_f16(tmem + 256, da + 2 * k, db2 + 2 * k, P.idesc, (u | k) != 0);
+                    for (int k = 0; k < MMQ_BK / 16; k++) {
+                        umma_f16(tmem, da + 2 * k, db + 2 * k, P.idesc, (u | k) != 0);
+                        if (nacc == 2) umma_f16(tmem + 256, da + 2 * k, db2 + 2 * k, P.idesc, (u | k) != 0);
+                    }
+                    umma_commit(&ctl->step_done[g % MMQ_B_NST]);
                 }
-                umma_commit(&ctl->step_done[u % MMQ_B_NST]);
+                umma_commit(&ctl->acc_ready);
+                w += sbe - sbb;
             }
-            umma_commit(&ctl->acc_ready);
         }
         __syncwarp();
     } else if (warp == 1) {
         // ================= activation producer: runs up to b_nst steps ahead of the tensor core =================
         if (lane == 0) {
-            const size_t tile_stride = (size_t) (P.K / MMQ_BK) * b1;
-            const uint8_t * Bt = P.B + (size_t) tt0 * tile_stride + (size_t) sb0 * 4 * b1;
-            for (int u = 0; u < nchunk; u++) {
-                const int sb = u % P.b_nst, rb = u / P.b_nst;
-                if (rb > 0) {   // step u - b_nst consumed this stage
-                    const int f = u - P.b_nst;
-                    if (!mmq_wait(ctl, &ctl->step_done[f % MMQ_B_NST], (f / MMQ_B_NST) & 1)) break;
+            const size_t tile_stride = (size_t) nstep_all * b1;
+            int g = 0;
+            bool ok = true;
+            for (int w = w0; w < w1 && ok;) {
+                const int tile = w / P.ngrp, sbb = w - tile * P.ngrp, sbe = min(P.ngrp, sbb + (w1 - w));
+                const int tt0 = (tile / P.rtiles) * P.nacc;
+                const int nacc = min(P.nacc, P.ttiles - tt0);
+                const int nsteps = min(4 * sbe, nstep_all) - 4 * sbb;
+                const uint8_t * Bt = P.B + (size_t) tt0 * tile_stride + (size_t) sbb * 4 * b1;
+                for (int u = 0; u < nsteps; u++, g++) {
+                    const int sb = g % P.b_nst;
+                    if (g >= P.b_nst) {   // step g - b_nst consumed this stage
+                        const int f = g - P.b_nst;
+                        if (!mmq_wait(ctl, &ctl->step_done[f % MMQ_B_NST], (f / MMQ_B_NST) & 1)) { ok = false; break; }
+                    }
+                    mbar_arrive_expect_tx(&ctl->b_full[sb], (uint32_t) (nacc * b1));
+                    for (int a = 0; a < nacc; a++)
+                        bulk_g2s_plain(b_st + (size_t) sb * b_bytes + (size_t) a * b1, Bt + (size_t) a * tile_stride + (size_t) u * b1, (uint32_t) b1,
+                                       &ctl->b_full[sb]);
                 }
-                mbar_arrive_expect_tx(&ctl->b_full[sb], (uint32_t) (nacc * b1));
-                for (int a = 0; a < nacc; a++)
-                    bulk_g2s_plain(b_st + (size_t) sb * b_bytes + (size_t) a * b1, Bt + (size_t) a * tile_stride + (size_t) u * b1, (uint32_t) b1,
-                                   &ctl->b_full[sb]);
+                w += sbe - sbb;
             }
         }
         __syncwarp();
@@ -332,89 +356,124 @@ __global__ void __launch_bounds__(MMQ_THREADS, 1) k_mmq_tc(const __grid_constant
         // ================= weight expansion =================
         const int dt = threadIdx.x - MMQ_DQ_WARP0 * 32;        // 0..255
         const int r = dt >> 1, h = dt & 1;
-        const int gr = min(row0 + r, P.N - 1);
         bool ok = true;
         // this thread fetches its own half of the row's block: 16-byte cp.async pieces of the 16-B aligned window around it
         const int64_t lim = (P.total_bytes + 15) & ~(int64_t) 15;
         const int cpr = P.slot >> 4, p_lo = h ? (cpr + 1) / 2 : 0, p_hi = h ? cpr : (cpr + 1) / 2;
+        const int nx = w1 - w0;                                 // groups this CTA walks, x = 0 .. nx-1 across its segments
         auto fetch = [&](int x) {
-            const int64_t src0 = ((int64_t) gr * P.row_bytes + (int64_t) (sb0 + x) * P.bpb) & ~(int64_t) 15;
+            const int wq = w0 + x, tile = wq / P.ngrp, sb = wq - tile * P.ngrp;
+            const int gr = min((tile % P.rtiles) * MMQ_BM + r, P.N - 1);
+            const int64_t src0 = ((int64_t) gr * P.row_bytes + (int64_t) sb * P.bpb) & ~(int64_t) 15;
             uint8_t * dst0 = raw + ((size_t) (x % P.nraw) * MMQ_BM + r) * P.slot;
             for (int pc = p_lo; pc < p_hi; pc++)
                 if (src0 + pc * 16 + 16 <= lim) cp_async16(dst0 + pc * 16, P.W + src0 + pc * 16);
             asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&ctl->raw_full[x % P.nraw])) : "memory");
         };
-        for (int x = 0; x < P.nraw - 1 && x < nsb; x++) fetch(x);
+        for (int x = 0; x < P.nraw - 1 && x < nx; x++) fetch(x);
         // the four 16-byte pieces this thread writes per step, already swizzled
         const uint32_t arow = r * 128;
         const uint32_t o0 = arow + (((4 * h + 0) ^ (r & 7)) << 4), o1 = arow + (((4 * h + 1) ^ (r & 7)) << 4);
         const uint32_t o2 = arow + (((4 * h + 2) ^ (r & 7)) << 4), o3 = arow + (((4 * h + 3) ^ (r & 7)) << 4);
-        int u = 0;
-        for (int sb = 0; sb < nsb && ok; sb++) {
-            const int rs = sb % P.nraw, rr = sb / P.nraw;
-            {   // refill the slot super-block sb-1 used, once every expansion warp has left it
-                const int x = sb + P.nraw - 1;
-                if (x < nsb) {
-                    if (sb > 0 && !mmq_wait(ctl, &ctl->raw_empty[(sb - 1) % P.nraw], ((sb - 1) / P.nraw) & 1)) { ok = false; break; }
-                    fetch(x);
-                }
-            }
-            if (!mmq_wait(ctl, &ctl->raw_full[rs], rr & 1)) { ok = false; break; }
-            const int64_t g0 = (int64_t) gr * P.row_bytes + (int64_t) (sb0 + sb) * P.bpb;
-            const uint8_t * blk = raw + (size_t) (rs * MMQ_BM + r) * P.slot + (g0 & 15);
-#pragma unroll
-            for (int c = 0; c < 4; c++, u++) {
-                if (u >= nchunk) break;
-                uint32_t v[16];
-                expand<TYPE>(blk, c, h, v);
-                if (u >= MMQ_A_NST) {   // step u - 2 has consumed this A stage
-                    const int f = u - MMQ_A_NST;
-                    if (!mmq_wait(ctl, &ctl->step_done[f % MMQ_B_NST], (f / MMQ_B_NST) & 1)) { ok = false; break; }
-                }
-                uint8_t * as = a_st + (size_t) (u % MMQ_A_NST) * MMQ_A_BYTES;
-                *reinterpret_cast<uint4 *>(as + o0) = make_uint4(v[0], v[1], v[2], v[3]);
-                *reinterpret_cast<uint4 *>(as + o1) = make_uint4(v[4], v[5], v[6], v[7]);
-                *reinterpret_cast<uint4 *>(as + o2) = make_uint4(v[8], v[9], v[10], v[11]);
-                *reinterpret_cast<uint4 *>(as + o3) = make_uint4(v[12], v[13], v[14], v[15]);
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core's async proxy
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&ctl->a_ready[u % MMQ_A_NST]);
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&ctl->raw_empty[rs]);
-        }
-        // ================= epilogue: four consecutive warps cover the four 32-lane quadrants of TMEM =================
-        if (warp < MMQ_DQ_WARP0 + 4) {
-            const bool acc_ok = mmq_wait(ctl, &ctl->acc_ready, 0);
-            tc_fence_after();
-            const int quad = warp & 3;
-            const int n = row0 + quad * 32 + lane;
-            const float bias = (P.bias && n < P.N && blockIdx.z == 0) ? P.bias[n] : 0.f;
-            for (int a = 0; a < nacc; a++) {
-                for (int c0 = 0; c0 < BN; c0 += 16) {
-                    uint32_t v[16];
-                    const uint32_t taddr = tmem + ((uint32_t) (quad * 32) << 16) + (uint32_t) (a * 256 + c0);
-                    asm volatile(
-                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-                          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                        : "r"(taddr)
-                        : "memory");
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (acc_ok && n < P.N) {
-#pragma unroll
-                        for (int i = 0; i < 16; i++) {
-                            const int t = (tt0 + a) * BN + c0 + i;
-                            if (t < P.T) {
-                                float y = __fadd_rn(__uint_as_float(v[i]), bias);
-                                if (P.resid && blockIdx.z == 0) y = __fadd_rn(y, P.resid[(size_t) t * P.N + n]);
-                                if (P.ksplit == 1) P.dst[(size_t) t * P.N + n] = y;
-                                else atomicAdd(&P.dst[(size_t) t * P.N + n], y);   // two addends onto 0: order-independent
-                            }
-                        }
+        int g = 0, x = 0, seg = 0;
+        for (int w = w0; w < w1 && ok; seg++) {
+            const int tile = w / P.ngrp, sbb = w - tile * P.ngrp, sbe = min(P.ngrp, sbb + (w1 - w));
+            const int row0 = (tile % P.rtiles) * MMQ_BM;
+            const int gr = min(row0 + r, P.N - 1);
+            for (int sb = sbb; sb < sbe && ok; sb++, x++) {
+                const int rs = x % P.nraw, rr = x / P.nraw;
+                {   // refill the slot group x-1 used, once every expansion warp has left it
+                    const int xf = x + P.nraw - 1;
+                    if (xf < nx) {
+                        if (x > 0 && !mmq_wait(ctl, &ctl->raw_empty[(x - 1) % P.nraw], ((x - 1) / P.nraw) & 1)) { ok = false; break; }
+                        fetch(xf);
                     }
                 }
+                if (!mmq_wait(ctl, &ctl->raw_full[rs], rr & 1)) { ok = false; break; }
+                const int64_t g0 = (int64_t) gr * P.row_bytes + (int64_t) sb * P.bpb;
+                const uint8_t * blk = raw + (size_t) (rs * MMQ_BM + r) * P.slot + (g0 & 15);
+                const int nst = min(4, nstep_all - 4 * sb);      // the last group of a K % 256 != 0 row (32-element block types) is short
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    if (c >= nst) break;
+                    uint32_t v[16];
+                    expand<TYPE>(blk, c, h, v);
+                    if (g >= MMQ_A_NST) {   // step g - 2 has consumed this A stage
+                        const int f = g - MMQ_A_NST;
+                        if (!mmq_wait(ctl, &ctl->step_done[f % MMQ_B_NST], (f / MMQ_B_NST) & 1)) { ok = false; break; }
+                    }
+                    uint8_t * as = a_st + (size_t) (g % MMQ_A_NST) * MMQ_A_BYTES;
+                    *reinterpret_cast<uint4 *>(as + o0) = make_uint4(v[0], v[1], v[2], v[3]);
+                    *reinterpret_cast<uint4 *>(as + o1) = make_uint4(v[4], v[5], v[6], v[7]);
+                    *reinterpret_cast<uint4 *>(as + o2) = make_uint4(v[8], v[9], v[10], v[11]);
+                    *reinterpret_cast<uint4 *>(as + o3) = make_uint4(v[12], v[13], v[14], v[15]);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core's async proxy
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&ctl->a_ready[g % MMQ_A_NST]);
+                    g++;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ctl->raw_empty[rs]);
             }
+            // ================= epilogue of the segment: four consecutive warps cover the four 32-lane quadrants of TMEM =================
+            if (warp < MMQ_DQ_WARP0 + 4) {
+                const bool acc_ok = ok && mmq_wait(ctl, &ctl->acc_ready, seg & 1);
+                tc_fence_after();
+                const int tt0 = (tile / P.rtiles) * P.nacc;
+                const int nacc = min(P.nacc, P.ttiles - tt0);
+                const bool first = sbb == 0, whole = first && sbe == P.ngrp;   // bias / residual ride on the K group 0 segment
+                const int quad = warp & 3;
+                const int n = row0 + quad * 32 + lane;
+                const float bias = (P.bias && n < P.N && first) ? P.bias[n] : 0.f;
+                // The residual rows are fetched one 16-token chunk AHEAD, all 16 loads in flight at once: written as "load, add, store" per
+                // element the loads serialise behind the stores / atomics (dst and resid may alias as far as the compiler knows), which cost
+                // 220-260 us per launch with a residual (wo, ffn_down: profiles/r2_prefill_launches_streamk_before_resid_fix.csv)
+                const float * __restrict__ rp = (P.resid && first && n < P.N) ? P.resid + n : nullptr;
+                float rcur[16], rnext[16];
+                auto load_resid = [&](float (&rv)[16], int a, int c0) {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        const int t = (tt0 + a) * BN + c0 + i;
+                        rv[i] = (rp && t < P.T) ? __ldg(rp + (size_t) t * P.N) : 0.f;
+                    }
+                };
+                load_resid(rcur, 0, 0);
+                for (int a = 0; a < nacc; a++) {
+                    for (int c0 = 0; c0 < BN; c0 += 16) {
+                        {   // next chunk's residual
+                            int a2 = a, c2 = c0 + 16;
+                            if (c2 >= BN) { a2++; c2 = 0; }
+                            if (a2 < nacc) load_resid(rnext, a2, c2);
+                        }
+                        uint32_t v[16];
+                        const uint32_t taddr = tmem + ((uint32_t) (quad * 32) << 16) + (uint32_t) (a * 256 + c0);
+                        asm volatile(
+                            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                              "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                            : "r"(taddr)
+                            : "memory");
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        if (acc_ok && n < P.N) {
+#pragma unroll
+                            for (int i = 0; i < 16; i++) {
+                                const int t = (tt0 + a) * BN + c0 + i;
+                                if (t < P.T) {
+                                    const float y = __fadd_rn(__fadd_rn(__uint_as_float(v[i]), bias), rcur[i]);
+                                    if (whole) P.dst[(size_t) t * P.N + n] = y;
+                                    else atomicAdd(&P.dst[(size_t) t * P.N + n], y);   // <= 3 addends onto 0
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int i = 0; i < 16; i++) rcur[i] = rnext[i];
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ctl->acc_free);      // the issuer may overwrite the accumulators
+            }
+            w += sbe - sbb;
         }
     }
     tc_fence_before();
@@ -428,14 +487,35 @@ __global__ void __launch_bounds__(MMQ_THREADS, 1) k_mmq_tc(const __grid_constant
 // ---- activation rows -> q8_K (exactly as the CPU backend quantizes them) -> fp16, written in the tiled UMMA image ----
 // blk32: the weight type is Q8_0 / Q5_1, whose CPU dot quantizes the activation per 32 values (q8_0 / q8_1: d = amax / 127 stored
 // as f16, q = round-half-even(x * 127 / amax), quantize_row_q8_0 ggml-quants.c:943-1010) instead of per 256 (q8_K).
+// Fused producers of the activation (pre_kind): 1 = silu(x) * aux[t][k] (llm_build_ffn's SILU + MUL in front of ffn_down, the f32 product never
+// goes to HBM), 2 = rms_norm(x) * aux[k] (llm_build_norm in front of q|k|v and gate|up): the same arithmetic, rounding for rounding, as
+// k_silu_mul / k_rms_norm_rows followed by the plain pass.
+__device__ __forceinline__ float mmq_silu(float x) { return __fdiv_rn(x, 1.0f + expf(-x)); }   // ggml.c:2560
 __global__ void __launch_bounds__(256) k_mmq_prep(const float * __restrict__ x, int64_t ldx, int T, int K, int BN, uint8_t * __restrict__ out,
-                                                  float * __restrict__ zero_dst, int N, int blk32) {
+                                                  int blk32, int pre_kind, const float * __restrict__ aux, int64_t ld_aux, float eps) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (zero_dst && (int) blockIdx.x < T)   // split-K launches accumulate into dst
-        for (int i = threadIdx.x; i < N; i += 256) zero_dst[(size_t) blockIdx.x * N + i] = 0.f;
     const int nblk = (K + 255) / 256;
     const int t = blockIdx.x;                       // 0 .. Tpad-1
     const int b_bytes = BN * 128;
+    float nscale = 1.f;
+    if (pre_kind == 2 && t < T) {                   // k_rms_norm_rows' sum, in its order (ggml.c:11950-11996: double-precision sum of squares)
+        __shared__ double red[8];
+        __shared__ float s_scale;
+        const float * xr = x + (size_t) t * ldx;
+        double sum = 0.0;
+        for (int i = threadIdx.x; i < K; i += 256) sum += (double) __fmul_rn(xr[i], xr[i]);
+        sum = warp_sum_d(sum);
+        if (lane == 0) red[warp] = sum;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double tt = 0;
+            for (int i = 0; i < 8; i++) tt += red[i];
+            const float mean = (float) (tt / (double) K);
+            s_scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, eps)));
+        }
+        __syncthreads();
+        nscale = s_scale;
+    }
     for (int b = warp; b < nblk; b += 8) {
         float v[8];
         const bool live = b * 256 + lane * 8 < K;   // K % 32 == 0: a 4-lane group (one 32-block) is live or dead as a whole
@@ -443,6 +523,13 @@ __global__ void __launch_bounds__(256) k_mmq_prep(const float * __restrict__ x, 
             const float4 * p = reinterpret_cast<const float4 *>(x + (size_t) t * ldx + (size_t) b * 256 + lane * 8);
             const float4 a = p[0], c = p[1];
             v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+            if (pre_kind) {
+                const float4 * q = reinterpret_cast<const float4 *>(aux + (pre_kind == 1 ? (size_t) t * ld_aux : (size_t) 0) + (size_t) b * 256 + lane * 8);
+                const float4 e = q[0], f = q[1];
+                const float w[8] = {e.x, e.y, e.z, e.w, f.x, f.y, f.z, f.w};
+#pragma unroll
+                for (int i = 0; i < 8; i++) v[i] = pre_kind == 1 ? __fmul_rn(mmq_silu(v[i]), w[i]) : __fmul_rn(__fmul_rn(v[i], nscale), w[i]);
+            }
         } else {
 #pragma unroll
             for (int i = 0; i < 8; i++) v[i] = 0.f;
@@ -521,7 +608,8 @@ static cudaError_t mmq_launch_typed(const MmqParams & P, dim3 grid, size_t smem,
 }
 
 cudaError_t launch_mmq(int type, const void * W, int64_t N, int64_t K, const float * x, int64_t ldx, int64_t T, float * dst, const float * bias,
-                       const float * resid, void * ws, cudaStream_t st) {
+                       const float * resid, void * ws, cudaStream_t st, bool reuse_prep, const MmqPre * pre) {
+    if (pre && pre->kind != 0 && (!pre->aux || K % 256 != 0 || pre->kind < 0 || pre->kind > 2)) return cudaErrorInvalidValue;
     if (!mmq_supported(type, K) || N <= 0 || T <= 0) return cudaErrorInvalidValue;
     const int BN = mmq_pick_bn((int) T);
     const int tpad = (int) ((T + BN - 1) / BN * BN);
@@ -543,29 +631,36 @@ cudaError_t launch_mmq(int type, const void * W, int64_t N, int64_t K, const flo
     P.bpb = type == T_Q4_K ? BYTES_Q4_K : type == T_Q5_K ? BYTES_Q5_K : type == T_Q6_K ? BYTES_Q6_K : type == T_Q8_0 ? 8 * BYTES_Q8_0 : 8 * BYTES_Q5_1;
     P.slot = type == T_Q6_K ? 240 : (type == T_Q8_0 ? 288 : P.bpb);
     P.ttiles = tpad / BN;
-    const int rtiles = (int) ((N + MMQ_BM - 1) / MMQ_BM);
-    // Configuration: two accumulators per CTA halve the weight-expansion work per FLOP (measured 1040 vs 590 TFLOP/s at full
-    // occupancy); splitting K in two doubles the CTA count for small N x T but costs ~20 % (zeroing, atomics, activations read
-    // twice).  Pick the best estimated (efficiency x SM occupancy).
+    P.rtiles = (int) ((N + MMQ_BM - 1) / MMQ_BM);
+    // two accumulators per output tile halve the weight-expansion work per FLOP (measured 1040 vs 590 TFLOP/s at full occupancy)
     static const int force_nacc = getenv("PB200_MMQ_NACC") ? atoi(getenv("PB200_MMQ_NACC")) : 0;
-    static const int force_ks = getenv("PB200_MMQ_KSPLIT") ? atoi(getenv("PB200_MMQ_KSPLIT")) : 0;
-    const int nsm = sm_count(), nsb_all = (int) (K % 256 == 0 ? K / 256 : 1);   // no split-K for a short last group
-    double best = -1.0;
-    P.nacc = 1; P.ksplit = 1;
-    for (int nacc = 1; nacc <= 2; nacc++)
-        for (int ks = 1; ks <= 2; ks++) {
-            if (nacc == 2 && P.ttiles < 2) continue;
-            if (ks == 2 && (nsb_all % 2 != 0 || nsb_all < 8)) continue;
-            if (force_nacc && nacc != force_nacc && !(force_nacc == 2 && P.ttiles < 2)) continue;
-            if (force_ks && ks != force_ks && !(ks == 1 && (nsb_all % 2 != 0 || nsb_all < 8))) continue;
-            const int64_t ctas = (int64_t) rtiles * ((P.ttiles + nacc - 1) / nacc) * ks;
-            const double occ = (double) ctas / (double) ((ctas + nsm - 1) / nsm * nsm);
-            const double score = occ * (nacc == 2 ? 1.0 : 0.57) * (ks == 2 ? 0.80 : 1.0);
-            if (score > best) { best = score; P.nacc = nacc; P.ksplit = ks; }
-        }
-    k_mmq_prep<<<tpad, 256, 0, st>>>(x, ldx, (int) T, (int) K, BN, (uint8_t *) ws, P.ksplit > 1 ? dst : nullptr, (int) N, is_kquant(type) ? 0 : 1);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
+    P.nacc = (P.ttiles >= 2 && force_nacc != 1) ? 2 : 1;
+    const int tgroups = (P.ttiles + P.nacc - 1) / P.nacc;
+    P.ngrp = (int) ((K / MMQ_BK + 3) / 4);
+    // stream-K: the tiles' K groups, tile after tile, in equal contiguous shares; a share is at least MMQ_MIN_UNITS groups (a segment's
+    // pipeline fill + 128 x 512 epilogue must stay small against its MMA steps) unless the whole launch is smaller than that
+    static const int min_units = getenv("PB200_MMQ_MIN_UNITS") ? std::max(1, atoi(getenv("PB200_MMQ_MIN_UNITS"))) : 8;
+    static const bool whole_tiles = getenv("PB200_MMQ_WHOLE_TILES") != nullptr;   // A/B: round 1's one tile per CTA (no split, no atomics)
+    const int64_t total = (int64_t) P.rtiles * tgroups * P.ngrp;
+    if (total > 0x7fffffff) return cudaErrorInvalidValue;
+    P.total_units = (int) total;
+    const int nsm = sm_count();
+    int upc = (int) ((total + nsm - 1) / nsm);
+    upc = std::max(upc, std::min(min_units, P.ngrp));
+    if (whole_tiles) upc = P.ngrp;
+    P.upc = upc;
+    const int grid_x = (int) ((total + upc - 1) / upc);
+    const bool split = upc % P.ngrp != 0;      // some tile is shared by two CTAs: partial results meet in dst by atomic add
+    if (!reuse_prep) {
+        k_mmq_prep<<<tpad, 256, 0, st>>>(x, ldx, (int) T, (int) K, BN, (uint8_t *) ws, is_kquant(type) ? 0 : 1, pre ? pre->kind : 0,
+                                         pre ? pre->aux : nullptr, pre ? pre->ld_aux : 0, pre ? pre->eps : 0.f);
+        cudaError_t e0 = cudaGetLastError();
+        if (e0 != cudaSuccess) return e0;
+    }
+    if (split) {
+        cudaError_t e0 = cudaMemsetAsync(dst, 0, (size_t) T * (size_t) N * sizeof(float), st);
+        if (e0 != cudaSuccess) return e0;
+    }
     uint32_t cols = 32;
     while ((int) cols < BN) cols <<= 1;
     P.tmem_cols = P.nacc == 2 ? 512 : cols;
@@ -581,7 +676,7 @@ cudaError_t launch_mmq(int type, const void * W, int64_t N, int64_t K, const flo
     while (P.b_nst > 2 && smem_for(P.nraw, P.b_nst) > 232448) P.b_nst--;
     const size_t smem = smem_for(P.nraw, P.b_nst);
     if (smem > 232448) return cudaErrorInvalidConfiguration;
-    dim3 grid((unsigned) rtiles, (unsigned) ((P.ttiles + P.nacc - 1) / P.nacc), (unsigned) P.ksplit);
+    dim3 grid((unsigned) grid_x, 1, 1);
     if (type == T_Q4_K) return mmq_launch_typed<T_Q4_K>(P, grid, smem, st);
     if (type == T_Q5_K) return mmq_launch_typed<T_Q5_K>(P, grid, smem, st);
     if (type == T_Q6_K) return mmq_launch_typed<T_Q6_K>(P, grid, smem, st);

@@ -80,6 +80,25 @@ def test_engine_vs_compiled_reference(cuda, pkg, ref):
     eng.close()
 
 
+def test_engine_llama3_70b_layer_shapes_vs_compiled_reference(cuda, pkg, ref):
+    """Whole-engine parity at the BASELINE config's layer shapes: 2 full-size Llama-3-70B layers (n_embd 8192, 64/8 heads,
+    n_ff 28672: the split-row ffn_down kernel, the 3-matrix q|k|v launch, the Q5_K / Q6_K v and down of the Q4_K_M mixture) + a
+    small vocabulary, decoded token by token against the UNMODIFIED reference CPU backend (oracle/_ref) on the same quantized bytes."""
+    tm = TinyModel(n_layer=2, n_embd=8192, n_head=64, n_head_kv=8, n_ff=28672, n_vocab=512, n_ctx=32, arch="llama", ftype="q4_K_M", seed=21,
+                   branch_scale=0.1)
+    toks = [(i * 7919 + 13) % 512 for i in range(8)]
+    want, hid = tm.ref_decode(ref, toks)
+    eng = tm.load_engine(pkg)
+    got = np.zeros_like(want)
+    for i, t in enumerate(toks):
+        eng.decode(int(t), i, got[i])
+        if i == 0:
+            assert np.max(np.abs(eng.hidden() - hid[0])) < TOL
+    check_decode_parity(got, want)
+    assert np.max(np.abs(got[0] - want[0])) < TOL
+    eng.close()
+
+
 def test_engine_chaotic_model_statistics(cuda, pkg, port):
     """Unit-gain random net (chaotic): quantization flips are amplified layer by layer.  Bound the noise statistically:
     every token's logits stay within 0.2 max-abs (|logits| ~ 3), the median token within 1e-3... and tokens with no flip

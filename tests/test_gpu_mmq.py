@@ -125,7 +125,7 @@ def test_mmq_bias_residual_ragged_rows_and_strided_input(cuda, lib, port):
     check(got, want, Wf, X)
 
 
-@pytest.mark.parametrize("T", [700, 512])   # 700: two accumulators per CTA + a ragged third tile; 512: two accumulators + split-K
+@pytest.mark.parametrize("T", [700, 512])   # 700: two accumulators per tile + a ragged third token tile; 512: two accumulators; both stream-K split
 def test_mmq_matches_gemv_columnwise_full_width(cuda, lib, T):
     """Size-independent property at a 70B shape (also the dual-accumulator configuration): every column of the batched product agrees with the decode GEMV (which is
     bit-exact with the oracle) to NMSE <= 4e-6."""
@@ -135,7 +135,9 @@ def test_mmq_matches_gemv_columnwise_full_width(cuda, lib, T):
     Wfull = np.tile(W.reshape(256, -1), (N // 256, 1)).reshape(-1)
     X = torch.randn((T, K), generator=g, device="cuda", dtype=torch.float32).cpu().numpy()
     got = run_mmq(lib, t, Wfull, N, K, X)
-    assert np.array_equal(got[:, :256], got[:, 256:512])    # identical weight rows -> identical outputs
+    # identical weight rows -> identical outputs up to the order of fp32 adds: the stream-K decomposition cuts different output tiles at
+    # different K groups, and the two or three partial accumulators of a cut tile meet in dst by fp32 atomic adds
+    assert np.max(np.abs(got[:, :256] - got[:, 256:512])) <= 2e-5 * np.max(np.abs(got))
     Wd = dev_u8(Wfull)
     ws = torch.zeros(lib.c.pb200_act_workspace_bytes(K) + 64, dtype=torch.uint8, device="cuda")
     for col in (0, 1, 255, 256, 511, 512, 600, 699):

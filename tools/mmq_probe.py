@@ -44,4 +44,4 @@ for (t, N, K, T) in [(O.Q4_K, 8192, 8192, 512), (O.Q4_K, 28672, 8192, 512), (O.Q
         lib.c.pb200_mul_mat_q(t, ptr(Wd), N, K, ptr(xd), K, T, ptr(y), None, None, ptr(ws), None)
     e1.record(); sync()
     ms = e0.elapsed_time(e1) / reps
-    print(f"perf {O.TYPE_NAME[t]} N {N} K {K} T {T}: {ms:.3f} ms  {2.0 * N * K * T / ms / 1e9:.1f} TFLOP/s aborted {lib.c.pb200_mul_mat_q_aborted()}", flush=True)
+    print(f"perf {O.TYPE_NAME[t]} N {N} K {K} T {T}: {ms:.3f} ms  {2.0 * N * K * T / ms / 1e9:.1f} TFLOP/s aborted {lib.c.pb200_aborted()}", flush=True)
