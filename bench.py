@@ -400,12 +400,17 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-boundary", action="store_true", help="skip the e2e leg through the ggml-backend plugin (keeps pb200_decode as e2e)")
     ap.add_argument("--prompt", type=int, default=PROMPT, help="untimed prompt tokens decoded before the timed region")
-    ap.add_argument("--pp", type=int, default=512, help="prompt-processing batch measured after the decode run (0 = skip; single GPU only)")
+    ap.add_argument("--pp", type=int, default=None, help="prompt tokens of the prompt-processing measurement that follows the decode run (0 = skip).  "
+                    "N = 1: one pb200_prefill call, default 512 (llama-bench pp512).  N > 1: only when given — the prompt goes through the layer "
+                    "pipeline in 512-token micro-batches (pb200_prefill_stage, NCCL hand-off of the hidden states), e.g. config C5: "
+                    "--model qwen2.5-72b --gpus 8 --pp 2048 --n-ctx 4096")
     ap.add_argument("--ncu", action="store_true", help="bracket the timed region with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     args = ap.parse_args()
     PROMPT = args.prompt
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.pp is None:
+        args.pp = 512 if world == 1 else 0
     local = int(os.environ.get("LOCAL_RANK", "0"))
     cfg = MODELS[args.model]
     hp = dict(cfg["hp"], n_ctx=args.n_ctx)
@@ -669,6 +674,51 @@ def main():
         out["pipeline"] = {"stages": world, "hand_offs_per_token": world, "sum_of_stage_ms": stage_ms, "pipelined_ms_per_token": ms_step,
                            "exposed_handoff_ms": max(0.0, ms_step - stage_ms), "exposed_frac": max(0.0, ms_step - stage_ms) / ms_step,
                            "note": "b=1 decode is serial across stages (SURVEY H7): N GPUs hold N x the model, they do not cut the token latency"}
+    if world > 1 and args.pp > 0 and args.pp <= args.n_ctx:
+        # Prompt processing through the layer pipeline (prima's windows during prefill): 512-token micro-batches, every stage works on a
+        # different micro-batch once the pipeline is full; hidden states [512][n_embd] f32 travel stage to stage by NCCL send/recv on the
+        # engine stream.  Timed on the device (events on the engine stream), max over ranks, best of 3 after a warm-up pass.
+        UB = 512
+        nub = (args.pp + UB - 1) // UB
+        hbuf = torch.empty((UB, E), dtype=torch.float32, device=cuda_dev)
+        toks_all = np.array([token_at(i, nv) for i in range(args.pp)], dtype=np.int32)
+
+        def pp_pass():
+            with torch.cuda.stream(ext):
+                for j in range(nub):
+                    n = min(UB, args.pp - j * UB)
+                    if rank > 0:
+                        dist.recv(hbuf[:n], src=rank - 1)
+                    hp_out = eng.prefill_stage(toks_all[j * UB:j * UB + n] if rank == 0 else None, hbuf.data_ptr() if rank > 0 else None, n, j * UB)
+                    if rank < world - 1:
+                        dist.send(torch.as_tensor(DevBuf(hp_out, n * E), device=cuda_dev).view(n, E), dst=rank + 1)
+        try:
+            eng.kv_clear()
+            pp_pass()
+            barrier()
+            best = None
+            for _ in range(3):
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                with torch.cuda.stream(ext):
+                    e0.record()
+                pp_pass()
+                with torch.cuda.stream(ext):
+                    e1.record()
+                barrier()
+                t = torch.tensor([e0.elapsed_time(e1)], device=cuda_dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                best = float(t.item()) if best is None else min(best, float(t.item()))
+            mm, att, head = prefill_flops(hp, args.pp)
+            tpeak, tsrc = tensor_peak()
+            out["prefill"] = {"metric": f"prompt tokens/s, {cfg['name']}, {args.pp} tokens in {nub} micro-batches of {UB} through the {world}-stage layer pipeline",
+                              "tokens": args.pp, "ms": best, "value": args.pp / (best * 1e-3), "unit": "tokens/s",
+                              "timing": "CUDA events on the engine stream around the whole prompt, max over ranks, best of 3",
+                              "roofline": {"bound": "tensor", "achieved": (mm + att + head) / (best * 1e-3) / 1e12 / world, "peak": tpeak, "unit": "TFLOP/s per GPU",
+                                           "frac": (mm + att + head) / (best * 1e-3) / 1e12 / world / tpeak, "peak_source": tsrc,
+                                           "note": f"per GPU; the pipeline is full for {nub} of {nub + world - 1} micro-batch slots (bubble {(world - 1) / (nub + world - 1):.2f})"}}
+        except Exception as ex:
+            out["prefill"] = {"value": None, "unit": "tokens/s", "error": repr(ex)}
     if world == 1 and args.pp > 0 and args.pp <= args.n_ctx:
         try:
             # prompt processing (prefill) of one ubatch through pb200_prefill: tensor-core mat-muls, batched attention

@@ -181,6 +181,16 @@ PB200_API int64_t pb200_model_weight_bytes(const pb200_model * m);    /* algorit
  * cache is left exactly as n_tokens pb200_decode calls would leave it up to fp16-rounding differences in the mat-muls;
  * logits of the LAST token go to logits_host (may be NULL).  Models created with with_embd and first_layer == 0 only. */
 PB200_API int pb200_prefill(pb200_model * m, const int32_t * tokens_host, int32_t n_tokens, int32_t pos0, float * logits_host);
+/* Prompt processing on a pipeline shard (prima's layer windows, src/llama.cpp:3838-3883, 17825-18029): ONE ubatch of n_tokens <= 512 through
+ * the layers of this model object.  The stage that holds the embedding takes tokens_host (hidden_in_dev ignored); every other stage takes
+ * the previous stage's hidden states hidden_in_dev [n_tokens][n_embd] f32 in device memory (not modified).  The stage's output hidden
+ * states stay on the device at pb200_prefill_hidden_device(m) until the next prefill call (the caller ships them to the next stage, e.g.
+ * with ncclSend on the model stream); the stage with the head also computes the last token's logits.  synchronize = 0: everything is
+ * only enqueued on the model stream (micro-batched pipelines keep several ubatches in flight across the stages); logits_host requires
+ * synchronize != 0.  K/V rows pos0 .. pos0+n_tokens-1 of this shard's layers are written like pb200_prefill writes them. */
+PB200_API int pb200_prefill_stage(pb200_model * m, const int32_t * tokens_host, const float * hidden_in_dev, int32_t n_tokens, int32_t pos0,
+                                  float * logits_host, int32_t synchronize);
+PB200_API float * pb200_prefill_hidden_device(pb200_model * m);
 PB200_API int pb200_kv_clear(pb200_model * m);
 
 /* one decode step, HOST in/out (the llama_decode-equivalent call): token id + position in, n_vocab logits out.

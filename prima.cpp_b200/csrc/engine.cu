@@ -644,26 +644,41 @@ __global__ void k_iota_pos(int32_t * pos, int pos0, int T) {
     if (i < T) pos[i] = pos0 + i;
 }
 
-static int prefill_ubatch(pb200_model * m, const int32_t * tokens_host, int32_t T, int32_t pos0, float * logits_host);
+static int prefill_ubatch(pb200_model * m, const int32_t * tokens_host, const float * hidden_in_dev, int32_t T, int32_t pos0, float * logits_host, bool sync);
 static const int PB200_N_UBATCH = 512;   // the reference's default n_ubatch (common/common.h): longer prompts go through in slices
 
 extern "C" int pb200_prefill(pb200_model * m, const int32_t * tokens_host, int32_t T, int32_t pos0, float * logits_host) {
     if (!m || !m->finalized) return PB200_ESTATE;
     if (!tokens_host || T <= 0 || pos0 < 0 || pos0 + T > m->hp.n_ctx) return PB200_EINVAL;
+    if (!m->with_embd || m->l0 != 0) return PB200_ENOTSUP;   // whole prompts start at the embedding; pipeline shards: pb200_prefill_stage
     for (int32_t done = 0; done < T; done += PB200_N_UBATCH) {
         const int32_t n = std::min<int32_t>(PB200_N_UBATCH, T - done);
-        const int rc = prefill_ubatch(m, tokens_host + done, n, pos0 + done, done + n == T ? logits_host : nullptr);
+        const int rc = prefill_ubatch(m, tokens_host + done, nullptr, n, pos0 + done, done + n == T ? logits_host : nullptr, true);
         if (rc) return rc;
     }
     return 0;
 }
-
-static int prefill_ubatch(pb200_model * m, const int32_t * tokens_host, int32_t T, int32_t pos0, float * logits_host) {
+// One ubatch (<= 512 tokens) through THIS shard's layers: prima's layer windows during prompt processing (src/llama.cpp:17825-18029: every
+// rank runs its window of the sub-graph on the ubatch and ships the hidden states on).  The first stage takes token ids, the others the
+// previous stage's hidden states [n_tokens][n_embd] f32 in device memory (left untouched); the result stays in pb200_prefill_hidden_device.
+extern "C" int pb200_prefill_stage(pb200_model * m, const int32_t * tokens_host, const float * hidden_in_dev, int32_t T, int32_t pos0, float * logits_host,
+                                   int32_t synchronize) {
     if (!m || !m->finalized) return PB200_ESTATE;
-    if (!tokens_host || T <= 0 || pos0 < 0 || pos0 + T > m->hp.n_ctx) return PB200_EINVAL;
-    if (!m->with_embd || m->l0 != 0) return PB200_ENOTSUP;   // batched prompt processing starts at the embedding (single-process models)
-    for (int t = 0; t < T; t++)
-        if (tokens_host[t] < 0 || tokens_host[t] >= m->hp.n_vocab) return PB200_EINVAL;
+    if (T <= 0 || T > PB200_N_UBATCH || pos0 < 0 || pos0 + T > m->hp.n_ctx) return PB200_EINVAL;
+    if (m->with_embd ? !tokens_host : !hidden_in_dev) return PB200_EINVAL;
+    if (logits_host && !synchronize) return PB200_EINVAL;   // host logits are read back at the synchronisation point
+    return prefill_ubatch(m, tokens_host, hidden_in_dev, T, pos0, logits_host, synchronize != 0);
+}
+extern "C" float * pb200_prefill_hidden_device(pb200_model * m) { return (m && m->finalized) ? m->pf.x0 : nullptr; }
+
+static int prefill_ubatch(pb200_model * m, const int32_t * tokens_host, const float * hidden_in_dev, int32_t T, int32_t pos0, float * logits_host, bool sync) {
+    if (!m || !m->finalized) return PB200_ESTATE;
+    if (T <= 0 || pos0 < 0 || pos0 + T > m->hp.n_ctx) return PB200_EINVAL;
+    if (m->with_embd) {
+        if (!tokens_host) return PB200_EINVAL;
+        for (int t = 0; t < T; t++)
+            if (tokens_host[t] < 0 || tokens_host[t] >= m->hp.n_vocab) return PB200_EINVAL;
+    } else if (!hidden_in_dev) return PB200_EINVAL;
     cudaSetDevice(m->device);
     CK(pf_reserve(m, T));
     pb200_model::Prefill & P = m->pf;
@@ -672,10 +687,14 @@ static int prefill_ubatch(pb200_model * m, const int32_t * tokens_host, int32_t 
     const int QD = H * D, EK = HK * D;
     cudaStream_t st = m->stream;
     uint64_t n = 0;
-    CK(cudaMemcpyAsync(P.tok, tokens_host, (size_t) T * 4, cudaMemcpyHostToDevice, st));
     k_iota_pos<<<(T + 255) / 256, 256, 0, st>>>(P.pos, pos0, T); n++;
     CK(cudaGetLastError());
-    CK(launch_get_rows(m->tok_embd.data, m->tok_embd.type, E, P.tok, T, P.x0, st, false)); n++;
+    if (m->with_embd) {
+        CK(cudaMemcpyAsync(P.tok, tokens_host, (size_t) T * 4, cudaMemcpyHostToDevice, st));
+        CK(launch_get_rows(m->tok_embd.data, m->tok_embd.type, E, P.tok, T, P.x0, st, false)); n++;
+    } else {
+        CK(cudaMemcpyAsync(P.x0, hidden_in_dev, (size_t) T * E * 4, cudaMemcpyDeviceToDevice, st));   // the layers update the residual stream in place
+    }
     const float kq_scale = 1.0f / sqrtf((float) D);
     float * x = P.x0, * y = P.x1;
     for (int il = m->l0; il < m->l1; il++) {
@@ -728,6 +747,7 @@ static int prefill_ubatch(pb200_model * m, const int32_t * tokens_host, int32_t 
         CK(launch_gemv(&d1, 1, E, m->actE.q, st, false)); n++;
     }
     g_launches += n;
+    if (!sync) return 0;
     if (m->with_head && logits_host) CK(cudaMemcpyAsync(m->logits_host, m->logits, (size_t) hp.n_vocab * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (check_clear_abort()) return PB200_EABORTED;   // a kernel's wait watchdog gave up: this batch's results are invalid (flag re-armed)

@@ -39,13 +39,13 @@ namespace pb {
 
 constexpr int MMQ_BM = 128;
 constexpr int MMQ_BK = 64;
-constexpr int MMQ_A_NST = 2;      // expanded-weight stages (filled by compute, no latency to hide)
+constexpr int MMQ_A_MAX = 4;      // expanded-weight stages: P.a_nst = 2 or 4 (a power of two) of 16 KB, chosen at launch from the shared-memory budget
 constexpr int MMQ_B_NST = 4;      // activation stages (L2 loads: the deep ring)
-constexpr int MMQ_DQ_WARPS = 8;
+constexpr int MMQ_DQ_WARPS = 16;  // expansion warps: 4 threads per weight row, 16 weights per thread and step (8 warps were the latency-bound bottleneck: 45 % tensor pipe)
 constexpr int MMQ_DQ_WARP0 = 2;   // warps 0,1 = MMA issuer (owns TMEM), activation producer
 constexpr int MMQ_THREADS = (MMQ_DQ_WARP0 + MMQ_DQ_WARPS) * 32;
 constexpr int MMQ_A_BYTES = MMQ_BM * 128;   // one A stage: 128 rows x 64 fp16
-constexpr int MMQ_CTL_BYTES = 256;
+constexpr int MMQ_CTL_BYTES = 320;
 
 struct MmqParams {
     int * abort_flag;      // host-mapped, raised by the wait watchdog
@@ -55,7 +55,7 @@ struct MmqParams {
     const float * bias;    // [N] or null
     const float * resid;   // [T][N] or null: residual added in the epilogue
     int64_t row_bytes, total_bytes;
-    int nraw, b_nst;       // ring depths chosen at launch from the shared-memory budget
+    int nraw, b_nst, a_nst;   // ring depths chosen at launch from the shared-memory budget (a_nst: 2 or 4)
     int nacc, ttiles;      // accumulators (token tiles) per output tile, number of token tiles
     int ngrp, rtiles;      // 256-K groups per row (the last one may be short: 32-element block types), row tiles
     int upc, total_units;  // work units per CTA (CTA c owns units [c * upc, min((c + 1) * upc, total_units)) ), units of the launch
@@ -65,9 +65,10 @@ struct MmqParams {
 
 struct MmqCtl {
     uint64_t raw_full[3], raw_empty[3];
-    uint64_t a_ready[MMQ_A_NST], b_full[MMQ_B_NST];
+    uint64_t a_ready[MMQ_A_MAX], b_full[MMQ_B_NST];
     uint64_t step_done[MMQ_B_NST];   // one tcgen05.commit per step: step u arrives on step_done[u % 4]; frees A stage u % 2 and B stage u % b_nst
-    uint64_t acc_ready, acc_free;    // per segment: accumulators complete (tcgen05.commit) / read out by the 4 epilogue warps
+    uint64_t acc_ready, acc_free;    // per segment: accumulators complete (tcgen05.commit) / read out by the 4 epilogue warps (of both CTAs of a pair)
+    uint64_t peer_ready[MMQ_B_NST];  // CTA pairs: step g's A and B stages of the peer CTA are filled (forwarded by the peer's otherwise idle warp 0)
     uint32_t tmem_base;
     volatile int abort;
 };
@@ -132,6 +133,35 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t 
 __device__ __forceinline__ void umma_commit(uint64_t * bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// cta_group::2: the CTA pair of a cluster executes one M = 256 MMA; A rows 0-127 / 128-255 and the two halves of B's N rows come from the two
+// CTAs' shared memory at the same offsets, each CTA's TMEM receives its own 128 rows of D.  Issued by the leader CTA (rank 0) only.
+__device__ __forceinline__ void umma_f16_cg2(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// completion of all prior MMAs of the pair -> the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_cg2(uint64_t * bar) {
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t mmq_cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void mmq_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t * bar, uint32_t rank) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(bar)), "r"(rank));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -173,8 +203,9 @@ __device__ __forceinline__ void scale_min_k4(const uint8_t * sc, int j, int & s,
     s = j < 4 ? s0 : s1;
     m = j < 4 ? m0 : m1;
 }
+// thread (row, h, hh) produces K elements [64c + 32h + 16hh, 64c + 32h + 16hh + 16) of its row as 8 half2 (two 16-byte pieces of the A stage)
 template <int TYPE>
-__device__ __forceinline__ void expand(const uint8_t * blk, int c, int h, uint32_t (&out)[16]) {
+__device__ __forceinline__ void expand(const uint8_t * blk, int c, int h, int hh, uint32_t (&out)[8]) {
     if (TYPE == T_Q8_0) {
         // 32-element blocks, 34 B each ([d f16][32 x i8]); blk = the group of 8 blocks covering 256 K, this thread's block is 2c + h.
         // Blocks are 2-byte aligned: qs (offset 2) is either word-aligned or straddles words -> one PRMT per word.
@@ -182,30 +213,29 @@ __device__ __forceinline__ void expand(const uint8_t * blk, int c, int h, uint32
         const uint32_t * wp = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(bb) & ~(uintptr_t) 3);
         const bool odd = (reinterpret_cast<uintptr_t>(bb) & 2) != 0;
         const uint32_t sel = odd ? 0x7654u : 0x5432u;
-        uint32_t w[9];
+        const uint32_t w0 = wp[0];
+        uint32_t w[5];
 #pragma unroll
-        for (int i = 0; i < 9; i++) w[i] = wp[i];
-        const __half dh = __ushort_as_half((unsigned short) ((w[0] >> (odd ? 16 : 0)) & 0xffff));
+        for (int i = 0; i < 5; i++) w[i] = wp[4 * hh + i];
+        const __half dh = __ushort_as_half((unsigned short) ((w0 >> (odd ? 16 : 0)) & 0xffff));
         const __half2 scale = __half2half2(dh), bias = __float2half2_rn(-1152.f), zero = __float2half2_rn(0.f);
 #pragma unroll
-        for (int i = 0; i < 8; i++)   // q + 128 as an unsigned byte, 0x6400 | u = 1024 + u, minus 1152 = q exactly
+        for (int i = 0; i < 4; i++)   // q + 128 as an unsigned byte, 0x6400 | u = 1024 + u, minus 1152 = q exactly
             expand_word<0x00FF00FFu>(__byte_perm(w[i], w[i + 1], sel) ^ 0x80808080u, bias, scale, zero, out[2 * i], out[2 * i + 1]);
     } else if (TYPE == T_Q5_1) {
         // 24 B blocks ([d f16][m f16][qh u32][16 x 2 nibbles]), 8-byte aligned; element j < 16 = low nibble of qs[j] | bit j of qh << 4,
-        // element j + 16 = high nibble | bit j + 16
+        // element j + 16 = high nibble | bit j + 16: hh = 0 takes the low nibbles, hh = 1 the high ones
         const uint8_t * bb = blk + (2 * c + h) * BYTES_Q5_1;
         const uint2 hd = *reinterpret_cast<const uint2 *>(bb);
         const __half2 dm = bits_h2(hd.x);
         const __half2 scale = __half2half2(__low2half(dm)), off = __half2half2(__high2half(dm)), bias = __float2half2_rn(-1024.f);
-        const uint32_t qh = hd.y;
+        const uint32_t qh = hd.y >> (16 * hh);
         const uint2 qa = *reinterpret_cast<const uint2 *>(bb + 8), qb = *reinterpret_cast<const uint2 *>(bb + 16);
         const uint32_t w[4] = {qa.x, qa.y, qb.x, qb.y};
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-            const uint32_t hb_lo = ((((qh >> (4 * i)) & 0xFu) * 0x00204081u) & 0x01010101u) << 4;
-            const uint32_t hb_hi = ((((qh >> (4 * i + 16)) & 0xFu) * 0x00204081u) & 0x01010101u) << 4;
-            expand_word<0x001F001Fu>((w[i] & 0x0F0F0F0Fu) | hb_lo, bias, scale, off, out[2 * i], out[2 * i + 1]);
-            expand_word<0x001F001Fu>(((w[i] >> 4) & 0x0F0F0F0Fu) | hb_hi, bias, scale, off, out[8 + 2 * i], out[8 + 2 * i + 1]);
+            const uint32_t hb = ((((qh >> (4 * i)) & 0xFu) * 0x00204081u) & 0x01010101u) << 4;
+            expand_word<0x001F001Fu>(((w[i] >> (4 * hh)) & 0x0F0F0F0Fu) | hb, bias, scale, off, out[2 * i], out[2 * i + 1]);
         }
     } else if (TYPE == T_Q4_K || TYPE == T_Q5_K) {
         const float d = __half2float(*reinterpret_cast<const __half *>(blk));
@@ -215,41 +245,39 @@ __device__ __forceinline__ void expand(const uint8_t * blk, int c, int h, uint32
         scale_min_k4(blk + 4, j, s, m);
         const __half2 scale = __float2half2_rn(__fmul_rn(d, (float) s)), off = __float2half2_rn(-__fmul_rn(dmin, (float) m));
         const __half2 bias = __float2half2_rn(-1024.f);
-        const uint4 * q = reinterpret_cast<const uint4 *>(blk + (TYPE == T_Q4_K ? 16 : 48) + 32 * c);
-        const uint4 qa = q[0], qb = q[1];
-        const uint32_t w[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+        const uint4 qa = *reinterpret_cast<const uint4 *>(blk + (TYPE == T_Q4_K ? 16 : 48) + 32 * c + 16 * hh);
+        const uint32_t w[4] = {qa.x, qa.y, qa.z, qa.w};
         if (TYPE == T_Q4_K) {
 #pragma unroll
-            for (int i = 0; i < 8; i++) expand_word<0x000F000Fu>(w[i] >> (4 * h), bias, scale, off, out[2 * i], out[2 * i + 1]);
+            for (int i = 0; i < 4; i++) expand_word<0x000F000Fu>(w[i] >> (4 * h), bias, scale, off, out[2 * i], out[2 * i + 1]);
         } else {
-            const uint4 * qh4 = reinterpret_cast<const uint4 *>(blk + 16);
-            const uint4 ha = qh4[0], hb = qh4[1];
-            const uint32_t hh[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+            const uint4 ha = *reinterpret_cast<const uint4 *>(blk + 16 + 16 * hh);
+            const uint32_t hq[4] = {ha.x, ha.y, ha.z, ha.w};
 #pragma unroll
-            for (int i = 0; i < 8; i++)
-                expand_word<0x001F001Fu>(((w[i] >> (4 * h)) & 0x0F0F0F0Fu) | (((hh[i] >> j) << 4) & 0x10101010u), bias, scale, off, out[2 * i],
+            for (int i = 0; i < 4; i++)
+                expand_word<0x001F001Fu>(((w[i] >> (4 * h)) & 0x0F0F0F0Fu) | (((hq[i] >> j) << 4) & 0x10101010u), bias, scale, off, out[2 * i],
                                          out[2 * i + 1]);
         }
     } else {
         // Q6_K: blk is 2-byte aligned only (210-byte blocks): words are fetched as aligned pairs and funnel-shifted
         const float d = __half2float(*reinterpret_cast<const __half *>(blk + 208));
         const int n = c >> 1, p = c & 1;
-        const uint8_t * ql = blk + 64 * n + 32 * h;
-        const uint8_t * qh = blk + 128 + 32 * n;
+        const uint8_t * ql = blk + 64 * n + 32 * h + 16 * hh;
+        const uint8_t * qh = blk + 128 + 32 * n + 16 * hh;
         const int8_t * sc = reinterpret_cast<const int8_t *>(blk + 192 + 8 * n + 2 * h + 4 * p);
-        const __half2 s0 = __float2half2_rn(__fmul_rn(d, (float) sc[0])), s1 = __float2half2_rn(__fmul_rn(d, (float) sc[1]));
+        const __half2 sca = __float2half2_rn(__fmul_rn(d, (float) sc[hh]));
         const __half2 bias = __float2half2_rn(-1056.f), zero = __float2half2_rn(0.f);
         const uint32_t shl = (uint32_t) (reinterpret_cast<uintptr_t>(blk) & 2) * 8;     // 0 or 16 (ql and qh share blk's alignment)
         const uint32_t * lw = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(ql) & ~(uintptr_t) 3);
         const uint32_t * hw = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(qh) & ~(uintptr_t) 3);
         uint32_t lprev = lw[0], hprev = hw[0];
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
+        for (int i = 0; i < 4; i++) {
             const uint32_t lnext = lw[i + 1], hnext = hw[i + 1];
             const uint32_t l = __funnelshift_r(lprev, lnext, shl), hq = __funnelshift_r(hprev, hnext, shl);
             lprev = lnext; hprev = hnext;
             const uint32_t t = ((l >> (4 * p)) & 0x0F0F0F0Fu) | (((hq >> (4 * p + 2 * h)) << 4) & 0x30303030u);
-            expand_word<0x003F003Fu>(t, bias, i < 4 ? s0 : s1, zero, out[2 * i], out[2 * i + 1]);
+            expand_word<0x003F003Fu>(t, bias, sca, zero, out[2 * i], out[2 * i + 1]);
         }
     }
 }
@@ -258,43 +286,70 @@ __device__ __forceinline__ void cp_async16(void * smem_dst, const void * gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
 
-template <int TYPE>
+template <int TYPE, int CG>
 __global__ void __launch_bounds__(MMQ_THREADS, 1) k_mmq_tc(const __grid_constant__ MmqParams P) {
     extern __shared__ uint8_t smem_raw[];
     // the swizzle-128B atoms (A and B stages) need 1024-byte alignment in the shared window
     uint8_t * smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int BN = P.BN;
-    const int b1 = BN * 128;                                     // one token tile's chunk
-    const int b_bytes = P.nacc * b1;                             // one B stage
+    const int b1 = BN * 128;                                     // one token tile's chunk in the activation image
+    const int b1c = b1 / CG;                                     // this CTA's part of it: BN / CG token rows (a pair splits B's N rows)
+    const int b_bytes = P.nacc * b1c;                            // one B stage
+    const uint32_t rank = CG == 2 ? mmq_cluster_rank() : 0u;     // CTA pairs: rank 0 leads (issues the MMAs), rank 1 expands the tile's other 128 rows
     uint8_t * a_st = smem;                                       // [A_NST][16 KB]
-    uint8_t * b_st = a_st + MMQ_A_NST * MMQ_A_BYTES;             // [b_nst][nacc][BN*128]
+    uint8_t * b_st = a_st + P.a_nst * MMQ_A_BYTES;               // [b_nst][nacc][BN/CG*128]
+    const int amask = P.a_nst - 1, ashift = P.a_nst == 4 ? 2 : 1;
     uint8_t * raw = b_st + P.b_nst * b_bytes;                    // [nraw][128 * slot]
     MmqCtl * ctl = reinterpret_cast<MmqCtl *>(raw + P.nraw * MMQ_BM * P.slot);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nstep_all = P.K / MMQ_BK;                          // 64-element steps of a whole row; group sb holds steps [4 sb, min(4 sb + 4, nstep_all))
-    const int w0 = blockIdx.x * P.upc, w1 = min(w0 + P.upc, P.total_units);   // this CTA's units
+    const int w0 = (int) (blockIdx.x / CG) * P.upc, w1 = min(w0 + P.upc, P.total_units);   // this CTA's (pair's) units
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 3; i++) { mbar_init(&ctl->raw_full[i], MMQ_DQ_WARPS * 32); mbar_init(&ctl->raw_empty[i], MMQ_DQ_WARPS); }
-        for (int i = 0; i < MMQ_A_NST; i++) mbar_init(&ctl->a_ready[i], MMQ_DQ_WARPS);
+        for (int i = 0; i < MMQ_A_MAX; i++) mbar_init(&ctl->a_ready[i], MMQ_DQ_WARPS);
         for (int i = 0; i < MMQ_B_NST; i++) { mbar_init(&ctl->b_full[i], 1); mbar_init(&ctl->step_done[i], 1); }
         mbar_init(&ctl->acc_ready, 1);
-        mbar_init(&ctl->acc_free, 4);
+        mbar_init(&ctl->acc_free, 8 * CG);
+        for (int i = 0; i < MMQ_B_NST; i++) mbar_init(&ctl->peer_ready[i], 1);
         ctl->abort = 0;
         mbar_fence_init();
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl->tmem_base)), "r"(P.tmem_cols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (CG == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl->tmem_base)), "r"(P.tmem_cols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl->tmem_base)), "r"(P.tmem_cols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if (CG == 2) mmq_cluster_sync();   // both CTAs' barriers are initialised before anything arrives on them from the other CTA
     tc_fence_after();
     const uint32_t tmem = *(volatile uint32_t *) &ctl->tmem_base;
 
     // Every role walks the same segments: unit w -> tile w / ngrp (token-tile group tile / rtiles, row tile tile % rtiles), K group w % ngrp.
-    if (warp == 0) {
+    if (warp == 0 && rank != 0) {
+        // ================= peer CTA of a pair: tell the leader when this CTA's stages of step g are filled =================
+        if (lane == 0) {
+            int g = 0;
+            bool ok = true;
+            for (int w = w0; w < w1 && ok;) {
+                const int tile = w / P.ngrp, sbb = w - tile * P.ngrp, sbe = min(P.ngrp, sbb + (w1 - w));
+                const int nsteps = min(4 * sbe, nstep_all) - 4 * sbb;
+                for (int u = 0; u < nsteps; u++, g++) {
+                    if (!mmq_wait(ctl, &ctl->b_full[g % P.b_nst], (g / P.b_nst) & 1)) { ok = false; break; }
+                    if (!mmq_wait(ctl, &ctl->a_ready[g & amask], (g >> ashift) & 1)) { ok = false; break; }
+                    mbar_arrive_cluster(&ctl->peer_ready[g % MMQ_B_NST], 0);
+                }
+                w += sbe - sbb;
+            }
+        }
+        __syncwarp();
+    } else if (warp == 0) {
         // ================= MMA issuer =================
         if (lane == 0) {
             int g = 0, seg = 0;                                  // CTA-wide step and segment counters (barrier phases follow them)
@@ -306,21 +361,27 @@ __global__ void __launch_bounds__(MMQ_THREADS, 1) k_mmq_tc(const __grid_constant
                 if (seg > 0 && !mmq_wait(ctl, &ctl->acc_free, (seg - 1) & 1)) break;   // the previous segment's accumulators have been read out
                 tc_fence_after();
                 for (int u = 0; u < nsteps; u++, g++) {
-                    const int sa = g % MMQ_A_NST, sb = g % P.b_nst;
+                    const int sa = g & amask, sb = g % P.b_nst;
                     if (!mmq_wait(ctl, &ctl->b_full[sb], (g / P.b_nst) & 1)) { ok = false; break; }
-                    if (!mmq_wait(ctl, &ctl->a_ready[sa], (g / MMQ_A_NST) & 1)) { ok = false; break; }
+                    if (!mmq_wait(ctl, &ctl->a_ready[sa], (g >> ashift) & 1)) { ok = false; break; }
+                    if (CG == 2 && !mmq_wait(ctl, &ctl->peer_ready[g % MMQ_B_NST], (g / MMQ_B_NST) & 1)) { ok = false; break; }
                     tc_fence_after();
                     const uint64_t da = umma_desc_sw128(smem_u32(a_st + (size_t) sa * MMQ_A_BYTES));
                     const uint64_t db = umma_desc_sw128(smem_u32(b_st + (size_t) sb * b_bytes));
-                    const uint64_t db2 = umma_desc_sw128(smem_u32(b_st + (size_t) sb * b_bytes + b1));
+                    const uint64_t db2 = umma_desc_sw128(smem_u32(b_st + (size_t) sb * b_bytes + b1c));
 #pragma unroll
                     for (int k = 0; k < MMQ_BK / 16; k++) {
-                        umma_f16(tmem, da + 2 * k, db + 2 * k, P.idesc, (u | k) != 0);
-                        if (nacc == 2) umma_f16(tmem + 256, da + 2 * k, db2 + 2 * k, P.idesc, (u | k) != 0);
+                        if (CG == 2) {
+                            umma_f16_cg2(tmem, da + 2 * k, db + 2 * k, P.idesc, (u | k) != 0);
+                            if (nacc == 2) umma_f16_cg2(tmem + 256, da + 2 * k, db2 + 2 * k, P.idesc, (u | k) != 0);
+                        } else {
+                            umma_f16(tmem, da + 2 * k, db + 2 * k, P.idesc, (u | k) != 0);
+                            if (nacc == 2) umma_f16(tmem + 256, da + 2 * k, db2 + 2 * k, P.idesc, (u | k) != 0);
+                        }
                     }
-                    umma_commit(&ctl->step_done[g % MMQ_B_NST]);
+                    if (CG == 2) umma_commit_cg2(&ctl->step_done[g % MMQ_B_NST]); else umma_commit(&ctl->step_done[g % MMQ_B_NST]);
                 }
-                umma_commit(&ctl->acc_ready);
+                if (CG == 2) umma_commit_cg2(&ctl->acc_ready); else umma_commit(&ctl->acc_ready);
                 w += sbe - sbb;
             }
         }
@@ -336,16 +397,16 @@ __global__ void __launch_bounds__(MMQ_THREADS, 1) k_mmq_tc(const __grid_constant
                 const int tt0 = (tile / P.rtiles) * P.nacc;
                 const int nacc = min(P.nacc, P.ttiles - tt0);
                 const int nsteps = min(4 * sbe, nstep_all) - 4 * sbb;
-                const uint8_t * Bt = P.B + (size_t) tt0 * tile_stride + (size_t) sbb * 4 * b1;
+                const uint8_t * Bt = P.B + (size_t) tt0 * tile_stride + (size_t) sbb * 4 * b1 + (size_t) rank * b1c;
                 for (int u = 0; u < nsteps; u++, g++) {
                     const int sb = g % P.b_nst;
                     if (g >= P.b_nst) {   // step g - b_nst consumed this stage
                         const int f = g - P.b_nst;
                         if (!mmq_wait(ctl, &ctl->step_done[f % MMQ_B_NST], (f / MMQ_B_NST) & 1)) { ok = false; break; }
                     }
-                    mbar_arrive_expect_tx(&ctl->b_full[sb], (uint32_t) (nacc * b1));
+                    mbar_arrive_expect_tx(&ctl->b_full[sb], (uint32_t) (nacc * b1c));
                     for (int a = 0; a < nacc; a++)
-                        bulk_g2s_plain(b_st + (size_t) sb * b_bytes + (size_t) a * b1, Bt + (size_t) a * tile_stride + (size_t) u * b1, (uint32_t) b1,
+                        bulk_g2s_plain(b_st + (size_t) sb * b_bytes + (size_t) a * b1c, Bt + (size_t) a * tile_stride + (size_t) u * b1, (uint32_t) b1c,
                                        &ctl->b_full[sb]);
                 }
                 w += sbe - sbb;
@@ -354,69 +415,73 @@ __global__ void __launch_bounds__(MMQ_THREADS, 1) k_mmq_tc(const __grid_constant
         __syncwarp();
     } else {
         // ================= weight expansion =================
-        const int dt = threadIdx.x - MMQ_DQ_WARP0 * 32;        // 0..255
-        const int r = dt >> 1, h = dt & 1;
+        const int dt = threadIdx.x - MMQ_DQ_WARP0 * 32;        // 0..511
+        const int r = dt >> 2, h = (dt >> 1) & 1, hh = dt & 1;
         bool ok = true;
         // this thread fetches its own half of the row's block: 16-byte cp.async pieces of the 16-B aligned window around it
         const int64_t lim = (P.total_bytes + 15) & ~(int64_t) 15;
-        const int cpr = P.slot >> 4, p_lo = h ? (cpr + 1) / 2 : 0, p_hi = h ? cpr : (cpr + 1) / 2;
+        const int cpr = P.slot >> 4, p_lo = cpr * (dt & 3) / 4, p_hi = cpr * ((dt & 3) + 1) / 4;   // this thread's quarter of the row's window
         const int nx = w1 - w0;                                 // groups this CTA walks, x = 0 .. nx-1 across its segments
-        auto fetch = [&](int x) {
-            const int wq = w0 + x, tile = wq / P.ngrp, sb = wq - tile * P.ngrp;
-            const int gr = min((tile % P.rtiles) * MMQ_BM + r, P.N - 1);
-            const int64_t src0 = ((int64_t) gr * P.row_bytes + (int64_t) sb * P.bpb) & ~(int64_t) 15;
-            uint8_t * dst0 = raw + ((size_t) (x % P.nraw) * MMQ_BM + r) * P.slot;
+        // fetch cursor: the group nraw-1 ahead of the one being expanded (tile / K group tracked incrementally: no divisions in the loop)
+        int f_x = 0, f_sb, f_rt;
+        { const int tile = w0 / P.ngrp; f_sb = w0 - tile * P.ngrp; f_rt = tile % P.rtiles; }
+        auto fetch_next = [&](int slot) {                       // issues group f_x of this CTA into raw slot `slot`, advances the cursor
+            const int gr = min((f_rt * CG + (int) rank) * MMQ_BM + r, P.N - 1);
+            const int64_t src0 = ((int64_t) gr * P.row_bytes + (int64_t) f_sb * P.bpb) & ~(int64_t) 15;
+            uint8_t * dst0 = raw + ((size_t) slot * MMQ_BM + r) * P.slot;
             for (int pc = p_lo; pc < p_hi; pc++)
                 if (src0 + pc * 16 + 16 <= lim) cp_async16(dst0 + pc * 16, P.W + src0 + pc * 16);
-            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&ctl->raw_full[x % P.nraw])) : "memory");
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&ctl->raw_full[slot])) : "memory");
+            f_x++;
+            if (++f_sb == P.ngrp) { f_sb = 0; if (++f_rt == P.rtiles) f_rt = 0; }
         };
-        for (int x = 0; x < P.nraw - 1 && x < nx; x++) fetch(x);
+        for (int i = 0; i < P.nraw - 1 && i < nx; i++) fetch_next(i);
         // the four 16-byte pieces this thread writes per step, already swizzled
         const uint32_t arow = r * 128;
-        const uint32_t o0 = arow + (((4 * h + 0) ^ (r & 7)) << 4), o1 = arow + (((4 * h + 1) ^ (r & 7)) << 4);
-        const uint32_t o2 = arow + (((4 * h + 2) ^ (r & 7)) << 4), o3 = arow + (((4 * h + 3) ^ (r & 7)) << 4);
-        int g = 0, x = 0, seg = 0;
+        const uint32_t o0 = arow + (((4 * h + 2 * hh + 0) ^ (r & 7)) << 4), o1 = arow + (((4 * h + 2 * hh + 1) ^ (r & 7)) << 4);
+        int g = 0, seg = 0;
+        int rs = 0, rph = 0;                                    // raw slot / phase of the group being expanded
+        int prs = P.nraw - 1, pph = 1;                          // ... of the group before it (the slot the next fetch goes into)
         for (int w = w0; w < w1 && ok; seg++) {
             const int tile = w / P.ngrp, sbb = w - tile * P.ngrp, sbe = min(P.ngrp, sbb + (w1 - w));
-            const int row0 = (tile % P.rtiles) * MMQ_BM;
+            const int row0 = ((tile % P.rtiles) * CG + (int) rank) * MMQ_BM;
             const int gr = min(row0 + r, P.N - 1);
-            for (int sb = sbb; sb < sbe && ok; sb++, x++) {
-                const int rs = x % P.nraw, rr = x / P.nraw;
-                {   // refill the slot group x-1 used, once every expansion warp has left it
-                    const int xf = x + P.nraw - 1;
-                    if (xf < nx) {
-                        if (x > 0 && !mmq_wait(ctl, &ctl->raw_empty[(x - 1) % P.nraw], ((x - 1) / P.nraw) & 1)) { ok = false; break; }
-                        fetch(xf);
-                    }
+            for (int sb = sbb; sb < sbe && ok; sb++) {
+                // refill the slot the previous group used, once every expansion warp has left it
+                if (f_x < nx) {
+                    if (f_x >= P.nraw && !mmq_wait(ctl, &ctl->raw_empty[prs], pph)) { ok = false; break; }
+                    fetch_next(prs);
                 }
-                if (!mmq_wait(ctl, &ctl->raw_full[rs], rr & 1)) { ok = false; break; }
+                if (!mmq_wait(ctl, &ctl->raw_full[rs], rph)) { ok = false; break; }
                 const int64_t g0 = (int64_t) gr * P.row_bytes + (int64_t) sb * P.bpb;
                 const uint8_t * blk = raw + (size_t) (rs * MMQ_BM + r) * P.slot + (g0 & 15);
                 const int nst = min(4, nstep_all - 4 * sb);      // the last group of a K % 256 != 0 row (32-element block types) is short
 #pragma unroll
                 for (int c = 0; c < 4; c++) {
                     if (c >= nst) break;
-                    uint32_t v[16];
-                    expand<TYPE>(blk, c, h, v);
-                    if (g >= MMQ_A_NST) {   // step g - 2 has consumed this A stage
-                        const int f = g - MMQ_A_NST;
+                    uint32_t v[8];
+                    expand<TYPE>(blk, c, h, hh, v);
+                    if (g >= P.a_nst) {     // step g - a_nst has consumed this A stage
+                        const int f = g - P.a_nst;
                         if (!mmq_wait(ctl, &ctl->step_done[f % MMQ_B_NST], (f / MMQ_B_NST) & 1)) { ok = false; break; }
                     }
-                    uint8_t * as = a_st + (size_t) (g % MMQ_A_NST) * MMQ_A_BYTES;
+                    uint8_t * as = a_st + (size_t) (g & amask) * MMQ_A_BYTES;
                     *reinterpret_cast<uint4 *>(as + o0) = make_uint4(v[0], v[1], v[2], v[3]);
                     *reinterpret_cast<uint4 *>(as + o1) = make_uint4(v[4], v[5], v[6], v[7]);
-                    *reinterpret_cast<uint4 *>(as + o2) = make_uint4(v[8], v[9], v[10], v[11]);
-                    *reinterpret_cast<uint4 *>(as + o3) = make_uint4(v[12], v[13], v[14], v[15]);
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core's async proxy
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&ctl->a_ready[g % MMQ_A_NST]);
+                    if (lane == 0) mbar_arrive(&ctl->a_ready[g & amask]);
                     g++;
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&ctl->raw_empty[rs]);
+                prs = rs; pph = rph;
+                if (++rs == P.nraw) { rs = 0; rph ^= 1; }
             }
             // ================= epilogue of the segment: four consecutive warps cover the four 32-lane quadrants of TMEM =================
-            if (warp < MMQ_DQ_WARP0 + 4) {
+            if (warp < MMQ_DQ_WARP0 + 8) {
+                // 8 epilogue warps: quadrant warp % 4 of the TMEM lanes (a warp may only read its own quadrant), accumulator (warp - 2) / 4
+                const int ehalf = (warp - MMQ_DQ_WARP0) >> 2;
                 const bool acc_ok = ok && mmq_wait(ctl, &ctl->acc_ready, seg & 1);
                 tc_fence_after();
                 const int tt0 = (tile / P.rtiles) * P.nacc;
@@ -437,13 +502,17 @@ __global__ void __launch_bounds__(MMQ_THREADS, 1) k_mmq_tc(const __grid_constant
                         rv[i] = (rp && t < P.T) ? __ldg(rp + (size_t) t * P.N) : 0.f;
                     }
                 };
-                load_resid(rcur, 0, 0);
-                for (int a = 0; a < nacc; a++) {
-                    for (int c0 = 0; c0 < BN; c0 += 16) {
+                // two accumulators: one per warp group; one accumulator: its column halves (when they split into whole 16-column chunks)
+                const bool csplit = nacc == 1 && BN % 32 == 0;
+                const int a_lo = nacc == 2 ? ehalf : 0, a_hi = nacc == 2 ? ehalf + 1 : ((csplit || ehalf == 0) ? 1 : 0);
+                const int c_lo = csplit ? ehalf * (BN / 2) : 0, c_hi = csplit ? c_lo + BN / 2 : BN;
+                if (a_lo < a_hi) load_resid(rcur, a_lo, c_lo);
+                for (int a = a_lo; a < a_hi; a++) {
+                    for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
                         {   // next chunk's residual
                             int a2 = a, c2 = c0 + 16;
-                            if (c2 >= BN) { a2++; c2 = 0; }
-                            if (a2 < nacc) load_resid(rnext, a2, c2);
+                            if (c2 >= c_hi) { a2++; c2 = c_lo; }
+                            if (a2 < a_hi) load_resid(rnext, a2, c2);
                         }
                         uint32_t v[16];
                         const uint32_t taddr = tmem + ((uint32_t) (quad * 32) << 16) + (uint32_t) (a * 256 + c0);
@@ -471,16 +540,20 @@ __global__ void __launch_bounds__(MMQ_THREADS, 1) k_mmq_tc(const __grid_constant
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&ctl->acc_free);      // the issuer may overwrite the accumulators
+                if (lane == 0) {                                 // the issuer (of the leader CTA) may overwrite the accumulators
+                    if (CG == 2) mbar_arrive_cluster(&ctl->acc_free, 0); else mbar_arrive(&ctl->acc_free);
+                }
             }
             w += sbe - sbb;
         }
     }
     tc_fence_before();
     __syncthreads();
+    if (CG == 2) mmq_cluster_sync();   // the pair leaves together: the leader's MMAs and commits reach into the peer's shared memory
     if (warp == 0) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(P.tmem_cols) : "memory");
+        if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(P.tmem_cols) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(P.tmem_cols) : "memory");
     }
 }
 
@@ -598,13 +671,26 @@ bool mmq_supported(int type, int64_t K) {
     return (type == T_Q8_0 || type == T_Q5_1) && K % 64 == 0 && K >= 256;   // 32-element blocks: two per 64-element step
 }
 
-template <int TYPE>
-static cudaError_t mmq_launch_typed(const MmqParams & P, dim3 grid, size_t smem, cudaStream_t st) {
+template <int TYPE, int CG>
+static cudaError_t mmq_launch_typed2(const MmqParams & P, dim3 grid, size_t smem, cudaStream_t st) {
     static FuncAttrCache attr_cache;
-    cudaError_t e = ensure_dyn_smem(attr_cache, (const void *) k_mmq_tc<TYPE>, smem, false);
+    cudaError_t e = ensure_dyn_smem(attr_cache, (const void *) k_mmq_tc<TYPE, CG>, smem, false);
     if (e != cudaSuccess) return e;
-    k_mmq_tc<TYPE><<<grid, MMQ_THREADS, smem, st>>>(P);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(MMQ_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = CG > 1 ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, k_mmq_tc<TYPE, CG>, P);
+}
+template <int TYPE>
+static cudaError_t mmq_launch_typed(const MmqParams & P, int cg, dim3 grid, size_t smem, cudaStream_t st) {
+    return cg == 2 ? mmq_launch_typed2<TYPE, 2>(P, grid, smem, st) : mmq_launch_typed2<TYPE, 1>(P, grid, smem, st);
 }
 
 cudaError_t launch_mmq(int type, const void * W, int64_t N, int64_t K, const float * x, int64_t ldx, int64_t T, float * dst, const float * bias,
@@ -631,7 +717,14 @@ cudaError_t launch_mmq(int type, const void * W, int64_t N, int64_t K, const flo
     P.bpb = type == T_Q4_K ? BYTES_Q4_K : type == T_Q5_K ? BYTES_Q5_K : type == T_Q6_K ? BYTES_Q6_K : type == T_Q8_0 ? 8 * BYTES_Q8_0 : 8 * BYTES_Q5_1;
     P.slot = type == T_Q6_K ? 240 : (type == T_Q8_0 ? 288 : P.bpb);
     P.ttiles = tpad / BN;
-    P.rtiles = (int) ((N + MMQ_BM - 1) / MMQ_BM);
+    // CTA pairs (tcgen05 cta_group::2, PB200_MMQ_CG=2): two row tiles form one M = 256 MMA, each CTA stages only half of the activation tile
+    // (L2 -> SM traffic halves, room for 4 expanded-weight stages).  Built and measured: parity green, but 5-7 % SLOWER than one CTA per
+    // MMA at every shape (profiles/r2_mmq_probe.txt) — neither the activation ring nor the weight-stage depth was the limiter, the
+    // weight-expansion warps were (8 -> 16 warps: +19 %).  The single-CTA form is the default.
+    static const int force_cg = getenv("PB200_MMQ_CG") ? atoi(getenv("PB200_MMQ_CG")) : 0;
+    const int rt1 = (int) ((N + MMQ_BM - 1) / MMQ_BM);
+    const int cg = (force_cg == 2 && rt1 >= 2 && BN % 32 == 0) ? 2 : 1;
+    P.rtiles = (rt1 + cg - 1) / cg;            // row-tile groups (pairs)
     // two accumulators per output tile halve the weight-expansion work per FLOP (measured 1040 vs 590 TFLOP/s at full occupancy)
     static const int force_nacc = getenv("PB200_MMQ_NACC") ? atoi(getenv("PB200_MMQ_NACC")) : 0;
     P.nacc = (P.ttiles >= 2 && force_nacc != 1) ? 2 : 1;
@@ -644,7 +737,7 @@ cudaError_t launch_mmq(int type, const void * W, int64_t N, int64_t K, const flo
     const int64_t total = (int64_t) P.rtiles * tgroups * P.ngrp;
     if (total > 0x7fffffff) return cudaErrorInvalidValue;
     P.total_units = (int) total;
-    const int nsm = sm_count();
+    const int nsm = sm_count() / cg;           // CTAs (pairs) that can be resident: one CTA per SM
     int upc = (int) ((total + nsm - 1) / nsm);
     upc = std::max(upc, std::min(min_units, P.ngrp));
     if (whole_tiles) upc = P.ngrp;
@@ -665,23 +758,28 @@ cudaError_t launch_mmq(int type, const void * W, int64_t N, int64_t K, const flo
     while ((int) cols < BN) cols <<= 1;
     P.tmem_cols = P.nacc == 2 ? 512 : cols;
     // kind::f16 instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): D=f32, A=B=f16, both K-major, N>>3, M>>4
-    P.idesc = (1u << 4) | ((uint32_t) (BN >> 3) << 17) | ((uint32_t) (MMQ_BM >> 4) << 24);
+    P.idesc = (1u << 4) | ((uint32_t) (BN >> 3) << 17) | ((uint32_t) ((MMQ_BM * cg) >> 4) << 24);
     // ring depths: 3 raw super-block slots (HBM latency) if they fit, and as many activation stages (2..4) as the 227 KB budget leaves
     auto smem_for = [&](int nraw, int b_nst) {
-        return 1024 + (size_t) MMQ_A_NST * MMQ_A_BYTES + (size_t) b_nst * P.nacc * BN * 128 + (size_t) nraw * MMQ_BM * P.slot + MMQ_CTL_BYTES;
+        return 1024 + (size_t) P.a_nst * MMQ_A_BYTES + (size_t) b_nst * P.nacc * (BN / cg) * 128 + (size_t) nraw * MMQ_BM * P.slot + MMQ_CTL_BYTES;
     };
+    // 4 expanded-weight stages when a CTA pair halves the activation stages (the handshake "MMA done -> store the next tile -> MMA" then
+    // has three MMA steps of slack instead of one), else 2; 3 raw slots if they fit; then as many activation stages (2..4) as are left
+    static const int force_a = getenv("PB200_MMQ_A_NST") ? atoi(getenv("PB200_MMQ_A_NST")) : 0;
+    P.a_nst = force_a == 2 || force_a == 4 ? force_a : (cg == 2 ? 4 : 2);
     P.nraw = 3;
     if (smem_for(3, 2) > 232448) P.nraw = 2;
+    if (smem_for(P.nraw, 2) > 232448) P.a_nst = 2;
     P.b_nst = MMQ_B_NST;
     while (P.b_nst > 2 && smem_for(P.nraw, P.b_nst) > 232448) P.b_nst--;
     const size_t smem = smem_for(P.nraw, P.b_nst);
     if (smem > 232448) return cudaErrorInvalidConfiguration;
-    dim3 grid((unsigned) grid_x, 1, 1);
-    if (type == T_Q4_K) return mmq_launch_typed<T_Q4_K>(P, grid, smem, st);
-    if (type == T_Q5_K) return mmq_launch_typed<T_Q5_K>(P, grid, smem, st);
-    if (type == T_Q6_K) return mmq_launch_typed<T_Q6_K>(P, grid, smem, st);
-    if (type == T_Q8_0) return mmq_launch_typed<T_Q8_0>(P, grid, smem, st);
-    return mmq_launch_typed<T_Q5_1>(P, grid, smem, st);
+    dim3 grid((unsigned) (grid_x * cg), 1, 1);
+    if (type == T_Q4_K) return mmq_launch_typed<T_Q4_K>(P, cg, grid, smem, st);
+    if (type == T_Q5_K) return mmq_launch_typed<T_Q5_K>(P, cg, grid, smem, st);
+    if (type == T_Q6_K) return mmq_launch_typed<T_Q6_K>(P, cg, grid, smem, st);
+    if (type == T_Q8_0) return mmq_launch_typed<T_Q8_0>(P, cg, grid, smem, st);
+    return mmq_launch_typed<T_Q5_1>(P, cg, grid, smem, st);
 }
 
 }  // namespace pb

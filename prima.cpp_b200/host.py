@@ -81,6 +81,9 @@ class Lib:
         c.pb200_kv_clear.argtypes = [vp]
         c.pb200_decode.argtypes = [vp, i32, i32, vp]
         c.pb200_prefill.argtypes = [vp, vp, i32, i32, vp]
+        c.pb200_prefill_stage.argtypes = [vp, vp, vp, i32, i32, vp, i32]
+        c.pb200_prefill_hidden_device.restype = vp
+        c.pb200_prefill_hidden_device.argtypes = [vp]
         c.pb200_decode_async.argtypes = [vp, i32, i32]
         c.pb200_synchronize.argtypes = [vp]
         for n in ("pb200_logits_device", "pb200_hidden_in_device", "pb200_hidden_out_device", "pb200_stream"):
@@ -155,6 +158,18 @@ class Model:
         self.lib.check(self.lib.c.pb200_prefill(self.h, toks.ctypes.data_as(C.c_void_p), int(toks.size), int(pos0), out.ctypes.data_as(C.c_void_p)),
                        "prefill")
         return out
+
+    def prefill_stage(self, tokens, hidden_in_ptr: int | None, n_tokens: int, pos0: int, logits_out=None, synchronize: bool = False) -> int:
+        """One ubatch through this shard (pb200_prefill_stage); returns the device pointer of the stage's output hidden states."""
+        import numpy as np
+        tp = None
+        if tokens is not None:
+            self._pf_toks = np.ascontiguousarray(tokens, dtype=np.int32)   # kept alive until the (possibly asynchronous) copy has run
+            tp = self._pf_toks.ctypes.data_as(C.c_void_p)
+        lp = None if logits_out is None else logits_out.ctypes.data_as(C.c_void_p)
+        self.lib.check(self.lib.c.pb200_prefill_stage(self.h, tp, C.c_void_p(hidden_in_ptr) if hidden_in_ptr else None, int(n_tokens), int(pos0), lp,
+                                                      1 if synchronize else 0), "prefill_stage")
+        return self.lib.c.pb200_prefill_hidden_device(self.h)
 
     def decode_async(self, token: int, pos: int) -> None:
         self.lib.check(self.lib.c.pb200_decode_async(self.h, token, pos), "decode_async")

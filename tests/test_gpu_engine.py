@@ -207,6 +207,39 @@ def test_prefill_longer_than_one_ubatch(cuda, pkg):
     assert b[a.argmax()] >= b.max() - 0.1
 
 
+def test_prefill_stage_pipeline_matches_single_model(cuda, pkg):
+    """pb200_prefill_stage: the prompt through two pipeline shards (layers [0,2) with the embedding, [2,4) with the head), two micro-batches
+    in flight order, hidden states handed over in device memory — against pb200_prefill on the unsplit model, and a decode step afterwards
+    on both (the shards' K/V rows must be the rows the single model wrote)."""
+    tm = TinyModel(n_layer=4, n_embd=512, n_head=4, n_head_kv=2, n_ff=1024, n_vocab=256, n_ctx=96, arch="llama", ftype="q4_K_M",
+                   freq_factors=False, seed=8, branch_scale=0.1)
+    toks = [(i * 31 + 7) % 256 for i in range(72)]
+    one = tm.load_engine(pkg)
+    want = one.prefill(toks, 0).copy()
+    want_next = np.zeros(256, np.float32)
+    one.decode(5, len(toks), want_next)
+    one.close()
+    a = tm.load_engine(pkg, layers=(0, 2), with_embd=True, with_head=False)
+    b = tm.load_engine(pkg, layers=(2, 4), with_embd=False, with_head=True)
+    got = np.zeros(256, np.float32)
+    import torch
+    for (p0, n) in ((0, 40), (40, 32)):                      # two micro-batches
+        h = a.prefill_stage(toks[p0:p0 + n], None, n, p0, synchronize=True)
+        b.prefill_stage(None, h, n, p0, got if p0 + n == len(toks) else None, synchronize=True)
+    assert float(np.sum((got - want) ** 2) / np.sum(want ** 2)) < 1e-6
+    # decode continues on the shards' caches
+    a.decode(5, len(toks))
+    b.set_hidden(a.hidden())
+    got_next = np.zeros(256, np.float32)
+    b.decode(0, len(toks), got_next)
+    assert float(np.sum((got_next - want_next) ** 2) / np.sum(want_next ** 2)) < 1e-6
+    # argument errors: a shard without the embedding needs hidden states, logits need a synchronising call
+    c = b.lib.c
+    assert c.pb200_prefill_stage(b.h, None, None, 8, 0, None, 1) != 0
+    assert c.pb200_prefill_stage(b.h, None, None, 600, 0, None, 1) != 0
+    a.close(); b.close()
+
+
 def test_prefill_argument_errors(cuda, pkg):
     tm = TinyModel(n_layer=1, n_embd=256, n_head=2, n_head_kv=1, n_ff=512, n_vocab=64, n_ctx=16, arch="llama", ftype="q4_K_M",
                    freq_factors=False, seed=1)
