@@ -167,6 +167,18 @@ PB200_API void          pb200_model_free(pb200_model * m);
  * "blk.%d.{attn_norm,attn_q,attn_k,attn_v,attn_output,ffn_norm,ffn_gate,ffn_up,ffn_down}.weight", "blk.%d.attn_{q,k,v}.bias".
  * data: HOST pointer to raw GGUF bytes (exactly ggml_nbytes) — the same bytes llm_load_tensors hands to set_tensor. */
 PB200_API int pb200_model_set_tensor(pb200_model * m, const char * name, int type, const void * host_data, size_t nbytes);
+/* The same without the copy: reserves the tensor's device memory and returns its address in *dev_ptr (NULL with return 0: the tensor
+ * belongs to another stage) for hosts that stream the bytes themselves (pb200_model_load_gguf does). */
+PB200_API int pb200_model_tensor_alloc(pb200_model * m, const char * name, int type, size_t nbytes, void ** dev_ptr);
+/* GGUF file -> finalized model shard (replaces gguf_init_from_file + llm_load_hparams + llm_load_tensors' per-tensor
+ * synchronous set_tensor, ggml-cuda.cu:464-487, for this path): v2 / v3 containers, architectures "llama" and "qwen2", tensors kept in
+ * their raw block layout; the file is streamed through two pinned 64-MiB buffers with cudaMemcpyAsync so reading chunk i+1 overlaps the
+ * PCIe copy of chunk i.  layer_end < 0: to the last layer; with_embd / with_head < 0: derived from the window; n_ctx <= 0:
+ * min(trained context, 4096).  seconds / bytes_loaded (optional) report the load.  pb200_gguf_probe only parses (no CUDA): hyper-parameters,
+ * tensor count, bytes of the data section, architecture string (16 bytes). */
+PB200_API int pb200_model_load_gguf(const char * path, int device, int layer_begin, int layer_end, int n_ctx, int with_embd, int with_head,
+                                    pb200_model ** out, double * seconds, int64_t * bytes_loaded);
+PB200_API int pb200_gguf_probe(const char * path, pb200_hparams * hp, int32_t * n_tensors, int64_t * data_bytes, char * arch_out16);
 /* random-init weights generated on the device with the Q4_K_M (ftype 0) or Q5_K_M (ftype 1) type mixture of
  * llama_tensor_get_type (src/llama.cpp:19271-19556); for benchmarking without a checkpoint */
 PB200_API int pb200_model_synth(pb200_model * m, int ftype, uint64_t seed);

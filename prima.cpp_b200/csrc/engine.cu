@@ -251,8 +251,11 @@ void pb200_model_free(pb200_model * m) {
     delete m;
 }
 
-int pb200_model_set_tensor(pb200_model * m, const char * name, int type, const void * host_data, size_t nbytes) {
-    if (!m || !name || !host_data) return PB200_EINVAL;
+// Reserves the device memory of one tensor of this shard and returns its address (NULL with rc 0: the tensor lives on another stage).
+// The caller fills it (pb200_model_set_tensor: one synchronous copy; gguf.cu: pinned double-buffered stream from the file).
+int pb200_model_tensor_alloc(pb200_model * m, const char * name, int type, size_t nbytes, void ** dev_ptr) {
+    if (!m || !name || !dev_ptr) return PB200_EINVAL;
+    *dev_ptr = nullptr;
     if (m->finalized) return PB200_ESTATE;
     cudaSetDevice(m->device);
     bool is_f32 = false;
@@ -263,7 +266,8 @@ int pb200_model_set_tensor(pb200_model * m, const char * name, int type, const v
         if (!slot) return 0;   // tensor belongs to another pipeline stage: ignore
         if (type != T_F32 || nbytes != (size_t) n_f32 * 4) return PB200_EINVAL;
         CK(m->alloc((void **) slot, nbytes));
-        return (int) cudaMemcpy(*slot, host_data, nbytes, cudaMemcpyHostToDevice);
+        *dev_ptr = *slot;
+        return 0;
     }
     if (!t) {
         const std::string s(name);
@@ -277,7 +281,16 @@ int pb200_model_set_tensor(pb200_model * m, const char * name, int type, const v
     t->type = type;
     t->bytes = need;
     CK(m->alloc(&t->data, need + 16));
-    return (int) cudaMemcpy(t->data, host_data, need, cudaMemcpyHostToDevice);
+    *dev_ptr = t->data;
+    return 0;
+}
+
+int pb200_model_set_tensor(pb200_model * m, const char * name, int type, const void * host_data, size_t nbytes) {
+    if (!host_data) return PB200_EINVAL;
+    void * dev = nullptr;
+    const int rc = pb200_model_tensor_alloc(m, name, type, nbytes, &dev);
+    if (rc || !dev) return rc;
+    return (int) cudaMemcpy(dev, host_data, nbytes, cudaMemcpyHostToDevice);
 }
 
 int pb200_model_synth(pb200_model * m, int ftype, uint64_t seed) {

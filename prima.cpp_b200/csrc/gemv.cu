@@ -239,6 +239,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_CTAS_PER_SM) k_gemv_kquant(
     const int group = warp / wpr, wsub = warp % wpr;
     // short rows (nblk <= 16, e.g. K = 4096 of Llama-3-8B): a warp holds 32 / nblk_p2 rows side by side, lane = (row in the slot, super-block)
     const int nbp = SPLIT ? 32 : P.nblk_p2, rpw = 32 / nbp;
+    const int rsh = SPLIT ? 0 : 31 - __clz(rpw);   // rpw is a power of two: the per-stage row-slot arithmetic below uses shifts (two integer divisions per stage visit before)
     const int sub = SPLIT ? 0 : lane / nbp;
     const int blk = SPLIT ? wsub * 32 + lane : (lane & (nbp - 1));
     const bool valid = blk < P.nblk;
@@ -308,13 +309,13 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_CTAS_PER_SM) k_gemv_kquant(
         const int bpb = type == T_Q4_K ? BYTES_Q4_K : (type == T_Q5_K ? BYTES_Q5_K : BYTES_Q6_K);
         const uint32_t mis = (uint32_t) (((int64_t) r0 * M.row_bytes) & 15);
         const uint8_t * tile = stages + (size_t) s * P.stage_bytes + mis;
-        const int spt = M.rows_per_tile / rpw;                                                // row slots per tile (a slot = rpw rows, one per sub-warp)
+        const int spt = M.rows_per_tile >> rsh;                                                // row slots per tile (a slot = rpw rows, one per sub-warp)
         const int first = (group - it * spt) & (ngroups - 1);                                 // this group's first slot in the stage
         if (P.owner_only && first >= spt) continue;   // not an owner of this stage (stable per stage: see gemv_plan)
         mbar_wait(&ctl->full[s], ph, &ctl->aborted, P.abort_flag);
         if (TRACE && it == 0) stamp<TRACE>(P, 4);
         if (!SPLIT) {
-            const int nslots = (nrows + rpw - 1) / rpw;
+            const int nslots = (nrows + rpw - 1) >> rsh;
             for (int slot = first; slot < nslots; slot += ngroups) {
                 const int rit = slot * rpw + sub;                 // row inside the tile
                 const int row = r0 + rit;

@@ -68,6 +68,10 @@ struct GemvMat {
 //     queue behind the prefetches: 107 -> 98-105 tok/s in every setting tried (cp.async.bulk.prefetch.L2 and per-line prefetch.global.L2);
 //   * a cluster variant of the distributed prologue (4 CTAs exchange their quarter of the activation through distributed shared memory
 //     instead of the grid barrier + L2 round trip): same tokens/s, and its code cost the hot loop 4 % (109.9 -> 105.4).
+//   * a "tail task": the last CTA of wo / ffn_down to finish (atomic arrival counter) produces q8_K(rms_norm(y) * w) of the vector the
+//     launch has just written, so that the next GEMV starts with PRO_NONE instead of the distributed prologue.  Bit-identical, but the
+//     single CTA needs ~9 us for it (its loads of y and of the norm weights queue behind the next launch's ring fill, which has the HBM
+//     queues full at that moment): 110.1 -> 101.8-103.3 tok/s (profiles/r2_ab_sweeps.txt ab24 / ab25, r2_token_trace_v7).
 enum : int { PRO_NONE = 0, PRO_RMSNORM_DIST = 4, PRO_SILU_DIST = 5 };
 
 struct GemvParams {

@@ -728,6 +728,8 @@ cudaError_t launch_mmq(int type, const void * W, int64_t N, int64_t K, const flo
     // two accumulators per output tile halve the weight-expansion work per FLOP (measured 1040 vs 590 TFLOP/s at full occupancy)
     static const int force_nacc = getenv("PB200_MMQ_NACC") ? atoi(getenv("PB200_MMQ_NACC")) : 0;
     P.nacc = (P.ttiles >= 2 && force_nacc != 1) ? 2 : 1;
+    // ... if the shared-memory budget allows it: Q8_0's 288-byte raw slots leave no room for two 64-KB activation stages
+    if (P.nacc == 2 && 1024 + (size_t) 2 * MMQ_A_BYTES + (size_t) 2 * 2 * (BN / cg) * 128 + (size_t) 2 * MMQ_BM * P.slot + MMQ_CTL_BYTES > 232448) P.nacc = 1;
     const int tgroups = (P.ttiles + P.nacc - 1) / P.nacc;
     P.ngrp = (int) ((K / MMQ_BK + 3) / 4);
     // stream-K: the tiles' K groups, tile after tile, in equal contiguous shares; a share is at least MMQ_MIN_UNITS groups (a segment's

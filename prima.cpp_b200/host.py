@@ -82,6 +82,9 @@ class Lib:
         c.pb200_decode.argtypes = [vp, i32, i32, vp]
         c.pb200_prefill.argtypes = [vp, vp, i32, i32, vp]
         c.pb200_prefill_stage.argtypes = [vp, vp, vp, i32, i32, vp, i32]
+        c.pb200_gguf_probe.argtypes = [C.c_char_p, C.POINTER(HParams), C.POINTER(i32), C.POINTER(i64), C.c_char_p]
+        c.pb200_model_load_gguf.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(C.c_double), C.POINTER(i64)]
+        c.pb200_model_tensor_alloc.argtypes = [vp, C.c_char_p, C.c_int, C.c_size_t, C.POINTER(vp)]
         c.pb200_prefill_hidden_device.restype = vp
         c.pb200_prefill_hidden_device.argtypes = [vp]
         c.pb200_decode_async.argtypes = [vp, i32, i32]
@@ -126,6 +129,26 @@ class Model:
         self.h = self.lib.c.pb200_model_create(C.byref(hp), device, l0, l1, int(with_embd), int(with_head))
         if not self.h:
             raise Pb200Error("pb200_model_create failed (bad hparams or no CUDA device)")
+
+    @classmethod
+    def from_gguf(cls, path, device: int = 0, layers: tuple[int, int] | None = None, n_ctx: int = 0, with_embd: int = -1, with_head: int = -1) -> "Model":
+        """pb200_model_load_gguf: a finalized shard straight from a GGUF file (pinned double-buffered stream to the device)."""
+        lib = Lib.get()
+        h = C.c_void_p()
+        secs, nbytes = C.c_double(), C.c_int64()
+        hp = HParams()
+        lib.check(lib.c.pb200_gguf_probe(str(path).encode(), C.byref(hp), None, None, None), "gguf_probe")
+        l0, l1 = layers if layers is not None else (0, -1)
+        lib.check(lib.c.pb200_model_load_gguf(str(path).encode(), device, l0, l1, n_ctx, with_embd, with_head, C.byref(h), C.byref(secs), C.byref(nbytes)),
+                  "model_load_gguf")
+        m = cls.__new__(cls)
+        m.lib = lib
+        if n_ctx > 0:
+            hp.n_ctx = n_ctx
+        m.hp = hp
+        m.h = h.value
+        m.load_seconds, m.load_bytes = secs.value, nbytes.value
+        return m
 
     def set_tensor(self, name: str, ttype: int, data) -> None:
         import numpy as np

@@ -153,6 +153,36 @@ class TinyModel:
         return eng
 
 
+    def write_gguf(self, path, with_tokenizer_array=True):
+        """The model as a GGUF v3 file written by the upstream gguf-py writer (raw quantized blocks, the KV pairs llm_load_hparams reads,
+        a string-array KV like a tokenizer table so that the parser's array skipping is exercised)."""
+        import gguf
+        w = gguf.GGUFWriter(str(path), self.arch)
+        hp = self.hp
+        w.add_block_count(hp["n_layer"]); w.add_embedding_length(hp["n_embd"]); w.add_head_count(hp["n_head"])
+        w.add_head_count_kv(hp["n_head_kv"]); w.add_feed_forward_length(hp["n_ff"]); w.add_context_length(hp["n_ctx_orig"])
+        w.add_rope_dimension_count(128); w.add_rope_freq_base(hp["rope_freq_base"]); w.add_layer_norm_rms_eps(hp["rms_eps"])
+        if with_tokenizer_array:
+            w.add_array("tokenizer.ggml.tokens", [f"t{i}" for i in range(hp["n_vocab"])])
+            w.add_array("tokenizer.ggml.scores", [float(i) for i in range(hp["n_vocab"])])
+        for name, (t, a) in self.tensors.items():
+            if t == O.F32:
+                w.add_tensor(name, np.ascontiguousarray(a, dtype=np.float32))
+            else:
+                K = self._row_len(name)
+                rb = O.row_size(t, K)
+                w.add_tensor(name, np.ascontiguousarray(a).view(np.uint8).reshape(-1, rb), raw_dtype=gguf.GGMLQuantizationType(t))
+        w.write_header_to_file(); w.write_kv_data_to_file(); w.write_tensors_to_file(); w.close()
+
+    def _row_len(self, name):
+        E, F, QD = self.hp["n_embd"], self.hp["n_ff"], self.hp["n_head"] * 128
+        if name.endswith("ffn_down.weight"):
+            return F
+        if name.endswith("attn_output.weight"):
+            return QD
+        return E
+
+
 def from_golden(path):
     """Rebuilds a TinyModel (weights + hparams) and its reference outputs from a committed golden fixture."""
     z = np.load(path)
