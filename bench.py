@@ -444,7 +444,9 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        # a rank that fails must take the job down in minutes, not in NCCL's default 10-minute watchdog period
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
     assert args.steps + args.warmup + PROMPT <= args.n_ctx, "n_ctx too small for prompt + warmup + steps"
 
     L = hp["n_layer"]
@@ -624,6 +626,72 @@ def main():
         t = torch.tensor([float(wb), gemv_ms, float(gemv_bytes), float(gemv_launches)], device=torch.device("cuda", local), dtype=torch.float64)
         dist.all_reduce(t)
         wb, gemv_ms, gemv_bytes, gemv_launches = int(t[0].item()), float(t[1].item()), int(t[2].item()), int(t[3].item())
+    pp_result = None
+    if world > 1 and args.pp > 0 and args.pp <= args.n_ctx:
+        # Prompt processing through the layer pipeline (prima's windows during prefill): 512-token micro-batches, every stage works on a
+        # different micro-batch once the pipeline is full; hidden states [512][n_embd] f32 travel stage to stage by NCCL send/recv on the
+        # engine stream.  Timed on the device (events on the engine stream), max over ranks, best of 3 after a warm-up pass.
+        UB = 512
+        nub = (args.pp + UB - 1) // UB
+        hbuf = torch.empty((UB, E), dtype=torch.float32, device=cuda_dev)
+        toks_all = np.array([token_at(i, nv) for i in range(args.pp)], dtype=np.int32)
+
+        def pp_pass():
+            with torch.cuda.stream(ext):
+                for j in range(nub):
+                    n = min(UB, args.pp - j * UB)
+                    if rank > 0:
+                        dist.recv(hbuf[:n], src=rank - 1)
+                    hp_out = eng.prefill_stage(toks_all[j * UB:j * UB + n] if rank == 0 else None, hbuf.data_ptr() if rank > 0 else None, n, j * UB)
+                    if rank < world - 1:
+                        dist.send(torch.as_tensor(DevBuf(hp_out, n * E), device=cuda_dev).view(n, E), dst=rank + 1)
+        def all_ok(err):
+            """Every rank learns whether any rank failed, so that no rank walks into a barrier alone."""
+            if err is not None:
+                print(f"[rank {rank}] pipelined prefill failed: {err}", file=sys.stderr, flush=True)
+            f = torch.tensor([0 if err is None else 1], device=cuda_dev)
+            dist.all_reduce(f, op=dist.ReduceOp.MAX)
+            return int(f.item()) == 0
+
+        def guarded_pass():
+            try:
+                pp_pass()
+                torch.cuda.synchronize()
+                return None
+            except Exception as ex:
+                return repr(ex)
+
+        best, ok = None, True
+        try:
+            eng.kv_clear()
+            ok = all_ok(guarded_pass())
+            for _ in range(3 if ok else 0):
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                with torch.cuda.stream(ext):
+                    e0.record()
+                err = guarded_pass()
+                with torch.cuda.stream(ext):
+                    e1.record()
+                if not all_ok(err):
+                    ok = False
+                    break
+                barrier()
+                t = torch.tensor([e0.elapsed_time(e1)], device=cuda_dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                best = float(t.item()) if best is None else min(best, float(t.item()))
+            if not ok or best is None:
+                raise RuntimeError("a rank failed (see stderr)")
+            mm, att, head = prefill_flops(hp, args.pp)
+            tpeak, tsrc = tensor_peak()
+            pp_result = {"metric": f"prompt tokens/s, {cfg['name']}, {args.pp} tokens in {nub} micro-batches of {UB} through the {world}-stage layer pipeline",
+                              "tokens": args.pp, "ms": best, "value": args.pp / (best * 1e-3), "unit": "tokens/s",
+                              "timing": "CUDA events on the engine stream around the whole prompt, max over ranks, best of 3",
+                              "roofline": {"bound": "tensor", "achieved": (mm + att + head) / (best * 1e-3) / 1e12 / world, "peak": tpeak, "unit": "TFLOP/s per GPU",
+                                           "frac": (mm + att + head) / (best * 1e-3) / 1e12 / world / tpeak, "peak_source": tsrc,
+                                           "note": f"per GPU; the pipeline is full for {nub} of {nub + world - 1} micro-batch slots (bubble {(world - 1) / (nub + world - 1):.2f})"}}
+        except Exception as ex:
+            pp_result = {"value": None, "unit": "tokens/s", "error": repr(ex)}
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -653,6 +721,8 @@ def main():
                                     "frac_of_8TBs_north_star": (wb + kv_bytes) / (ms_step * 1e-3) / 8e12}},
         "model_load_s": t_load,
     }
+    if pp_result is not None:
+        out["prefill"] = pp_result
     if ring is not None:
         # headline at N > 1: aggregate decode throughput of the ring with N sequences (each b = 1) in flight; the single-sequence
         # latency run above stays in `latency_b1` (serial across stages by nature: N GPUs cannot cut one token's latency)
@@ -674,51 +744,6 @@ def main():
         out["pipeline"] = {"stages": world, "hand_offs_per_token": world, "sum_of_stage_ms": stage_ms, "pipelined_ms_per_token": ms_step,
                            "exposed_handoff_ms": max(0.0, ms_step - stage_ms), "exposed_frac": max(0.0, ms_step - stage_ms) / ms_step,
                            "note": "b=1 decode is serial across stages (SURVEY H7): N GPUs hold N x the model, they do not cut the token latency"}
-    if world > 1 and args.pp > 0 and args.pp <= args.n_ctx:
-        # Prompt processing through the layer pipeline (prima's windows during prefill): 512-token micro-batches, every stage works on a
-        # different micro-batch once the pipeline is full; hidden states [512][n_embd] f32 travel stage to stage by NCCL send/recv on the
-        # engine stream.  Timed on the device (events on the engine stream), max over ranks, best of 3 after a warm-up pass.
-        UB = 512
-        nub = (args.pp + UB - 1) // UB
-        hbuf = torch.empty((UB, E), dtype=torch.float32, device=cuda_dev)
-        toks_all = np.array([token_at(i, nv) for i in range(args.pp)], dtype=np.int32)
-
-        def pp_pass():
-            with torch.cuda.stream(ext):
-                for j in range(nub):
-                    n = min(UB, args.pp - j * UB)
-                    if rank > 0:
-                        dist.recv(hbuf[:n], src=rank - 1)
-                    hp_out = eng.prefill_stage(toks_all[j * UB:j * UB + n] if rank == 0 else None, hbuf.data_ptr() if rank > 0 else None, n, j * UB)
-                    if rank < world - 1:
-                        dist.send(torch.as_tensor(DevBuf(hp_out, n * E), device=cuda_dev).view(n, E), dst=rank + 1)
-        try:
-            eng.kv_clear()
-            pp_pass()
-            barrier()
-            best = None
-            for _ in range(3):
-                barrier()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                with torch.cuda.stream(ext):
-                    e0.record()
-                pp_pass()
-                with torch.cuda.stream(ext):
-                    e1.record()
-                barrier()
-                t = torch.tensor([e0.elapsed_time(e1)], device=cuda_dev)
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                best = float(t.item()) if best is None else min(best, float(t.item()))
-            mm, att, head = prefill_flops(hp, args.pp)
-            tpeak, tsrc = tensor_peak()
-            out["prefill"] = {"metric": f"prompt tokens/s, {cfg['name']}, {args.pp} tokens in {nub} micro-batches of {UB} through the {world}-stage layer pipeline",
-                              "tokens": args.pp, "ms": best, "value": args.pp / (best * 1e-3), "unit": "tokens/s",
-                              "timing": "CUDA events on the engine stream around the whole prompt, max over ranks, best of 3",
-                              "roofline": {"bound": "tensor", "achieved": (mm + att + head) / (best * 1e-3) / 1e12 / world, "peak": tpeak, "unit": "TFLOP/s per GPU",
-                                           "frac": (mm + att + head) / (best * 1e-3) / 1e12 / world / tpeak, "peak_source": tsrc,
-                                           "note": f"per GPU; the pipeline is full for {nub} of {nub + world - 1} micro-batch slots (bubble {(world - 1) / (nub + world - 1):.2f})"}}
-        except Exception as ex:
-            out["prefill"] = {"value": None, "unit": "tokens/s", "error": repr(ex)}
     if world == 1 and args.pp > 0 and args.pp <= args.n_ctx:
         try:
             # prompt processing (prefill) of one ubatch through pb200_prefill: tensor-core mat-muls, batched attention

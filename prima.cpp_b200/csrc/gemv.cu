@@ -98,6 +98,8 @@ __device__ __forceinline__ float dot_block(int type, const uint8_t * bp, const A
     if (TYPE == T_Q4_K) return dot_q4K(bp, r);
     if (TYPE == T_Q5_K) return dot_q5K(bp, r);
     if (TYPE == T_Q6_K) return dot_q6K(bp, r);
+    if (TYPE == T_Q8_0) return dot_q8_0x8(bp, r);
+    if (TYPE == T_Q5_1) return dot_q5_1x8(bp, r);
     if (type == T_Q4_K) return dot_q4K(bp, r);
     if (type == T_Q6_K) return dot_q6K(bp, r);
     return dot_q5K(bp, r);
@@ -257,7 +259,35 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_CTAS_PER_SM) k_gemv_kquant(
         dist_prologue(P, ctl, warp, lane);
         grid_barrier(P, ctl);
     }
-    {
+    constexpr bool BLK32 = TYPE == T_Q8_0 || TYPE == T_Q5_1;
+    if (BLK32) {
+        // q8_0 / q8_1 activation (qs[K] | d[K/32] | s[K/32]): columns of 8 blocks, qs with the padded column stride, the scales dense
+        // (8 floats per column) behind them
+        float * sd = reinterpret_cast<float *>(act_smem + P.nblk * ACT_SMEM_QS_STRIDE);
+        float * ss = sd + P.nblk * 8;
+        const int nq = P.K / 16, nb32 = P.K / 32;
+        for (int i = threadIdx.x; i < nq; i += GEMV_THREADS)
+            *reinterpret_cast<int4 *>(sa.qs + (i >> 4) * ACT_SMEM_QS_STRIDE + (i & 15) * 16) = __ldcg(reinterpret_cast<const int4 *>(P.act.qs) + i);
+        for (int i = threadIdx.x; i < P.nblk * 8; i += GEMV_THREADS) {
+            sd[i] = i < nb32 ? __ldcg(P.act.d + i) : 0.f;
+            if (TYPE == T_Q5_1) ss[i] = i < nb32 ? __ldcg(P.act.s + i) : 0.f;
+        }
+        fill_rest(P, ctl, stages, pol);
+        __syncthreads();
+        r.nb = valid ? min(8, nb32 - 8 * blk) : 0;
+        if (valid) {
+            const int4 * q = reinterpret_cast<const int4 *>(sa.qs + blk * ACT_SMEM_QS_STRIDE);
+            const int nq4 = r.nb * 2;                                  // the blocks that exist: 2 x 16 bytes each
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                int4 v = make_int4(0, 0, 0, 0);
+                if (i < nq4) v = q[i];
+                r.a[4 * i + 0] = v.x; r.a[4 * i + 1] = v.y; r.a[4 * i + 2] = v.z; r.a[4 * i + 3] = v.w;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) { r.d8[j] = sd[blk * 8 + j]; r.s8[j] = TYPE == T_Q5_1 ? ss[blk * 8 + j] : 0.f; }
+        }
+    } else {
         // ONE coalesced copy of the quantized activation per CTA (qs | bsums | d), staged with the padded strides
         constexpr int NQ_MAX = (GEMV_ACT_MAX_NBLK * 16 + GEMV_THREADS - 1) / GEMV_THREADS;   // int4 of qs per thread (7)
         const int nq = P.K / 16, nb16 = P.K / 128;
@@ -279,9 +309,9 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_CTAS_PER_SM) k_gemv_kquant(
         if ((int) threadIdx.x < nb16) *reinterpret_cast<int4 *>(reinterpret_cast<char *>(sa.bsums) + (threadIdx.x >> 1) * (2 * ACT_SMEM_BS_STRIDE) + (threadIdx.x & 1) * 16) = cb;
         if ((int) threadIdx.x < P.nblk) sa.d[threadIdx.x] = cd;
         __syncthreads();
+        load_act_regs(r, sa, blk, valid);
+        finish_act_regs(r);
     }
-    load_act_regs(r, sa, blk, valid);
-    finish_act_regs(r);
     if (P.nstage_init < P.nstage) {
         __syncthreads();   // every warp has its registers: hand the staging area to the ring
         if (threadIdx.x == 0) {
@@ -306,7 +336,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, GEMV_CTAS_PER_SM) k_gemv_kquant(
         tile_info(P, t, m, r0, nrows);
         const GemvMat & M = P.mat[m];
         const int type = TYPE ? TYPE : M.type;
-        const int bpb = type == T_Q4_K ? BYTES_Q4_K : (type == T_Q5_K ? BYTES_Q5_K : BYTES_Q6_K);
+        const int bpb = type == T_Q4_K ? BYTES_Q4_K : type == T_Q5_K ? BYTES_Q5_K : type == T_Q6_K ? BYTES_Q6_K : type == T_Q8_0 ? 8 * BYTES_Q8_0 : 8 * BYTES_Q5_1;
         const uint32_t mis = (uint32_t) (((int64_t) r0 * M.row_bytes) & 15);
         const uint8_t * tile = stages + (size_t) s * P.stage_bytes + mis;
         const int spt = M.rows_per_tile >> rsh;                                                // row slots per tile (a slot = rpw rows, one per sub-warp)
@@ -700,9 +730,12 @@ static const GemvTune tune = [] {
     if (const char * e = getenv("PB200_GEMV_MAX_STAGE")) t.max_stage = std::min(GEMV_MAX_STAGE, std::max(2, atoi(e)));
     return t;
 }();
+static bool is_blk32(int t) { return t == T_Q8_0 || t == T_Q5_1; }
 static bool gemv_plan(const int * types, const int * Ns, int nmat, int K, GemvPlan & pl) {
-    if (!gemv_fused_prologue_ok(K)) return false;
-    const int nblk = K / 256;
+    // k-quants: K a multiple of 256; 32-element block types (one matrix per launch): K a multiple of 32, columns of 8 blocks
+    const bool b32 = nmat == 1 && is_blk32(types[0]);
+    if (b32 ? !(K > 0 && K % 32 == 0 && (K + 255) / 256 <= GEMV_ACT_MAX_NBLK) : !gemv_fused_prologue_ok(K)) return false;
+    const int nblk = (K + 255) / 256;
     int wpr = 1;
     while (wpr * 32 < nblk) wpr *= 2;
     const int ngroups = GEMV_NW / wpr;
@@ -712,8 +745,9 @@ static bool gemv_plan(const int * types, const int * Ns, int nmat, int K, GemvPl
     pl.nblk_p2 = nbp;
     int64_t biggest = 0;
     for (int i = 0; i < nmat; i++) {
-        if (!is_kquant(types[i]) || Ns[i] < 1) return false;
+        if (!(is_kquant(types[i]) || b32) || Ns[i] < 1) return false;
         const int64_t rb = row_bytes(types[i], K);
+        if (b32 && rb % 8 != 0) return false;          // the column dots read 64-bit words
         int R = (int) std::max<int64_t>(1, tune.stage_target / rb);
         R = std::max(rpw, R / rpw * rpw);              // whole slots
         if (wpr > 1) {                             // split rows: at most one row per warp group and stage, and a ring of >= 4 stages
@@ -753,7 +787,7 @@ static bool gemv_plan(const int * types, const int * Ns, int nmat, int K, GemvPl
         }
     }
     pl.nstage_init = pl.nstage - act_stages;
-    if (pl.nstage_init < 2) return false;
+    if (pl.nstage_init < (b32 ? 1 : 2)) return false;   // (31-KB Q8_0 rows: a ring of 3, one stage before the activation is in registers)
     pl.smem = GEMV_CTL_BYTES + pl.nstage * pl.stage_bytes;
     return true;
 }
@@ -783,18 +817,21 @@ int launch_gemv_kquant(const GemvDesc * d, int nmat, int K, const ActQ & act, cu
 }
 
 int launch_gemv_kquant_fused(const GemvDesc * d, int nmat, int K, const ActQ & act, const GemvFused & pro, cudaStream_t stream, bool pdl) {
-    if (nmat < 1 || nmat > GEMV_MAX_MAT || K <= 0 || K % 256 != 0) return (int) cudaErrorInvalidValue;
+    const bool b32 = nmat == 1 && is_blk32(d[0].type);   // Q8_0 / Q5_1 (act: q8_0 / q8_1): same ring, columns of 8 blocks, no fused prologue
+    if (nmat < 1 || nmat > GEMV_MAX_MAT || K <= 0 || (b32 ? K % 32 != 0 : K % 256 != 0)) return (int) cudaErrorInvalidValue;
+    if (b32 && pro.kind != PRO_NONE) return (int) cudaErrorInvalidValue;
     int types[GEMV_MAX_MAT], Ns[GEMV_MAX_MAT];
     bool fast = true;
     for (int i = 0; i < nmat; i++) {
         types[i] = d[i].type; Ns[i] = d[i].N;
-        if (!is_kquant(d[i].type)) return (int) cudaErrorInvalidValue;
+        if (!is_kquant(d[i].type) && !b32) return (int) cudaErrorInvalidValue;
         if ((uintptr_t) d[i].W & 15) fast = false;      // bulk copies need 16-byte aligned sources
     }
     GemvPlan pl;
     fast = fast && gemv_plan(types, Ns, nmat, K, pl);
     if (!fast) {
         if (pro.kind != PRO_NONE) return (int) cudaErrorInvalidValue;   // callers must check gemv_fused_prologue_ok / alignment
+        if (b32) return (int) cudaErrorNotSupported;                     // launch_gemv_generic falls back to its own kernels
         for (int i = 0; i < nmat; i++) {
             int e = launch_gemv_generic(d[i], K, act, stream, pdl);
             if (e) return e;
@@ -804,7 +841,7 @@ int launch_gemv_kquant_fused(const GemvDesc * d, int nmat, int K, const ActQ & a
     GemvParams P{};
     P.wpr = pl.wpr;
     P.nblk_p2 = pl.nblk_p2;
-    P.nblk = K / 256;
+    P.nblk = (K + 255) / 256;
     P.K = K;
     P.nmat = nmat;
     P.nstage = pl.nstage;
@@ -841,15 +878,17 @@ int launch_gemv_kquant_fused(const GemvDesc * d, int nmat, int K, const ActQ & a
     // instantiation: weight type (0 = mixed) x split rows x instrumented
     int ty = types[0];
     for (int i = 1; i < nmat; i++) if (types[i] != ty) ty = 0;
-    const int ti = ty == T_Q4_K ? 1 : ty == T_Q5_K ? 2 : ty == T_Q6_K ? 3 : 0;
+    const int ti = ty == T_Q4_K ? 1 : ty == T_Q5_K ? 2 : ty == T_Q6_K ? 3 : ty == T_Q8_0 ? 4 : ty == T_Q5_1 ? 5 : 0;
     const bool tr = g_trace_buf != nullptr;
     typedef void (*kern_t)(const GemvParams);
-    static const kern_t table[4][2][2] = {
+    static const kern_t table[6][2][2] = {
         {{k_gemv_kquant<0, false, false>, k_gemv_kquant<0, false, true>}, {k_gemv_kquant<0, true, false>, k_gemv_kquant<0, true, true>}},
         {{k_gemv_kquant<T_Q4_K, false, false>, k_gemv_kquant<T_Q4_K, false, true>}, {k_gemv_kquant<T_Q4_K, true, false>, k_gemv_kquant<T_Q4_K, true, true>}},
         {{k_gemv_kquant<T_Q5_K, false, false>, k_gemv_kquant<T_Q5_K, false, true>}, {k_gemv_kquant<T_Q5_K, true, false>, k_gemv_kquant<T_Q5_K, true, true>}},
-        {{k_gemv_kquant<T_Q6_K, false, false>, k_gemv_kquant<T_Q6_K, false, true>}, {k_gemv_kquant<T_Q6_K, true, false>, k_gemv_kquant<T_Q6_K, true, true>}}};
-    static FuncAttrCache attr_cache[4][2][2];
+        {{k_gemv_kquant<T_Q6_K, false, false>, k_gemv_kquant<T_Q6_K, false, true>}, {k_gemv_kquant<T_Q6_K, true, false>, k_gemv_kquant<T_Q6_K, true, true>}},
+        {{k_gemv_kquant<T_Q8_0, false, false>, k_gemv_kquant<T_Q8_0, false, true>}, {k_gemv_kquant<T_Q8_0, true, false>, k_gemv_kquant<T_Q8_0, true, true>}},
+        {{k_gemv_kquant<T_Q5_1, false, false>, k_gemv_kquant<T_Q5_1, false, true>}, {k_gemv_kquant<T_Q5_1, true, false>, k_gemv_kquant<T_Q5_1, true, true>}}};
+    static FuncAttrCache attr_cache[6][2][2];
     const int si = pl.wpr > 1 ? 1 : 0;
     const kern_t fn = table[ti][si][tr ? 1 : 0];
     cudaError_t e = ensure_dyn_smem(attr_cache[ti][si][tr ? 1 : 0], (const void *) fn, GEMV_SMEM_LIMIT, true);
@@ -904,7 +943,14 @@ static int launch_gemv_blk32(const GemvDesc & d, int K, const ActQ & act, cudaSt
 }
 
 int launch_gemv_generic(const GemvDesc & d, int K, const ActQ & act, cudaStream_t stream, bool pdl) {
-    // 32-element block types with 8-byte aligned rows and an activation that fits in shared memory: the streaming kernel
+    // 32-element block types: the bulk-copy ring of the k-quant kernel (columns of 8 blocks) when the shape fits it ...
+    static const bool no_ring32 = getenv("PB200_NO_BLK32_RING") != nullptr;
+    if (!no_ring32 && (d.type == T_Q8_0 || d.type == T_Q5_1)) {
+        GemvFused none{};
+        const int rc = launch_gemv_kquant_fused(&d, 1, K, act, none, stream, pdl);
+        if (rc != (int) cudaErrorNotSupported && rc != (int) cudaErrorInvalidValue) return rc;
+    }
+    // ... else, with 8-byte aligned rows and an activation that fits in shared memory, the per-warp cp.async streaming kernel
     static const bool no_b32 = getenv("PB200_NO_BLK32") != nullptr;
     if (!no_b32 && (d.type == T_Q8_0 || d.type == T_Q5_1) && K % 32 == 0 && row_bytes(d.type, K) % 8 == 0 && K % 16 == 0 && K <= 131072 &&
         ((uintptr_t) d.W & 7) == 0)

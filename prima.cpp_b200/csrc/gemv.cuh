@@ -36,9 +36,9 @@ constexpr int GEMV_CTAS_PER_SM = 2;
 constexpr int GEMV_MAX_STAGE = 8;
 constexpr int GEMV_SMEM_LIMIT = 113 * 1024;       // 2 x (113 KB + 1 KB reserved per CTA) = the 228 KB of an SM
 constexpr int GEMV_STAGE_TARGET = 28 * 1024;      // bytes per ring stage aimed for (rows per stage = target / row bytes)
-constexpr int GEMV_ACT_MAX_NBLK = 112;            // K <= 28 672 on the fast path
+constexpr int GEMV_ACT_MAX_NBLK = 116;            // K <= 29 696 on the fast path (Qwen2.5-72B's n_ff = 29 568)
 constexpr int GEMV_MAX_MAT = 3;
-__host__ __device__ inline int gemv_act_smem_bytes(int nblk) { return nblk * (ACT_SMEM_QS_STRIDE + 2 * ACT_SMEM_BS_STRIDE + 4) + 64; }   // padded qs | padded bsums | d
+__host__ __device__ inline int gemv_act_smem_bytes(int nblk) { return nblk * (ACT_SMEM_QS_STRIDE + 64) + 64; }   // padded qs | padded bsums + d (k-quants: 52 B per column) or d8 | s8 (32-element block types: 64 B)
 
 struct GemvMat {
     const uint8_t * W;     // raw GGUF blocks, row-major [N][K/256 blocks]
@@ -105,6 +105,10 @@ struct ActRegs {
     int bs[8];      // 16 x int16 bsums (pairs)
     int bs32[4];    // 8 x int16: bsums per 32 (pairs)
     float d;        // q8_K scale (0 for an out-of-range block => contributes nothing)
+    // 32-element block weight types (Q8_0 / Q5_1): the column = 8 consecutive blocks, activation q8_0 / q8_1 with one scale (and one
+    // d * sum) per block; nb = how many of the 8 blocks exist (the last column of a K % 256 != 0 row is short)
+    float d8[8], s8[8];
+    int nb;
 };
 
 __device__ __forceinline__ void load_act_regs(ActRegs & r, const ActQ & act, int blk, bool valid) {
@@ -161,12 +165,18 @@ __device__ __forceinline__ float dot_q4K(const uint8_t * blk, const ActRegs & r)
     for (int c = 0; c < 4; c++) {
         const uint4 q0 = p[1 + 2 * c], q1 = p[2 + 2 * c];
         const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-        int dlo = 0, dhi = 0;
+        // four dependency chains of 4 dp4a per chunk instead of two of 8 (integer sums: the regrouping is exact).  With 4 warps per
+        // scheduler the kernel is bound by dependent-issue latency (~7 cycles between two instructions of a warp, 50-60 % issue slots used),
+        // so instruction-level parallelism inside the dot is what the streaming rate of the issue-bound launches follows.
+        int dlo0 = 0, dlo1 = 0, dhi0 = 0, dhi1 = 0;
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            dlo = dp4a_us(w[i] & 0x0f0f0f0fu, r.a[16 * c + i], dlo);
-            dhi = dp4a_us(w[i] & 0xf0f0f0f0u, r.a[16 * c + 8 + i], dhi);   // 16 x the high-nibble dot (exact)
+        for (int i = 0; i < 8; i += 2) {
+            dlo0 = dp4a_us(w[i] & 0x0f0f0f0fu, r.a[16 * c + i], dlo0);
+            dlo1 = dp4a_us(w[i + 1] & 0x0f0f0f0fu, r.a[16 * c + i + 1], dlo1);
+            dhi0 = dp4a_us(w[i] & 0xf0f0f0f0u, r.a[16 * c + 8 + i], dhi0);   // 16 x the high-nibble dot (exact)
+            dhi1 = dp4a_us(w[i + 1] & 0xf0f0f0f0u, r.a[16 * c + 8 + i + 1], dhi1);
         }
+        const int dlo = dlo0 + dlo1, dhi = dhi0 + dhi1;
         const uint32_t scw = c < 2 ? sc_lo : sc_hi;
         sumi += ubyte(scw, (2 * c) & 3) * dlo + ubyte(scw, (2 * c + 1) & 3) * (dhi >> 4);
     }
@@ -266,6 +276,67 @@ __device__ __forceinline__ float dot_q6K(const uint8_t * blk, const ActRegs & r)
         sb = (k & 1) ? dp2a_hi_ss(r.bs[k], scw[k >> 1], sb) : dp2a_lo_ss(r.bs[k], scw[k >> 1], sb);
     }
     return (dw * r.d) * (float) (sumi - 32 * sb);
+}
+
+// ---- 32-element block types on the same ring: a lane's column is 8 consecutive blocks (272 B of Q8_0, 192 B of Q5_1) ----
+// Follows ggml_vec_dot_q8_0_q8_0 (ggml-quants.c:5518) and ggml_vec_dot_q5_1_q8_1 (:5144) block by block, like k_gemv_generic: the integer
+// block sums are exact, the per-block fp32 scale products and the running fp32 sum are formed in the same order.
+// Q8_0: rows are 8-byte aligned in the stage (row bytes = 34 * K/32; 31 416 for K = 29 568), so a column is read with 64-bit loads and
+// the 2-byte phase of every block inside it is a compile-time constant (even blocks start on a word, odd ones in its upper half).
+__device__ __forceinline__ float dot_q8_0x8(const uint8_t * col, const ActRegs & r) {
+    const uint2 * c2 = reinterpret_cast<const uint2 *>(col);
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        if (j < r.nb) {
+            const int wj = (34 * j) >> 2;            // first 32-bit word of the block inside the column
+            const bool odd = (j & 1) != 0;           // block starts 2 bytes into that word
+            uint32_t w[10];
+#pragma unroll
+            for (int i = 0; i < 5; i++) { const uint2 t = c2[(wj >> 1) + i]; w[2 * i] = t.x; w[2 * i + 1] = t.y; }
+            const int o = wj & 1;
+            const float d = __half2float(__ushort_as_half((unsigned short) (odd ? (w[o] >> 16) : (w[o] & 0xffffu))));
+            int sumi = 0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const uint32_t q = odd ? w[o + 1 + i] : __byte_perm(w[o + i], w[o + i + 1], 0x5432);
+                sumi = dp4a_ss((int) q, r.a[8 * j + i], sumi);
+            }
+            acc += (float) sumi * (d * r.d8[j]);
+        }
+    }
+    return acc;
+}
+// Q5_1: 24-byte blocks [d f16][m f16][qh u32][16 x 2 nibbles]; rows are 16-byte aligned when K % 64 == 0, 8-byte otherwise.
+__device__ __forceinline__ float dot_q5_1x8(const uint8_t * col, const ActRegs & r) {
+    const uint2 * c2 = reinterpret_cast<const uint2 *>(col);
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        if (j < r.nb) {
+            const uint2 hd = c2[3 * j], qa = c2[3 * j + 1], qb = c2[3 * j + 2];
+            const float d = __half2float(__ushort_as_half((unsigned short) (hd.x & 0xffffu)));
+            const float mm = __half2float(__ushort_as_half((unsigned short) (hd.x >> 16)));
+            const uint32_t qh = hd.y;
+            const uint32_t w[4] = {qa.x, qa.y, qb.x, qb.y};
+            // sum (nibble + 16 * bit) * a  =  sum nibble * a  +  16 * sum bit * a: the fifth bits get their own dp4a instead of being merged into
+            // the nibble bytes (13 instead of 18 instructions per 8 elements; integer sums, exact).  bit k of a nibble of qh -> bit 0 of byte k:
+            // x * 0x00204081 puts bit k at 8k (no carries)
+            int sumi = 0, sumb = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const uint32_t hb_lo = (((qh >> (4 * i)) & 0xFu) * 0x00204081u) & 0x01010101u;
+                const uint32_t hb_hi = (((qh >> (4 * i + 16)) & 0xFu) * 0x00204081u) & 0x01010101u;
+                sumi = dp4a_us(w[i] & 0x0f0f0f0fu, r.a[8 * j + i], sumi);
+                sumb = dp4a_us(hb_lo, r.a[8 * j + i], sumb);
+                sumi = dp4a_us((w[i] >> 4) & 0x0f0f0f0fu, r.a[8 * j + 4 + i], sumi);
+                sumb = dp4a_us(hb_hi, r.a[8 * j + 4 + i], sumb);
+            }
+            sumi += 16 * sumb;
+            acc += (d * r.d8[j]) * (float) sumi + mm * r.s8[j];
+        }
+    }
+    return acc;
 }
 
 }  // namespace pb

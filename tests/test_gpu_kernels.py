@@ -53,7 +53,7 @@ def test_gemv_kquant_vs_oracle(cuda, lib, port, t, N, K):
 
 
 @pytest.mark.parametrize("t", [O.Q8_0, O.Q5_1], ids=lambda t: O.TYPE_NAME[t])
-@pytest.mark.parametrize("N,K", [(16, 64), (33, 7392), (5, 29568)])
+@pytest.mark.parametrize("N,K", [(16, 64), (33, 7392), (5, 29568), (301, 29568), (64, 1280), (40, 4096), (7, 8192), (130, 14336)])   # K % 128 == 0: the bulk-copy ring (columns of 8 blocks; 29 568 = 115.5 columns, split rows), else the per-warp kernels
 def test_gemv_small_block_types_vs_oracle(cuda, lib, port, t, N, K):
     W = O.synth_blocks(t, N, K, seed=N + K)
     x = np.random.default_rng(K).standard_normal(K).astype(np.float32)
