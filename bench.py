@@ -496,7 +496,7 @@ def main():
                 eng.decode_async(token, pos)
 
     stage = EngineStage()
-    runner = pkg.PipelineRunner(stage, rank, world, dist, tok_t)
+    runner = pkg.PipelineRunner(stage, rank, world, dist, tok_t, stream=ext if world > 1 else None)
 
     def sample_dev(_logits):
         eng.argmax_seq(0, False)      # device argmax (pb200_argmax_seq): no torch kernel, no host sync on the step path
@@ -593,7 +593,7 @@ def main():
                 if rank == world - 1:
                     eng.argmax_seq(s, False)
 
-        rr = pkg.RingRunner(RingStage(), rank, world, dist)
+        rr = pkg.RingRunner(RingStage(), rank, world, dist, stream=ext)
         seeds = [(token_at(1000 + s, nv), PROMPT) for s in range(world)]
         barrier()
         with torch.cuda.stream(ext):

@@ -8,8 +8,22 @@ the sampled token id returns from the last rank to rank 0 (prima returns the res
 decoding strictly sequential.  No collective is involved: the path has no reduction step.
 
 The stage object only needs: decode_async(token, pos), and the tensors hidden_in / hidden_out / logits that alias the
-engine's device buffers.  The same class drives CPU tensors over gloo in the tests."""
+engine's device buffers.  The same class drives CPU tensors over gloo in the tests.
+
+Stream contract: NCCL orders its transfers against torch's CURRENT stream, the engine enqueues on its own stream (pb200_stream).  Pass
+that stream (a torch.cuda.ExternalStream over it) as `stream=` and the runners enter it around every exchange + step themselves; without
+it the caller must have made it current (bench.py does both)."""
 from __future__ import annotations
+
+import contextlib
+
+
+def _entered(stream):
+    """Context manager that makes `stream` torch's current stream (no-op for None / CPU runs)."""
+    if stream is None:
+        return contextlib.nullcontext()
+    import torch
+    return torch.cuda.stream(stream)
 
 
 def layer_windows(n_layer: int, world: int) -> list[int]:
@@ -20,8 +34,9 @@ def layer_windows(n_layer: int, world: int) -> list[int]:
 
 
 class PipelineRunner:
-    def __init__(self, stage, rank: int, world: int, dist=None, token_tensor=None):
+    def __init__(self, stage, rank: int, world: int, dist=None, token_tensor=None, stream=None):
         self.stage, self.rank, self.world, self.dist = stage, rank, world, dist
+        self.stream = stream      # the engine's stream as a torch stream: entered around every step (see the module docstring)
         self.tok = token_tensor   # int64[1] on the stage's device
         if world > 1 and dist is None:
             raise ValueError("world > 1 needs torch.distributed")
@@ -37,6 +52,10 @@ class PipelineRunner:
     def step(self, token: int, pos: int, sample=None) -> int | None:
         """Runs one token through the pipeline.  Returns the sampled token on rank 0 (None elsewhere / when world == 1 and no
         sampler is given).  `sample(logits_tensor) -> int64[1] tensor` runs on the last rank."""
+        with _entered(self.stream):
+            return self._step(token, pos, sample)
+
+    def _step(self, token: int, pos: int, sample=None) -> int | None:
         st, d = self.stage, self.dist
         if self.world == 1:
             st.decode_async(token, pos)
@@ -75,14 +94,19 @@ class RingRunner:
     (stage 0: first token of a sequence; other stages: position only) and run(seq) (one step of the slot, sampling included on the
     last stage).  The same class drives CPU tensors over gloo in tests/test_pipeline_gloo.py."""
 
-    def __init__(self, stage, rank: int, world: int, dist):
+    def __init__(self, stage, rank: int, world: int, dist, stream=None):
         if world < 2 or dist is None:
             raise ValueError("RingRunner needs world >= 2 and torch.distributed")
         self.stage, self.rank, self.world, self.dist = stage, rank, world, dist
+        self.stream = stream
         self.t = 0
 
     def slots(self, n: int, first_tokens=None) -> None:
         """Runs time slots self.t .. self.t + n - 1 (the same n on every rank).  first_tokens[s] = (token, pos) seeds sequence s."""
+        with _entered(self.stream):
+            self._slots(n, first_tokens)
+
+    def _slots(self, n: int, first_tokens=None) -> None:
         st, d, r, N = self.stage, self.dist, self.rank, self.world
         nxt, prv = (r + 1) % N, (r - 1) % N
         for _ in range(n):
