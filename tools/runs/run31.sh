@@ -1,0 +1,9 @@
+mkdir -p gpurun_out
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29519"
+(timeout 300 $TR bench.py --gpus 2 --steps 20 --warmup 5 2>gpurun_out/bench31.err | tail -1) > gpurun_out/bench31_pp2.json; python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/bench31_pp2.json').read().strip().splitlines()[-1])
+print("N=2 llama70b value",d["value"],"latency",d.get("latency_b1",{}).get("value"),"exposed",d.get("pipeline",{}).get("exposed_frac"))
+PY
+grep -i "error\|Traceback" gpurun_out/bench31.err | head -3
+(timeout 200 python -m pytest tests/test_gpu_ring.py -x -q 2>&1 | tail -2)
