@@ -636,15 +636,18 @@ def main():
         hbuf = torch.empty((UB, E), dtype=torch.float32, device=cuda_dev)
         toks_all = np.array([token_at(i, nv) for i in range(args.pp)], dtype=np.int32)
 
+        class PrefillStage:   # adapter: pb200_prefill_stage behind the interface prima.cpp_b200.pipeline.PrefillPipeline drives
+            hidden_buf = hbuf
+
+            def prefill_stage(self, tokens, hidden_in, n, pos):
+                hp_out = eng.prefill_stage(tokens, hidden_in.data_ptr() if hidden_in is not None else None, n, pos)
+                return torch.as_tensor(DevBuf(hp_out, n * E), device=cuda_dev).view(n, E)
+
+        pipe = pkg.PrefillPipeline(PrefillStage(), rank, world, dist, ubatch=UB, stream=ext)
+
         def pp_pass():
-            with torch.cuda.stream(ext):
-                for j in range(nub):
-                    n = min(UB, args.pp - j * UB)
-                    if rank > 0:
-                        dist.recv(hbuf[:n], src=rank - 1)
-                    hp_out = eng.prefill_stage(toks_all[j * UB:j * UB + n] if rank == 0 else None, hbuf.data_ptr() if rank > 0 else None, n, j * UB)
-                    if rank < world - 1:
-                        dist.send(torch.as_tensor(DevBuf(hp_out, n * E), device=cuda_dev).view(n, E), dst=rank + 1)
+            pipe.run(toks_all, args.pp, 0)
+
         def all_ok(err):
             """Every rank learns whether any rank failed, so that no rank walks into a barrier alone."""
             if err is not None:

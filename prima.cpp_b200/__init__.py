@@ -6,4 +6,4 @@ This Python package is only the thin ctypes binding used by tests and bench.py; 
 path: importing :mod:`host` raises if the CUDA library is missing.
 """
 from .host import Lib, Model, HParams, lib_path, build, TYPES  # noqa: F401
-from .pipeline import PipelineRunner, RingRunner, layer_windows  # noqa: F401
+from .pipeline import PipelineRunner, RingRunner, PrefillPipeline, layer_windows  # noqa: F401

@@ -132,3 +132,35 @@ class RingRunner:
                     st.begin(sq, *first_tokens[sq])
                 st.run(sq)
             self.t += 1
+
+
+class PrefillPipeline:
+    """Prompt processing through the layer pipeline in micro-batches (the reference's n_ubatch = 512; prima ships the ubatch's hidden states
+    from window to window, src/llama.cpp:17825-18029): stage r works on micro-batch j while stage r + 1 works on j - 1.
+
+    The stage object provides prefill_stage(tokens | None, hidden_in | None, n, pos0) -> tensor [n, n_embd] (the stage's output hidden
+    states, valid until its next call; pb200_prefill_stage enqueues on the engine stream and returns at once) and, on every stage but the
+    first, a receive buffer hidden_buf [ubatch, n_embd].  One send / recv pair per stage boundary and micro-batch, in micro-batch order on
+    both sides, so the exchange cannot deadlock; with NCCL everything is ordered on `stream`.  Every rank must call run() with the same
+    token count.  The same class drives CPU tensors over gloo in tests/test_pipeline_gloo.py."""
+
+    def __init__(self, stage, rank: int, world: int, dist, ubatch: int = 512, stream=None):
+        if world < 2 or dist is None:
+            raise ValueError("PrefillPipeline needs world >= 2 and torch.distributed")
+        self.stage, self.rank, self.world, self.dist, self.ubatch, self.stream = stage, rank, world, dist, ubatch, stream
+
+    def run(self, tokens, n_tokens: int, pos0: int = 0):
+        """tokens: the prompt's token ids (read on rank 0 only).  Returns the last micro-batch's output of this stage."""
+        st, d, r = self.stage, self.dist, self.rank
+        out = None
+        with _entered(self.stream):
+            for j0 in range(0, n_tokens, self.ubatch):
+                n = min(self.ubatch, n_tokens - j0)
+                hin = None
+                if r > 0:
+                    hin = st.hidden_buf[:n]
+                    d.recv(hin, src=r - 1)
+                out = st.prefill_stage(tokens[j0:j0 + n] if r == 0 else None, hin, n, pos0 + j0)
+                if r < self.world - 1:
+                    d.send(out, dst=r + 1)
+        return out

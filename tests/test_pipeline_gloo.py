@@ -3,6 +3,7 @@ single-process run of the same toy layers (bit-identical, like the N-rank == 1-r
 import os
 import socket
 
+import numpy as np
 import pytest
 import torch
 import torch.multiprocessing as mp
@@ -160,3 +161,73 @@ def test_ring_of_sequences_matches_sequential_decoding(world):
     [p.join(60) for p in procs]
     assert all(p.exitcode == 0 for p in procs)
     assert [h[:rounds] for h in got] == want
+
+
+# ---- prompt processing through the pipeline in micro-batches (PrefillPipeline; the engine side is pb200_prefill_stage) ----
+class ToyPrefillStage:
+    """A stage whose 'layers' are an affine map per layer that also depends on the token position, so that a wrong micro-batch order,
+    a wrong pos0 or a stale receive buffer changes the result."""
+    E, UB = 8, 4
+
+    def __init__(self, l0, l1, first):
+        self.l0, self.l1, self.first = l0, l1, first
+        self.hidden_buf = torch.zeros((self.UB, self.E), dtype=torch.float64)
+        self.calls = []
+
+    def prefill_stage(self, tokens, hidden_in, n, pos0):
+        self.calls.append((n, pos0))
+        if self.first:
+            x = torch.stack([torch.arange(self.E, dtype=torch.float64) * 0.01 + float(t) for t in tokens])
+        else:
+            x = hidden_in.clone()
+        pos = torch.arange(pos0, pos0 + n, dtype=torch.float64)[:, None]
+        for il in range(self.l0, self.l1):
+            x = x * (1.0 + 0.05 * (il + 1)) + 0.001 * (il + 1) * pos + torch.roll(x, 1, dims=1) * 0.1
+        return x
+
+
+def _prefill_worker(rank, world, port, q, n_tokens):
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+    import pkgload
+    import torch.distributed as dist
+    pkg = pkgload.load()
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    b = pkg.layer_windows(ToyStage.L, world)
+    st = ToyPrefillStage(b[rank], b[rank + 1], rank == 0)
+    pipe = pkg.PrefillPipeline(st, rank, world, dist, ubatch=ToyPrefillStage.UB)
+    toks = [(7 * i + 3) % 11 for i in range(n_tokens)]
+    outs = []
+    orig = st.prefill_stage
+
+    def spy(tokens, hidden_in, n, pos0):
+        y = orig(tokens, hidden_in, n, pos0)
+        outs.append(y.clone())
+        return y
+    st.prefill_stage = spy
+    pipe.run(toks, n_tokens, pos0=2)
+    if rank == world - 1:
+        q.put((torch.cat(outs).tolist(), st.calls))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_tokens", [(2, 10), (3, 9), (2, 4)])
+def test_prefill_pipeline_micro_batches_match_single_stage(world, n_tokens):
+    """N stages x ceil(n / ubatch) micro-batches (the last one ragged) over gloo == one stage over the whole prompt."""
+    single = ToyPrefillStage(0, ToyStage.L, True)
+    toks = [(7 * i + 3) % 11 for i in range(n_tokens)]
+    want = single.prefill_stage(toks, None, n_tokens, 2).tolist()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_prefill_worker, args=(r, world, port, q, n_tokens)) for r in range(world)]
+    [p.start() for p in procs]
+    got, calls = q.get(timeout=120)
+    [p.join(60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    assert np.allclose(np.array(got), np.array(want), rtol=0, atol=1e-12)
+    ub = ToyPrefillStage.UB
+    assert calls == [(min(ub, n_tokens - j), 2 + j) for j in range(0, n_tokens, ub)]
