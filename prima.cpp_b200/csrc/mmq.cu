@@ -21,11 +21,13 @@
 // (two or three addends per element: the order of fp32 adds is the only non-determinism, below the kernel's own fp16 rounding).
 // Inside a CTA the pipeline never drains between segments (raw-block ring, A and B stages and their barriers run on CTA-wide counters):
 //   warp 0      owns TMEM; one lane issues 4 x tcgen05.mma (M=128, N=BN, K=16, kind::f16) per step and accumulator, one commit per step
-//   warp 1      activation producer: one cp.async.bulk per step of the pre-tiled fp16 chunk (BN x 128 B, already in the
-//               UMMA swizzle-128B image), 4-deep ring
-//   warps 2..9  fetch their own rows' raw quantized blocks (16-byte cp.async pieces, 3 super-blocks deep, completion through
-//               cp.async.mbarrier.arrive) and expand 128 x 64 weights per step to fp16 straight into the swizzled A stage (generic-proxy stores +
-//               fence.proxy.async), 2 stages; afterwards warps 2..5 read the accumulator out of TMEM (tcgen05.ld 32x32b) and store dst
+//   warp 1      activation producer: one cp.async.bulk per step and accumulator of the pre-tiled fp16 chunk (BN x 128 B, already in the
+//               UMMA swizzle-128B image), 2-4 stages deep
+//   warps 2..17 (16 expansion warps, 4 threads per weight row) fetch their rows' raw quantized blocks (16-byte cp.async pieces, 3 K groups
+//               deep, completion through cp.async.mbarrier.arrive) and expand 128 x 64 weights per step to fp16 straight into the swizzled A
+//               stage (generic-proxy stores + fence.proxy.async), 2 stages (4 with CTA pairs); at the end of a segment warps 2..9 read the
+//               accumulators out of TMEM (tcgen05.ld 32x32b: quadrant = warp % 4, accumulator = (warp - 2) / 4) and store / add into dst
+// CG = 2 (opt-in): the CTA pair of a cluster shares one M = 256 MMA (cta_group::2), see launch_mmq.
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
