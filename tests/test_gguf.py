@@ -49,6 +49,40 @@ def test_probe_rejects_bad_files(pkg, tmp_path):
     assert lib.c.pb200_gguf_probe(str(tmp_path / "v1.gguf").encode(), C.byref(hp), None, None, None) != 0
 
 
+def test_probe_accepts_version_2_and_custom_alignment(pkg, tmp_path):
+    """GGUF v2 has the v3 layout (64-bit counts and lengths); general.alignment moves the data section (gguf_init_from_file honours both)."""
+    import gguf
+    lib = pkg.Lib.get()
+    tm = _tiny()
+    v3 = tmp_path / "v3.gguf"
+    tm.write_gguf(v3)
+    raw = v3.read_bytes()
+    v2 = tmp_path / "v2.gguf"
+    v2.write_bytes(raw[:4] + (2).to_bytes(4, "little") + raw[8:])
+    hp = pkg.HParams()
+    n = C.c_int32()
+    assert lib.c.pb200_gguf_probe(str(v2).encode(), C.byref(hp), C.byref(n), None, None) == 0
+    assert hp.n_layer == tm.hp["n_layer"] and n.value == len(tm.tensors)
+    # a writer with 64-byte alignment: every tensor offset and the data section start move
+    al = tmp_path / "al.gguf"
+    w = gguf.GGUFWriter(str(al), "llama")
+    w.add_custom_alignment(64)
+    h = tm.hp
+    w.add_block_count(h["n_layer"]); w.add_embedding_length(h["n_embd"]); w.add_head_count(h["n_head"]); w.add_head_count_kv(h["n_head_kv"])
+    w.add_feed_forward_length(h["n_ff"]); w.add_context_length(h["n_ctx_orig"]); w.add_rope_dimension_count(128)
+    for name, (t, a) in tm.tensors.items():
+        if t == 0:
+            w.add_tensor(name, np.ascontiguousarray(a, dtype=np.float32))
+        else:
+            import oracle_lib as O
+            w.add_tensor(name, np.ascontiguousarray(a).view(np.uint8).reshape(-1, O.row_size(t, tm._row_len(name))), raw_dtype=gguf.GGMLQuantizationType(t))
+    w.write_header_to_file(); w.write_kv_data_to_file(); w.write_tensors_to_file(); w.close()
+    nb = C.c_int64()
+    assert lib.c.pb200_gguf_probe(str(al).encode(), C.byref(hp), C.byref(n), C.byref(nb), None) == 0
+    assert hp.n_embd == h["n_embd"] and hp.rope_freq_base == 10000.0      # rope base absent: the loader's default, like llm_load_hparams
+    assert (al.stat().st_size - nb.value) % 64 == 0                          # the data section starts on the custom alignment
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("arch", ["llama", "qwen2"])
 def test_gguf_loaded_model_decodes_like_set_tensor_model(cuda, pkg, tmp_path, arch):
